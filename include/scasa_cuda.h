@@ -1,0 +1,159 @@
+/*
+ * scasa_cuda.h — C ABI of libscasa_cuda: Scasa's 2QUANT quantification path on B200 (sm_100a).
+ *
+ * The reference has no FFI layer: the seam is three R closures sourced into the quant
+ * driver (paths relative to /root/reference/scasa/SCRIPTS/):
+ *
+ *   crpcount_td(mytd)                         Scasa_Rsource.R:416-557  (+ hamming_correction :562-648)
+ *       called per cell at scasa_quant_step2_v1.0.0.R:95
+ *   estim_chunk(Y, DM0, maxiter.bt=1000)      Scasa_Rsource.R:944-1051 (estim.BETA :726-761, estim.X.em :898-922)
+ *       called per chunk at scasa_quant_step2_v1.0.0.R:132
+ *   scasa_genemat(scasa_iso, txmap)           scasa_quant_step3_v1.0.0.R:32-46, called at :48
+ *
+ * plus the chunk split (step2:64-68) and the all-zero-row filter (step2:167).  This header is
+ * what an R shim (.C / .Call) binds instead.  Plain C: pointers and sizes
+ * only, caller-owned buffers, an opaque context that owns everything on the device.
+ *
+ * Conventions
+ *   - every function returns SCASA_OK (0) or a negative SCASA_ERR_*; scasa_last_error()
+ *     gives the message.  Nothing aborts, nothing throws across the boundary.
+ *   - "cell-major": matrix[cell * ncol + col] (R's t(matrix) stored column-major).
+ *   - global row index: rows of all blocks concatenated, row r of block k = q_off[k] + r.
+ *   - global column index: DM0 columns of all blocks concatenated = column order of
+ *     estim_chunk's result (Rsource:1042).
+ *   - there is no CPU fallback: without a CUDA device scasa_ctx_create fails.
+ */
+#ifndef SCASA_CUDA_H
+#define SCASA_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCASA_OK 0
+#define SCASA_ERR_ARG (-1)         /* bad argument / malformed input            */
+#define SCASA_ERR_CUDA (-2)        /* CUDA runtime error (message has the text) */
+#define SCASA_ERR_NOMEM (-3)       /* host or device allocation failed          */
+#define SCASA_ERR_UNSUPPORTED (-4) /* input exceeds a documented limit          */
+#define SCASA_ERR_STATE (-5)       /* call order (nothing staged / not run yet) */
+
+typedef struct scasa_ctx scasa_ctx;
+
+/* The "same convergence options": estim_chunk's defaults (Rsource:944) and the constants
+ * hard-wired next to it.  scasa_opts_default() fills exactly these. */
+typedef struct {
+    int32_t maxiter_x;    /* 1000  maxiter.X                              Rsource:944  */
+    int32_t maxiter_bt;   /* 1000  maxiter.bt as passed at step2:132                   */
+    double maxerr;        /* 0.01                                         Rsource:944  */
+    double lim;           /* 0.01                                         Rsource:944  */
+    int32_t modify;       /* 1     digamma-modified EM                    Rsource:738  */
+    double adjust_esp;    /* 2     pseudo count for poor 2-column blocks  Rsource:973  */
+    int32_t hamming_dist; /* 1                                            Rsource:534  */
+    int32_t fixed_iter;   /* 0     1 = never break: exactly maxiter_x x maxiter_bt iterations (parity mode) */
+    int32_t fp32;         /* 0     reserved (fp32 arithmetic); must be 0 in this version */
+} scasa_opts_t;
+
+/* A block list (R list of small dense matrices) flattened; blocks column-major like R. */
+typedef struct {
+    int32_t n_blocks;
+    const int32_t *q_off; /* [n_blocks+1] first global row of each block      */
+    const int32_t *p_off; /* [n_blocks+1] first global column of each block   */
+    const int64_t *x_off; /* [n_blocks+1] first value of each block in x      */
+    const double *x;      /* values, block k column-major q_k x p_k           */
+} scasa_xmat_t;
+
+/* CRP (un-merged X-matrix) plus what crpcount_td reads from its dimnames. */
+typedef struct {
+    scasa_xmat_t m;
+    const int32_t *col_tx;    /* [sum p] transcript id of each column (caller's dictionary;
+                                 the same ids are used in eqclass transcript sets)            */
+    const uint8_t *row_pat;   /* [sum q*p] 0/1 row-name patterns, row-major inside a block     */
+    const int32_t *name_rank; /* [n_blocks] rank of names(CRP)[k] under sort() (Rsource:484);
+                                 R passes its own order so the session collation is honoured  */
+} scasa_crp_t;
+
+int scasa_opts_default(scasa_opts_t *opts);
+
+/* Uploads DM0 (and CRP when the eqclass entry points are wanted) once; they stay resident.
+ * device = CUDA ordinal (one context per GPU; one host thread or process per context). */
+int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp_or_null,
+                     const scasa_opts_t *opts_or_null, int device, scasa_ctx **out);
+void scasa_ctx_destroy(scasa_ctx *ctx);
+const char *scasa_last_error(const scasa_ctx *ctx_or_null);
+int scasa_set_opts(scasa_ctx *ctx, const scasa_opts_t *opts);
+
+/* sizes a caller needs to allocate outputs */
+int64_t scasa_n_rows(const scasa_ctx *ctx);       /* sum q                         */
+int64_t scasa_n_cols(const scasa_ctx *ctx);       /* sum p of DM0                  */
+int32_t scasa_n_em_blocks(const scasa_ctx *ctx);  /* blocks with nrow > 1          */
+int scasa_em_blocks(const scasa_ctx *ctx, int32_t *block_ids /* [n_em_blocks] */);
+int scasa_poor_blocks(const scasa_ctx *ctx, uint8_t *is_poor /* [n_blocks] */); /* poorCondX, Rsource:957-971 */
+
+/* step2:64-68.  chunk_off[0..*n_chunks] (0-based cell offsets).  `core` is only read when
+ * n_cells <= 100 (step2:66). */
+int scasa_chunk_split(int64_t n_cells, int32_t core, int64_t *chunk_off, int64_t cap,
+                      int32_t *n_chunks);
+
+/* ---- estim_chunk over all chunks of a sample (host buffers; H2D, kernels, D2H inside) ----
+ * Y as CSR by cell: entries of cell c are y_rowptr[c] .. y_rowptr[c+1]-1, y_rowidx = global
+ * row, strictly ascending inside a cell.  iso_out: n_cells x n_cols cell-major.
+ * iters_out (nullable): [n_chunks][n_em_blocks][2] = {outer, total inner} iterations.
+ * gene_* optional (see scasa_set_gene_map). */
+int scasa_estimate(scasa_ctx *ctx, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off,
+                   const int64_t *y_rowptr, const int32_t *y_rowidx, const double *y_val,
+                   double *iso_out, int32_t *iters_out);
+
+/* ---- the same in resident stages (what scasa_estimate is made of) ----------------------- */
+int scasa_stage_counts(scasa_ctx *ctx, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off,
+                       const int64_t *y_rowptr, const int32_t *y_rowidx, const double *y_val);
+/* eqclass-level counts (the crpcount_td input): per cell (eqclass id, UMI count) plus the
+ * eqclass -> global row map from scasa_eqclass_map (row < 0: dropped). */
+int scasa_stage_eqcounts(scasa_ctx *ctx, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off,
+                         const int64_t *cell_ptr, const int32_t *eq_id, const int32_t *eq_count,
+                         int64_t n_eq, const int32_t *eq_row);
+int scasa_run(scasa_ctx *ctx);   /* pack -> EM -> (gene sums); everything on the device */
+int scasa_fetch_iso(scasa_ctx *ctx, double *iso_out);            /* n_cells x n_cols           */
+int scasa_fetch_iters(scasa_ctx *ctx, int32_t *iters_out);       /* [n_chunks][n_em_blocks][2] */
+int scasa_fetch_colsum(scasa_ctx *ctx, double *colsum /* [n_cols] */); /* rowSums of step2:167 */
+int scasa_fetch_counts(scasa_ctx *ctx, int64_t *y_rowptr /* [n_cells+1] */, int32_t *y_rowidx,
+                       double *y_val, int64_t cap, int64_t *nnz);  /* Y built by the pack stage */
+
+/* ---- scasa_genemat ----------------------------------------------------------------------
+ * gene_of_col[j] = output gene row of isoform column j, -1 = not summed (NA gene, or row
+ * dropped at step2:167).  Single-isoform genes are copies, others sums in column order. */
+int scasa_set_gene_map(scasa_ctx *ctx, const int32_t *gene_of_col, int32_t n_genes);
+int scasa_fetch_gene(scasa_ctx *ctx, double *gene_out /* n_cells x n_genes cell-major */);
+int scasa_gene_sum(scasa_ctx *ctx, const int32_t *gene_of_col, int32_t n_genes, const double *iso,
+                   int64_t n_cells, double *gene_out);
+
+/* ---- crpcount_td's decision, once per distinct eqclass ------------------------------------
+ * eqclass e = transcript ids eq_tx[eq_off[e] .. eq_off[e+1]-1].  eq_row[e] = global row the
+ * eqclass' counts are added to, or -1 (dropped). */
+int scasa_eqclass_map(scasa_ctx *ctx, int64_t n_eq, const int64_t *eq_off, const int32_t *eq_tx,
+                      int32_t *eq_row, int32_t n_threads);
+
+/* ---- measurement ---------------------------------------------------------------------------
+ * device time (CUDA events on the library's stream) of the last scasa_run, per phase */
+typedef struct {
+    float total_ms, pack_ms, tasks_ms, em_ms, finish_ms, gene_ms;
+    int64_t n_tasks;        /* non-empty (chunk, EM block) tasks            */
+    int64_t n_entries;      /* Y entries inside EM blocks                   */
+    int64_t n_active;       /* (cell, EM block) pairs with counts           */
+    int64_t inner_iters;    /* sum over tasks of estim.BETA iterations      */
+    int64_t outer_iters;    /* sum over tasks of AEM iterations             */
+    double alg_bytes;       /* SURVEY.md 8(d) streaming-model bytes of the run */
+    int32_t launches;       /* kernels launched by the last run             */
+} scasa_timing_t;
+int scasa_last_timing(scasa_ctx *ctx, scasa_timing_t *out);
+
+void *scasa_host_alloc(int64_t bytes); /* pinned host memory for fast H2D/D2H */
+void scasa_host_free(void *p);
+int scasa_device_count(void);
+const char *scasa_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCASA_CUDA_H */

@@ -1,0 +1,153 @@
+"""ctypes front end of the CPU oracle (oracle/scasa_oracle*.c).  TEST INFRASTRUCTURE.
+
+Imported only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs — never by scasa_b200 (the product fails loudly without its
+CUDA library instead of falling back to this).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libscasa_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith(".c")]
+    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-s", "-C", _HERE] + (["-B"] if force else []))
+    return _SO
+
+
+class Opts(C.Structure):
+    """estim_chunk's defaults, Scasa_Rsource.R:944 (+ adjust_esp :973)."""
+    _fields_ = [("maxiter_x", C.c_int), ("maxiter_bt", C.c_int), ("maxerr", C.c_double),
+                ("lim", C.c_double), ("modify", C.c_int), ("adjust_esp", C.c_double),
+                ("fixed_iter", C.c_int)]
+
+    @classmethod
+    def make(cls, maxiter_x=1000, maxiter_bt=1000, maxerr=0.01, lim=0.01, modify=1,
+             adjust_esp=2.0, fixed_iter=0):
+        return cls(maxiter_x, maxiter_bt, maxerr, lim, modify, adjust_esp, fixed_iter)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _lib.oracle_digamma.restype = C.c_double
+        _lib.oracle_digamma.argtypes = [C.c_double]
+        _lib.oracle_keep_rows.restype = C.c_int64
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def digamma(x):
+    f = lib().oracle_digamma
+    return np.array([f(float(v)) for v in np.atleast_1d(x)])
+
+
+def chunk_split(n: int, core: int = 4) -> np.ndarray:
+    """0-based chunk offsets, scasa_quant_step2_v1.0.0.R:64-68."""
+    br = np.zeros(max(n // 50 + 8, core + 2), np.int64)
+    k = lib().oracle_chunk_split(C.c_int64(n), C.c_int(core), _p(br, C.c_int64), C.c_int64(len(br)))
+    if k < 0:
+        raise RuntimeError("chunk_split: buffer too small")
+    return br[: k + 1].copy()
+
+
+def estim_chunks(xm, y_dense: np.ndarray, chunk_off, opts: Opts | None = None, nthreads: int = 1,
+                 x_override=None):
+    """estim_chunk (Scasa_Rsource.R:944-1051) on every chunk.
+
+    xm: XMatrix (DM0 part used); y_dense: (n_cells, Σq) float64 cell-major.
+    Returns (iso (n_cells, Σp), iters (n_chunks, B, 2))."""
+    opts = opts or Opts.make()
+    y_dense = np.ascontiguousarray(y_dense, np.float64)
+    n_cells = y_dense.shape[0]
+    assert y_dense.shape[1] == xm.n_rows
+    chunk_off = np.ascontiguousarray(chunk_off, np.int64)
+    n_chunks = len(chunk_off) - 1
+    out = np.zeros((n_cells, xm.n_cols), np.float64)
+    iters = np.zeros((n_chunks, xm.n_blocks, 2), np.int32)
+    x = xm.dm0_x if x_override is None else np.ascontiguousarray(x_override, np.float64)
+    rc = lib().oracle_estim_chunks(
+        C.c_int(xm.n_blocks), _p(xm.q_off, C.c_int32), _p(xm.dm0_p_off, C.c_int32),
+        _p(xm.dm0_x_off, C.c_int64), _p(x, C.c_double), C.c_int(n_chunks), _p(chunk_off, C.c_int64),
+        _p(y_dense, C.c_double), C.byref(opts), _p(out, C.c_double), _p(iters, C.c_int32),
+        C.c_int(nthreads))
+    if rc:
+        raise RuntimeError(f"oracle_estim_chunks failed ({rc})")
+    return out, iters
+
+
+def estim_block(X0: np.ndarray, Ymat: np.ndarray, opts: Opts | None = None):
+    """estim_chunk on a single ad-hoc block: X0 (q,p), Ymat (q,n) → (BT (n,p), (outer, inner))."""
+    opts = opts or Opts.make()
+    q, p = X0.shape
+    n = Ymat.shape[1]
+    q_off = np.array([0, q], np.int32)
+    p_off = np.array([0, p], np.int32)
+    x_off = np.array([0, q * p], np.int64)
+    x = np.ascontiguousarray(X0.T, np.float64).reshape(-1)        # column-major
+    y = np.ascontiguousarray(Ymat.T, np.float64)                  # cell-major (n, q)
+    out = np.zeros((n, p), np.float64)
+    it = np.zeros(2, np.int32)
+    rc = lib().oracle_estim_chunk(C.c_int(1), _p(q_off, C.c_int32), _p(p_off, C.c_int32),
+                                  _p(x_off, C.c_int64), _p(x, C.c_double), C.c_int(n),
+                                  _p(y, C.c_double), C.byref(opts), _p(out, C.c_double), _p(it, C.c_int32))
+    if rc:
+        raise RuntimeError("oracle_estim_chunk failed")
+    return out, (int(it[0]), int(it[1]))
+
+
+def keep_rows(iso: np.ndarray) -> np.ndarray:
+    """step2:167 — which isoform rows survive (rowSums > 0)."""
+    iso = np.ascontiguousarray(iso, np.float64)
+    keep = np.zeros(iso.shape[1], np.uint8)
+    lib().oracle_keep_rows(_p(iso, C.c_double), C.c_int64(iso.shape[0]), C.c_int64(iso.shape[1]),
+                           _p(keep, C.c_uint8))
+    return keep.astype(bool)
+
+
+def gene_layout(col_gene_names, keep):
+    """Row layout of scasa_genemat (scasa_quant_step3_v1.0.0.R:34-43), LC_COLLATE=C.
+
+    col_gene_names[j]: gene name of isoform column j (None = NA, dropped by tapply).
+    Returns (gene_of_col int32[ncol], n_members int32[G], gene_names list[G]): singles
+    (sorted by name) first, then multis (sorted by name)."""
+    members: dict = {}
+    for j, g in enumerate(col_gene_names):
+        if keep[j] and g is not None:
+            members.setdefault(g, []).append(j)
+    singles = sorted((g for g, v in members.items() if len(v) == 1), key=lambda s: s.encode())
+    multis = sorted((g for g, v in members.items() if len(v) > 1), key=lambda s: s.encode())
+    names = singles + multis
+    gene_of_col = np.full(len(col_gene_names), -1, np.int32)
+    n_members = np.zeros(len(names), np.int32)
+    for gi, g in enumerate(names):
+        n_members[gi] = len(members[g])
+        gene_of_col[members[g]] = gi
+    return gene_of_col, n_members, names
+
+
+def gene_sum(iso: np.ndarray, gene_of_col, n_members) -> np.ndarray:
+    iso = np.ascontiguousarray(iso, np.float64)
+    gene_of_col = np.ascontiguousarray(gene_of_col, np.int32)
+    n_members = np.ascontiguousarray(n_members, np.int32)
+    out = np.zeros((iso.shape[0], len(n_members)), np.float64)
+    lib().oracle_gene_sum(_p(iso, C.c_double), C.c_int64(iso.shape[0]), C.c_int64(iso.shape[1]),
+                          _p(gene_of_col, C.c_int32), C.c_int32(len(n_members)),
+                          _p(n_members, C.c_int32), _p(out, C.c_double))
+    return out

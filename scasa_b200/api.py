@@ -1,0 +1,261 @@
+"""Host-side mirror of the reference's quant interface on top of libscasa_cuda.
+
+The names are the reference's (paths relative to /root/reference/scasa/SCRIPTS/):
+
+* ``chunk_split``           scasa_quant_step2_v1.0.0.R:64-68
+* ``Scasa.crpcount_td``     Scasa_Rsource.R:416-557   (per cell; list over blocks of count vectors)
+* ``Scasa.estim_chunk``     Scasa_Rsource.R:944-1051  (per chunk; cells x isoform-columns matrix)
+* ``Scasa.scasa_genemat``   scasa_quant_step3_v1.0.0.R:32-46
+* ``Scasa.quant``           the body of step2 (:88-136) + step3 (:48) in one call on all chunks
+
+Everything numeric happens in the CUDA library; this file only converts between the
+reference's shapes (lists of per-block matrices) and the flat arrays of the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import lib as _l
+from .xmatrix import XMatrix
+
+
+def chunk_split(n_cells: int, core: int = 4) -> np.ndarray:
+    """0-based cell offsets of the chunks step2 would form (``core`` matters only for n <= 100)."""
+    L = _l.load()
+    cap = max(n_cells // 50 + 8, core + 2)
+    br = np.zeros(cap, np.int64)
+    k = C.c_int32(0)
+    rc = L.scasa_chunk_split(n_cells, core, _l.ptr(br, C.c_int64), cap, C.byref(k))
+    if rc:
+        raise _l.ScasaError(rc, L.scasa_last_error(None).decode())
+    return br[: k.value + 1].copy()
+
+
+@dataclass
+class QuantResult:
+    iso: np.ndarray            # (n_cells, Σp) — estim_chunk's result for all chunks, cell order
+    gene: np.ndarray | None    # (n_cells, n_genes)
+    colsum: np.ndarray         # (Σp,) sums over cells: rows with colsum > 0 survive step2:167
+    iters: np.ndarray          # (n_chunks, n_em_blocks, 2) outer / total inner iterations
+    timing: dict
+
+
+class Scasa:
+    """One GPU context with the X-matrix resident (``load(design.matrix)`` + ``DM0``)."""
+
+    def __init__(self, xm: XMatrix, device: int = 0, with_crp: bool = True, **opts):
+        self.xm = xm
+        self._L = _l.load()
+        self._ctx = C.c_void_p()
+        self._keep = []
+        dm0 = self._xmat(xm.q_off, xm.dm0_p_off, xm.dm0_x_off, xm.dm0_x)
+        crp = None
+        if with_crp:
+            crp = _l.Crp()
+            crp.m = self._xmat(xm.q_off, xm.crp_p_off, xm.crp_x_off, xm.crp_x)
+            crp.col_tx = _l.ptr(self._hold(xm.crp_tx, np.int32), C.c_int32)
+            crp.row_pat = _l.ptr(self._hold(xm.crp_pat, np.uint8), C.c_uint8)
+            crp.name_rank = _l.ptr(self._hold(xm.name_rank, np.int32), C.c_int32)
+        o = _l.default_opts(**opts)
+        rc = self._L.scasa_ctx_create(C.byref(dm0), C.byref(crp) if crp is not None else None, C.byref(o),
+                                      device, C.byref(self._ctx))
+        if rc:
+            raise _l.ScasaError(rc, self._L.scasa_last_error(None).decode())
+        self.n_rows = int(self._L.scasa_n_rows(self._ctx))
+        self.n_cols = int(self._L.scasa_n_cols(self._ctx))
+        self.n_em = int(self._L.scasa_n_em_blocks(self._ctx))
+        self.em_blocks = np.zeros(self.n_em, np.int32)
+        self._L.scasa_em_blocks(self._ctx, _l.ptr(self.em_blocks, C.c_int32))
+        self.n_cells = 0
+        self.n_chunks = 0
+        self.n_genes = 0
+
+    # ------------------------------------------------------------------ plumbing
+    def _hold(self, a, dt):
+        a = np.ascontiguousarray(a, dt)
+        self._keep.append(a)
+        return a
+
+    def _xmat(self, q_off, p_off, x_off, x) -> _l.XMat:
+        m = _l.XMat()
+        m.n_blocks = len(q_off) - 1
+        m.q_off = _l.ptr(self._hold(q_off, np.int32), C.c_int32)
+        m.p_off = _l.ptr(self._hold(p_off, np.int32), C.c_int32)
+        m.x_off = _l.ptr(self._hold(x_off, np.int64), C.c_int64)
+        m.x = _l.ptr(self._hold(x, np.float64), C.c_double)
+        return m
+
+    def _ck(self, rc: int) -> None:
+        if rc:
+            raise _l.ScasaError(rc, self._L.scasa_last_error(self._ctx).decode())
+
+    def close(self) -> None:
+        if self._ctx:
+            self._L.scasa_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_opts(self, **opts) -> None:
+        o = _l.default_opts(**opts)
+        self._ck(self._L.scasa_set_opts(self._ctx, C.byref(o)))
+
+    def poor_blocks(self) -> np.ndarray:
+        f = np.zeros(self.xm.n_blocks, np.uint8)
+        self._ck(self._L.scasa_poor_blocks(self._ctx, _l.ptr(f, C.c_uint8)))
+        return f.astype(bool)
+
+    # ------------------------------------------------------------------ staged pipeline
+    def stage_counts(self, chunk_off, y_rowptr, y_rowidx, y_val) -> None:
+        chunk_off = np.ascontiguousarray(chunk_off, np.int64)
+        y_rowptr = np.ascontiguousarray(y_rowptr, np.int64)
+        y_rowidx = np.ascontiguousarray(y_rowidx, np.int32)
+        y_val = np.ascontiguousarray(y_val, np.float64)
+        self.n_cells, self.n_chunks = len(y_rowptr) - 1, len(chunk_off) - 1
+        self._ck(self._L.scasa_stage_counts(self._ctx, self.n_cells, self.n_chunks, _l.ptr(chunk_off, C.c_int64),
+                                            _l.ptr(y_rowptr, C.c_int64), _l.ptr(y_rowidx, C.c_int32),
+                                            _l.ptr(y_val, C.c_double)))
+
+    def stage_eqcounts(self, chunk_off, cell_ptr, eq_id, eq_count, eq_row) -> None:
+        chunk_off = np.ascontiguousarray(chunk_off, np.int64)
+        cell_ptr = np.ascontiguousarray(cell_ptr, np.int64)
+        eq_id = np.ascontiguousarray(eq_id, np.int32)
+        eq_count = np.ascontiguousarray(eq_count, np.int32)
+        eq_row = np.ascontiguousarray(eq_row, np.int32)
+        self.n_cells, self.n_chunks = len(cell_ptr) - 1, len(chunk_off) - 1
+        self._ck(self._L.scasa_stage_eqcounts(self._ctx, self.n_cells, self.n_chunks, _l.ptr(chunk_off, C.c_int64),
+                                              _l.ptr(cell_ptr, C.c_int64), _l.ptr(eq_id, C.c_int32),
+                                              _l.ptr(eq_count, C.c_int32), len(eq_row), _l.ptr(eq_row, C.c_int32)))
+
+    def set_gene_map(self, gene_of_col, n_genes: int) -> None:
+        g = np.ascontiguousarray(gene_of_col, np.int32)
+        assert len(g) == self.n_cols
+        self._ck(self._L.scasa_set_gene_map(self._ctx, _l.ptr(g, C.c_int32), n_genes))
+        self.n_genes = n_genes
+
+    def run(self) -> dict:
+        self._ck(self._L.scasa_run(self._ctx))
+        return self.timing()
+
+    def timing(self) -> dict:
+        t = _l.Timing()
+        self._ck(self._L.scasa_last_timing(self._ctx, C.byref(t)))
+        return t.as_dict()
+
+    def fetch_iso(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.n_cells, self.n_cols), np.float64)
+        self._ck(self._L.scasa_fetch_iso(self._ctx, _l.ptr(out, C.c_double)))
+        return out
+
+    def fetch_gene(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.n_cells, self.n_genes), np.float64)
+        self._ck(self._L.scasa_fetch_gene(self._ctx, _l.ptr(out, C.c_double)))
+        return out
+
+    def fetch_iters(self) -> np.ndarray:
+        out = np.empty((self.n_chunks, self.n_em, 2), np.int32)
+        self._ck(self._L.scasa_fetch_iters(self._ctx, _l.ptr(out, C.c_int32)))
+        return out
+
+    def fetch_colsum(self) -> np.ndarray:
+        out = np.empty(self.n_cols, np.float64)
+        self._ck(self._L.scasa_fetch_colsum(self._ctx, _l.ptr(out, C.c_double)))
+        return out
+
+    def fetch_counts(self):
+        """Y as built by the pack stage: CSR (rowptr, rowidx, val)."""
+        rowptr = np.zeros(self.n_cells + 1, np.int64)
+        nnz = C.c_int64(0)
+        self._L.scasa_fetch_counts(self._ctx, _l.ptr(rowptr, C.c_int64), None, None, 0, C.byref(nnz))
+        idx = np.zeros(max(nnz.value, 1), np.int32)
+        val = np.zeros(max(nnz.value, 1), np.float64)
+        self._ck(self._L.scasa_fetch_counts(self._ctx, _l.ptr(rowptr, C.c_int64), _l.ptr(idx, C.c_int32),
+                                            _l.ptr(val, C.c_double), len(idx), C.byref(nnz)))
+        return rowptr, idx[: nnz.value], val[: nnz.value]
+
+    # ------------------------------------------------------------------ reference-shaped calls
+    def eqclass_map(self, eq_off, eq_tx, n_threads: int = 8) -> np.ndarray:
+        """crpcount_td's decision per distinct eqclass: global row or -1."""
+        eq_off = np.ascontiguousarray(eq_off, np.int64)
+        eq_tx = np.ascontiguousarray(eq_tx, np.int32)
+        out = np.empty(len(eq_off) - 1, np.int32)
+        self._ck(self._L.scasa_eqclass_map(self._ctx, len(out), _l.ptr(eq_off, C.c_int64), _l.ptr(eq_tx, C.c_int32),
+                                           _l.ptr(out, C.c_int32), n_threads))
+        return out
+
+    def crpcount_td(self, transcript, count, eqclass) -> list:
+        """One cell's table (columns Transcript [ids], Count, eqClass) -> list over blocks of
+        count vectors, like crpcount_td(mytd)."""
+        transcript, count, eqclass = (np.asarray(a) for a in (transcript, count, eqclass))
+        ids, inv = np.unique(eqclass, return_inverse=True)
+        order = np.argsort(inv, kind="stable")
+        eq_off = np.concatenate([[0], np.cumsum(np.bincount(inv, minlength=len(ids)))]).astype(np.int64)
+        eq_tx = transcript[order].astype(np.int32)
+        first = np.zeros(len(ids), np.int64)
+        first[inv[::-1]] = np.arange(len(inv))[::-1]
+        eq_cnt = count[first].astype(np.int32)
+        eq_row = self.eqclass_map(eq_off, eq_tx, 1)
+        self.stage_eqcounts([0, 1], [0, len(ids)], np.arange(len(ids), dtype=np.int32), eq_cnt, eq_row)
+        self.run()
+        rowptr, idx, val = self.fetch_counts()
+        dense = np.zeros(self.n_rows)
+        dense[idx] = val
+        return [dense[self.xm.q_off[k]:self.xm.q_off[k + 1]] for k in range(self.xm.n_blocks)]
+
+    def estim_chunk(self, Y: list, **opts) -> np.ndarray:
+        """estim_chunk(Y, DM0, ...) for ONE chunk: Y = list over blocks of (q_k, n) arrays."""
+        if opts:
+            self.set_opts(**opts)
+        n = Y[0].shape[1]
+        dense = np.concatenate([np.asarray(y, np.float64).reshape(-1, n) for y in Y], axis=0).T   # (n, Σq)
+        return self.estimate_dense(dense, [0, n])[0]
+
+    def estimate_dense(self, y_dense: np.ndarray, chunk_off):
+        rowptr, idx, val = dense_to_csr(y_dense)
+        return self.estimate(chunk_off, rowptr, idx, val)
+
+    def estimate(self, chunk_off, y_rowptr, y_rowidx, y_val):
+        """scasa_estimate: (iso, iters)."""
+        self.stage_counts(chunk_off, y_rowptr, y_rowidx, y_val)
+        self.run()
+        return self.fetch_iso(), self.fetch_iters()
+
+    def scasa_genemat(self, iso: np.ndarray, gene_of_col, n_genes: int) -> np.ndarray:
+        iso = np.ascontiguousarray(iso, np.float64)
+        g = np.ascontiguousarray(gene_of_col, np.int32)
+        out = np.empty((iso.shape[0], n_genes), np.float64)
+        self._ck(self._L.scasa_gene_sum(self._ctx, _l.ptr(g, C.c_int32), n_genes, _l.ptr(iso, C.c_double),
+                                        iso.shape[0], _l.ptr(out, C.c_double)))
+        self.n_genes = n_genes
+        return out
+
+    def quant(self, cell_ptr, eq_id, eq_count, eq_off, eq_tx, core: int = 4, gene_of_col=None, n_genes: int = 0,
+              n_threads: int = 8) -> QuantResult:
+        """step2's two foreach bodies (+ step3's gene sums) for a whole sample."""
+        n_cells = len(cell_ptr) - 1
+        chunks = chunk_split(n_cells, core)
+        eq_row = self.eqclass_map(eq_off, eq_tx, n_threads)
+        self.stage_eqcounts(chunks, cell_ptr, eq_id, eq_count, eq_row)
+        if gene_of_col is not None:
+            self.set_gene_map(gene_of_col, n_genes)
+        t = self.run()
+        return QuantResult(self.fetch_iso(), self.fetch_gene() if self.n_genes else None, self.fetch_colsum(),
+                           self.fetch_iters(), t)
+
+
+def dense_to_csr(y_dense: np.ndarray):
+    """(n_cells, Σq) dense counts -> CSR by cell (rows ascending)."""
+    y_dense = np.asarray(y_dense)
+    nz = y_dense != 0
+    rowptr = np.concatenate([[0], np.cumsum(nz.sum(axis=1))]).astype(np.int64)
+    cells, rows = np.nonzero(nz)
+    return rowptr, rows.astype(np.int32), y_dense[cells, rows].astype(np.float64)

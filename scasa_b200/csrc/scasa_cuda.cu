@@ -1,0 +1,770 @@
+// scasa_cuda.cu — host side of libscasa_cuda: context, staging, launch orchestration, C ABI.
+// See include/scasa_cuda.h for the contract and scasa_kernels.cuh for the device code.
+#include "scasa_cuda.h"
+#include "scasa_kernels.cuh"
+#include "scasa_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace scasa;
+
+namespace {
+
+thread_local std::string g_err;   // errors raised before a context exists
+
+struct CudaErr { cudaError_t e; const char *what; };
+#define CK(call)                                                       \
+    do {                                                               \
+        cudaError_t e_ = (call);                                       \
+        if (e_ != cudaSuccess) throw CudaErr{e_, #call};               \
+    } while (0)
+struct ArgErr { int code; std::string msg; };
+
+template <class T> struct DBuf {   // grow-only device buffer
+    T *p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t n) {
+        if (n <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 16;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; throw CudaErr{e, "cudaMalloc"}; }
+        cap = want;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class V> void upload(const V &v, cudaStream_t s) {
+        ensure(v.size());
+        if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+};
+
+struct Group {           // EM blocks that share one em_kernel<PMAX> launch
+    int pmax = 0;
+    int xcap = 0;
+    std::vector<int32_t> em;   // EM-block indices, heaviest first
+    DBuf<int32_t> d_em;
+};
+
+}  // namespace
+
+struct scasa_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    int n_sm = 148;
+    std::string err;
+    scasa_opts_t opts;
+
+    // ---- X-matrix (host copies + resident device copies)
+    int B = 0, n_em = 0;
+    int64_t n_rows = 0, n_cols = 0;
+    std::vector<int32_t> q_off, p_off, em_blocks, em_index, row_block, poor_em;
+    std::vector<int64_t> x_off;
+    std::vector<double> x;
+    std::vector<uint8_t> poor;
+    int64_t poor_rows = 0;           // sum of q over poor blocks
+    DBuf<int32_t> d_q_off, d_p_off, d_row_block, d_em_index, d_em_blocks, d_poor_em;
+    DBuf<int64_t> d_x_off;
+    DBuf<double> d_x;
+    DBuf<uint8_t> d_poor;
+    std::vector<Group> groups;
+    scasa::CrpIndex crp;             // eqclass -> row map (host), built when CRP is given
+
+    // ---- staged sample
+    bool staged = false, have_eq = false, ran = false;
+    int64_t n_cells = 0, nnz = 0, n_eq = 0;
+    int n_chunks = 0;
+    std::vector<int64_t> chunk_off;
+    DBuf<int64_t> d_chunk_off, d_y_start, d_cell_ptr;
+    DBuf<int32_t> d_cell_chunk, d_y_len, d_y_row, d_eq_id, d_eq_count, d_eq_row;
+    DBuf<double> d_y_val;
+    int64_t max_cell_entries = 0;
+
+    // ---- task arrays
+    DBuf<int32_t> d_cnt, d_runs, d_bw, d_ent_key, d_iters;
+    DBuf<int64_t> d_ent_off, d_run_off, d_beta_off, d_ent_cur, d_run_cur, d_run_start, d_scan_sums, d_totals;
+    DBuf<double> d_ent_val, d_beta, d_lnorm;
+    DBuf<unsigned int> d_next;
+    DBuf<unsigned long long> d_stats;
+    DBuf<int> d_flag;
+
+    // ---- results
+    DBuf<double> d_iso, d_partial, d_colsum, d_gene;
+    int n_genes = 0;
+    DBuf<int32_t> d_gene_of_col, d_gene_ptr, d_gene_cols;
+    scasa_timing_t timing{};
+};
+
+namespace {
+
+int fail(scasa_ctx *c, int code, const std::string &m)
+{
+    if (c) c->err = m; else g_err = m;
+    return code;
+}
+
+template <class F> int guarded(scasa_ctx *c, F &&f)
+{
+    try {
+        if (c) CK(cudaSetDevice(c->device));
+        f();
+        return SCASA_OK;
+    } catch (const CudaErr &e) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s", (int)e.e, cudaGetErrorString(e.e), e.what);
+        cudaGetLastError();
+        return fail(c, e.e == cudaErrorMemoryAllocation ? SCASA_ERR_NOMEM : SCASA_ERR_CUDA, buf);
+    } catch (const ArgErr &e) {
+        return fail(c, e.code, e.msg);
+    } catch (const std::bad_alloc &) {
+        return fail(c, SCASA_ERR_NOMEM, "host allocation failed");
+    } catch (const std::exception &e) {
+        return fail(c, SCASA_ERR_ARG, e.what());
+    }
+}
+
+// poorCondX (Scasa_Rsource.R:957-971): a 2-column block is poor unless some pairwise cosine
+// similarity (self pairs included) is < 0.99.  long double sums like R's sum().
+bool is_poor(const double *X0, int q, int p)
+{
+    if (p != 2) return false;
+    for (int i = 0; i < 2; i++)
+        for (int k = 0; k < 2; k++) {
+            long double ab = 0, aa = 0, bb = 0;
+            for (int r = 0; r < q; r++) {
+                long double a = X0[(size_t)k * q + r], b = X0[(size_t)i * q + r];
+                ab += a * b; aa += a * a; bb += b * b;
+            }
+            double sim = (double)ab / std::sqrt((double)aa * (double)bb);
+            if (sim < 0.99) return false;
+        }
+    return true;
+}
+
+XDev xdev(scasa_ctx *c)
+{
+    XDev X;
+    X.n_blocks = c->B; X.n_em = c->n_em; X.n_rows = c->n_rows; X.n_cols = c->n_cols;
+    X.q_off = c->d_q_off.p; X.p_off = c->d_p_off.p; X.x_off = c->d_x_off.p; X.x = c->d_x.p;
+    X.row_block = c->d_row_block.p; X.em_index = c->d_em_index.p; X.em_blocks = c->d_em_blocks.p;
+    X.poor = c->d_poor.p; X.poor_em = c->d_poor_em.p; X.n_poor = (int)c->poor_em.size();
+    return X;
+}
+Sample sdev(scasa_ctx *c)
+{
+    Sample S;
+    S.n_cells = c->n_cells; S.n_chunks = c->n_chunks; S.chunk_off = c->d_chunk_off.p;
+    S.cell_chunk = c->d_cell_chunk.p; S.y_start = c->d_y_start.p; S.y_len = c->d_y_len.p;
+    S.y_row = c->d_y_row.p; S.y_val = c->d_y_val.p;
+    return S;
+}
+Tasks tdev(scasa_ctx *c)
+{
+    Tasks T;
+    T.cnt = c->d_cnt.p; T.runs = c->d_runs.p; T.bw = c->d_bw.p;
+    T.ent_off = c->d_ent_off.p; T.run_off = c->d_run_off.p; T.beta_off = c->d_beta_off.p;
+    T.ent_cur = c->d_ent_cur.p; T.run_cur = c->d_run_cur.p;
+    T.ent_key = c->d_ent_key.p; T.ent_val = c->d_ent_val.p; T.run_start = c->d_run_start.p;
+    T.beta = c->d_beta.p; T.lnorm = c->d_lnorm.p;
+    return T;
+}
+
+void exclusive_scan(scasa_ctx *c, const int32_t *in, int64_t n, int64_t *out, int64_t *total_slot, int &launches)
+{
+    const int64_t per = (int64_t)kScanThreads * kScanItems;
+    const int64_t nb = (n + per - 1) / per;
+    c->d_scan_sums.ensure((size_t)nb + 1);
+    scan_block_sums<<<(unsigned)nb, kScanThreads, 0, c->stream>>>(in, n, c->d_scan_sums.p);
+    scan_sums<<<1, kScanThreads, 0, c->stream>>>(c->d_scan_sums.p, nb, total_slot);
+    scan_add_back<<<(unsigned)nb, kScanThreads, 0, c->stream>>>(in, n, c->d_scan_sums.p, total_slot, out);
+    launches += 3;
+}
+
+template <int PMAX> void launch_em(scasa_ctx *c, Group &g, EmArgs &A, int slot)
+{
+    const int warps = 4;
+    size_t per_warp = (size_t)(2 * g.xcap + 2 * PMAX + (g.xcap + 7) / 8) * sizeof(double);
+    size_t smem = per_warp * warps;
+    if (smem > 220 * 1024) throw ArgErr{SCASA_ERR_UNSUPPORTED, "an EM block is too large for shared memory (q*p limit ~3400)"};
+    CK(cudaFuncSetAttribute(em_kernel<PMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_kernel<PMAX>, warps * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long total = (long long)g.em.size() * c->n_chunks;
+    long long want = (total + warps - 1) / warps;
+    int grid = (int)std::min<long long>((long long)c->n_sm * per_sm, std::max<long long>(want, 1));
+    A.grp_em = g.d_em.p; A.grp_n = (int)g.em.size(); A.xcap = g.xcap;
+    A.next_task = c->d_next.p + slot;
+    em_kernel<PMAX><<<grid, warps * 32, smem, c->stream>>>(A);
+    CK(cudaGetLastError());
+}
+
+void check_xmat(const scasa_xmat_t *m, const char *what)
+{
+    if (!m || m->n_blocks <= 0 || !m->q_off || !m->p_off || !m->x_off || !m->x)
+        throw ArgErr{SCASA_ERR_ARG, std::string(what) + ": null or empty block list"};
+    if (m->q_off[0] != 0 || m->p_off[0] != 0 || m->x_off[0] != 0)
+        throw ArgErr{SCASA_ERR_ARG, std::string(what) + ": offsets must start at 0"};
+    for (int k = 0; k < m->n_blocks; k++) {
+        int64_t q = m->q_off[k + 1] - m->q_off[k], p = m->p_off[k + 1] - m->p_off[k];
+        if (q <= 0 || p <= 0 || m->x_off[k + 1] - m->x_off[k] != q * p)
+            throw ArgErr{SCASA_ERR_ARG, std::string(what) + ": block " + std::to_string(k) + " has inconsistent offsets"};
+    }
+}
+
+void stage_common(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off)
+{
+    if (n_cells <= 0 || n_chunks <= 0 || !chunk_off) throw ArgErr{SCASA_ERR_ARG, "no cells / no chunks"};
+    if (chunk_off[0] != 0 || chunk_off[n_chunks] != n_cells)
+        throw ArgErr{SCASA_ERR_ARG, "chunk_off must cover [0, n_cells]"};
+    std::vector<int32_t> cell_chunk((size_t)n_cells);
+    for (int h = 0; h < n_chunks; h++) {
+        int64_t a = chunk_off[h], b = chunk_off[h + 1];
+        if (b < a) throw ArgErr{SCASA_ERR_ARG, "chunk_off must be non-decreasing"};
+        if (b - a >= 65536) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a chunk may hold at most 65535 cells"};
+        for (int64_t i = a; i < b; i++) cell_chunk[(size_t)i] = h;
+    }
+    if ((int64_t)n_chunks * c->n_em >= (int64_t)1 << 31)
+        throw ArgErr{SCASA_ERR_UNSUPPORTED, "n_chunks * n_em_blocks must stay below 2^31 per call"};
+    c->n_cells = n_cells; c->n_chunks = n_chunks;
+    c->chunk_off.assign(chunk_off, chunk_off + n_chunks + 1);
+    c->d_chunk_off.upload(c->chunk_off, c->stream);
+    c->d_cell_chunk.upload(cell_chunk, c->stream);
+    c->staged = true; c->ran = false;
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+const char *scasa_version(void) { return "scasa_b200 0.1 (sm_100a)"; }
+
+int scasa_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int scasa_opts_default(scasa_opts_t *o)
+{
+    if (!o) return SCASA_ERR_ARG;
+    o->maxiter_x = 1000; o->maxiter_bt = 1000; o->maxerr = 0.01; o->lim = 0.01; o->modify = 1;
+    o->adjust_esp = 2.0; o->hamming_dist = 1; o->fixed_iter = 0; o->fp32 = 0;
+    return SCASA_OK;
+}
+
+const char *scasa_last_error(const scasa_ctx *c) { return c ? c->err.c_str() : g_err.c_str(); }
+
+int scasa_set_opts(scasa_ctx *c, const scasa_opts_t *o)
+{
+    if (!c || !o) return fail(c, SCASA_ERR_ARG, "null argument");
+    if (o->maxiter_x < 1 || o->maxiter_bt < 1) return fail(c, SCASA_ERR_ARG, "iteration caps must be >= 1");
+    if (o->fp32) return fail(c, SCASA_ERR_UNSUPPORTED, "fp32 arithmetic is not available in this version");
+    c->opts = *o;
+    return SCASA_OK;
+}
+
+int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scasa_opts_t *opts, int device,
+                     scasa_ctx **out)
+{
+    if (!out) return fail(nullptr, SCASA_ERR_ARG, "out is null");
+    *out = nullptr;
+    int ndev = scasa_device_count();
+    if (ndev <= 0) return fail(nullptr, SCASA_ERR_CUDA, "no CUDA device: libscasa_cuda has no CPU path");
+    if (device < 0 || device >= ndev) return fail(nullptr, SCASA_ERR_ARG, "device ordinal out of range");
+    scasa_ctx *c = new (std::nothrow) scasa_ctx();
+    if (!c) return fail(nullptr, SCASA_ERR_NOMEM, "host allocation failed");
+    c->device = device;
+    scasa_opts_default(&c->opts);
+    int rc = guarded(c, [&] {
+        if (opts) { int r = scasa_set_opts(c, opts); if (r) throw ArgErr{r, c->err}; }
+        check_xmat(dm0, "dm0");
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        c->n_sm = prop.multiProcessorCount;
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        for (auto &e : c->ev) CK(cudaEventCreate(&e));
+
+        const int B = dm0->n_blocks;
+        c->B = B;
+        c->q_off.assign(dm0->q_off, dm0->q_off + B + 1);
+        c->p_off.assign(dm0->p_off, dm0->p_off + B + 1);
+        c->x_off.assign(dm0->x_off, dm0->x_off + B + 1);
+        c->x.assign(dm0->x, dm0->x + dm0->x_off[B]);
+        c->n_rows = c->q_off[B]; c->n_cols = c->p_off[B];
+        c->em_index.assign(B, -1);
+        c->poor.assign(B, 0);
+        c->row_block.resize((size_t)c->n_rows);
+        for (int k = 0; k < B; k++) {
+            int q = c->q_off[k + 1] - c->q_off[k], p = c->p_off[k + 1] - c->p_off[k];
+            for (int r = 0; r < q; r++) c->row_block[(size_t)c->q_off[k] + r] = k;
+            if (q >= 65536) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a block may have at most 65535 rows"};
+            if (q == 1) {
+                // Rsource:981 assigns colnames(X0) as the single row name: only p == 1 is valid R
+                if (p != 1) throw ArgErr{SCASA_ERR_ARG, "block " + std::to_string(k) + ": one row but several columns"};
+                continue;
+            }
+            c->em_index[k] = (int)c->em_blocks.size();
+            c->em_blocks.push_back(k);
+            if (is_poor(c->x.data() + c->x_off[k], q, p)) {
+                c->poor[k] = 1;
+                c->poor_em.push_back(c->em_index[k]);
+                c->poor_rows += q;
+            }
+        }
+        c->n_em = (int)c->em_blocks.size();
+
+        // launch groups by register-array width; inside a group heaviest blocks first
+        const int classes[] = {2, 4, 8, 32, 128};
+        c->groups.clear();
+        for (int cl : classes) { Group g; g.pmax = cl; c->groups.push_back(std::move(g)); }
+        for (int e = 0; e < c->n_em; e++) {
+            int k = c->em_blocks[e];
+            int q = c->q_off[k + 1] - c->q_off[k], p = c->p_off[k + 1] - c->p_off[k];
+            if (p > 128) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a block may have at most 128 columns"};
+            for (auto &g : c->groups)
+                if (p <= g.pmax) { g.em.push_back(e); g.xcap = std::max(g.xcap, q * p); break; }
+        }
+        for (auto &g : c->groups) {
+            std::stable_sort(g.em.begin(), g.em.end(), [&](int a, int b) {
+                int ka = c->em_blocks[a], kb = c->em_blocks[b];
+                int64_t wa = c->x_off[ka + 1] - c->x_off[ka], wb = c->x_off[kb + 1] - c->x_off[kb];
+                return wa > wb;
+            });
+            g.xcap = (g.xcap + 7) & ~7;
+            g.d_em.upload(g.em, c->stream);
+        }
+
+        c->d_q_off.upload(c->q_off, c->stream);
+        c->d_p_off.upload(c->p_off, c->stream);
+        c->d_x_off.upload(c->x_off, c->stream);
+        c->d_x.upload(c->x, c->stream);
+        c->d_row_block.upload(c->row_block, c->stream);
+        c->d_em_index.upload(c->em_index, c->stream);
+        c->d_em_blocks.upload(c->em_blocks, c->stream);
+        c->d_poor.upload(c->poor, c->stream);
+        c->d_poor_em.ensure(c->poor_em.size() + 1);
+        c->d_poor_em.upload(c->poor_em, c->stream);
+        c->d_next.ensure(16); c->d_stats.ensure(8); c->d_totals.ensure(4); c->d_flag.ensure(1);
+        CK(cudaStreamSynchronize(c->stream));
+
+        if (crp) {
+            check_xmat(&crp->m, "crp");
+            if (crp->m.n_blocks != B) throw ArgErr{SCASA_ERR_ARG, "crp and dm0 differ in block count"};
+            for (int k = 0; k <= B; k++)
+                if (crp->m.q_off[k] != dm0->q_off[k]) throw ArgErr{SCASA_ERR_ARG, "crp and dm0 differ in rows"};
+            if (!crp->col_tx || !crp->row_pat || !crp->name_rank) throw ArgErr{SCASA_ERR_ARG, "crp: null dimnames arrays"};
+            c->crp.build(crp->m.n_blocks, crp->m.q_off, crp->m.p_off, crp->m.x_off, crp->m.x, crp->col_tx,
+                         crp->row_pat, crp->name_rank, c->opts.hamming_dist);
+        }
+    });
+    if (rc != SCASA_OK) { g_err = c->err; scasa_ctx_destroy(c); return rc; }
+    *out = c;
+    return SCASA_OK;
+}
+
+void scasa_ctx_destroy(scasa_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    DBuf<int32_t> *i32[] = {&c->d_q_off, &c->d_p_off, &c->d_row_block, &c->d_em_index, &c->d_em_blocks, &c->d_poor_em,
+                            &c->d_cell_chunk, &c->d_y_len, &c->d_y_row, &c->d_eq_id, &c->d_eq_count, &c->d_eq_row,
+                            &c->d_cnt, &c->d_runs, &c->d_bw, &c->d_ent_key, &c->d_iters, &c->d_gene_of_col,
+                            &c->d_gene_ptr, &c->d_gene_cols};
+    for (auto b : i32) b->release();
+    DBuf<int64_t> *i64[] = {&c->d_x_off, &c->d_chunk_off, &c->d_y_start, &c->d_cell_ptr, &c->d_ent_off, &c->d_run_off,
+                            &c->d_beta_off, &c->d_ent_cur, &c->d_run_cur, &c->d_run_start, &c->d_scan_sums, &c->d_totals};
+    for (auto b : i64) b->release();
+    DBuf<double> *f64[] = {&c->d_x, &c->d_y_val, &c->d_ent_val, &c->d_beta, &c->d_lnorm, &c->d_iso, &c->d_partial,
+                           &c->d_colsum, &c->d_gene};
+    for (auto b : f64) b->release();
+    c->d_poor.release(); c->d_next.release(); c->d_stats.release(); c->d_flag.release();
+    for (auto &g : c->groups) g.d_em.release();
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int64_t scasa_n_rows(const scasa_ctx *c) { return c ? c->n_rows : 0; }
+int64_t scasa_n_cols(const scasa_ctx *c) { return c ? c->n_cols : 0; }
+int32_t scasa_n_em_blocks(const scasa_ctx *c) { return c ? c->n_em : 0; }
+int scasa_em_blocks(const scasa_ctx *c, int32_t *ids)
+{
+    if (!c || !ids) return SCASA_ERR_ARG;
+    std::copy(c->em_blocks.begin(), c->em_blocks.end(), ids);
+    return SCASA_OK;
+}
+int scasa_poor_blocks(const scasa_ctx *c, uint8_t *is)
+{
+    if (!c || !is) return SCASA_ERR_ARG;
+    std::copy(c->poor.begin(), c->poor.end(), is);
+    return SCASA_OK;
+}
+
+int scasa_chunk_split(int64_t n, int32_t core, int64_t *chunk_off, int64_t cap, int32_t *n_chunks)
+{
+    // scasa_quant_step2_v1.0.0.R:64-68: chunkNum = round(n/100) (half to even), or `core` when
+    // n <= 100; brPos = round(seq(1, n+1, length.out = chunkNum+1)).
+    if (n <= 0 || !chunk_off || !n_chunks) return fail(nullptr, SCASA_ERR_ARG, "bad argument");
+    int64_t k = (n > 100) ? (int64_t)std::nearbyint((double)n / 100.0) : core;
+    if (k < 1) return fail(nullptr, SCASA_ERR_ARG, "core must be >= 1 when n_cells <= 100");
+    if (k + 1 > cap) return fail(nullptr, SCASA_ERR_ARG, "chunk_off too small");
+    const double from = 1.0, to = (double)n + 1.0;
+    const double by = (to - from) / (double)k;
+    for (int64_t i = 0; i <= k; i++) {
+        double v = (i == 0) ? from : (i == k ? to : from + (double)i * by);
+        chunk_off[i] = (int64_t)std::nearbyint(v) - 1;
+    }
+    *n_chunks = (int32_t)k;
+    return SCASA_OK;
+}
+
+int scasa_stage_counts(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off,
+                       const int64_t *y_rowptr, const int32_t *y_rowidx, const double *y_val)
+{
+    if (!c) return fail(c, SCASA_ERR_ARG, "null context");
+    return guarded(c, [&] {
+        if (!y_rowptr || (!y_rowidx && y_rowptr[n_cells] > 0) || (!y_val && y_rowptr[n_cells] > 0))
+            throw ArgErr{SCASA_ERR_ARG, "null count arrays"};
+        stage_common(c, n_cells, n_chunks, chunk_off);
+        const int64_t nnz = y_rowptr[n_cells];
+        if (y_rowptr[0] != 0 || nnz < 0) throw ArgErr{SCASA_ERR_ARG, "y_rowptr must start at 0"};
+        std::vector<int32_t> len((size_t)n_cells);
+        for (int64_t i = 0; i < n_cells; i++) {
+            int64_t a = y_rowptr[i], b = y_rowptr[i + 1];
+            if (b < a || b - a > c->n_rows) throw ArgErr{SCASA_ERR_ARG, "y_rowptr is not a valid CSR pointer"};
+            len[(size_t)i] = (int32_t)(b - a);
+            for (int64_t k = a; k < b; k++) {
+                int32_t r = y_rowidx[k];
+                if (r < 0 || r >= c->n_rows || (k > a && r <= y_rowidx[k - 1]))
+                    throw ArgErr{SCASA_ERR_ARG, "y_rowidx must be strictly ascending inside a cell and < n_rows"};
+            }
+        }
+        c->nnz = nnz; c->have_eq = false;
+        c->d_y_start.ensure((size_t)n_cells); c->d_y_len.ensure((size_t)n_cells);
+        c->d_y_row.ensure((size_t)nnz + 1); c->d_y_val.ensure((size_t)nnz + 1);
+        CK(cudaMemcpyAsync(c->d_y_start.p, y_rowptr, n_cells * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_y_len.p, len.data(), n_cells * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        if (nnz) {
+            CK(cudaMemcpyAsync(c->d_y_row.p, y_rowidx, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(c->d_y_val.p, y_val, nnz * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        }
+        CK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int scasa_stage_eqcounts(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off,
+                         const int64_t *cell_ptr, const int32_t *eq_id, const int32_t *eq_count,
+                         int64_t n_eq, const int32_t *eq_row)
+{
+    if (!c) return fail(c, SCASA_ERR_ARG, "null context");
+    return guarded(c, [&] {
+        if (!cell_ptr || !eq_id || !eq_count || !eq_row || n_eq <= 0) throw ArgErr{SCASA_ERR_ARG, "null eqclass arrays"};
+        stage_common(c, n_cells, n_chunks, chunk_off);
+        const int64_t nnz = cell_ptr[n_cells];
+        if (cell_ptr[0] != 0 || nnz < 0) throw ArgErr{SCASA_ERR_ARG, "cell_ptr must start at 0"};
+        int64_t mx = 0;
+        for (int64_t i = 0; i < n_cells; i++) {
+            int64_t d = cell_ptr[i + 1] - cell_ptr[i];
+            if (d < 0) throw ArgErr{SCASA_ERR_ARG, "cell_ptr must be non-decreasing"};
+            mx = std::max(mx, d);
+        }
+        if (mx > 16384) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a cell may list at most 16384 eqclasses"};
+        for (int64_t e = 0; e < n_eq; e++)
+            if (eq_row[e] >= c->n_rows) throw ArgErr{SCASA_ERR_ARG, "eq_row out of range"};
+        c->max_cell_entries = mx; c->nnz = nnz; c->n_eq = n_eq; c->have_eq = true;
+        c->d_cell_ptr.ensure((size_t)n_cells + 1); c->d_eq_id.ensure((size_t)nnz + 1);
+        c->d_eq_count.ensure((size_t)nnz + 1); c->d_eq_row.ensure((size_t)n_eq);
+        c->d_y_start.ensure((size_t)n_cells); c->d_y_len.ensure((size_t)n_cells);
+        c->d_y_row.ensure((size_t)nnz + 1); c->d_y_val.ensure((size_t)nnz + 1);
+        CK(cudaMemcpyAsync(c->d_cell_ptr.p, cell_ptr, (n_cells + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_y_start.p, cell_ptr, n_cells * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        if (nnz) {
+            CK(cudaMemcpyAsync(c->d_eq_id.p, eq_id, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(c->d_eq_count.p, eq_count, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        }
+        CK(cudaMemcpyAsync(c->d_eq_row.p, eq_row, n_eq * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int scasa_set_gene_map(scasa_ctx *c, const int32_t *gene_of_col, int32_t n_genes)
+{
+    if (!c) return fail(c, SCASA_ERR_ARG, "null context");
+    return guarded(c, [&] {
+        if (!gene_of_col || n_genes <= 0) { c->n_genes = 0; return; }
+        std::vector<int32_t> ptr((size_t)n_genes + 1, 0), cols;
+        for (int64_t j = 0; j < c->n_cols; j++) {
+            int g = gene_of_col[j];
+            if (g >= n_genes) throw ArgErr{SCASA_ERR_ARG, "gene_of_col out of range"};
+            if (g >= 0) ptr[(size_t)g + 1]++;
+        }
+        for (int g = 0; g < n_genes; g++) ptr[(size_t)g + 1] += ptr[(size_t)g];
+        cols.resize((size_t)ptr[(size_t)n_genes]);
+        std::vector<int32_t> cur(ptr.begin(), ptr.end() - 1);
+        for (int64_t j = 0; j < c->n_cols; j++) {        // members in column order (step3:27)
+            int g = gene_of_col[j];
+            if (g >= 0) cols[(size_t)cur[(size_t)g]++] = (int32_t)j;
+        }
+        c->n_genes = n_genes;
+        std::vector<int32_t> goc(gene_of_col, gene_of_col + c->n_cols);
+        c->d_gene_of_col.upload(goc, c->stream);
+        c->d_gene_ptr.upload(ptr, c->stream);
+        c->d_gene_cols.ensure(cols.size() + 1);
+        c->d_gene_cols.upload(cols, c->stream);
+        CK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int scasa_run(scasa_ctx *c)
+{
+    if (!c) return fail(c, SCASA_ERR_ARG, "null context");
+    if (!c->staged) return fail(c, SCASA_ERR_STATE, "nothing staged: call scasa_stage_counts / scasa_stage_eqcounts first");
+    return guarded(c, [&] {
+        cudaStream_t s = c->stream;
+        int launches = 0;
+        const int64_t n_tasks = (int64_t)c->n_chunks * c->n_em;
+        const int64_t iso_elems = c->n_cells * c->n_cols;
+        c->d_iso.ensure((size_t)iso_elems);
+        c->d_cnt.ensure((size_t)n_tasks + 1); c->d_runs.ensure((size_t)n_tasks + 1); c->d_bw.ensure((size_t)n_tasks + 1);
+        c->d_ent_off.ensure((size_t)n_tasks + 1); c->d_run_off.ensure((size_t)n_tasks + 1);
+        c->d_beta_off.ensure((size_t)n_tasks + 1);
+        c->d_ent_cur.ensure((size_t)n_tasks + 1); c->d_run_cur.ensure((size_t)n_tasks + 1);
+        c->d_iters.ensure((size_t)n_tasks * 2 + 2);
+
+        CK(cudaEventRecord(c->ev[0], s));
+        CK(cudaMemsetAsync(c->d_iso.p, 0, iso_elems * sizeof(double), s));
+        CK(cudaMemsetAsync(c->d_cnt.p, 0, (n_tasks + 1) * sizeof(int32_t), s));
+        CK(cudaMemsetAsync(c->d_runs.p, 0, (n_tasks + 1) * sizeof(int32_t), s));
+        CK(cudaMemsetAsync(c->d_stats.p, 0, 8 * sizeof(unsigned long long), s));
+        CK(cudaMemsetAsync(c->d_next.p, 0, 16 * sizeof(unsigned int), s));
+        CK(cudaMemsetAsync(c->d_flag.p, 0, sizeof(int), s));
+
+        // ---- pack: eqclass counts -> Y
+        if (c->have_eq) {
+            int cap = 32;
+            while (cap < c->max_cell_entries) cap <<= 1;
+            size_t smem = (size_t)cap * sizeof(unsigned long long);
+            CK(cudaFuncSetAttribute(pack_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int grid = (int)std::min<int64_t>(c->n_cells, (int64_t)c->n_sm * 8);
+            pack_cells_kernel<<<grid, 256, smem, s>>>(c->n_cells, c->d_cell_ptr.p, c->d_eq_id.p, c->d_eq_count.p,
+                                                      c->d_eq_row.p, c->n_eq, cap, c->d_y_row.p, c->d_y_val.p,
+                                                      c->d_y_len.p, c->d_flag.p);
+            CK(cudaGetLastError());
+            launches++;
+        }
+        CK(cudaEventRecord(c->ev[1], s));
+
+        // ---- task extents
+        XDev X = xdev(c);
+        Sample S = sdev(c);
+        Tasks T = tdev(c);
+        if (c->n_em > 0) {
+            const int wpb = 8;
+            task_count_kernel<<<(unsigned)((c->n_cells + wpb - 1) / wpb), wpb * 32, 0, s>>>(X, S, T);
+            poor_fix_kernel<<<(unsigned)((n_tasks + 255) / 256), 256, 0, s>>>(X, S, T, n_tasks);
+            launches += 2;
+            exclusive_scan(c, c->d_cnt.p, n_tasks, c->d_ent_off.p, c->d_totals.p + 0, launches);
+            exclusive_scan(c, c->d_runs.p, n_tasks, c->d_run_off.p, c->d_totals.p + 1, launches);
+            exclusive_scan(c, c->d_bw.p, n_tasks, c->d_beta_off.p, c->d_totals.p + 2, launches);
+            int64_t tot[3];
+            CK(cudaMemcpyAsync(tot, c->d_totals.p, sizeof tot, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            c->d_ent_key.ensure((size_t)tot[0] + 1); c->d_ent_val.ensure((size_t)tot[0] + 1);
+            c->d_run_start.ensure((size_t)tot[1] + 1); c->d_lnorm.ensure((size_t)tot[1] + 1);
+            c->d_beta.ensure((size_t)tot[2] + 1);
+            T = tdev(c);
+            CK(cudaMemcpyAsync(c->d_ent_cur.p, c->d_ent_off.p, n_tasks * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+            CK(cudaMemcpyAsync(c->d_run_cur.p, c->d_run_off.p, n_tasks * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+            // sentinel: run_start[total runs] = total entries
+            CK(cudaMemcpyAsync(c->d_run_start.p + tot[1], c->d_totals.p + 0, sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+            c->timing.n_entries = tot[0];
+        }
+        task_scatter_kernel<<<c->n_chunks, 256, 0, s>>>(X, S, T, c->d_iso.p);
+        CK(cudaGetLastError());
+        launches++;
+        CK(cudaEventRecord(c->ev[2], s));
+
+        // ---- EM
+        EmArgs A;
+        A.X = X; A.S = S; A.T = T; A.out = c->d_iso.p; A.iters = c->d_iters.p; A.stats = c->d_stats.p;
+        A.maxiter_x = c->opts.maxiter_x; A.maxiter_bt = c->opts.maxiter_bt; A.modify = c->opts.modify;
+        A.fixed_iter = c->opts.fixed_iter; A.maxerr = c->opts.maxerr; A.lim = c->opts.lim;
+        A.adjust_esp = c->opts.adjust_esp;
+        int slot = 0;
+        for (auto &g : c->groups) {
+            if (g.em.empty()) { slot++; continue; }
+            switch (g.pmax) {
+                case 2: launch_em<2>(c, g, A, slot); break;
+                case 4: launch_em<4>(c, g, A, slot); break;
+                case 8: launch_em<8>(c, g, A, slot); break;
+                case 32: launch_em<32>(c, g, A, slot); break;
+                default: launch_em<128>(c, g, A, slot); break;
+            }
+            launches++; slot++;
+        }
+        CK(cudaEventRecord(c->ev[3], s));
+
+        // ---- column sums (+ gene sums)
+        const int n_tiles = (int)((c->n_cells + kTileCells - 1) / kTileCells);
+        c->d_partial.ensure((size_t)n_tiles * c->n_cols);
+        c->d_colsum.ensure((size_t)c->n_cols);
+        double *gene = nullptr;
+        if (c->n_genes > 0) { c->d_gene.ensure((size_t)c->n_cells * c->n_genes); gene = c->d_gene.p; }
+        finish_kernel<<<n_tiles, 1024, 0, s>>>(c->d_iso.p, c->n_cells, c->n_cols, c->d_partial.p, c->d_gene_of_col.p,
+                                              c->d_gene_ptr.p, c->d_gene_cols.p, c->n_genes, gene);
+        colsum_reduce<<<(unsigned)((c->n_cols + 255) / 256), 256, 0, s>>>(c->d_partial.p, n_tiles, c->n_cols, c->d_colsum.p);
+        CK(cudaGetLastError());
+        launches += 2;
+        CK(cudaEventRecord(c->ev[4], s));
+
+        unsigned long long st[8];
+        int flag = 0;
+        CK(cudaMemcpyAsync(st, c->d_stats.p, sizeof st, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(&flag, c->d_flag.p, sizeof flag, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (flag) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a cell exceeded the eqclass capacity of the pack kernel"};
+        scasa_timing_t &tm = c->timing;
+        CK(cudaEventElapsedTime(&tm.total_ms, c->ev[0], c->ev[4]));
+        CK(cudaEventElapsedTime(&tm.pack_ms, c->ev[0], c->ev[1]));
+        CK(cudaEventElapsedTime(&tm.tasks_ms, c->ev[1], c->ev[2]));
+        CK(cudaEventElapsedTime(&tm.em_ms, c->ev[2], c->ev[3]));
+        CK(cudaEventElapsedTime(&tm.finish_ms, c->ev[3], c->ev[4]));
+        tm.gene_ms = c->n_genes > 0 ? tm.finish_ms : 0.f;
+        tm.inner_iters = (int64_t)st[0]; tm.outer_iters = (int64_t)st[1];
+        tm.n_tasks = (int64_t)st[4]; tm.n_active = (int64_t)st[5];
+        // sum_tasks [in*8*(q+2p)*n_c + out*8*(q+p)*n_c] + n_cells*8*(sum q + sum p)
+        tm.alg_bytes = 8.0 * ((double)st[2] + (double)st[3]) + (double)c->n_cells * 8.0 * (double)(c->n_rows + c->n_cols);
+        tm.launches = launches;
+        c->ran = true;
+    });
+}
+
+int scasa_last_timing(scasa_ctx *c, scasa_timing_t *out)
+{
+    if (!c || !out) return fail(c, SCASA_ERR_ARG, "null argument");
+    if (!c->ran) return fail(c, SCASA_ERR_STATE, "scasa_run has not completed");
+    *out = c->timing;
+    return SCASA_OK;
+}
+
+static int fetch(scasa_ctx *c, void *dst, const void *src, size_t bytes)
+{
+    if (!c || !dst) return fail(c, SCASA_ERR_ARG, "null argument");
+    if (!c->ran) return fail(c, SCASA_ERR_STATE, "scasa_run has not completed");
+    return guarded(c, [&] {
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int scasa_fetch_iso(scasa_ctx *c, double *out)
+{
+    return fetch(c, out, c ? c->d_iso.p : nullptr, c ? (size_t)(c->n_cells * c->n_cols) * sizeof(double) : 0);
+}
+int scasa_fetch_iters(scasa_ctx *c, int32_t *out)
+{
+    return fetch(c, out, c ? c->d_iters.p : nullptr, c ? (size_t)c->n_chunks * c->n_em * 2 * sizeof(int32_t) : 0);
+}
+int scasa_fetch_colsum(scasa_ctx *c, double *out)
+{
+    return fetch(c, out, c ? c->d_colsum.p : nullptr, c ? (size_t)c->n_cols * sizeof(double) : 0);
+}
+int scasa_fetch_gene(scasa_ctx *c, double *out)
+{
+    if (c && c->n_genes <= 0) return fail(c, SCASA_ERR_STATE, "no gene map set");
+    return fetch(c, out, c ? c->d_gene.p : nullptr, c ? (size_t)c->n_cells * c->n_genes * sizeof(double) : 0);
+}
+
+int scasa_fetch_counts(scasa_ctx *c, int64_t *rowptr, int32_t *rowidx, double *val, int64_t cap, int64_t *nnz_out)
+{
+    if (!c || !rowptr || !nnz_out) return fail(c, SCASA_ERR_ARG, "null argument");
+    if (!c->ran) return fail(c, SCASA_ERR_STATE, "scasa_run has not completed");
+    return guarded(c, [&] {
+        std::vector<int64_t> start((size_t)c->n_cells);
+        std::vector<int32_t> len((size_t)c->n_cells), rows((size_t)c->nnz + 1);
+        std::vector<double> vals((size_t)c->nnz + 1);
+        CK(cudaMemcpyAsync(start.data(), c->d_y_start.p, c->n_cells * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(len.data(), c->d_y_len.p, c->n_cells * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        if (c->nnz) {
+            CK(cudaMemcpyAsync(rows.data(), c->d_y_row.p, c->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(vals.data(), c->d_y_val.p, c->nnz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        }
+        CK(cudaStreamSynchronize(c->stream));
+        int64_t n = 0;
+        rowptr[0] = 0;
+        for (int64_t i = 0; i < c->n_cells; i++) {
+            for (int k = 0; k < len[(size_t)i]; k++) {
+                if (n < cap && rowidx && val) { rowidx[n] = rows[(size_t)start[(size_t)i] + k]; val[n] = vals[(size_t)start[(size_t)i] + k]; }
+                n++;
+            }
+            rowptr[i + 1] = n;
+        }
+        *nnz_out = n;
+        if (n > cap && rowidx) throw ArgErr{SCASA_ERR_ARG, "count buffers too small (nnz returned)"};
+    });
+}
+
+int scasa_estimate(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off,
+                   const int64_t *y_rowptr, const int32_t *y_rowidx, const double *y_val,
+                   double *iso_out, int32_t *iters_out)
+{
+    int rc = scasa_stage_counts(c, n_cells, n_chunks, chunk_off, y_rowptr, y_rowidx, y_val);
+    if (rc) return rc;
+    rc = scasa_run(c);
+    if (rc) return rc;
+    rc = scasa_fetch_iso(c, iso_out);
+    if (rc) return rc;
+    if (iters_out) rc = scasa_fetch_iters(c, iters_out);
+    return rc;
+}
+
+int scasa_gene_sum(scasa_ctx *c, const int32_t *gene_of_col, int32_t n_genes, const double *iso, int64_t n_cells,
+                   double *gene_out)
+{
+    if (!c || !gene_of_col || !iso || !gene_out || n_cells <= 0 || n_genes <= 0) return fail(c, SCASA_ERR_ARG, "bad argument");
+    int rc = scasa_set_gene_map(c, gene_of_col, n_genes);
+    if (rc) return rc;
+    return guarded(c, [&] {
+        cudaStream_t s = c->stream;
+        c->d_iso.ensure((size_t)(n_cells * c->n_cols));
+        c->d_gene.ensure((size_t)n_cells * n_genes);
+        const int n_tiles = (int)((n_cells + kTileCells - 1) / kTileCells);
+        c->d_partial.ensure((size_t)n_tiles * c->n_cols);
+        CK(cudaMemcpyAsync(c->d_iso.p, iso, n_cells * c->n_cols * sizeof(double), cudaMemcpyHostToDevice, s));
+        finish_kernel<<<n_tiles, 1024, 0, s>>>(c->d_iso.p, n_cells, c->n_cols, c->d_partial.p, c->d_gene_of_col.p,
+                                              c->d_gene_ptr.p, c->d_gene_cols.p, n_genes, c->d_gene.p);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(gene_out, c->d_gene.p, (size_t)n_cells * n_genes * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    });
+}
+
+int scasa_eqclass_map(scasa_ctx *c, int64_t n_eq, const int64_t *eq_off, const int32_t *eq_tx, int32_t *eq_row,
+                      int32_t n_threads)
+{
+    if (!c || !eq_off || !eq_row || n_eq < 0) return fail(c, SCASA_ERR_ARG, "bad argument");
+    if (!c->crp.ready()) return fail(c, SCASA_ERR_STATE, "context was created without CRP");
+    return guarded(c, [&] { c->crp.map(n_eq, eq_off, eq_tx, eq_row, n_threads); });
+}
+
+void *scasa_host_alloc(int64_t bytes)
+{
+    void *p = nullptr;
+    if (bytes <= 0) return nullptr;
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void scasa_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

@@ -1,0 +1,262 @@
+// scasa_host.cpp — eqclass -> (block, row) map: crpcount_td + hamming_correction, once per
+// distinct equivalence class.  Line numbers: /root/reference/scasa/SCRIPTS/Scasa_Rsource.R.
+#include "scasa_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <thread>
+
+namespace scasa {
+
+// ---------------------------------------------------------------------------------------------
+// format(x) at getOption("digits") = 7 for one numeric column, then as.numeric() of the text.
+// This is what apply(current, 1, ...) at :617/:626 does to the numeric columns of `current`
+// because its first column is character (as.matrix.data.frame formats every numeric column):
+// common number of decimals (or common mantissa length in scientific notation) over the rows
+// that are candidates, fixed notation unless scientific is narrower (R's formatReal).
+void r_format_roundtrip(const double *v, int n, double *back, uint8_t *is_zero_text)
+{
+    const int digits = 7;
+    int rgt = -1000000, mxsl = -1000000, mxe = -1000000, mne = 1000000, mxns = -1000000, neg = 0;
+    bool any = false;
+    char buf[64];
+    for (int i = 0; i < n; i++) {
+        double x = v[i];
+        if (!std::isfinite(x)) continue;
+        any = true;
+        int kp = 0, nsig = 1, neg_i = x < 0;
+        bool widens = false;
+        if (x != 0.0) {
+            snprintf(buf, sizeof buf, "%.*e", digits - 1, std::fabs(x));   // d.dddddde[+-]XX
+            kp = atoi(strchr(buf, 'e') + 1);
+            nsig = digits;
+            for (int k = digits; k >= 2; k--) {                            // strip trailing zeros of the mantissa
+                if (buf[k] == '0') nsig--; else break;                     // buf[0]='d', buf[1]='.', buf[2..7]
+            }
+            widens = kp > 0 && std::fabs(x) < std::pow(10.0, kp);
+        }
+        int left = kp + 1;
+        if (widens) left--;
+        int sleft = neg_i + (left <= 0 ? 1 : left);
+        int right = nsig - left;
+        if (neg_i) neg = 1;
+        rgt = std::max(rgt, right);
+        mxsl = std::max(mxsl, sleft);
+        mxe = std::max(mxe, kp);
+        mne = std::min(mne, kp);
+        mxns = std::max(mxns, nsig);
+    }
+    bool fixed = true;
+    int d = 0;
+    if (any) {
+        if (mxsl < 0) mxsl = 1 + neg;
+        if (rgt < 0) rgt = 0;
+        if (rgt > 350) rgt = 350;
+        int wF = mxsl + rgt + (rgt != 0);
+        int e = (mxe >= 100 || mne <= -99) ? 2 : 1;
+        int dE = mxns - 1;
+        int wE = neg + (dE > 0) + dE + 4 + e;
+        if (wF <= wE) { fixed = true; d = rgt; } else { fixed = false; d = dE; }
+    }
+    for (int i = 0; i < n; i++) {
+        double x = v[i];
+        if (!std::isfinite(x)) { back[i] = x; is_zero_text[i] = 0; continue; }
+        if (x == 0.0) x = 0.0;                                              // strip negative zero
+        char out[512];
+        if (fixed) snprintf(out, sizeof out, "%.*f", d, x); else snprintf(out, sizeof out, "%.*e", d, x);
+        back[i] = strtod(out, nullptr);
+        is_zero_text[i] = (strcmp(out, "0") == 0);
+    }
+}
+
+static double r_median(std::vector<double> &v)
+{
+    if (v.empty()) return NAN;
+    for (double x : v) if (std::isnan(x)) return NAN;
+    std::sort(v.begin(), v.end());
+    size_t n = v.size(), h = n / 2;
+    return (n & 1) ? v[h] : (v[h - 1] + v[h]) / 2.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+void CrpIndex::build(int n_blocks, const int32_t *q_off, const int32_t *p_off, const int64_t *x_off,
+                     const double *x, const int32_t *col_tx, const uint8_t *row_pat, const int32_t *name_rank,
+                     int hamming_dist)
+{
+    B_ = n_blocks; hd_ = hamming_dist;
+    q_off_.assign(q_off, q_off + B_ + 1);
+    p_off_.assign(p_off, p_off + B_ + 1);
+    x_off_.assign(x_off, x_off + B_ + 1);
+    x_.assign(x, x + x_off[B_]);
+    col_tx_.assign(col_tx, col_tx + p_off[B_]);
+    pat_.assign(row_pat, row_pat + x_off[B_]);
+    name_rank_.assign(name_rank, name_rank + B_);
+    supported_.assign((size_t)p_off[B_], 0);
+    hits_.clear(); hits_.reserve((size_t)p_off[B_]);
+    for (int k = 0; k < B_; k++) {
+        int q = q_off_[k + 1] - q_off_[k], p = p_off_[k + 1] - p_off_[k];
+        for (int j = 0; j < p; j++) {
+            long double s = 0;                                   // colSums(crp) > 0   :468, :490
+            for (int r = 0; r < q; r++) s += x_[(size_t)x_off_[k] + (size_t)j * q + r];
+            uint8_t sup = (double)s > 0;
+            supported_[(size_t)p_off_[k] + j] = sup;
+            hits_.push_back(Hit{k, p_off_[k] + j, sup});
+        }
+        if (q * p == 1 && !supported_[(size_t)p_off_[k]])
+            throw std::runtime_error("crp: a 1x1 block with value 0 would count an eqclass twice; not supported");
+    }
+    std::stable_sort(hits_.begin(), hits_.end(), [&](const Hit &a, const Hit &b) {
+        return col_tx_[(size_t)a.col] < col_tx_[(size_t)b.col];
+    });
+    tx_range_.clear(); tx_range_.reserve(hits_.size() * 2);
+    for (size_t i = 0; i < hits_.size();) {
+        size_t j = i;
+        int32_t t = col_tx_[(size_t)hits_[i].col];
+        while (j < hits_.size() && col_tx_[(size_t)hits_[j].col] == t) j++;
+        tx_range_[t] = {(int32_t)i, (int32_t)j};
+        i = j;
+    }
+}
+
+// which.max(apply(current, 1, function(x) median(as.numeric(as.character(x[x > 0])))))  :616-617, :625-626
+int32_t CrpIndex::tie_break(int block, const std::vector<int> &cand) const
+{
+    const int q = q_off_[block + 1] - q_off_[block], p = p_off_[block + 1] - p_off_[block];
+    const size_t xo = (size_t)x_off_[block];
+    const int nc = (int)cand.size();
+    std::vector<double> col(nc), back((size_t)nc * p);
+    std::vector<uint8_t> zt((size_t)nc * p), z(nc);
+    std::vector<double> b(nc);
+    for (int j = 0; j < p; j++) {
+        for (int i = 0; i < nc; i++) col[i] = x_[xo + (size_t)j * q + cand[i]];
+        r_format_roundtrip(col.data(), nc, b.data(), z.data());
+        for (int i = 0; i < nc; i++) { back[(size_t)i * p + j] = b[i]; zt[(size_t)i * p + j] = z[i]; }
+    }
+    int best = -1;
+    double bestv = 0;
+    std::vector<double> vals;
+    std::string s;
+    for (int i = 0; i < nc; i++) {
+        vals.clear();
+        s.assign((size_t)p, '0');
+        for (int j = 0; j < p; j++) if (pat_[xo + (size_t)cand[i] * p + j]) s[(size_t)j] = '1';
+        if (s != "0") vals.push_back(strtod(s.c_str(), nullptr));   // "0110" > "0" as strings; read back as 110
+        for (int j = 0; j < p; j++)
+            if (!zt[(size_t)i * p + j]) vals.push_back(back[(size_t)i * p + j]);
+        double m = r_median(vals);
+        if (std::isnan(m)) continue;                                 // which.max skips NA
+        if (best < 0 || m > bestv) { best = i; bestv = m; }
+    }
+    if (best < 0) best = 0;   // the reference stops with an error here (zero-length replacement)
+    return cand[best];
+}
+
+// hamming_correction for one observed pattern  :562-648
+int32_t CrpIndex::pick_row(int block, const std::vector<uint8_t> &obs) const
+{
+    const int q = q_off_[block + 1] - q_off_[block], p = p_off_[block + 1] - p_off_[block];
+    const size_t xo = (size_t)x_off_[block];
+    std::vector<int> dist(q);
+    int dmin = 1 << 30;
+    for (int r = 0; r < q; r++) {
+        int d = 0;
+        const uint8_t *pr = &pat_[xo + (size_t)r * p];
+        for (int j = 0; j < p; j++) d += (pr[j] != obs[(size_t)j]);
+        dist[r] = d;
+        dmin = std::min(dmin, d);
+        if (d == 0) return r;                                        // :609-610
+    }
+    std::vector<int> cand;
+    for (int r = 0; r < q; r++) if (dist[r] <= hd_) cand.push_back(r);
+    if (cand.size() == 1) return cand[0];                            // :620-622
+    if (cand.empty())                                                // :624-627
+        for (int r = 0; r < q; r++) if (dist[r] <= dmin) cand.push_back(r);
+    if (cand.size() == 1) return cand[0];
+    return tie_break(block, cand);                                   // :613-618
+}
+
+int32_t CrpIndex::map_one(const int32_t *tx_in, int n_in, std::vector<int32_t> &tx) const
+{
+    tx.assign(tx_in, tx_in + n_in);
+    std::sort(tx.begin(), tx.end());
+    tx.erase(std::unique(tx.begin(), tx.end()), tx.end());
+    const int n = (int)tx.size();
+    if (n == 0) return -1;
+
+    struct Cand { int32_t block; int32_t inter; uint8_t sup; };
+    Cand small[64];
+    std::vector<Cand> big;
+    int nc = 0;
+    auto add = [&](const Hit &h) {
+        Cand *arr = big.empty() ? small : big.data();
+        for (int i = 0; i < nc; i++)
+            if (arr[i].block == h.block) { arr[i].inter++; arr[i].sup |= h.supported; return; }
+        if (big.empty() && nc == 64) big.assign(small, small + 64);
+        if (big.empty()) small[nc++] = Cand{h.block, 1, h.supported};
+        else { big.push_back(Cand{h.block, 1, h.supported}); nc++; }
+    };
+    for (int i = 0; i < n; i++) {
+        auto it = tx_range_.find(tx[(size_t)i]);
+        if (it == tx_range_.end()) continue;                         // transcript in no block (t2c gives NA)
+        for (int32_t h = it->second.first; h < it->second.second; h++) add(hits_[(size_t)h]);
+    }
+    const Cand *arr = big.empty() ? small : big.data();
+
+    // 1x1 blocks (length(crp) == 1) take the classes made of exactly their transcript  :457-464
+    if (n == 1)
+        for (int i = 0; i < nc; i++) {
+            int k = arr[i].block;
+            if ((q_off_[k + 1] - q_off_[k]) * (p_off_[k + 1] - p_off_[k]) == 1) return q_off_[k];
+        }
+
+    // best block by Jaccard score against the block's full transcript list  :484-505
+    int best = -1;
+    double bestsc = -1;
+    for (int i = 0; i < nc; i++) {
+        if (!arr[i].sup) continue;                                   // :487-493
+        int k = arr[i].block;
+        int pk = p_off_[k + 1] - p_off_[k];
+        double sc = (double)arr[i].inter / (double)(pk + n - arr[i].inter);      // :502
+        if (best < 0 || sc > bestsc || (sc == bestsc && name_rank_[k] < name_rank_[best])) { best = k; bestsc = sc; }
+    }
+    if (best < 0) return -1;
+    const int q = q_off_[best + 1] - q_off_[best], p = p_off_[best + 1] - p_off_[best];
+    if (q * p == 1) return -1;      // best match is a 1x1 block: dropped from every other block (:506), n > 1 here
+
+    std::vector<uint8_t> obs((size_t)p, 0);                          // raw3 pattern  :516-525
+    for (int i = 0; i < n; i++) {
+        auto it = tx_range_.find(tx[(size_t)i]);
+        if (it == tx_range_.end()) continue;
+        for (int32_t h = it->second.first; h < it->second.second; h++) {
+            const Hit &hh = hits_[(size_t)h];
+            if (hh.block == best && hh.supported) obs[(size_t)(hh.col - p_off_[best])] = 1;
+        }
+    }
+    return q_off_[best] + pick_row(best, obs);
+}
+
+void CrpIndex::map(int64_t n_eq, const int64_t *eq_off, const int32_t *eq_tx, int32_t *eq_row, int n_threads) const
+{
+    if (n_threads < 1) n_threads = 1;
+    n_threads = (int)std::min<int64_t>(n_threads, std::max<int64_t>(1, n_eq / 1024));
+    auto work = [&](int64_t lo, int64_t hi) {
+        std::vector<int32_t> scratch;
+        for (int64_t e = lo; e < hi; e++)
+            eq_row[e] = map_one(eq_tx + eq_off[e], (int)(eq_off[e + 1] - eq_off[e]), scratch);
+    };
+    if (n_threads == 1) { work(0, n_eq); return; }
+    std::vector<std::thread> th;
+    int64_t per = (n_eq + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; t++) {
+        int64_t lo = t * per, hi = std::min<int64_t>(n_eq, lo + per);
+        if (lo < hi) th.emplace_back(work, lo, hi);
+    }
+    for (auto &t : th) t.join();
+}
+
+}  // namespace scasa
