@@ -151,3 +151,78 @@ def gene_sum(iso: np.ndarray, gene_of_col, n_members) -> np.ndarray:
                           _p(gene_of_col, C.c_int32), C.c_int32(len(n_members)),
                           _p(n_members, C.c_int32), _p(out, C.c_double))
     return out
+
+
+# ------------------------------------------------------------------ crpcount_td / hamming_correction
+class CrpHandle:
+    """oracle_crp_create over an XMatrix' CRP part (keeps the arrays alive)."""
+
+    def __init__(self, xm, name_rank=None):
+        L = lib()
+        L.oracle_crp_create.restype = C.c_void_p
+        self.xm = xm
+        self._a = [np.ascontiguousarray(xm.q_off, np.int32), np.ascontiguousarray(xm.crp_p_off, np.int32),
+                   np.ascontiguousarray(xm.crp_x_off, np.int64), np.ascontiguousarray(xm.crp_x, np.float64),
+                   np.ascontiguousarray(xm.crp_tx, np.int32), np.ascontiguousarray(xm.crp_pat, np.uint8),
+                   np.ascontiguousarray(xm.name_rank if name_rank is None else name_rank, np.int32)]
+        self.n_tx = int(max(len(xm.tx_names), int(self._a[4].max(initial=0)) + 1))
+        a = self._a
+        self.h = C.c_void_p(L.oracle_crp_create(
+            C.c_int(xm.n_blocks), _p(a[0], C.c_int32), _p(a[1], C.c_int32), _p(a[2], C.c_int64), _p(a[3], C.c_double),
+            _p(a[4], C.c_int32), _p(a[5], C.c_uint8), _p(a[6], C.c_int32), C.c_int(self.n_tx)))
+
+    def __del__(self):
+        try:
+            lib().oracle_crp_free(self.h)
+        except Exception:
+            pass
+
+
+def crpcount_td(handle: CrpHandle, transcript, count, eqclass, hamming_dist: int = 1) -> np.ndarray:
+    """crpcount_td(mytd) for one cell: table columns Transcript (ids), Count, eqClass (rows of one
+    class contiguous, as in Sample_eqClass).  Returns the dense count vector over all rows (Σq)."""
+    tx = np.ascontiguousarray(transcript, np.int32)
+    cnt = np.ascontiguousarray(count, np.int32)
+    eq = np.ascontiguousarray(eqclass, np.int32)
+    y = np.zeros(handle.xm.n_rows, np.float64)
+    lib().oracle_crpcount_td(handle.h, C.c_int(len(tx)), _p(tx, C.c_int32), _p(cnt, C.c_int32), _p(eq, C.c_int32),
+                             C.c_int(hamming_dist), _p(y, C.c_double))
+    return y
+
+
+def crpcount_cells(handle_or_xm, eq_off, eq_tx, cell_ptr, eq_id, eq_count, hamming_dist: int = 1,
+                   nthreads: int = 1) -> np.ndarray:
+    """crpcount_td for every cell of a sample given as per-cell (eqclass id, count) lists plus the
+    eqclass dictionary.  Returns dense Y (n_cells, Σq)."""
+    h = handle_or_xm if isinstance(handle_or_xm, CrpHandle) else CrpHandle(handle_or_xm)
+    eq_off = np.ascontiguousarray(eq_off, np.int64)
+    eq_tx = np.ascontiguousarray(eq_tx, np.int32)
+    cell_ptr = np.ascontiguousarray(cell_ptr, np.int64)
+    eq_id = np.ascontiguousarray(eq_id, np.int32)
+    eq_count = np.ascontiguousarray(eq_count, np.int32)
+    n = len(cell_ptr) - 1
+    y = np.zeros((n, h.xm.n_rows), np.float64)
+    lib().oracle_crpcount_cells(h.h, C.c_int64(n), _p(cell_ptr, C.c_int64), _p(eq_id, C.c_int32),
+                                _p(eq_count, C.c_int32), _p(eq_off, C.c_int64), _p(eq_tx, C.c_int32),
+                                C.c_int(hamming_dist), C.c_int(nthreads), _p(y, C.c_double))
+    return y
+
+
+def eqclass_rows(handle: CrpHandle, eq_off, eq_tx, nthreads: int = 1) -> np.ndarray:
+    """Where crpcount_td puts each eqclass when it is the only class of a cell (count 1): the global
+    row, or -1 if it is dropped.  This is the per-eqclass view the GPU library's map must equal."""
+    n = len(eq_off) - 1
+    y = crpcount_cells(handle, eq_off, eq_tx, np.arange(n + 1), np.arange(n), np.ones(n), nthreads=nthreads)
+    out = np.full(n, -1, np.int32)
+    cells, rows = np.nonzero(y)
+    assert len(np.unique(cells)) == len(cells), "an eqclass was counted in two rows"
+    out[cells] = rows
+    return out
+
+
+def format_roundtrip(v):
+    v = np.ascontiguousarray(v, np.float64)
+    back = np.zeros_like(v)
+    z = np.zeros(len(v), np.uint8)
+    lib().oracle_format_roundtrip(_p(v, C.c_double), C.c_int(len(v)), _p(back, C.c_double), _p(z, C.c_uint8))
+    return back, z.astype(bool)
