@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -45,13 +46,6 @@ template <class T> struct DBuf {   // grow-only device buffer
     }
 };
 
-struct Group {           // EM blocks that share one em_kernel<PMAX> launch
-    int pmax = 0;
-    int xcap = 0;
-    std::vector<int32_t> em;   // EM-block indices, heaviest first
-    DBuf<int32_t> d_em;
-};
-
 }  // namespace
 
 struct scasa_ctx {
@@ -74,7 +68,6 @@ struct scasa_ctx {
     DBuf<int64_t> d_x_off;
     DBuf<double> d_x;
     DBuf<uint8_t> d_poor;
-    std::vector<Group> groups;
     scasa::CrpIndex crp;             // eqclass -> row map (host), built when CRP is given
 
     // ---- staged sample
@@ -88,10 +81,15 @@ struct scasa_ctx {
     int64_t max_cell_entries = 0;
 
     // ---- task arrays
-    DBuf<int32_t> d_cnt, d_runs, d_bw, d_ent_key, d_iters;
-    DBuf<int64_t> d_ent_off, d_run_off, d_beta_off, d_ent_cur, d_run_cur, d_run_start, d_scan_sums, d_totals;
-    DBuf<double> d_ent_val, d_beta, d_lnorm;
-    DBuf<unsigned int> d_next;
+    DBuf<int32_t> d_cnt, d_runs, d_tbytes, d_save, d_iters, d_small[2], d_big[2], d_alive_s[2], d_alive_b[2], d_ncell, d_r_task;
+    DBuf<int64_t> d_toff, d_run_off, d_byte_cur, d_run_cur, d_rec_pos, d_scan_sums, d_totals, d_r_off, d_lpos;
+    DBuf<char> d_tdata, d_scr;
+    DBuf<unsigned int> d_next, d_counters;
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int big_xcap = 8, big_pcap = 2, big_qcap = 2;
+    int rounds = 0, rebuilds = 0, handover_rounds = 16, handover_pct = 5;
+    unsigned handed_over = 0;
     DBuf<unsigned long long> d_stats;
     DBuf<int> d_flag;
 
@@ -168,11 +166,11 @@ Sample sdev(scasa_ctx *c)
 Tasks tdev(scasa_ctx *c)
 {
     Tasks T;
-    T.cnt = c->d_cnt.p; T.runs = c->d_runs.p; T.bw = c->d_bw.p;
-    T.ent_off = c->d_ent_off.p; T.run_off = c->d_run_off.p; T.beta_off = c->d_beta_off.p;
-    T.ent_cur = c->d_ent_cur.p; T.run_cur = c->d_run_cur.p;
-    T.ent_key = c->d_ent_key.p; T.ent_val = c->d_ent_val.p; T.run_start = c->d_run_start.p;
-    T.beta = c->d_beta.p; T.lnorm = c->d_lnorm.p;
+    T.cnt = c->d_cnt.p; T.runs = c->d_runs.p; T.tbytes = c->d_tbytes.p; T.save = c->d_save.p;
+    T.toff = c->d_toff.p; T.run_off = c->d_run_off.p; T.byte_cur = c->d_byte_cur.p; T.run_cur = c->d_run_cur.p;
+    T.tdata = c->d_tdata.p; T.scr = c->d_scr.p; T.rec_pos = c->d_rec_pos.p;
+    T.small_list = c->d_small[0].p; T.big_list = c->d_big[0].p;
+    T.counters = c->d_counters.p;
     return T;
 }
 
@@ -187,22 +185,40 @@ void exclusive_scan(scasa_ctx *c, const int32_t *in, int64_t n, int64_t *out, in
     launches += 3;
 }
 
-template <int PMAX> void launch_em(scasa_ctx *c, Group &g, EmArgs &A, int slot)
+int persistent_grid(scasa_ctx *c, const void *kernel, int threads, size_t smem)
 {
-    const int warps = 4;
-    size_t per_warp = (size_t)(2 * g.xcap + 2 * PMAX + (g.xcap + 7) / 8) * sizeof(double);
-    size_t smem = per_warp * warps;
     if (smem > 220 * 1024) throw ArgErr{SCASA_ERR_UNSUPPORTED, "an EM block is too large for shared memory (q*p limit ~3400)"};
-    CK(cudaFuncSetAttribute(em_kernel<PMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_kernel<PMAX>, warps * 32, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     if (per_sm < 1) per_sm = 1;
-    long long total = (long long)g.em.size() * c->n_chunks;
-    long long want = (total + warps - 1) / warps;
-    int grid = (int)std::min<long long>((long long)c->n_sm * per_sm, std::max<long long>(want, 1));
-    A.grp_em = g.d_em.p; A.grp_n = (int)g.em.size(); A.xcap = g.xcap;
-    A.next_task = c->d_next.p + slot;
-    em_kernel<PMAX><<<grid, warps * 32, smem, c->stream>>>(A);
+    return c->n_sm * per_sm;
+}
+
+// column sums (+ gene sums) of a resident isoform matrix
+void launch_finish(scasa_ctx *c, int64_t n_cells, double *gene, int &launches)
+{
+    cudaStream_t s = c->stream;
+    const int n_tiles = (int)((n_cells + kTileCells - 1) / kTileCells);
+    c->d_partial.ensure((size_t)n_tiles * c->n_cols);
+    c->d_colsum.ensure((size_t)c->n_cols);
+    colsum_kernel<<<dim3(n_tiles, (unsigned)((c->n_cols + kFinCols - 1) / kFinCols)), kFinThreads, 0, s>>>(
+        c->d_iso.p, n_cells, c->n_cols, c->d_partial.p);
+    colsum_reduce<<<(unsigned)((c->n_cols + 255) / 256), 256, 0, s>>>(c->d_partial.p, n_tiles, c->n_cols, c->d_colsum.p);
+    launches += 2;
+    if (gene) {
+        const size_t smem = (size_t)c->n_genes * sizeof(double);
+        const int grid = (int)std::min<int64_t>(n_cells, (int64_t)c->n_sm * 4);
+        if (smem <= 220 * 1024) {
+            CK(cudaFuncSetAttribute(gene_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gene_smem_kernel<<<std::min<int>(grid, c->n_sm), 1024, smem, s>>>(c->d_iso.p, n_cells, c->n_cols, c->d_gene_of_col.p,
+                                                                           c->d_gene_ptr.p, c->d_gene_cols.p, c->n_genes, gene);
+        } else {
+            gene_direct_kernel<<<grid, 1024, 0, s>>>(c->d_iso.p, n_cells, c->n_cols, c->d_gene_ptr.p, c->d_gene_cols.p,
+                                                     c->n_genes, gene);
+        }
+        launches++;
+    }
     CK(cudaGetLastError());
 }
 
@@ -323,26 +339,21 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
         }
         c->n_em = (int)c->em_blocks.size();
 
-        // launch groups by register-array width; inside a group heaviest blocks first
-        const int classes[] = {2, 4, 8, 32, 128};
-        c->groups.clear();
-        for (int cl : classes) { Group g; g.pmax = cl; c->groups.push_back(std::move(g)); }
+        // shared-memory sizing of the warp-per-task step kernel: the largest block
         for (int e = 0; e < c->n_em; e++) {
             int k = c->em_blocks[e];
             int q = c->q_off[k + 1] - c->q_off[k], p = c->p_off[k + 1] - c->p_off[k];
             if (p > 128) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a block may have at most 128 columns"};
-            for (auto &g : c->groups)
-                if (p <= g.pmax) { g.em.push_back(e); g.xcap = std::max(g.xcap, q * p); break; }
+            c->big_xcap = std::max(c->big_xcap, q * p); c->big_pcap = std::max(c->big_pcap, p); c->big_qcap = std::max(c->big_qcap, q);
         }
-        for (auto &g : c->groups) {
-            std::stable_sort(g.em.begin(), g.em.end(), [&](int a, int b) {
-                int ka = c->em_blocks[a], kb = c->em_blocks[b];
-                int64_t wa = c->x_off[ka + 1] - c->x_off[ka], wb = c->x_off[kb + 1] - c->x_off[kb];
-                return wa > wb;
-            });
-            g.xcap = (g.xcap + 7) & ~7;
-            g.d_em.upload(g.em, c->stream);
-        }
+        c->big_xcap = (c->big_xcap + 7) & ~7;
+        c->big_pcap = (c->big_pcap + 1) & ~1;
+        c->big_qcap = (c->big_qcap + 1) & ~1;
+        if (const char *env = getenv("SCASA_HANDOVER_ROUNDS")) c->handover_rounds = std::max(1, atoi(env));
+        if (const char *env = getenv("SCASA_HANDOVER_PCT")) c->handover_pct = std::max(0, atoi(env));
+        CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 
         c->d_q_off.upload(c->q_off, c->stream);
         c->d_p_off.upload(c->p_off, c->stream);
@@ -354,7 +365,7 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
         c->d_poor.upload(c->poor, c->stream);
         c->d_poor_em.ensure(c->poor_em.size() + 1);
         c->d_poor_em.upload(c->poor_em, c->stream);
-        c->d_next.ensure(16); c->d_stats.ensure(8); c->d_totals.ensure(4); c->d_flag.ensure(1);
+        c->d_next.ensure(16); c->d_counters.ensure(8); c->d_stats.ensure(8); c->d_totals.ensure(4); c->d_flag.ensure(1);
         CK(cudaStreamSynchronize(c->stream));
 
         if (crp) {
@@ -379,17 +390,22 @@ void scasa_ctx_destroy(scasa_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     DBuf<int32_t> *i32[] = {&c->d_q_off, &c->d_p_off, &c->d_row_block, &c->d_em_index, &c->d_em_blocks, &c->d_poor_em,
                             &c->d_cell_chunk, &c->d_y_len, &c->d_y_row, &c->d_eq_id, &c->d_eq_count, &c->d_eq_row,
-                            &c->d_cnt, &c->d_runs, &c->d_bw, &c->d_ent_key, &c->d_iters, &c->d_gene_of_col,
+                            &c->d_cnt, &c->d_runs, &c->d_tbytes, &c->d_save, &c->d_iters, &c->d_small[0], &c->d_small[1], &c->d_big[0], &c->d_big[1],
+                            &c->d_alive_s[0], &c->d_alive_s[1], &c->d_alive_b[0], &c->d_alive_b[1], &c->d_ncell, &c->d_r_task,
+                            &c->d_gene_of_col,
                             &c->d_gene_ptr, &c->d_gene_cols};
     for (auto b : i32) b->release();
-    DBuf<int64_t> *i64[] = {&c->d_x_off, &c->d_chunk_off, &c->d_y_start, &c->d_cell_ptr, &c->d_ent_off, &c->d_run_off,
-                            &c->d_beta_off, &c->d_ent_cur, &c->d_run_cur, &c->d_run_start, &c->d_scan_sums, &c->d_totals};
+    DBuf<int64_t> *i64[] = {&c->d_x_off, &c->d_chunk_off, &c->d_y_start, &c->d_cell_ptr, &c->d_toff, &c->d_run_off,
+                            &c->d_byte_cur, &c->d_run_cur, &c->d_rec_pos, &c->d_scan_sums, &c->d_totals, &c->d_r_off, &c->d_lpos};
     for (auto b : i64) b->release();
-    DBuf<double> *f64[] = {&c->d_x, &c->d_y_val, &c->d_ent_val, &c->d_beta, &c->d_lnorm, &c->d_iso, &c->d_partial,
+    DBuf<double> *f64[] = {&c->d_x, &c->d_y_val, &c->d_iso, &c->d_partial,
                            &c->d_colsum, &c->d_gene};
     for (auto b : f64) b->release();
     c->d_poor.release(); c->d_next.release(); c->d_stats.release(); c->d_flag.release();
-    for (auto &g : c->groups) g.d_em.release();
+    c->d_tdata.release(); c->d_scr.release(); c->d_counters.release();
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -518,7 +534,16 @@ int scasa_set_gene_map(scasa_ctx *c, const int32_t *gene_of_col, int32_t n_genes
         }
         c->n_genes = n_genes;
         std::vector<int32_t> goc(gene_of_col, gene_of_col + c->n_cols);
-        c->d_gene_of_col.upload(goc, c->stream);
+        // per column: >= 0 copy into that gene row; <= -2 first member of gene -(a+2): sum; -1 nothing
+        std::vector<int32_t> action((size_t)c->n_cols, -1);
+        for (int64_t j = 0; j < c->n_cols; j++) {
+            int g = goc[(size_t)j];
+            if (g < 0) continue;
+            int k0 = ptr[(size_t)g], k1 = ptr[(size_t)g + 1];
+            if (k1 - k0 == 1) action[(size_t)j] = g;
+            else if (cols[(size_t)k0] == (int32_t)j) action[(size_t)j] = -(g + 2);
+        }
+        c->d_gene_of_col.upload(action, c->stream);
         c->d_gene_ptr.upload(ptr, c->stream);
         c->d_gene_cols.ensure(cols.size() + 1);
         c->d_gene_cols.upload(cols, c->stream);
@@ -536,10 +561,15 @@ int scasa_run(scasa_ctx *c)
         const int64_t n_tasks = (int64_t)c->n_chunks * c->n_em;
         const int64_t iso_elems = c->n_cells * c->n_cols;
         c->d_iso.ensure((size_t)iso_elems);
-        c->d_cnt.ensure((size_t)n_tasks + 1); c->d_runs.ensure((size_t)n_tasks + 1); c->d_bw.ensure((size_t)n_tasks + 1);
-        c->d_ent_off.ensure((size_t)n_tasks + 1); c->d_run_off.ensure((size_t)n_tasks + 1);
-        c->d_beta_off.ensure((size_t)n_tasks + 1);
-        c->d_ent_cur.ensure((size_t)n_tasks + 1); c->d_run_cur.ensure((size_t)n_tasks + 1);
+        c->d_cnt.ensure((size_t)n_tasks + 1); c->d_runs.ensure((size_t)n_tasks + 1);
+        c->d_tbytes.ensure((size_t)n_tasks + 1); c->d_save.ensure((size_t)n_tasks + 1);
+        c->d_toff.ensure((size_t)n_tasks + 1); c->d_run_off.ensure((size_t)n_tasks + 1);
+        c->d_byte_cur.ensure((size_t)n_tasks + 1); c->d_run_cur.ensure((size_t)n_tasks + 1);
+        for (int k = 0; k < 2; k++) {
+            c->d_small[k].ensure((size_t)n_tasks + 1); c->d_big[k].ensure((size_t)n_tasks + 1);
+            c->d_alive_s[k].ensure((size_t)n_tasks + 1); c->d_alive_b[k].ensure((size_t)n_tasks + 1);
+        }
+        c->d_ncell.ensure((size_t)n_tasks + 1); c->d_lpos.ensure((size_t)n_tasks + 2);
         c->d_iters.ensure((size_t)n_tasks * 2 + 2);
 
         CK(cudaEventRecord(c->ev[0], s));
@@ -548,46 +578,61 @@ int scasa_run(scasa_ctx *c)
         CK(cudaMemsetAsync(c->d_runs.p, 0, (n_tasks + 1) * sizeof(int32_t), s));
         CK(cudaMemsetAsync(c->d_stats.p, 0, 8 * sizeof(unsigned long long), s));
         CK(cudaMemsetAsync(c->d_next.p, 0, 16 * sizeof(unsigned int), s));
+        CK(cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(unsigned int), s));
         CK(cudaMemsetAsync(c->d_flag.p, 0, sizeof(int), s));
 
         // ---- pack: eqclass counts -> Y
         if (c->have_eq) {
-            int cap = 32;
-            while (cap < c->max_cell_entries) cap <<= 1;
-            size_t smem = (size_t)cap * sizeof(unsigned long long);
-            CK(cudaFuncSetAttribute(pack_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int grid = (int)std::min<int64_t>(c->n_cells, (int64_t)c->n_sm * 8);
-            pack_cells_kernel<<<grid, 256, smem, s>>>(c->n_cells, c->d_cell_ptr.p, c->d_eq_id.p, c->d_eq_count.p,
-                                                      c->d_eq_row.p, c->n_eq, cap, c->d_y_row.p, c->d_y_val.p,
-                                                      c->d_y_len.p, c->d_flag.p);
+            int seg = (int)((c->n_rows + 511) / 512);
+            seg |= 1;                                             // odd segment length: conflict-free strided reads
+            const size_t dense_smem = (size_t)seg * 512 * sizeof(int);
+            if (dense_smem <= 200 * 1024 && !getenv("SCASA_PACK_SORT")) {
+                CK(cudaFuncSetAttribute(pack_cells_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_smem));
+                int grid = (int)std::min<int64_t>(c->n_cells, (int64_t)c->n_sm);
+                pack_cells_dense_kernel<<<grid, 512, dense_smem, s>>>(c->n_cells, c->d_cell_ptr.p, c->d_eq_id.p, c->d_eq_count.p,
+                                                                      c->d_eq_row.p, c->n_eq, (int)c->n_rows, seg, c->d_y_row.p,
+                                                                      c->d_y_val.p, c->d_y_len.p);
+            } else {
+                int cap = 32;
+                while (cap < c->max_cell_entries) cap <<= 1;
+                size_t smem = (size_t)cap * sizeof(unsigned long long);
+                CK(cudaFuncSetAttribute(pack_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int grid = (int)std::min<int64_t>(c->n_cells, (int64_t)c->n_sm * 8);
+                pack_cells_kernel<<<grid, 256, smem, s>>>(c->n_cells, c->d_cell_ptr.p, c->d_eq_id.p, c->d_eq_count.p,
+                                                          c->d_eq_row.p, c->n_eq, cap, c->d_y_row.p, c->d_y_val.p,
+                                                          c->d_y_len.p, c->d_flag.p);
+            }
             CK(cudaGetLastError());
             launches++;
         }
         CK(cudaEventRecord(c->ev[1], s));
 
-        // ---- task extents
+        // ---- task extents, work lists, blobs
         XDev X = xdev(c);
         Sample S = sdev(c);
         Tasks T = tdev(c);
+        EmOpts O;
+        O.maxiter_x = c->opts.maxiter_x; O.maxiter_bt = c->opts.maxiter_bt; O.modify = c->opts.modify;
+        O.fixed_iter = c->opts.fixed_iter;
+        O.maxerr = c->opts.maxerr; O.lim = c->opts.lim; O.adjust_esp = c->opts.adjust_esp;
+        int64_t tot[2] = {0, 0};
+        unsigned int cnts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (c->n_em > 0) {
             const int wpb = 8;
             task_count_kernel<<<(unsigned)((c->n_cells + wpb - 1) / wpb), wpb * 32, 0, s>>>(X, S, T);
-            poor_fix_kernel<<<(unsigned)((n_tasks + 255) / 256), 256, 0, s>>>(X, S, T, n_tasks);
+            classify_kernel<<<(unsigned)((n_tasks + 255) / 256), 256, 0, s>>>(X, S, T, n_tasks, O, c->d_iters.p, c->d_stats.p);
             launches += 2;
-            exclusive_scan(c, c->d_cnt.p, n_tasks, c->d_ent_off.p, c->d_totals.p + 0, launches);
+            exclusive_scan(c, c->d_tbytes.p, n_tasks, c->d_toff.p, c->d_totals.p + 0, launches);
             exclusive_scan(c, c->d_runs.p, n_tasks, c->d_run_off.p, c->d_totals.p + 1, launches);
-            exclusive_scan(c, c->d_bw.p, n_tasks, c->d_beta_off.p, c->d_totals.p + 2, launches);
-            int64_t tot[3];
             CK(cudaMemcpyAsync(tot, c->d_totals.p, sizeof tot, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(cnts, c->d_counters.p, sizeof cnts, cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
-            c->d_ent_key.ensure((size_t)tot[0] + 1); c->d_ent_val.ensure((size_t)tot[0] + 1);
-            c->d_run_start.ensure((size_t)tot[1] + 1); c->d_lnorm.ensure((size_t)tot[1] + 1);
-            c->d_beta.ensure((size_t)tot[2] + 1);
+            if (cnts[7]) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a poor-condition (2-column) block may have at most 64 rows"};
+            c->d_tdata.ensure((size_t)tot[0] + 64); c->d_scr.ensure((size_t)tot[0] + 64);
+            c->d_rec_pos.ensure((size_t)tot[1] + 1); c->d_r_task.ensure((size_t)tot[1] + 1); c->d_r_off.ensure((size_t)tot[1] + 1);
             T = tdev(c);
-            CK(cudaMemcpyAsync(c->d_ent_cur.p, c->d_ent_off.p, n_tasks * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
-            CK(cudaMemcpyAsync(c->d_run_cur.p, c->d_run_off.p, n_tasks * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
-            // sentinel: run_start[total runs] = total entries
-            CK(cudaMemcpyAsync(c->d_run_start.p + tot[1], c->d_totals.p + 0, sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+            cursor_init_kernel<<<(unsigned)((n_tasks + 255) / 256), 256, 0, s>>>(T, n_tasks);
+            launches++;
             c->timing.n_entries = tot[0];
         }
         task_scatter_kernel<<<c->n_chunks, 256, 0, s>>>(X, S, T, c->d_iso.p);
@@ -595,37 +640,131 @@ int scasa_run(scasa_ctx *c)
         launches++;
         CK(cudaEventRecord(c->ev[2], s));
 
-        // ---- EM
-        EmArgs A;
-        A.X = X; A.S = S; A.T = T; A.out = c->d_iso.p; A.iters = c->d_iters.p; A.stats = c->d_stats.p;
-        A.maxiter_x = c->opts.maxiter_x; A.maxiter_bt = c->opts.maxiter_bt; A.modify = c->opts.modify;
-        A.fixed_iter = c->opts.fixed_iter; A.maxerr = c->opts.maxerr; A.lim = c->opts.lim;
-        A.adjust_esp = c->opts.adjust_esp;
-        int slot = 0;
-        for (auto &g : c->groups) {
-            if (g.em.empty()) { slot++; continue; }
-            switch (g.pmax) {
-                case 2: launch_em<2>(c, g, A, slot); break;
-                case 4: launch_em<4>(c, g, A, slot); break;
-                case 8: launch_em<8>(c, g, A, slot); break;
-                case 32: launch_em<32>(c, g, A, slot); break;
-                default: launch_em<128>(c, g, A, slot); break;
+        // ---- EM rounds
+        c->rounds = 0; c->rebuilds = 0;
+        if (c->n_em > 0 && cnts[3] > 0) {
+            RoundArgs A;
+            A.X = X; A.S = S; A.T = T; A.O = O; A.out = c->d_iso.p; A.iters = c->d_iters.p; A.stats = c->d_stats.p;
+            A.r_task = c->d_r_task.p; A.r_off = c->d_r_off.p; A.xcap = c->big_xcap; A.pcap = c->big_pcap; A.qcap = c->big_qcap;
+            unsigned n_small = cnts[0], n_big = cnts[2];
+            int cur = 0;                               // ping-pong index of the task lists
+            int64_t n_rec = 0;
+            const size_t smem_small = (size_t)128 * kStepSlot * sizeof(double);
+            const size_t smem_big = (size_t)4 * (c->big_xcap + c->big_pcap + c->big_qcap) * sizeof(double);
+            if (smem_big > 200 * 1024) throw ArgErr{SCASA_ERR_UNSUPPORTED, "an EM block is too large for shared memory"};
+            CK(cudaFuncSetAttribute(task_step_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
+            auto grid = [](int64_t n, int per) { return (unsigned)std::max<int64_t>(1, (n + per - 1) / per); };
+
+            // record list of the listed tasks: small tasks first, then big ones, list order = block-major
+            auto build_records = [&]() {
+                int64_t base = 0;
+                for (int cls = 0; cls < 2; cls++) {
+                    const unsigned n = cls ? n_big : n_small;
+                    const int32_t *lst = cls ? c->d_big[cur].p : c->d_small[cur].p;
+                    const unsigned int *dn = c->d_counters.p + (cls ? 2 : 0);
+                    if (n == 0) continue;
+                    gather_ncell_kernel<<<grid(n, 256), 256, 0, s>>>(T, lst, dn, c->d_ncell.p);
+                    exclusive_scan(c, c->d_ncell.p, n, c->d_lpos.p, c->d_totals.p + 2, launches);
+                    fill_records_kernel<<<grid(n, 256), 256, 0, s>>>(T, lst, dn, c->d_lpos.p, base, c->d_r_task.p, c->d_r_off.p);
+                    launches += 2;
+                    int64_t nr = 0;
+                    CK(cudaMemcpyAsync(&nr, c->d_totals.p + 2, sizeof nr, cudaMemcpyDeviceToHost, s));
+                    CK(cudaStreamSynchronize(s));
+                    base += nr;
+                }
+                n_rec = base;
+            };
+            build_records();
+            auto args_for = [&](int cls) {
+                RoundArgs R = A;
+                R.tlist = cls ? c->d_big[cur].p : c->d_small[cur].p;
+                R.tlist_n = c->d_counters.p + (cls ? 2 : 0);
+                R.alive_flags = cls ? c->d_alive_b[cur].p : c->d_alive_s[cur].p;
+                R.n_rec = n_rec;
+                return R;
+            };
+            if (n_small) task_init_kernel<<<grid(n_small, 128), 128, 0, s>>>(args_for(0));
+            if (n_big) task_init_kernel<<<grid(n_big, 128), 128, 0, s>>>(args_for(1));
+            rec_init_kernel<<<grid(n_rec, 256), 256, 0, s>>>(args_for(0));
+            launches += 3;
+            CK(cudaGetLastError());
+
+            CK(cudaEventRecord(c->ev[5], s));
+            unsigned alive = cnts[3], listed = n_small + n_big;
+            const unsigned cnts0_alive = cnts[3];
+            c->handed_over = 0;
+            const long long max_rounds = (long long)c->opts.maxiter_x * c->opts.maxiter_bt + 2;
+            while (alive > 0 && c->rounds < max_rounds) {
+                const int burst = alive > 20000 ? 1 : (alive > 2000 ? 4 : 16);
+                for (int k = 0; k < burst; k++) {
+                    beta_pass_kernel<<<grid(n_rec, 256), 256, 0, s>>>(args_for(0));
+                    if (n_small) task_step_small_kernel<<<grid(n_small, 128 / kTile), 128, smem_small, s>>>(args_for(0));
+                    if (n_big) task_step_big_kernel<<<grid(n_big, 4), 128, smem_big, s>>>(args_for(1));
+                    launches += 1 + (n_small ? 1 : 0) + (n_big ? 1 : 0);
+                    c->rounds++;
+                }
+                CK(cudaMemcpyAsync(cnts, c->d_counters.p, sizeof cnts, cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                alive = cnts[3];
+                const bool hand_over = alive > 0 && c->rounds >= c->handover_rounds &&
+                                       (uint64_t)alive * 100 <= (uint64_t)cnts0_alive * (unsigned)c->handover_pct;
+                if (alive > 0 && ((uint64_t)alive * 2 <= listed || hand_over)) {
+                    // stable compaction of both task lists, then a fresh record list
+                    const int nxt = cur ^ 1;
+                    for (int cls = 0; cls < 2; cls++) {
+                        const unsigned n = cls ? n_big : n_small;
+                        if (n == 0) continue;
+                        int32_t *al = cls ? c->d_alive_b[cur].p : c->d_alive_s[cur].p;
+                        exclusive_scan(c, al, n, c->d_lpos.p, c->d_totals.p + 3, launches);
+                        compact_list_kernel<<<grid(n, 256), 256, 0, s>>>(cls ? c->d_big[cur].p : c->d_small[cur].p, al, c->d_lpos.p,
+                                                                        c->d_counters.p + (cls ? 2 : 0),
+                                                                        cls ? c->d_big[nxt].p : c->d_small[nxt].p,
+                                                                        cls ? c->d_alive_b[nxt].p : c->d_alive_s[nxt].p);
+                        set_count_kernel<<<1, 1, 0, s>>>(c->d_counters.p + (cls ? 2 : 0), c->d_totals.p + 3);
+                        launches += 2;
+                        int64_t kept = 0;
+                        CK(cudaMemcpyAsync(&kept, c->d_totals.p + 3, sizeof kept, cudaMemcpyDeviceToHost, s));
+                        CK(cudaStreamSynchronize(s));
+                        if (cls) n_big = (unsigned)kept; else n_small = (unsigned)kept;
+                    }
+                    cur = nxt;
+                    listed = n_small + n_big;
+                    if (!hand_over) build_records();
+                    c->rebuilds++;
+                }
+                if (hand_over) {
+                    CK(cudaEventRecord(c->ev[6], s));
+                    // the stragglers: persistent warp-per-task kernels, narrow and wide blocks side by side
+                    CK(cudaEventRecord(c->ev_fork, s));
+                    CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+                    for (int cls = 0; cls < 2; cls++) {
+                        const unsigned n = cls ? n_big : n_small;
+                        if (n == 0) continue;
+                        RoundArgs R = args_for(cls);
+                        if (!cls) { R.xcap = 32; R.pcap = kSmallP; R.qcap = 32; }
+                        const size_t smem = (size_t)4 * (2 * R.xcap + 2 * R.pcap + R.qcap) * sizeof(double);
+                        CK(cudaFuncSetAttribute(em_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)((size_t)4 * (2 * c->big_xcap + 2 * c->big_pcap + c->big_qcap) * sizeof(double))));
+                        int per_sm = 0;
+                        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_finish_kernel, 128, smem));
+                        const unsigned g = (unsigned)std::min<int64_t>((int64_t)c->n_sm * std::max(per_sm, 1), (n + 3) / 4);
+                        em_finish_kernel<<<g, 128, smem, cls ? c->stream2 : s>>>(R, c->d_next.p + cls);
+                        launches++;
+                    }
+                    CK(cudaEventRecord(c->ev_join, c->stream2));
+                    CK(cudaStreamWaitEvent(s, c->ev_join, 0));
+                    c->handed_over = alive;
+                    alive = 0;
+                }
             }
-            launches++; slot++;
+            CK(cudaGetLastError());
         }
         CK(cudaEventRecord(c->ev[3], s));
 
         // ---- column sums (+ gene sums)
-        const int n_tiles = (int)((c->n_cells + kTileCells - 1) / kTileCells);
-        c->d_partial.ensure((size_t)n_tiles * c->n_cols);
-        c->d_colsum.ensure((size_t)c->n_cols);
         double *gene = nullptr;
         if (c->n_genes > 0) { c->d_gene.ensure((size_t)c->n_cells * c->n_genes); gene = c->d_gene.p; }
-        finish_kernel<<<n_tiles, 1024, 0, s>>>(c->d_iso.p, c->n_cells, c->n_cols, c->d_partial.p, c->d_gene_of_col.p,
-                                              c->d_gene_ptr.p, c->d_gene_cols.p, c->n_genes, gene);
-        colsum_reduce<<<(unsigned)((c->n_cols + 255) / 256), 256, 0, s>>>(c->d_partial.p, n_tiles, c->n_cols, c->d_colsum.p);
-        CK(cudaGetLastError());
-        launches += 2;
+        launch_finish(c, c->n_cells, gene, launches);
         CK(cudaEventRecord(c->ev[4], s));
 
         unsigned long long st[8];
@@ -640,9 +779,17 @@ int scasa_run(scasa_ctx *c)
         CK(cudaEventElapsedTime(&tm.tasks_ms, c->ev[1], c->ev[2]));
         CK(cudaEventElapsedTime(&tm.em_ms, c->ev[2], c->ev[3]));
         CK(cudaEventElapsedTime(&tm.finish_ms, c->ev[3], c->ev[4]));
+        tm.em_setup_ms = tm.em_rounds_ms = tm.em_stragglers_ms = 0.f;
+        if (c->rounds > 0) {
+            CK(cudaEventElapsedTime(&tm.em_setup_ms, c->ev[2], c->ev[5]));
+            if (c->handed_over) {
+                CK(cudaEventElapsedTime(&tm.em_rounds_ms, c->ev[5], c->ev[6]));
+                CK(cudaEventElapsedTime(&tm.em_stragglers_ms, c->ev[6], c->ev[3]));
+            } else CK(cudaEventElapsedTime(&tm.em_rounds_ms, c->ev[5], c->ev[3]));
+        }
         tm.gene_ms = c->n_genes > 0 ? tm.finish_ms : 0.f;
         tm.inner_iters = (int64_t)st[0]; tm.outer_iters = (int64_t)st[1];
-        tm.n_tasks = (int64_t)st[4]; tm.n_active = (int64_t)st[5];
+        tm.n_tasks = (int64_t)st[4]; tm.n_active = (int64_t)st[5]; tm.n_handed_over = c->handed_over; tm.rounds = c->rounds; tm.rebuilds = c->rebuilds;
         // sum_tasks [in*8*(q+2p)*n_c + out*8*(q+p)*n_c] + n_cells*8*(sum q + sum p)
         tm.alg_bytes = 8.0 * ((double)st[2] + (double)st[3]) + (double)c->n_cells * 8.0 * (double)(c->n_rows + c->n_cols);
         tm.launches = launches;
@@ -739,12 +886,9 @@ int scasa_gene_sum(scasa_ctx *c, const int32_t *gene_of_col, int32_t n_genes, co
         cudaStream_t s = c->stream;
         c->d_iso.ensure((size_t)(n_cells * c->n_cols));
         c->d_gene.ensure((size_t)n_cells * n_genes);
-        const int n_tiles = (int)((n_cells + kTileCells - 1) / kTileCells);
-        c->d_partial.ensure((size_t)n_tiles * c->n_cols);
         CK(cudaMemcpyAsync(c->d_iso.p, iso, n_cells * c->n_cols * sizeof(double), cudaMemcpyHostToDevice, s));
-        finish_kernel<<<n_tiles, 1024, 0, s>>>(c->d_iso.p, n_cells, c->n_cols, c->d_partial.p, c->d_gene_of_col.p,
-                                              c->d_gene_ptr.p, c->d_gene_cols.p, n_genes, c->d_gene.p);
-        CK(cudaGetLastError());
+        int launches = 0;
+        launch_finish(c, n_cells, c->d_gene.p, launches);
         CK(cudaMemcpyAsync(gene_out, c->d_gene.p, (size_t)n_cells * n_genes * sizeof(double), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
     });

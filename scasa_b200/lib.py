@@ -40,9 +40,10 @@ class Crp(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("total_ms", C.c_float), ("pack_ms", C.c_float), ("tasks_ms", C.c_float), ("em_ms", C.c_float),
-                ("finish_ms", C.c_float), ("gene_ms", C.c_float), ("n_tasks", C.c_int64), ("n_entries", C.c_int64),
-                ("n_active", C.c_int64), ("inner_iters", C.c_int64), ("outer_iters", C.c_int64),
-                ("alg_bytes", C.c_double), ("launches", C.c_int32)]
+                ("finish_ms", C.c_float), ("gene_ms", C.c_float), ("em_setup_ms", C.c_float), ("em_rounds_ms", C.c_float),
+                ("em_stragglers_ms", C.c_float), ("n_tasks", C.c_int64), ("n_entries", C.c_int64),
+                ("n_active", C.c_int64), ("n_handed_over", C.c_int64), ("inner_iters", C.c_int64), ("outer_iters", C.c_int64),
+                ("alg_bytes", C.c_double), ("launches", C.c_int32), ("rounds", C.c_int32), ("rebuilds", C.c_int32)]
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}
