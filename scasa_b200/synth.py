@@ -53,7 +53,7 @@ def _x_sparse(xm: XMatrix, device) -> torch.Tensor:
     idx = torch.tensor(np.stack([np.concatenate(rows), np.concatenate(cols)]), dtype=torch.int64)
     v = torch.tensor(np.concatenate(vals), dtype=torch.float32)
     del q, p
-    return torch.sparse_coo_tensor(idx, v, (xm.n_rows, xm.n_cols)).coalesce().to(device)
+    return torch.sparse_coo_tensor(idx, v, (xm.n_rows, xm.n_cols), check_invariants=False).coalesce().to(device)
 
 
 class CellGenerator:

@@ -106,3 +106,32 @@ def test_quant_from_eqclasses_equals_estimate_from_counts(gpu, xm, eqdata):
     iso2, it2 = gpu.estimate(chunk_split(200, 4), rowptr, idx, val)
     assert np.array_equal(r.iso, iso2)
     assert np.array_equal(r.iters, it2)
+
+
+def test_hand_built_blocks_and_tie_break(oracle):
+    """The hand-computed cases of tests/test_oracle.py through the library's own eqclass map
+    (1x1 rule, Jaccard best block, dropped classes, Hamming-1 correction, the R-coercion tie-break)."""
+    from scasa_b200.api import Scasa
+    from tests.test_oracle import _xm_from_blocks
+    A = np.array([[1.0]])
+    B = np.array([[0.7, 0.0], [0.3, 0.4], [0.0, 0.6]])
+    C = np.array([[0.5, 1.0, 0.0], [0.5, 0.0, 0.0]])
+    xm3 = _xm_from_blocks([A, B, C], pats=[[[1]], [[1, 0], [1, 1], [0, 1]], [[1, 1, 0], [1, 0, 1]]], tx=[0, 1, 2, 2, 3, 4])
+    classes = [[0], [0, 1], [1], [1, 2], [2], [2, 3], [3], [4], [5]]
+    want = [0, -1, 1, 2, 3, 4, 4, -1, -1]
+    off = np.concatenate([[0], np.cumsum([len(c) for c in classes])])
+    g = Scasa(xm3, device=0)
+    try:
+        got = g.eqclass_map(off, np.concatenate(classes), 1)
+    finally:
+        g.close()
+    assert list(got) == want
+    assert list(oracle.eqclass_rows(oracle.CrpHandle(xm3), off, np.concatenate(classes))) == want
+    D = np.array([[0.7, 0.8, 0.0], [0.0, 0.2, 0.5], [0.3, 0.0, 0.5]])
+    xmd = _xm_from_blocks([D], pats=[[[1, 1, 0], [0, 1, 1], [1, 0, 1]]], tx=[0, 1, 2])
+    g = Scasa(xmd, device=0)
+    try:
+        got = g.eqclass_map([0, 1, 3], [2, 1, 2], 1)
+    finally:
+        g.close()
+    assert list(got) == [2, 1]            # pattern 001 -> row 101 by the median tie-break; 011 is an exact match

@@ -1,0 +1,219 @@
+"""CPU tests of the oracle (oracle/): it is the checker of the CUDA path, so it is pinned here
+against (a) an independent literal transcription, (b) analytic cases, (c) R's documented
+behaviour for the primitives it restates, (d) the data relations of the shipped X-matrix."""
+import os
+
+import numpy as np
+import pytest
+from scipy.special import digamma as sp_digamma
+
+
+def _xm_from_blocks(blocks, pats=None, tx=None, name_rank=None):
+    from scasa_b200.xmatrix import XMatrix
+    q_off = np.concatenate([[0], np.cumsum([b.shape[0] for b in blocks])]).astype(np.int32)
+    p_off = np.concatenate([[0], np.cumsum([b.shape[1] for b in blocks])]).astype(np.int32)
+    x_off = np.concatenate([[0], np.cumsum([b.size for b in blocks])]).astype(np.int64)
+    x = np.concatenate([np.asarray(b, float).T.reshape(-1) for b in blocks])
+    if pats is None:
+        pats = [(np.asarray(b) > 0).astype(np.uint8) for b in blocks]
+    pat = np.concatenate([np.asarray(p_, np.uint8).reshape(-1) for p_ in pats])
+    n_tx = int(p_off[-1])
+    tx = np.arange(n_tx, dtype=np.int32) if tx is None else np.asarray(tx, np.int32)
+    rank = np.arange(len(blocks), dtype=np.int32) if name_rank is None else np.asarray(name_rank, np.int32)
+    member = np.arange(n_tx, dtype=np.int32)
+    return XMatrix(q_off, p_off, x_off, x, tx, pat, p_off, x_off, x, member, rank,
+                   [f"tx{i}" for i in range(max(int(tx.max()) + 1, n_tx))])
+
+
+# ------------------------------------------------------------------ primitives
+def test_digamma_matches_reference_implementation(oracle):
+    xs = np.concatenate([10 ** np.random.default_rng(0).uniform(-8, 6, 4000), np.arange(1, 40) + 1e-8,
+                         [1e-8, 8.999999, 9.0, 9.000001, 1.4616321449683623]])
+    d, r = oracle.digamma(xs), sp_digamma(xs)
+    assert np.max(np.abs(d - r) / np.maximum(1.0, np.abs(r))) < 5e-15
+    assert oracle.digamma([1e-8])[0] < -9.9e7                      # the sparsifier: exp(psi(1e-8) - ..) == 0
+    assert np.exp(oracle.digamma([1e-8])[0] - oracle.digamma([5.0])[0]) == 0.0
+
+
+def test_chunk_split_follows_step2(oracle):
+    # step2:64-68: chunkNum = round(n/100) half-to-even (or `core` when n <= 100), brPos = round(seq(..))
+    assert list(oracle.chunk_split(200, 4)) == [0, 100, 200]
+    assert list(oracle.chunk_split(149, 4)) == [0, 149]            # round(1.49) = 1
+    assert list(oracle.chunk_split(150, 4)) == [0, 75, 150]        # round(1.5)  = 2 (half to even)
+    assert list(oracle.chunk_split(250, 4)) == [0, 125, 250]       # round(2.5)  = 2
+    assert list(oracle.chunk_split(80, 4)) == [0, 20, 40, 60, 80]  # n <= 100: chunkNum = core
+    assert list(oracle.chunk_split(100, 3)) == [0, 33, 67, 100]    # round(34.33)=34, round(67.67)=68 (1-based)
+    c = oracle.chunk_split(3955, 4)                                # BASELINE config 2: 40 chunks of 98-99
+    assert len(c) == 41 and set(np.diff(c)) == {98, 99} and c[-1] == 3955
+    c = oracle.chunk_split(100000, 4)
+    assert len(c) == 1001 and set(np.diff(c)) == {100}
+
+
+def test_format_roundtrip_known_r_outputs(oracle):
+    """format() at 7 significant digits as R prints it (common decimals per column)."""
+    f = oracle.format_roundtrip
+    back, z = f([0.5, 0.25]);            assert list(back) == [0.5, 0.25] and not z.any()           # "0.50" "0.25"
+    back, z = f([1.0, 0.0]);             assert list(back) == [1.0, 0.0] and list(z) == [False, True]  # "1" "0"
+    back, z = f([0.0, 0.0]);             assert z.all()                                               # "0" "0"
+    back, z = f([0.0, 1e-5]);            assert not z.any() and list(back) == [0.0, 1e-5]             # "0e+00" "1e-05"
+    back, z = f([1 / 3, 0.5]);           assert list(back) == [0.3333333, 0.5]                        # "0.3333333" "0.5000000"
+    back, z = f([0.0, 1 / 3]);           assert list(back) == [0.0, 0.3333333] and not z.any()        # "0.0000000" is not "0"
+    back, z = f([0.123456789, 0.9]);     assert list(back) == [0.1234568, 0.9]
+    back, z = f([0.9999999999, 0.0]);    assert list(back) == [1.0, 0.0] and list(z) == [False, True]
+
+
+# ------------------------------------------------------------------ EM: oracle vs literal transcription
+@pytest.mark.parametrize("shape", [(2, 1), (3, 2), (5, 3), (8, 4), (12, 7)])
+@pytest.mark.parametrize("fixed", [0, 1])
+def test_estim_chunk_matches_literal_transcription(oracle, shape, fixed):
+    from oracle import estim_literal as L
+    q, p = shape
+    rng = np.random.default_rng(q * 31 + p)
+    X = rng.random((q, p)) * (rng.random((q, p)) < 0.7)
+    X[rng.integers(0, q, p), np.arange(p)] += 0.1
+    X /= X.sum(0)
+    n = 17
+    B = rng.gamma(0.5, 20, (n, p)) * (rng.random((n, 1)) < 0.7)
+    Y = rng.poisson(X @ B.T).astype(float)
+    o = oracle.Opts.make(fixed_iter=fixed, maxiter_x=4 if fixed else 1000, maxiter_bt=8 if fixed else 1000)
+    bt, it = oracle.estim_block(X, Y, o)
+    ref, it2 = L.estim_chunk([Y], [X], maxiter_X=o.maxiter_x, maxiter_bt=o.maxiter_bt, fixed_iter=bool(fixed),
+                             return_iters=True)
+    assert it == it2[0]
+    assert np.max(np.abs(bt - ref) / np.maximum(1e-9, np.abs(ref))) < 1e-10
+
+
+def test_poor_condition_block_matches_literal(oracle):
+    """A nearly collinear 2-column block gets +2 on the rows of the best-matching column for all
+    cells and is de-adjusted at the end (Rsource:987-1008, :1027-1037)."""
+    from oracle import estim_literal as L
+    X = np.array([[0.5, 0.52], [0.3, 0.29], [0.2, 0.19]])
+    X /= X.sum(0)
+    rng = np.random.default_rng(3)
+    Y = rng.poisson(np.outer(X[:, 0], rng.gamma(1, 10, 9))).astype(float)
+    Y[:, 4] = 0                                                   # a cell without counts is adjusted too
+    for fixed in (0, 1):
+        o = oracle.Opts.make(fixed_iter=fixed, maxiter_x=3 if fixed else 1000, maxiter_bt=4 if fixed else 1000)
+        bt, it = oracle.estim_block(X, Y, o)
+        ref, it2 = L.estim_chunk([Y], [X], maxiter_X=o.maxiter_x, maxiter_bt=o.maxiter_bt, fixed_iter=bool(fixed),
+                                 return_iters=True)
+        assert it == it2[0]
+        assert np.max(np.abs(bt - ref)) < 1e-9
+    assert abs(bt[4].sum()) < 1e-6                                # the pseudo counts are taken out again
+    # all-zero chunk: rs/sum(rs) is NaN, which.max finds nothing, no adjustment, zeros come back
+    bt0, it0 = oracle.estim_block(X, np.zeros((3, 5)), oracle.Opts.make())
+    assert not bt0.any() and it0 == (1, 1)
+
+
+def test_analytic_cases(oracle):
+    # p = 1: beta = sum of the counts on supported rows after one step; X' = empirical row distribution
+    X = np.array([[0.6], [0.4], [0.0]])
+    Y = np.array([[3., 0., 5.], [1., 2., 0.], [7., 0., 0.]])      # rows x cells
+    bt, it = oracle.estim_block(X, Y, oracle.Opts.make())
+    assert np.allclose(bt[:, 0], [4., 2., 5.], rtol=0, atol=1e-12)
+    # identity-like X: every transcript has its own row -> beta == y
+    bt, _ = oracle.estim_block(np.eye(3), Y, oracle.Opts.make())
+    assert np.allclose(bt, Y.T, atol=1e-9)
+    # mass conservation in a non-adjusted block with column sums 1
+    rng = np.random.default_rng(5)
+    X = rng.random((6, 3)); X /= X.sum(0)
+    Y = rng.poisson(5.0, (6, 11)).astype(float)
+    bt, _ = oracle.estim_block(X, Y, oracle.Opts.make(fixed_iter=1, maxiter_x=1, maxiter_bt=3))
+    assert np.allclose(bt.sum(1), Y.sum(0), rtol=1e-12)
+    # permutation of cells inside a chunk permutes the rows of the result (X update pools the chunk)
+    perm = rng.permutation(11)
+    bt2, _ = oracle.estim_block(X, Y[:, perm], oracle.Opts.make(fixed_iter=1, maxiter_x=3, maxiter_bt=3))
+    bt1, _ = oracle.estim_block(X, Y, oracle.Opts.make(fixed_iter=1, maxiter_x=3, maxiter_bt=3))
+    assert np.allclose(bt2, bt1[perm], rtol=1e-10)
+
+
+def test_gene_layout_and_sums(oracle):
+    names = ["B", "A", "B", None, "C", "A", "D"]
+    keep = np.array([1, 1, 1, 1, 0, 1, 1], bool)                  # column 4 was dropped at step2:167
+    goc, nmem, order = oracle.gene_layout(names, keep)
+    assert order == ["D", "A", "B"]                               # singles (sorted), then multis (sorted)
+    assert list(goc) == [2, 1, 2, -1, -1, 1, 0] and list(nmem) == [1, 2, 2]
+    iso = np.arange(14, dtype=float).reshape(2, 7)
+    g = oracle.gene_sum(iso, goc, nmem)
+    assert np.array_equal(g, [[6., 1 + 5., 0 + 2.], [13., 8 + 12., 7 + 9.]])
+    assert list(oracle.keep_rows(np.array([[0., 1e-300, -1.], [0., 0., 0.5]]))) == [False, True, False]
+
+
+# ------------------------------------------------------------------ crpcount_td / hamming_correction
+def test_crpcount_hand_built_blocks(oracle):
+    """Three blocks over transcripts 0..5:
+       A (1x1)  = {0};  B (3x2) = {1,2};  C (2x3) = {2,3,4} with an unsupported column 4."""
+    A = np.array([[1.0]])
+    B = np.array([[0.7, 0.0], [0.3, 0.4], [0.0, 0.6]]);           pB = [[1, 0], [1, 1], [0, 1]]
+    C = np.array([[0.5, 1.0, 0.0], [0.5, 0.0, 0.0]]);             pC = [[1, 1, 0], [1, 0, 1]]
+    xm = _xm_from_blocks([A, B, C], pats=[[[1]], pB, pC], tx=[0, 1, 2, 2, 3, 4])
+    h = oracle.CrpHandle(xm)
+
+    def y(classes):
+        tx = np.concatenate([c for c, _ in classes]); cnt = np.concatenate([[n] * len(c) for c, n in classes])
+        eq = np.concatenate([[i + 1] * len(c) for i, (c, _) in enumerate(classes)])
+        return oracle.crpcount_td(h, tx, cnt, eq)
+
+    assert list(y([([0], 5)])) == [5, 0, 0, 0, 0, 0]              # size-1 class on the 1x1 block
+    assert not y([([0, 1], 5)]).any()                             # {0,1}: A scores 1/2, B 1/3 -> best is the 1x1 block -> dropped (Q7)
+    assert list(y([([1], 4)])) == [0, 4, 0, 0, 0, 0]              # pattern 10 = row 0 of B
+    assert list(y([([1, 2], 3)])) == [0, 0, 3, 0, 0, 0]           # {1,2}: B scores 1, C 1/4 -> pattern 11 = row 1 of B
+    assert list(y([([2], 2)])) == [0, 0, 0, 2, 0, 0]              # {2}: B 1/2 beats C 1/3; pattern 01 = row 2
+    assert list(y([([2, 3], 6)])) == [0, 0, 0, 0, 6, 0]           # {2,3}: C 2/3; pattern 110 = row 0 of C
+    assert list(y([([3], 1)])) == [0, 0, 0, 0, 1, 0]              # {3}: pattern 010, distance 1 from row 0 only
+    assert not y([([4], 9)]).any()                                # only an unsupported column: never a candidate
+    assert not y([([5], 9)]).any()                                # transcript outside the X-matrix
+    assert list(y([([1], 4), ([1, 2], 3), ([0], 5)])) == [5, 4, 3, 0, 0, 0]     # classes of one cell add up
+
+
+def test_hamming_tie_break_uses_r_coercion_semantics(oracle):
+    """Observed pattern 001 against rows 110 / 011 / 101 (distance 3, 1, 1): two rows are close, the
+    winner is which.max of the 'median' R computes over the character row:
+    row 011 -> median(11, 0.2, 0.5) = 0.5 with the zero column printed "0.0" and kept -> (0, .2, .5, 11) -> 0.35;
+    row 101 -> (101, 0.3, 0.0, 0.5) -> 0.4  => row 101 wins."""
+    D = np.array([[0.7, 0.8, 0.0], [0.0, 0.2, 0.5], [0.3, 0.0, 0.5]])
+    pD = [[1, 1, 0], [0, 1, 1], [1, 0, 1]]
+    xm = _xm_from_blocks([D], pats=[pD], tx=[0, 1, 2])
+    h = oracle.CrpHandle(xm)
+    yy = oracle.crpcount_td(h, np.array([2]), np.array([7]), np.array([1]))
+    assert list(yy) == [0, 0, 7]
+    # with distance-0 match present nothing is corrected
+    yy = oracle.crpcount_td(h, np.array([1, 2]), np.array([7, 7]), np.array([1, 1]))
+    assert list(yy) == [0, 7, 0]
+
+
+# ------------------------------------------------------------------ shipped X-matrix: K1-K8
+def test_shipped_xmatrix_relations(xm):
+    assert (xm.n_blocks, xm.n_rows, int(xm.crp_p_off[-1]), xm.n_cols) == (29351, 41251, 78545, 33428)
+    assert len(xm.em_blocks()) == 3960 and len(xm.gene_names) == 27712
+    q = np.diff(xm.q_off); pc = np.diff(xm.crp_p_off)
+    starts = np.concatenate([[0], np.cumsum(np.repeat(q, pc))[:-1]])
+    colsum = np.add.reduceat(xm.crp_x, starts)
+    assert np.all((np.abs(colsum - 1) < 1e-9) | (colsum == 0)) and (colsum == 0).sum() == 7679         # K3
+    assert np.array_equal(colsum > 0, xm.crp_member >= 0)                                             # K5
+    worst = 0.0
+    for k in np.random.default_rng(0).choice(xm.n_blocks, 1500, replace=False):
+        crp, dm0 = xm.crp_block(k), xm.dm0_block(k)
+        pats = xm.crp_patterns(k)
+        rows = ["".join(map(str, r)) for r in pats]
+        assert rows == sorted(rows) and len(set(rows)) == len(rows)                                   # K2
+        mem = xm.crp_member[xm.crp_p_off[k]:xm.crp_p_off[k + 1]] - xm.dm0_p_off[k]
+        for j in range(dm0.shape[1]):                                                                 # K4: mean of members
+            assert np.max(np.abs(crp[:, mem == j].mean(axis=1) - dm0[:, j])) == 0.0
+        if dm0.shape[1] >= 2:
+            sv = np.linalg.svd(dm0, compute_uv=False)
+            worst = max(worst, sv.max() / sv.min())
+    assert worst < 30                                                                                 # K6: clim = 30
+    assert (xm.gene_of_col >= 0).all()                                                                # K7
+    assert sum(" " in n for n in xm.dm0_colnames()) == 12140                                          # K8
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/scasa/REFERENCE/Xmatrix_hg38_alevin.RData"),
+                    reason="reference not mounted (GPU box)")
+def test_fixture_equals_reference_rdata(xm):
+    from scasa_b200.xmatrix import XMatrix
+    ref = XMatrix.from_rdata("/root/reference/scasa/REFERENCE/Xmatrix_hg38_alevin.RData",
+                             "/root/reference/scasa/REFERENCE/isoform_groups_UCSC_hg38_alevin.RData")
+    for k in XMatrix._ARRAYS:
+        assert np.array_equal(getattr(xm, k), getattr(ref, k)), k
+    assert xm.tx_names == ref.tx_names and xm.gene_names == ref.gene_names

@@ -1,0 +1,56 @@
+"""The .RData reader on a stream written here byte by byte (R's XDR serialisation, version 3)."""
+import gzip
+import struct
+
+import numpy as np
+
+
+def _i(v):
+    return struct.pack(">i", v)
+
+
+def _chars(s, flags=0x00040009):      # CHARSXP, UTF8 bit in gp
+    b = s.encode()
+    return _i(flags) + _i(len(b)) + b
+
+
+def _sym(name):
+    return _i(1) + _chars(name)
+
+
+def _strvec(v):
+    return _i(16) + _i(len(v)) + b"".join(_chars(s) for s in v)
+
+
+def _intvec(v):
+    return _i(13) + _i(len(v)) + b"".join(_i(x) for x in v)
+
+
+def _pairlist(items, nil=True):
+    out = b""
+    for tag, val in items:
+        out += _i(2 | (1 << 10)) + tag + val
+    return out + (_i(254) if nil else b"")
+
+
+def test_reads_a_matrix_with_dimnames_and_altrep(tmp_path):
+    from scasa_b200.rdata import load_rdata
+    vals = [0.6, 0.4, 0.0, 1.0]
+    dimnames = _i(19) + _i(2) + _strvec(["10", "11"]) + _strvec(["NM_1", "NM_2"])
+    attrs = _pairlist([(_sym("dim"), _intvec([2, 2])), (_sym("dimnames"), dimnames)])
+    mat = _i(14 | (1 << 9)) + _i(4) + b"".join(struct.pack(">d", x) for x in vals) + attrs
+    # a compact integer sequence 1:5 as ALTREP: info = (class sym, package sym, type), state = c(n, start, step)
+    info = _pairlist([(_sym("a"), _sym("compact_intseq")), (_sym("b"), _sym("base")), (_sym("c"), _intvec([13]))])
+    state = _i(14) + _i(3) + b"".join(struct.pack(">d", x) for x in (5.0, 1.0, 1.0))
+    alt = _i(238) + info + state + _i(254)
+    top = _pairlist([(_sym("X"), mat), (_sym("seq"), alt), (_i(0x2FF), _strvec(["again"]))])  # 0x2FF: REFSXP back-reference to symbol 2 ("dim")
+    enc = b"UTF-8"
+    payload = b"RDX3\nX\n" + _i(3) + _i(0x030600) + _i(0x030500) + _i(len(enc)) + enc + top
+    path = tmp_path / "t.RData"
+    path.write_bytes(gzip.compress(payload))
+    ws = load_rdata(str(path))
+    m = ws["X"]
+    assert m.dim == (2, 2) and m.dimnames == [["10", "11"], ["NM_1", "NM_2"]]
+    assert np.array_equal(m.as_matrix(), [[0.6, 0.0], [0.4, 1.0]])       # column-major payload
+    assert list(ws["seq"].value) == [1, 2, 3, 4, 5]
+    assert ws["dim"].value == ["again"]                                  # tag resolved through the reference table

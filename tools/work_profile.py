@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Where the EM work is: per (chunk, block) task the active cells, entries and iterations, split by
+block class (narrow = q*p+p <= 32 and p <= 8, else wide).  Needs a GPU (runs the library once)."""
+import os, sys, json
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from scasa_b200 import synth
+from scasa_b200.api import Scasa, chunk_split
+from scasa_b200.xmatrix import XMatrix
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
+xm = XMatrix.load_npz(os.path.join(ROOT, "tests", "golden", "xmatrix_hg38_alevin.npz"))
+rowptr, rows, vals = synth.CellGenerator(xm, seed=4, device="cuda").counts_csr(0, n)
+g = Scasa(xm, device=0)
+chunks = chunk_split(n, 4)
+iso, it = g.estimate(chunks, rowptr, rows, vals)
+em = g.em_blocks
+q = np.diff(xm.q_off)[em]; p = np.diff(xm.dm0_p_off)[em]
+narrow = (q * p + p <= 32) & (p <= 8)
+poor = g.poor_blocks()[em]
+# active cells per task
+row_block = np.repeat(np.arange(xm.n_blocks), np.diff(xm.q_off))
+em_index = np.full(xm.n_blocks, -1); em_index[em] = np.arange(len(em))
+cells = np.repeat(np.arange(n), np.diff(rowptr))
+e = em_index[row_block[rows]]
+keep = e >= 0
+chunk_of = np.searchsorted(chunks, cells[keep], side="right") - 1
+pair = np.unique(np.stack([chunk_of, e[keep], cells[keep]]), axis=1)       # distinct (chunk, em, cell)
+nact = np.zeros((len(chunks) - 1, len(em)), np.int64)
+np.add.at(nact, (pair[0], pair[1]), 1)
+ents = np.zeros_like(nact); np.add.at(ents, (chunk_of, e[keep]), 1)
+inner, outer = it[..., 1].astype(np.int64), it[..., 0].astype(np.int64)
+nonempty = nact > 0
+ncell = np.where(poor[None, :] & nonempty, nact + 1, nact)
+for name, sel in (("narrow", narrow & ~poor), ("narrow-poor", narrow & poor), ("wide", ~narrow & ~poor), ("wide-poor", ~narrow & poor)):
+    m = nonempty & sel[None, :]
+    if not m.any():
+        continue
+    dig = (ncell * p[None, :] * inner)[m].sum()          # digamma evaluations
+    print(f"{name:12s} blocks {sel.sum():5d} tasks {m.sum():8d} cells/task {ncell[m].mean():6.1f} p {np.broadcast_to(p, nact.shape)[m].mean():4.1f} "
+          f"inner mean {inner[m].mean():6.1f} p99 {np.percentile(inner[m], 99):5.0f} max {inner[m].max():4d} outer mean {outer[m].mean():5.1f} "
+          f"cell-steps {(ncell * inner)[m].sum() / 1e6:8.2f}M digammas {dig / 1e6:8.2f}M")
+m = nonempty
+cs = (ncell * p[None, :] * inner)
+for thr in (2, 4, 8, 16, 32, 64, 128):
+    print(f"  digammas in tasks with inner > {thr:3d}: {cs[m & (inner > thr)].sum() / cs[m].sum():.3f}   tasks {((inner > thr) & m).sum() / m.sum():.4f}")
