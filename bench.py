@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--cells", type=int, default=100000, help="cells per GPU")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-cells", type=int, default=0, help="cells per GPU for the e2e leg (0 = same, capped by host RAM)")
-    ap.add_argument("--cpu-cells", type=int, default=300, help="cells of the cpu_baseline sample")
+    ap.add_argument("--cpu-cells", type=int, default=0, help="cells of the cpu_baseline sample (0 = 100 per host thread, max 3200)")
     ap.add_argument("--seed", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -111,7 +111,7 @@ def cpu_reference(xm, args, nthreads: int, steps: int = 1, warmup: int = 0):
     from scasa_b200 import synth
     from scasa_b200.api import chunk_split  # pure host arithmetic in the library (no GPU needed)
     O.build()
-    n = args.cpu_cells
+    n = args.cpu_cells or min(3200, 100 * nthreads)
     gen = synth.CellGenerator(xm, seed=args.seed, device="cpu")
     rowptr, rows, vals = gen.counts_csr(0, n)
     chunks = O.chunk_split(n, nthreads)
@@ -119,15 +119,15 @@ def cpu_reference(xm, args, nthreads: int, steps: int = 1, warmup: int = 0):
     nthreads = max(1, min(nthreads, len(chunks) - 1))
     goc, n_genes = gene_map(xm)
     nmem = np.bincount(goc[goc >= 0], minlength=n_genes).astype(np.int32)
-    have_counts = hasattr(O, "crpcount_cells")
-    if have_counts:
-        ed = synth.eqclass_dictionary(xm, args.seed)
-        cell_ptr, eq_id, eq_cnt = synth.counts_to_eqcounts(rowptr, rows, vals, args.seed)
+    have_counts = True
+    ed = synth.eqclass_dictionary(xm, args.seed)
+    cell_ptr, eq_id, eq_cnt = synth.counts_to_eqcounts(rowptr, rows, vals, args.seed)
+    handle = O.CrpHandle(xm)      # the reference rebuilds c2t/t2c per cell (Rsource:423-427); the port does it once
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         if have_counts:
-            y = O.crpcount_cells(xm, ed.eq_off, ed.eq_tx, cell_ptr, eq_id, eq_cnt, nthreads=nthreads)
+            y = O.crpcount_cells(handle, ed.eq_off, ed.eq_tx, cell_ptr, eq_id, eq_cnt, nthreads=nthreads)
         else:
             y = synth.csr_to_dense(rowptr, rows, vals, xm.n_rows)
         iso, _ = O.estim_chunks(xm, y, chunks, None, nthreads=nthreads)
@@ -282,7 +282,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     em_bytes = t["alg_bytes"] - n * B_IO
-    roofline = {"bound": "hbm", "kernel": "em_kernel<PMAX> (5 launches per step, one per block-width class)",
+    roofline = {"bound": "hbm", "kernel": "EM phase: beta_pass_kernel + task_step_{small,big}_kernel per round, em_finish_kernel",
                 "achieved": em_bytes / (t["em_ms"] * 1e-3) / 1e9, "peak": peak,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
                 "unit": "GB/s", "traffic": None,
@@ -303,7 +303,8 @@ def main():
                              ((eq_id.nbytes + eq_cnt.nbytes) / 1e9, n * (xm.n_cols + n_genes) * 8 / 1e9),
                        "parallelism": f"cells sharded by chunk over {world} GPU(s), no collective"},
             "device_ms_per_step": dev_max * 1e3 / args.steps,
-            "phases_ms": {k: t[k] for k in ("pack_ms", "tasks_ms", "em_ms", "finish_ms")},
+            "phases_ms": {k: t[k] for k in ("pack_ms", "tasks_ms", "em_ms", "em_rounds_ms", "em_stragglers_ms", "finish_ms")},
+            "em_rounds": t["rounds"], "tasks_handed_to_straggler_kernel": t["n_handed_over"],
             "work": {"tasks": t["n_tasks"], "active_cell_blocks": t["n_active"], "em_entries": t["n_entries"],
                      "inner_iters": t["inner_iters"], "outer_iters": t["outer_iters"]},
             "gpu_launches": int(sum(x["launches"] for x in tms)),
