@@ -281,8 +281,8 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    em_bytes = t["alg_bytes"] - n * B_IO
-    roofline = {"bound": "hbm", "kernel": "EM phase: beta_pass_kernel + task_step_{small,big}_kernel per round, em_finish_kernel",
+    em_bytes = t["em_alg_bytes"]
+    roofline = {"bound": "hbm", "kernel": "em_task_kernel<W> (4 persistent launches per step, W = 1/2/4/8 warps per task, side by side on 4 streams; em_ms = fork to join)",
                 "achieved": em_bytes / (t["em_ms"] * 1e-3) / 1e9, "peak": peak,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
                 "unit": "GB/s", "traffic": None,
@@ -303,8 +303,8 @@ def main():
                              ((eq_id.nbytes + eq_cnt.nbytes) / 1e9, n * (xm.n_cols + n_genes) * 8 / 1e9),
                        "parallelism": f"cells sharded by chunk over {world} GPU(s), no collective"},
             "device_ms_per_step": dev_max * 1e3 / args.steps,
-            "phases_ms": {k: t[k] for k in ("pack_ms", "tasks_ms", "em_ms", "em_rounds_ms", "em_stragglers_ms", "finish_ms")},
-            "em_rounds": t["rounds"], "tasks_handed_to_straggler_kernel": t["n_handed_over"],
+            "phases_ms": {k: t[k] for k in ("pack_ms", "tasks_ms", "em_ms", "finish_ms")},
+            "em_class_ms": t["em_class_ms"], "em_class_tasks": t["em_class_tasks"], "max_slot_bytes": t["max_slot_bytes"],
             "work": {"tasks": t["n_tasks"], "active_cell_blocks": t["n_active"], "em_entries": t["n_entries"],
                      "inner_iters": t["inner_iters"], "outer_iters": t["outer_iters"]},
             "gpu_launches": int(sum(x["launches"] for x in tms)),

@@ -138,17 +138,17 @@ int scasa_eqclass_map(scasa_ctx *ctx, int64_t n_eq, const int64_t *eq_off, const
  * device time (CUDA events on the library's stream) of the last scasa_run, per phase */
 typedef struct {
     float total_ms, pack_ms, tasks_ms, em_ms, finish_ms, gene_ms;
-    float em_setup_ms, em_rounds_ms, em_stragglers_ms;   /* split of em_ms */
+    float em_class_ms[4];   /* EM kernel time per work class (1, 2, 4, 8 warps per task); they overlap */
+    int64_t em_class_tasks[4];
     int64_t n_tasks;        /* non-empty (chunk, EM block) tasks            */
     int64_t n_entries;      /* bytes of the task blobs built for the EM     */
     int64_t n_active;       /* cell records processed (cells with counts, + 1 pseudo cell per poor task) */
-    int64_t n_handed_over;  /* tasks the thread-per-task kernel passed to the warp-per-task kernel */
     int64_t inner_iters;    /* sum over tasks of estim.BETA iterations      */
     int64_t outer_iters;    /* sum over tasks of AEM iterations             */
     double alg_bytes;       /* SURVEY.md 8(d) streaming-model bytes of the run */
+    double em_alg_bytes;    /* ... of the EM kernels alone (per-iteration terms) */
     int32_t launches;       /* kernels launched by the last run             */
-    int32_t rounds;         /* batched EM iterations (beta_pass launches)   */
-    int32_t rebuilds;       /* work-list compactions                        */
+    int32_t max_slot_bytes; /* largest shared-memory slot a task needed     */
 } scasa_timing_t;
 int scasa_last_timing(scasa_ctx *ctx, scasa_timing_t *out);
 

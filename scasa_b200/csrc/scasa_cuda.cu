@@ -59,12 +59,12 @@ struct scasa_ctx {
     // ---- X-matrix (host copies + resident device copies)
     int B = 0, n_em = 0;
     int64_t n_rows = 0, n_cols = 0;
-    std::vector<int32_t> q_off, p_off, em_blocks, em_index, row_block, poor_em;
+    std::vector<int32_t> q_off, p_off, em_blocks, em_index, row_block, poor_em, em_order;
     std::vector<int64_t> x_off;
     std::vector<double> x;
     std::vector<uint8_t> poor;
     int64_t poor_rows = 0;           // sum of q over poor blocks
-    DBuf<int32_t> d_q_off, d_p_off, d_row_block, d_em_index, d_em_blocks, d_poor_em;
+    DBuf<int32_t> d_q_off, d_p_off, d_row_block, d_em_index, d_em_blocks, d_poor_em, d_em_order;
     DBuf<int64_t> d_x_off;
     DBuf<double> d_x;
     DBuf<uint8_t> d_poor;
@@ -81,15 +81,18 @@ struct scasa_ctx {
     int64_t max_cell_entries = 0;
 
     // ---- task arrays
-    DBuf<int32_t> d_cnt, d_runs, d_tbytes, d_save, d_iters, d_small[2], d_big[2], d_alive_s[2], d_alive_b[2], d_ncell, d_r_task;
-    DBuf<int64_t> d_toff, d_run_off, d_byte_cur, d_run_cur, d_rec_pos, d_scan_sums, d_totals, d_r_off, d_lpos;
-    DBuf<char> d_tdata, d_scr;
+    DBuf<int32_t> d_cnt, d_runs, d_tbytes, d_iters, d_rec_cur, d_ent_cur, d_list[kClasses];
+    DBuf<int64_t> d_toff, d_scan_sums, d_totals;
+    DBuf<char> d_tdata;
     DBuf<unsigned int> d_next, d_counters;
-    cudaStream_t stream2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int big_xcap = 8, big_pcap = 2, big_qcap = 2;
-    int rounds = 0, rebuilds = 0, handover_rounds = 16, handover_pct = 5;
-    unsigned handed_over = 0;
+    cudaStream_t cls_stream[kClasses] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kClasses] = {}, ev_cls[kClasses][2] = {};
+    // work classes of the EM kernel: warps per task, pairs and slot limits, resident CTAs per SM
+    int cls_warps[kClasses] = {1, 2, 4, 8};
+    int cls_pairs[kClasses] = {32, 96, 256, 1 << 30};
+    int cls_bytes[kClasses] = {2048, 6144, 16384, 1 << 30};
+    int cls_cta_threads[kClasses] = {128, 128, 128, 256};
+    int cls_ctas_per_sm[kClasses] = {8, 4, 2, 1};
     DBuf<unsigned long long> d_stats;
     DBuf<int> d_flag;
 
@@ -153,6 +156,7 @@ XDev xdev(scasa_ctx *c)
     X.q_off = c->d_q_off.p; X.p_off = c->d_p_off.p; X.x_off = c->d_x_off.p; X.x = c->d_x.p;
     X.row_block = c->d_row_block.p; X.em_index = c->d_em_index.p; X.em_blocks = c->d_em_blocks.p;
     X.poor = c->d_poor.p; X.poor_em = c->d_poor_em.p; X.n_poor = (int)c->poor_em.size();
+    X.em_order = c->d_em_order.p;
     return X;
 }
 Sample sdev(scasa_ctx *c)
@@ -166,10 +170,10 @@ Sample sdev(scasa_ctx *c)
 Tasks tdev(scasa_ctx *c)
 {
     Tasks T;
-    T.cnt = c->d_cnt.p; T.runs = c->d_runs.p; T.tbytes = c->d_tbytes.p; T.save = c->d_save.p;
-    T.toff = c->d_toff.p; T.run_off = c->d_run_off.p; T.byte_cur = c->d_byte_cur.p; T.run_cur = c->d_run_cur.p;
-    T.tdata = c->d_tdata.p; T.scr = c->d_scr.p; T.rec_pos = c->d_rec_pos.p;
-    T.small_list = c->d_small[0].p; T.big_list = c->d_big[0].p;
+    T.cnt = c->d_cnt.p; T.runs = c->d_runs.p; T.tbytes = c->d_tbytes.p;
+    T.toff = c->d_toff.p; T.rec_cur = c->d_rec_cur.p; T.ent_cur = c->d_ent_cur.p;
+    T.tdata = c->d_tdata.p;
+    for (int k = 0; k < kClasses; k++) T.list[k] = c->d_list[k].p;
     T.counters = c->d_counters.p;
     return T;
 }
@@ -183,16 +187,6 @@ void exclusive_scan(scasa_ctx *c, const int32_t *in, int64_t n, int64_t *out, in
     scan_sums<<<1, kScanThreads, 0, c->stream>>>(c->d_scan_sums.p, nb, total_slot);
     scan_add_back<<<(unsigned)nb, kScanThreads, 0, c->stream>>>(in, n, c->d_scan_sums.p, total_slot, out);
     launches += 3;
-}
-
-int persistent_grid(scasa_ctx *c, const void *kernel, int threads, size_t smem)
-{
-    if (smem > 220 * 1024) throw ArgErr{SCASA_ERR_UNSUPPORTED, "an EM block is too large for shared memory (q*p limit ~3400)"};
-    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
-    if (per_sm < 1) per_sm = 1;
-    return c->n_sm * per_sm;
 }
 
 // column sums (+ gene sums) of a resident isoform matrix
@@ -254,6 +248,12 @@ void stage_common(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const int64_t
     c->d_chunk_off.upload(c->chunk_off, c->stream);
     c->d_cell_chunk.upload(cell_chunk, c->stream);
     c->staged = true; c->ran = false;
+}
+
+template <int W> void launch_em(const EmArgs &A, unsigned grid, int threads, size_t smem, cudaStream_t s)
+{
+    CK(cudaFuncSetAttribute(em_task_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    em_task_kernel<W><<<grid, threads, smem, s>>>(A);
 }
 
 }  // namespace
@@ -339,21 +339,44 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
         }
         c->n_em = (int)c->em_blocks.size();
 
-        // shared-memory sizing of the warp-per-task step kernel: the largest block
-        for (int e = 0; e < c->n_em; e++) {
-            int k = c->em_blocks[e];
-            int q = c->q_off[k + 1] - c->q_off[k], p = c->p_off[k + 1] - c->p_off[k];
-            if (p > 128) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a block may have at most 128 columns"};
-            c->big_xcap = std::max(c->big_xcap, q * p); c->big_pcap = std::max(c->big_pcap, p); c->big_qcap = std::max(c->big_qcap, q);
+        // queue order of the EM blocks: expensive shapes first (long tasks start early)
+        c->em_order.resize((size_t)c->n_em);
+        std::iota(c->em_order.begin(), c->em_order.end(), 0);
+        {
+            std::vector<int64_t> cost((size_t)c->n_em);
+            for (int e = 0; e < c->n_em; e++) {
+                int k = c->em_blocks[e];
+                int64_t q = c->q_off[k + 1] - c->q_off[k], p = c->p_off[k + 1] - c->p_off[k];
+                if (p > 1024) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a block may have at most 1024 columns"};
+                cost[(size_t)e] = q * p * p;
+            }
+            std::stable_sort(c->em_order.begin(), c->em_order.end(),
+                             [&](int32_t x, int32_t y) { return cost[(size_t)x] > cost[(size_t)y]; });
         }
-        c->big_xcap = (c->big_xcap + 7) & ~7;
-        c->big_pcap = (c->big_pcap + 1) & ~1;
-        c->big_qcap = (c->big_qcap + 1) & ~1;
-        if (const char *env = getenv("SCASA_HANDOVER_ROUNDS")) c->handover_rounds = std::max(1, atoi(env));
-        if (const char *env = getenv("SCASA_HANDOVER_PCT")) c->handover_pct = std::max(0, atoi(env));
-        CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        // EM work classes; SCASA_EM_CFG="warps:pairs:bytes:cta_threads:ctas_per_sm,..." overrides (tuning)
+        if (const char *env = getenv("SCASA_EM_CFG")) {
+            int k = 0;
+            const char *s = env;
+            while (k < kClasses && *s) {
+                int w, pr, by, th, cps, used = 0;
+                if (sscanf(s, "%d:%d:%d:%d:%d%n", &w, &pr, &by, &th, &cps, &used) != 5) break;
+                if ((w == 1 || w == 2 || w == 4 || w == 8) && th >= 32 * w && th <= 256 && th % (32 * w) == 0 && cps >= 1) {
+                    c->cls_warps[k] = w; c->cls_pairs[k] = pr; c->cls_bytes[k] = by; c->cls_cta_threads[k] = th;
+                    c->cls_ctas_per_sm[k] = cps;
+                }
+                k++;
+                s += used;
+                if (*s == ',') s++;
+            }
+        }
+        c->cls_pairs[kClasses - 1] = 1 << 30; c->cls_bytes[kClasses - 1] = 1 << 30;
+        for (int k = 0; k < kClasses; k++) {
+            CK(cudaStreamCreateWithFlags(&c->cls_stream[k], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
+            CK(cudaEventCreate(&c->ev_cls[k][0]));
+            CK(cudaEventCreate(&c->ev_cls[k][1]));
+        }
         CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 
         c->d_q_off.upload(c->q_off, c->stream);
         c->d_p_off.upload(c->p_off, c->stream);
@@ -365,6 +388,8 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
         c->d_poor.upload(c->poor, c->stream);
         c->d_poor_em.ensure(c->poor_em.size() + 1);
         c->d_poor_em.upload(c->poor_em, c->stream);
+        c->d_em_order.ensure(c->em_order.size() + 1);
+        c->d_em_order.upload(c->em_order, c->stream);
         c->d_next.ensure(16); c->d_counters.ensure(8); c->d_stats.ensure(8); c->d_totals.ensure(4); c->d_flag.ensure(1);
         CK(cudaStreamSynchronize(c->stream));
 
@@ -388,24 +413,25 @@ void scasa_ctx_destroy(scasa_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    DBuf<int32_t> *i32[] = {&c->d_q_off, &c->d_p_off, &c->d_row_block, &c->d_em_index, &c->d_em_blocks, &c->d_poor_em,
+    DBuf<int32_t> *i32[] = {&c->d_q_off, &c->d_p_off, &c->d_row_block, &c->d_em_index, &c->d_em_blocks, &c->d_poor_em, &c->d_em_order,
                             &c->d_cell_chunk, &c->d_y_len, &c->d_y_row, &c->d_eq_id, &c->d_eq_count, &c->d_eq_row,
-                            &c->d_cnt, &c->d_runs, &c->d_tbytes, &c->d_save, &c->d_iters, &c->d_small[0], &c->d_small[1], &c->d_big[0], &c->d_big[1],
-                            &c->d_alive_s[0], &c->d_alive_s[1], &c->d_alive_b[0], &c->d_alive_b[1], &c->d_ncell, &c->d_r_task,
-                            &c->d_gene_of_col,
-                            &c->d_gene_ptr, &c->d_gene_cols};
+                            &c->d_cnt, &c->d_runs, &c->d_tbytes, &c->d_iters, &c->d_rec_cur, &c->d_ent_cur,
+                            &c->d_list[0], &c->d_list[1], &c->d_list[2], &c->d_list[3],
+                            &c->d_gene_of_col, &c->d_gene_ptr, &c->d_gene_cols};
     for (auto b : i32) b->release();
-    DBuf<int64_t> *i64[] = {&c->d_x_off, &c->d_chunk_off, &c->d_y_start, &c->d_cell_ptr, &c->d_toff, &c->d_run_off,
-                            &c->d_byte_cur, &c->d_run_cur, &c->d_rec_pos, &c->d_scan_sums, &c->d_totals, &c->d_r_off, &c->d_lpos};
+    DBuf<int64_t> *i64[] = {&c->d_x_off, &c->d_chunk_off, &c->d_y_start, &c->d_cell_ptr, &c->d_toff, &c->d_scan_sums, &c->d_totals};
     for (auto b : i64) b->release();
     DBuf<double> *f64[] = {&c->d_x, &c->d_y_val, &c->d_iso, &c->d_partial,
                            &c->d_colsum, &c->d_gene};
     for (auto b : f64) b->release();
     c->d_poor.release(); c->d_next.release(); c->d_stats.release(); c->d_flag.release();
-    c->d_tdata.release(); c->d_scr.release(); c->d_counters.release();
+    c->d_tdata.release(); c->d_counters.release();
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-    if (c->ev_join) cudaEventDestroy(c->ev_join);
-    if (c->stream2) cudaStreamDestroy(c->stream2);
+    for (int k = 0; k < kClasses; k++) {
+        if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
+        for (auto &e : c->ev_cls[k]) if (e) cudaEventDestroy(e);
+        if (c->cls_stream[k]) cudaStreamDestroy(c->cls_stream[k]);
+    }
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -562,20 +588,17 @@ int scasa_run(scasa_ctx *c)
         const int64_t iso_elems = c->n_cells * c->n_cols;
         c->d_iso.ensure((size_t)iso_elems);
         c->d_cnt.ensure((size_t)n_tasks + 1); c->d_runs.ensure((size_t)n_tasks + 1);
-        c->d_tbytes.ensure((size_t)n_tasks + 1); c->d_save.ensure((size_t)n_tasks + 1);
-        c->d_toff.ensure((size_t)n_tasks + 1); c->d_run_off.ensure((size_t)n_tasks + 1);
-        c->d_byte_cur.ensure((size_t)n_tasks + 1); c->d_run_cur.ensure((size_t)n_tasks + 1);
-        for (int k = 0; k < 2; k++) {
-            c->d_small[k].ensure((size_t)n_tasks + 1); c->d_big[k].ensure((size_t)n_tasks + 1);
-            c->d_alive_s[k].ensure((size_t)n_tasks + 1); c->d_alive_b[k].ensure((size_t)n_tasks + 1);
-        }
-        c->d_ncell.ensure((size_t)n_tasks + 1); c->d_lpos.ensure((size_t)n_tasks + 2);
+        c->d_tbytes.ensure((size_t)n_tasks + 1); c->d_toff.ensure((size_t)n_tasks + 1);
+        c->d_rec_cur.ensure((size_t)n_tasks + 1); c->d_ent_cur.ensure((size_t)n_tasks + 1);
+        for (int k = 0; k < kClasses; k++) c->d_list[k].ensure((size_t)n_tasks + 1);
         c->d_iters.ensure((size_t)n_tasks * 2 + 2);
 
         CK(cudaEventRecord(c->ev[0], s));
         CK(cudaMemsetAsync(c->d_iso.p, 0, iso_elems * sizeof(double), s));
         CK(cudaMemsetAsync(c->d_cnt.p, 0, (n_tasks + 1) * sizeof(int32_t), s));
         CK(cudaMemsetAsync(c->d_runs.p, 0, (n_tasks + 1) * sizeof(int32_t), s));
+        CK(cudaMemsetAsync(c->d_rec_cur.p, 0, (n_tasks + 1) * sizeof(int32_t), s));
+        CK(cudaMemsetAsync(c->d_ent_cur.p, 0, (n_tasks + 1) * sizeof(int32_t), s));
         CK(cudaMemsetAsync(c->d_stats.p, 0, 8 * sizeof(unsigned long long), s));
         CK(cudaMemsetAsync(c->d_next.p, 0, 16 * sizeof(unsigned int), s));
         CK(cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(unsigned int), s));
@@ -607,7 +630,7 @@ int scasa_run(scasa_ctx *c)
         }
         CK(cudaEventRecord(c->ev[1], s));
 
-        // ---- task extents, work lists, blobs
+        // ---- task extents, work classes, blobs
         XDev X = xdev(c);
         Sample S = sdev(c);
         Tasks T = tdev(c);
@@ -615,24 +638,24 @@ int scasa_run(scasa_ctx *c)
         O.maxiter_x = c->opts.maxiter_x; O.maxiter_bt = c->opts.maxiter_bt; O.modify = c->opts.modify;
         O.fixed_iter = c->opts.fixed_iter;
         O.maxerr = c->opts.maxerr; O.lim = c->opts.lim; O.adjust_esp = c->opts.adjust_esp;
+        ClassCfg CC;
+        for (int k = 0; k < kClasses; k++) { CC.pairs[k] = c->cls_pairs[k]; CC.bytes[k] = c->cls_bytes[k]; }
         int64_t tot[2] = {0, 0};
         unsigned int cnts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (c->n_em > 0) {
             const int wpb = 8;
             task_count_kernel<<<(unsigned)((c->n_cells + wpb - 1) / wpb), wpb * 32, 0, s>>>(X, S, T);
-            classify_kernel<<<(unsigned)((n_tasks + 255) / 256), 256, 0, s>>>(X, S, T, n_tasks, O, c->d_iters.p, c->d_stats.p);
+            classify_kernel<<<(unsigned)((n_tasks + 255) / 256), 256, 0, s>>>(X, S, T, n_tasks, O, CC, c->d_iters.p, c->d_stats.p);
             launches += 2;
             exclusive_scan(c, c->d_tbytes.p, n_tasks, c->d_toff.p, c->d_totals.p + 0, launches);
-            exclusive_scan(c, c->d_runs.p, n_tasks, c->d_run_off.p, c->d_totals.p + 1, launches);
             CK(cudaMemcpyAsync(tot, c->d_totals.p, sizeof tot, cudaMemcpyDeviceToHost, s));
             CK(cudaMemcpyAsync(cnts, c->d_counters.p, sizeof cnts, cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
-            if (cnts[7]) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a poor-condition (2-column) block may have at most 64 rows"};
-            c->d_tdata.ensure((size_t)tot[0] + 64); c->d_scr.ensure((size_t)tot[0] + 64);
-            c->d_rec_pos.ensure((size_t)tot[1] + 1); c->d_r_task.ensure((size_t)tot[1] + 1); c->d_r_off.ensure((size_t)tot[1] + 1);
+            if (cnts[7] == 1) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a poor-condition (2-column) block may have at most 64 rows"};
+            if (cnts[7] == 2) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a (chunk, block) task may hold at most 65535 cells-with-counts and 65535 count entries"};
+            if (cnts[5] > 200 * 1024) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a (chunk, block) task needs more than 200 KB of shared memory (chunk too large for this block)"};
+            c->d_tdata.ensure((size_t)tot[0] + 64);
             T = tdev(c);
-            cursor_init_kernel<<<(unsigned)((n_tasks + 255) / 256), 256, 0, s>>>(T, n_tasks);
-            launches++;
             c->timing.n_entries = tot[0];
         }
         task_scatter_kernel<<<c->n_chunks, 256, 0, s>>>(X, S, T, c->d_iso.p);
@@ -640,122 +663,38 @@ int scasa_run(scasa_ctx *c)
         launches++;
         CK(cudaEventRecord(c->ev[2], s));
 
-        // ---- EM rounds
-        c->rounds = 0; c->rebuilds = 0;
-        if (c->n_em > 0 && cnts[3] > 0) {
-            RoundArgs A;
-            A.X = X; A.S = S; A.T = T; A.O = O; A.out = c->d_iso.p; A.iters = c->d_iters.p; A.stats = c->d_stats.p;
-            A.r_task = c->d_r_task.p; A.r_off = c->d_r_off.p; A.xcap = c->big_xcap; A.pcap = c->big_pcap; A.qcap = c->big_qcap;
-            unsigned n_small = cnts[0], n_big = cnts[2];
-            int cur = 0;                               // ping-pong index of the task lists
-            int64_t n_rec = 0;
-            const size_t smem_small = (size_t)128 * kStepSlot * sizeof(double);
-            const size_t smem_big = (size_t)4 * (c->big_xcap + c->big_pcap + c->big_qcap) * sizeof(double);
-            if (smem_big > 200 * 1024) throw ArgErr{SCASA_ERR_UNSUPPORTED, "an EM block is too large for shared memory"};
-            CK(cudaFuncSetAttribute(task_step_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
-            auto grid = [](int64_t n, int per) { return (unsigned)std::max<int64_t>(1, (n + per - 1) / per); };
-
-            // record list of the listed tasks: small tasks first, then big ones, list order = block-major
-            auto build_records = [&]() {
-                int64_t base = 0;
-                for (int cls = 0; cls < 2; cls++) {
-                    const unsigned n = cls ? n_big : n_small;
-                    const int32_t *lst = cls ? c->d_big[cur].p : c->d_small[cur].p;
-                    const unsigned int *dn = c->d_counters.p + (cls ? 2 : 0);
-                    if (n == 0) continue;
-                    gather_ncell_kernel<<<grid(n, 256), 256, 0, s>>>(T, lst, dn, c->d_ncell.p);
-                    exclusive_scan(c, c->d_ncell.p, n, c->d_lpos.p, c->d_totals.p + 2, launches);
-                    fill_records_kernel<<<grid(n, 256), 256, 0, s>>>(T, lst, dn, c->d_lpos.p, base, c->d_r_task.p, c->d_r_off.p);
-                    launches += 2;
-                    int64_t nr = 0;
-                    CK(cudaMemcpyAsync(&nr, c->d_totals.p + 2, sizeof nr, cudaMemcpyDeviceToHost, s));
-                    CK(cudaStreamSynchronize(s));
-                    base += nr;
+        // ---- EM: one persistent kernel per work class, side by side on their own streams
+        bool ran_cls[kClasses] = {false, false, false, false};
+        if (c->n_em > 0 && cnts[4] > 0) {
+            CK(cudaEventRecord(c->ev_fork, s));
+            for (int k = kClasses - 1; k >= 0; k--) {          // long tasks first
+                const unsigned n = cnts[k];
+                if (n == 0) continue;
+                const int W = c->cls_warps[k];
+                const int threads = c->cls_cta_threads[k];
+                const int groups = threads / (32 * W);
+                int slot = (k == kClasses - 1) ? (int)cnts[5] : std::min<int>(c->cls_bytes[k], (int)cnts[5]);
+                slot = (slot + 15) & ~15;
+                const size_t smem = (size_t)slot * groups;
+                if (smem > 220 * 1024) throw ArgErr{SCASA_ERR_UNSUPPORTED, "EM work class needs more shared memory than an SM has"};
+                EmArgs A;
+                A.X = X; A.S = S; A.T = T; A.O = O; A.out = c->d_iso.p; A.iters = c->d_iters.p; A.stats = c->d_stats.p;
+                A.list = c->d_list[k].p; A.list_n = c->d_counters.p + k; A.next = c->d_next.p + k; A.slot_bytes = slot;
+                const unsigned grid = (unsigned)std::min<int64_t>((int64_t)c->n_sm * c->cls_ctas_per_sm[k], ((int64_t)n + groups - 1) / groups);
+                cudaStream_t cs = c->cls_stream[k];
+                CK(cudaStreamWaitEvent(cs, c->ev_fork, 0));
+                CK(cudaEventRecord(c->ev_cls[k][0], cs));
+                switch (W) {
+                case 1: launch_em<1>(A, grid, threads, smem, cs); break;
+                case 2: launch_em<2>(A, grid, threads, smem, cs); break;
+                case 4: launch_em<4>(A, grid, threads, smem, cs); break;
+                default: launch_em<8>(A, grid, threads, smem, cs); break;
                 }
-                n_rec = base;
-            };
-            build_records();
-            auto args_for = [&](int cls) {
-                RoundArgs R = A;
-                R.tlist = cls ? c->d_big[cur].p : c->d_small[cur].p;
-                R.tlist_n = c->d_counters.p + (cls ? 2 : 0);
-                R.alive_flags = cls ? c->d_alive_b[cur].p : c->d_alive_s[cur].p;
-                R.n_rec = n_rec;
-                return R;
-            };
-            if (n_small) task_init_kernel<<<grid(n_small, 128), 128, 0, s>>>(args_for(0));
-            if (n_big) task_init_kernel<<<grid(n_big, 128), 128, 0, s>>>(args_for(1));
-            rec_init_kernel<<<grid(n_rec, 256), 256, 0, s>>>(args_for(0));
-            launches += 3;
-            CK(cudaGetLastError());
-
-            CK(cudaEventRecord(c->ev[5], s));
-            unsigned alive = cnts[3], listed = n_small + n_big;
-            const unsigned cnts0_alive = cnts[3];
-            c->handed_over = 0;
-            const long long max_rounds = (long long)c->opts.maxiter_x * c->opts.maxiter_bt + 2;
-            while (alive > 0 && c->rounds < max_rounds) {
-                const int burst = alive > 20000 ? 1 : (alive > 2000 ? 4 : 16);
-                for (int k = 0; k < burst; k++) {
-                    beta_pass_kernel<<<grid(n_rec, 256), 256, 0, s>>>(args_for(0));
-                    if (n_small) task_step_small_kernel<<<grid(n_small, 128 / kTile), 128, smem_small, s>>>(args_for(0));
-                    if (n_big) task_step_big_kernel<<<grid(n_big, 4), 128, smem_big, s>>>(args_for(1));
-                    launches += 1 + (n_small ? 1 : 0) + (n_big ? 1 : 0);
-                    c->rounds++;
-                }
-                CK(cudaMemcpyAsync(cnts, c->d_counters.p, sizeof cnts, cudaMemcpyDeviceToHost, s));
-                CK(cudaStreamSynchronize(s));
-                alive = cnts[3];
-                const bool hand_over = alive > 0 && c->rounds >= c->handover_rounds &&
-                                       (uint64_t)alive * 100 <= (uint64_t)cnts0_alive * (unsigned)c->handover_pct;
-                if (alive > 0 && ((uint64_t)alive * 2 <= listed || hand_over)) {
-                    // stable compaction of both task lists, then a fresh record list
-                    const int nxt = cur ^ 1;
-                    for (int cls = 0; cls < 2; cls++) {
-                        const unsigned n = cls ? n_big : n_small;
-                        if (n == 0) continue;
-                        int32_t *al = cls ? c->d_alive_b[cur].p : c->d_alive_s[cur].p;
-                        exclusive_scan(c, al, n, c->d_lpos.p, c->d_totals.p + 3, launches);
-                        compact_list_kernel<<<grid(n, 256), 256, 0, s>>>(cls ? c->d_big[cur].p : c->d_small[cur].p, al, c->d_lpos.p,
-                                                                        c->d_counters.p + (cls ? 2 : 0),
-                                                                        cls ? c->d_big[nxt].p : c->d_small[nxt].p,
-                                                                        cls ? c->d_alive_b[nxt].p : c->d_alive_s[nxt].p);
-                        set_count_kernel<<<1, 1, 0, s>>>(c->d_counters.p + (cls ? 2 : 0), c->d_totals.p + 3);
-                        launches += 2;
-                        int64_t kept = 0;
-                        CK(cudaMemcpyAsync(&kept, c->d_totals.p + 3, sizeof kept, cudaMemcpyDeviceToHost, s));
-                        CK(cudaStreamSynchronize(s));
-                        if (cls) n_big = (unsigned)kept; else n_small = (unsigned)kept;
-                    }
-                    cur = nxt;
-                    listed = n_small + n_big;
-                    if (!hand_over) build_records();
-                    c->rebuilds++;
-                }
-                if (hand_over) {
-                    CK(cudaEventRecord(c->ev[6], s));
-                    // the stragglers: persistent warp-per-task kernels, narrow and wide blocks side by side
-                    CK(cudaEventRecord(c->ev_fork, s));
-                    CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-                    for (int cls = 0; cls < 2; cls++) {
-                        const unsigned n = cls ? n_big : n_small;
-                        if (n == 0) continue;
-                        RoundArgs R = args_for(cls);
-                        if (!cls) { R.xcap = 32; R.pcap = kSmallP; R.qcap = 32; }
-                        const size_t smem = (size_t)4 * (2 * R.xcap + 2 * R.pcap + R.qcap) * sizeof(double);
-                        CK(cudaFuncSetAttribute(em_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)((size_t)4 * (2 * c->big_xcap + 2 * c->big_pcap + c->big_qcap) * sizeof(double))));
-                        int per_sm = 0;
-                        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_finish_kernel, 128, smem));
-                        const unsigned g = (unsigned)std::min<int64_t>((int64_t)c->n_sm * std::max(per_sm, 1), (n + 3) / 4);
-                        em_finish_kernel<<<g, 128, smem, cls ? c->stream2 : s>>>(R, c->d_next.p + cls);
-                        launches++;
-                    }
-                    CK(cudaEventRecord(c->ev_join, c->stream2));
-                    CK(cudaStreamWaitEvent(s, c->ev_join, 0));
-                    c->handed_over = alive;
-                    alive = 0;
-                }
+                CK(cudaEventRecord(c->ev_cls[k][1], cs));
+                CK(cudaEventRecord(c->ev_join[k], cs));
+                CK(cudaStreamWaitEvent(s, c->ev_join[k], 0));
+                ran_cls[k] = true;
+                launches++;
             }
             CK(cudaGetLastError());
         }
@@ -779,19 +718,18 @@ int scasa_run(scasa_ctx *c)
         CK(cudaEventElapsedTime(&tm.tasks_ms, c->ev[1], c->ev[2]));
         CK(cudaEventElapsedTime(&tm.em_ms, c->ev[2], c->ev[3]));
         CK(cudaEventElapsedTime(&tm.finish_ms, c->ev[3], c->ev[4]));
-        tm.em_setup_ms = tm.em_rounds_ms = tm.em_stragglers_ms = 0.f;
-        if (c->rounds > 0) {
-            CK(cudaEventElapsedTime(&tm.em_setup_ms, c->ev[2], c->ev[5]));
-            if (c->handed_over) {
-                CK(cudaEventElapsedTime(&tm.em_rounds_ms, c->ev[5], c->ev[6]));
-                CK(cudaEventElapsedTime(&tm.em_stragglers_ms, c->ev[6], c->ev[3]));
-            } else CK(cudaEventElapsedTime(&tm.em_rounds_ms, c->ev[5], c->ev[3]));
+        for (int k = 0; k < kClasses; k++) {
+            tm.em_class_ms[k] = 0.f;
+            tm.em_class_tasks[k] = cnts[k];
+            if (ran_cls[k]) CK(cudaEventElapsedTime(&tm.em_class_ms[k], c->ev_cls[k][0], c->ev_cls[k][1]));
         }
         tm.gene_ms = c->n_genes > 0 ? tm.finish_ms : 0.f;
         tm.inner_iters = (int64_t)st[0]; tm.outer_iters = (int64_t)st[1];
-        tm.n_tasks = (int64_t)st[4]; tm.n_active = (int64_t)st[5]; tm.n_handed_over = c->handed_over; tm.rounds = c->rounds; tm.rebuilds = c->rebuilds;
+        tm.n_tasks = (int64_t)st[4]; tm.n_active = (int64_t)st[5];
+        tm.max_slot_bytes = (int32_t)cnts[5];
         // sum_tasks [in*8*(q+2p)*n_c + out*8*(q+p)*n_c] + n_cells*8*(sum q + sum p)
-        tm.alg_bytes = 8.0 * ((double)st[2] + (double)st[3]) + (double)c->n_cells * 8.0 * (double)(c->n_rows + c->n_cols);
+        tm.em_alg_bytes = 8.0 * ((double)st[2] + (double)st[3]);
+        tm.alg_bytes = tm.em_alg_bytes + (double)c->n_cells * 8.0 * (double)(c->n_rows + c->n_cols);
         tm.launches = launches;
         c->ran = true;
     });

@@ -1,0 +1,376 @@
+// scasa_em.cuh — the alternating EM of estim_chunk (Scasa_Rsource.R:1010-1042), one (chunk, block)
+// task at a time, run to completion on chip.
+//
+// A GROUP of W warps (W = 1, 2, 4 or 8 by task size) takes a task from an atomic work queue, copies
+// its blob into its shared-memory slot, builds the per-task index (record of each entry, entries by
+// row) and then iterates without touching HBM again:
+//
+//   estim.BETA (Rsource:726-761), one iteration =
+//     S1  thread per (cell, transcript) pair:  gamma0 = exp(digamma(beta + 1e-8) - logNorm)   :738
+//     S2  thread per count entry (cell, row):  mu = sum_j X[row,j] gamma0[j];  w = y / mu      :739-741
+//     S3  thread per pair:                     beta' = gamma0[j] * sum_rows X[row,j] w / csum[j],
+//                                              err vote over the whole chunk                    :745,:755-756
+//   estim.X.em (Rsource:898-922) =
+//     thread per entry:  w = y / (sum_j X[row,j] beta[j])                                        :905-910
+//     thread per X element (row, j): sum of beta[j] X w over the cells with counts in that row,
+//     in cell order;  column normalisation, revert, and the outer test                           :911-920, :1019
+//
+// Nothing in a task's arithmetic depends on which group runs it, on the queue order or on the
+// number of GPUs: every sum is taken in a fixed order (cell order, or row order) by one thread.
+#pragma once
+
+namespace scasa {
+
+// gamma0 of estim.BETA's fn1 (Rsource:737-738) without the logarithm:
+//   digamma(x) = log(xs) - 1/(2 xs) - series(1/xs^2) - sum_{i<9} 1/(x+i),   xs = x + 9 for x < 9
+//   => exp(digamma(x) - L) = xs * exp(-(1/(2 xs) + series + rec + L)),
+// one division serving both 1/xs and the folded reciprocal sum (see digamma_pos).
+__device__ __forceinline__ double em_gamma_fast(double beta, double lnorm)
+{
+    const double x = beta + 0.00000001;
+    double xs = x, num = 0.0, den = 1.0;
+    if (x < 9.0) {
+        const double u = x * (x + 8.0);
+        const double a = u + 7.0, b = u + 12.0, c = u + 15.0;
+        const double bc = b * c;
+        const double D = u * a * bc;
+        const double N = a * bc + u * (bc + a * (b + c));
+        const double x4 = x + 4.0;
+        num = (2.0 * x + 8.0) * N * x4 + D;
+        den = D * x4;
+        xs = x + 9.0;
+    }
+    const double inv = 1.0 / (xs * den);
+    const double r = den * inv;
+    const double rec = num * xs * inv;
+    const double r2 = r * r;
+    const double s = r2 * (1.0 / 12.0 - r2 * (1.0 / 120.0 - r2 * (1.0 / 252.0 - r2 * (1.0 / 240.0 -
+                     r2 * (1.0 / 132.0 - r2 * (691.0 / 32760.0 - r2 * (1.0 / 12.0)))))));
+    return xs * exp(-(0.5 * r + s + rec + lnorm));
+}
+
+struct EmArgs {
+    XDev X;
+    Sample S;
+    Tasks T;
+    EmOpts O;
+    double *out;
+    int32_t *iters;
+    unsigned long long *stats;
+    const int32_t *list;          // task ids of this work class
+    const unsigned int *list_n;
+    unsigned int *next;           // queue head
+    int slot_bytes;               // shared memory per group
+};
+
+template <int W> struct Group {
+    static constexpr int kThreads = 32 * W;
+    int gl;    // thread index inside the group
+    int bar;   // named barrier of the group (W > 1)
+    __device__ __forceinline__ void sync() const
+    {
+        if (W == 1) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(kThreads) : "memory");
+    }
+    // group-wide OR (also a barrier)
+    __device__ __forceinline__ bool any(bool v) const
+    {
+        if (W == 1) return __any_sync(kFull, v);
+        int out;
+        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(out) : "r"((int)v), "r"(bar), "n"(kThreads) : "memory");
+        return out != 0;
+    }
+};
+
+template <int W> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs A)
+{
+    extern __shared__ __align__(16) unsigned char em_smem[];
+    constexpr int GT = 32 * W;
+    const int lane = threadIdx.x & 31;
+    const int grp = threadIdx.x / GT;
+    Group<W> G;
+    G.gl = threadIdx.x - grp * GT;
+    G.bar = 1 + grp;
+    const int gl = G.gl;
+    unsigned char *slot = em_smem + (size_t)grp * A.slot_bytes;
+    __shared__ unsigned int s_ticket[8];
+    const XDev &X = A.X;
+    const EmOpts &O = A.O;
+    const unsigned n_list = *A.list_n;
+
+    for (;;) {
+        // ---- next task
+        unsigned ti = 0;
+        if (W == 1) {
+            if (lane == 0) ti = atomicAdd(A.next, 1u);
+            ti = __shfl_sync(kFull, ti, 0);
+        } else {
+            if (gl == 0) s_ticket[grp] = atomicAdd(A.next, 1u);
+            G.sync();
+            ti = s_ticket[grp];
+            G.sync();
+        }
+        if (ti >= n_list) break;
+        const int64_t t = A.list[ti];
+        const int e = (int)(t % X.n_em), h = (int)(t / X.n_em);
+        const int b = X.em_blocks[e];
+        const int q = X.q_off[b + 1] - X.q_off[b], p = X.p_off[b + 1] - X.p_off[b];
+        const int qp = q * p;
+        const int n = A.T.runs[t], E = A.T.cnt[t];
+        const int np = n * p;
+        const bool poor = X.poor[b] != 0;
+        const int nc = (int)(A.S.chunk_off[h + 1] - A.S.chunk_off[h]);
+        const BlobLayout BL = blob_layout(n, E);
+
+        // ---- carve the slot
+        double *ey = (double *)slot;
+        const uint32_t *rcell = (const uint32_t *)(slot + BL.off_cell);
+        const uint16_t *eptr = (const uint16_t *)(slot + BL.off_ptr);
+        const uint16_t *erow = (const uint16_t *)(slot + BL.off_row);
+        double *ew = (double *)(slot + BL.bytes);
+        double *Xc = ew + E, *Xn = Xc + qp, *cs = Xn + qp, *bts = cs + p, *lnorm = bts + p;
+        double *beta = lnorm + n, *gam = beta + np;
+        uint16_t *erec = (uint16_t *)(gam + np), *rptr = erec + E, *perm = rptr + q + 1;
+        int *cur = (int *)Xn;                        // q ints of scratch until the first X update
+
+        // ---- stage: blob image, X.est0 = X0 (:1011)
+        {
+            const uint4 *src = (const uint4 *)(A.T.tdata + A.T.toff[t]);
+            uint4 *dst = (uint4 *)slot;
+            for (int i = gl; i < (BL.bytes >> 4); i += GT) dst[i] = __ldcs(src + i);
+            const double *X0 = X.x + X.x_off[b];
+            for (int k = gl; k < qp; k += GT) Xc[k] = X0[k];
+        }
+        G.sync();
+        for (int a = gl; a < n; a += GT) {
+            const int k1 = eptr[a + 1];
+            for (int k = eptr[a]; k < k1; k++) erec[k] = (uint16_t)a;
+        }
+        for (int r = gl; r < q; r += GT) cur[r] = 0;
+        G.sync();
+        // entries by row, stable in cell order (one warp: counting sort with match_any)
+        if (gl < 32) {
+            for (int k0 = 0; k0 < E; k0 += 32) {
+                const int k = k0 + lane;
+                const bool valid = k < E;
+                const unsigned act = __ballot_sync(kFull, valid);
+                if (valid) {
+                    const int r = erow[k];
+                    const unsigned peers = __match_any_sync(act, r);
+                    if (lane == __ffs(peers) - 1) cur[r] += __popc(peers);
+                }
+                __syncwarp();
+            }
+            if (lane == 0) {
+                int s = 0;
+                for (int r = 0; r < q; r++) { const int c = cur[r]; rptr[r] = (uint16_t)s; cur[r] = s; s += c; }
+                rptr[q] = (uint16_t)s;
+            }
+            __syncwarp();
+            for (int k0 = 0; k0 < E; k0 += 32) {
+                const int k = k0 + lane;
+                const bool valid = k < E;
+                const unsigned act = __ballot_sync(kFull, valid);
+                int r = 0;
+                unsigned peers = 0;
+                if (valid) {
+                    r = erow[k];
+                    peers = __match_any_sync(act, r);
+                    perm[cur[r] + __popc(peers & ((1u << lane) - 1u))] = (uint16_t)k;
+                }
+                __syncwarp();
+                if (valid && lane == __ffs(peers) - 1) cur[r] += __popc(peers);
+                __syncwarp();
+            }
+        }
+        G.sync();
+
+        // ---- poor blocks: rowSums(Ymat), bestTx, adjID, Ymat[adjID,] += adjust_esp (:989-1004)
+        int nadj = 0;
+        if (poor) {
+            double *rs = Xn;
+            for (int r = gl; r < q; r += GT) {
+                double s = 0;
+                const int i1 = rptr[r + 1];
+                for (int i = rptr[r]; i < i1; i++) {
+                    const int k = perm[i];
+                    const uint32_t cw = rcell[erec[k]];
+                    s += ((cw & kPseudo) ? (double)(cw & 0xffff) : 1.0) * ey[k];
+                }
+                rs[r] = s;
+            }
+            G.sync();
+            const double *X0 = X.x + X.x_off[b];
+            double tot = 0;
+            for (int r = 0; r < q; r++) tot += rs[r];
+            int best = -1;
+            double bestv = -INFINITY;
+            for (int j = 0; j < p; j++) {                               // which.max(cos_sim(X0[,j], rs/sum(rs)))  :991-995
+                double ab = 0, aa = 0, bb = 0;
+                for (int r = 0; r < q; r++) {
+                    const double xv = X0[j * q + r], rv = rs[r] / tot;
+                    ab += xv * rv; aa += xv * xv; bb += rv * rv;
+                }
+                const double sim = ab / sqrt(aa * bb);
+                if (sim == sim && sim > bestv) { bestv = sim; best = j; }
+            }
+            unsigned long long adjmask = 0;
+            if (best >= 0)
+                for (int r = 0; r < q; r++)
+                    if (X0[best * q + r] > 0) { adjmask |= 1ull << r; nadj++; }   // adjID  :997
+            G.sync();
+            for (int k = gl; k < E; k += GT)
+                if ((adjmask >> erow[k]) & 1ull) ey[k] += O.adjust_esp;
+            G.sync();
+        }
+
+        // ---- csum = colSums(X) (:731), logNorm (:732-733), beta0 = colSums(Ymat)/p (:1012-1013)
+        for (int j = gl; j < p; j += GT) {
+            double s = 0;
+            for (int r = 0; r < q; r++) s += Xc[j * q + r];
+            cs[j] = s;
+        }
+        for (int a = gl; a < n; a += GT) {
+            double ys = 0;
+            const int k1 = eptr[a + 1];
+            for (int k = eptr[a]; k < k1; k++) ys += ey[k];
+            lnorm[a] = digamma_pos(ys + 0.00000001);
+            const double b0 = ys / p;
+            for (int j = 0; j < p; j++) beta[j * n + a] = b0;
+        }
+        G.sync();
+
+        // pair index idx = j*n + a walks in steps of GT
+        const int j_first = gl / n, a_first = gl - j_first * n;
+        const int dj = GT / n, da = GT - dj * n;
+
+        int outer = 0, inner_total = 0;
+        for (;;) {
+            // ================= estim.BETA(X.est0, Ymat, beta0)  :726-761
+            for (int it = 1;; it++) {
+                for (int idx = gl, a = a_first; idx < np; idx += GT) {          // S1
+                    gam[idx] = O.modify ? em_gamma_fast(beta[idx], lnorm[a]) : beta[idx];
+                    a += da;
+                    if (a >= n) a -= n;
+                }
+                G.sync();
+                for (int k = gl; k < E; k += GT) {                               // S2
+                    const int r = erow[k], a = erec[k];
+                    double mu = 0.0;                                             // rowSums(t(t(X)*gamma0))  :739-740
+                    for (int j = 0; j < p; j++) mu += Xc[j * q + r] * gam[j * n + a];
+                    ew[k] = ey[k] / (mu > 0 ? mu : 1.0);                         // :741
+                }
+                G.sync();
+                bool fail = false;
+                for (int idx = gl, a = a_first, j = j_first; idx < np; idx += GT) {   // S3
+                    double s = 0.0;
+                    const int k1 = eptr[a + 1];
+                    for (int k = eptr[a]; k < k1; k++) s += Xc[j * q + erow[k]] * ew[k];
+                    const double old = beta[idx];
+                    double nb = gam[idx] * s / cs[j];                            // :745
+                    if (nb != nb) nb = 0.0;                                      // :754
+                    const double den = old > O.lim ? old : O.lim;               // :755
+                    if (!(fabs(nb - old) < O.maxerr * den)) fail = true;
+                    beta[idx] = nb;
+                    a += da; j += dj;
+                    if (a >= n) { a -= n; j++; }
+                }
+                inner_total++;
+                const bool any_fail = G.any(fail);                               // :756
+                if ((!O.fixed_iter && !any_fail) || it >= O.maxiter_bt) break;
+            }
+
+            // ================= estim.X.em(X.est0, BT, Ymat)  :898-922
+            for (int j = gl; j < p; j += GT) {                                   // BTsum = colSums(BETA)  :904
+                double s = 0;
+                for (int a = 0; a < n; a++) {
+                    const uint32_t cw = rcell[a];
+                    s += ((cw & kPseudo) ? (double)(cw & 0xffff) : 1.0) * beta[j * n + a];
+                }
+                bts[j] = s;
+            }
+            for (int k = gl; k < E; k += GT) {
+                const int r = erow[k], a = erec[k];
+                double mu = 0.0;                                                  // sumx1 = rowSums(x1)  :907
+                for (int j = 0; j < p; j++) mu += beta[j * n + a] * Xc[j * q + r];
+                const uint32_t cw = rcell[a];
+                const double mult = (cw & kPseudo) ? (double)(cw & 0xffff) : 1.0;
+                ew[k] = mult * ey[k] / (mu > 0 ? mu : 0.1);                      // :908-910
+            }
+            G.sync();
+            for (int idx = gl; idx < qp; idx += GT) {                            // T = colSums(x2 * Y) per row  :911-914
+                const int j = idx / q, r = idx - j * q;
+                const double x = Xc[idx];
+                double acc = 0.0;
+                const int i1 = rptr[r + 1];
+                for (int i = rptr[r]; i < i1; i++) {
+                    const int k = perm[i];
+                    acc += beta[j * n + erec[k]] * x * ew[k];
+                }
+                Xn[idx] = acc;
+            }
+            G.sync();
+            for (int j = gl; j < p; j += GT) {
+                const double d = bts[j] > 0 ? bts[j] : 0.1;                      // :917
+                double csum = 0.0;
+                for (int r = 0; r < q; r++) { const double v = Xn[j * q + r] / d; Xn[j * q + r] = v; csum += v; }
+                const double d2 = csum > 0 ? csum : 0.1;                         // :919
+                for (int r = 0; r < q; r++) Xn[j * q + r] /= d2;
+                if (csum < 0.00001)                                              // :920
+                    for (int r = 0; r < q; r++) Xn[j * q + r] = Xc[j * q + r];
+            }
+            G.sync();
+            bool xfail = false;                                                  // :1019
+            for (int idx = gl; idx < qp; idx += GT) {
+                const double x0 = Xc[idx];
+                const double er = fabs(Xn[idx] - x0) / (fabs(x0) > O.lim ? x0 : O.lim);
+                if (!(er < O.maxerr)) xfail = true;
+            }
+            outer++;
+            const bool any_x = G.any(xfail);
+            if ((!O.fixed_iter && !any_x) || outer >= O.maxiter_x) break;        // :1020
+            for (int idx = gl; idx < qp; idx += GT) Xc[idx] = Xn[idx];           // X.est0 = X.est  :1022
+            G.sync();
+            for (int j = gl; j < p; j += GT) {                                   // csum of the next estim.BETA call
+                double s = 0;
+                for (int r = 0; r < q; r++) s += Xc[j * q + r];
+                cs[j] = s;
+            }
+            G.sync();
+        }
+
+        // ---- de-adjust (:1027-1037) and scatter BT into the result (:1042)
+        const double deduct = nadj * O.adjust_esp;
+        const int64_t cbase = A.S.chunk_off[h];
+        const int64_t col0 = X.p_off[b];
+        for (int a = gl; a < n; a += GT) {
+            const uint32_t cw = rcell[a];
+            double s = 0;
+            if (nadj > 0) for (int j = 0; j < p; j++) s += beta[j * n + a];
+            if (!(cw & kPseudo)) {
+                double *o = A.out + (cbase + (int64_t)cw) * X.n_cols + col0;
+                for (int j = 0; j < p; j++) { double v = beta[j * n + a]; if (nadj > 0) v = v - deduct * (v / s); o[j] = v; }
+            }
+        }
+        if (n > 0 && (rcell[n - 1] & kPseudo) && (rcell[n - 1] & 0xffff) != 0) {
+            // cells of the chunk without a record of their own take the pseudo cell's values; the real
+            // cells are listed in ascending order, so walk the gaps
+            const int ap = n - 1;
+            double s = 0;
+            if (nadj > 0) for (int j = 0; j < p; j++) s += beta[j * n + ap];
+            for (int a = gl; a < n; a += GT) {
+                const int lo = a == 0 ? 0 : (int)rcell[a - 1] + 1;
+                const int hi = a == n - 1 ? nc : (int)rcell[a];
+                for (int cc = lo; cc < hi; cc++) {
+                    double *o = A.out + (cbase + cc) * X.n_cols + col0;
+                    for (int j = 0; j < p; j++) { double v = beta[j * n + ap]; if (nadj > 0) v = v - deduct * (v / s); o[j] = v; }
+                }
+            }
+        }
+        if (gl == 0) task_done_stats(A.iters, A.stats, t, outer, inner_total, q, p, nc, n);
+        G.sync();
+    }
+}
+
+}  // namespace scasa

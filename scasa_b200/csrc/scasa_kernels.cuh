@@ -2,19 +2,19 @@
 //
 // Data flow of one scasa_run() (everything resident in HBM):
 //
-//   [eqclass counts] --pack_cells_kernel--> Y as CSR by cell (rows ascending, duplicates summed)
-//   Y --task_count_kernel--> entries / runs per (chunk, EM block) "task"
-//     --classify_kernel--> blob size per task, light / heavy work lists; scans give the offsets
-//   Y --task_scatter_kernel--> one blob per task: per cell-with-counts a record
-//        {logNorm, m, cell | beta[p] | m x (count, row)}; pass-through blocks (nrow == 1,
-//        Scasa_Rsource.R:979-983) are written straight into the result
-//   blobs --rounds of beta_pass_kernel + task_step_{small,big}_kernel--> the alternating EM, one
-//        batched estim.BETA iteration over all still-running cells per round (see below)
-//   result --finish_kernel--> per-column sums (step2:167) and gene sums (step3:32-46)
+//   [eqclass counts] --pack_cells_*_kernel--> Y as CSR by cell (rows ascending, duplicates summed)
+//   Y --task_count_kernel--> entries / cells-with-counts per (chunk, EM block) "task"
+//     --classify_kernel--> blob size, shared-memory need and work class per task; a scan gives
+//                          the blob offsets
+//   Y --task_scatter_kernel--> one compact blob per task (counts by cell, rows, cell ids);
+//        pass-through blocks (nrow == 1, Scasa_Rsource.R:979-983) go straight into the result
+//   blobs --em_task_kernel<W>--> the alternating EM (estim_chunk's loop, Rsource:1010-1042): W warps
+//        stage one task in shared memory and run it to the end; persistent, atomic work queue
+//   result --colsum / gene kernels--> per-column sums (step2:167) and gene sums (step3:32-46)
 //
 // Why sparse: a cell with no counts in a block keeps beta = 0 through every iteration of
 // estim.BETA and contributes 0 to every sum of estim.X.em, so only (cell, block) pairs with
-// counts ("runs") are stored.  The convergence tests stay what the reference has: maxima over
+// counts ("records") are stored.  The convergence tests stay what the reference has: maxima over
 // the whole chunk (Rsource:755-756, :1019-1020).
 // Poor 2-column blocks add adjust_esp to EVERY cell of the chunk (Rsource:1004); the cells
 // without counts then all follow one identical trajectory, so they are stored once as a
@@ -82,6 +82,7 @@ struct XDev {                 // resident X-matrix (DM0) and its derived index m
     const int32_t *em_blocks; // [n_em]    block id
     const uint8_t *poor;      // [n_blocks] poorCondX (Rsource:957-971)
     const int32_t *poor_em;   // [n_poor]  EM indices of the poor blocks
+    const int32_t *em_order;  // [n_em]    EM indices, most expensive block shape first (work-queue order)
     int n_poor;
 };
 
@@ -97,28 +98,45 @@ struct Sample {               // what is staged for one scasa_run
 };
 
 // ---- task blob ----------------------------------------------------------------------------
-// blob(t) = [TaskState | Xc | Xn | cs | bts] [record of cell 0] [record of cell 1] ...
-// record  = CellHdr | beta[ppad] | Ent[m]          (16-byte aligned throughout)
-struct alignas(16) CellHdr { double lnorm; int32_t m; uint32_t cell; };  // cell: bit 31 = pseudo cell, low 16 bits = cell in chunk / multiplicity
-struct alignas(16) Ent { double y; int32_t row; int32_t pad; };
+// One (chunk, EM block) task with n records (cells with counts, in cell order; for a poor block
+// the last record is the pseudo cell) and E entries (record-major, rows ascending inside a record;
+// poor blocks store every row of every record).  The blob is what the EM kernel copies verbatim
+// into the head of its shared-memory slot:
+//     ey[E] f64 | rcell[n] u32 | eptr[n+1] u16 | erow[E] u16 | pad to 16
+// rcell: cell index inside the chunk, or kPseudo | multiplicity.
 constexpr uint32_t kPseudo = 0x80000000u;
+__host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
+struct BlobLayout { int off_cell, off_ptr, off_row, bytes; };
+__host__ __device__ inline BlobLayout blob_layout(int n, int E)
+{
+    BlobLayout L;
+    L.off_cell = 8 * E;
+    L.off_ptr = L.off_cell + 4 * n;
+    L.off_row = L.off_ptr + 2 * (n + 1);
+    L.bytes = align16(L.off_row + 2 * E);
+    return L;
+}
+// shared memory one task needs in the EM kernel: blob image, then
+//     ew[E] Xc[qp] Xn[qp] cs[p] bts[p] lnorm[n] beta[p*n] gam[p*n]  (f64)
+//     erec[E] rptr[q+1] perm[E]                                     (u16)
+__host__ __device__ inline int slot_bytes_of(int q, int p, int n, int E)
+{
+    return blob_layout(n, E).bytes + 8 * (E + 2 * q * p + 2 * p + n + 2 * p * n) + align16(2 * (2 * E + q + 1));
+}
 
-__host__ __device__ inline int ppad_of(int p) { return (p + 1) & ~1; }
-__host__ __device__ inline int rec_bytes(int p, int m) { return 16 + 8 * ppad_of(p) + 16 * m; }
-__host__ __device__ inline int state_bytes(int q, int p) { return 64 + 8 * ((2 * q * p + 2 * p + 1) & ~1); }
-
-constexpr int kStepSlot = 32;       // doubles of X.est + colSums(BETA) per thread of the small step kernel: q*p + p
-constexpr int kSmallP = 8;          // widest block the thread-per-task step kernel takes
+// work classes: W warps per task, a slot of at most kClassBytes[c] (the last class takes the rest)
+constexpr int kClasses = 4;
+struct ClassCfg { int pairs[kClasses]; int bytes[kClasses]; };
 
 struct Tasks {                // task t = chunk * n_em + em index
-    int32_t *cnt, *runs;      // [n_tasks] Y entries / cells with counts (after classify: records incl. pseudo cell)
-    int32_t *tbytes, *save;   // [n_tasks] blob bytes / bytes of the state area in front of the records
-    int64_t *toff, *run_off;  // [n_tasks+1] exclusive scans of tbytes / runs
-    int64_t *byte_cur, *run_cur;  // [n_tasks] cursors of the scatter
-    char *tdata, *scr;        // blobs; scratch of the same shape for the heavy kernel (gamma, w)
-    int64_t *rec_pos;         // [total records] byte offset of each record, in run order
-    int32_t *small_list, *big_list;   // task ids, block-major
-    unsigned int *counters;   // [0] n_small [2] n_big [3] tasks still running
+    int32_t *cnt;             // [n_tasks] Y entries; after classify: stored entries E (dense for poor blocks)
+    int32_t *runs;            // [n_tasks] cells with counts; after classify: records n (incl. the pseudo cell)
+    int32_t *tbytes;          // [n_tasks] blob bytes
+    int64_t *toff;            // [n_tasks+1] exclusive scan of tbytes
+    int32_t *rec_cur, *ent_cur;   // [n_tasks] cursors of the scatter (zeroed)
+    char *tdata;              // blobs
+    int32_t *list[kClasses];  // task ids per work class, expensive block shapes first
+    unsigned int *counters;   // [0..3] list lengths [4] non-empty tasks [5] largest slot need [7] error flag
 };
 // ------------------------------------------------------------------------------------------
 // crpcount_td's accumulation (Scasa_Rsource.R:528-531, :643-646 and :461-462), fast path: when the
@@ -274,23 +292,23 @@ struct EmOpts {
     double maxerr, lim, adjust_esp;
 };
 
-// Per task: blob size, work list.  Threads enumerate tasks block-major (e outer, chunk inner) so
-// that neighbouring list entries — hence the lanes of a warp of the light kernel — mostly work
-// on the same block shape.  All-zero tasks finish here: the reference runs one inner and one
-// outer iteration on them and returns zeros (the result buffer is pre-zeroed).
-__global__ void classify_kernel(XDev X, Sample S, Tasks T, int64_t n_tasks, EmOpts O, int32_t *iters,
+// Per task: records, stored entries, blob size, work class.  Threads enumerate tasks block-major
+// in X.em_order (expensive block shapes first), so the work queues start with the long tasks.
+// All-zero tasks finish here: the reference runs one inner and one outer iteration on them and
+// returns zeros (the result buffer is pre-zeroed).
+__global__ void classify_kernel(XDev X, Sample S, Tasks T, int64_t n_tasks, EmOpts O, ClassCfg C, int32_t *iters,
                                 unsigned long long *stats)
 {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_tasks) return;
-    const int e = (int)(idx / S.n_chunks), h = (int)(idx % S.n_chunks);
+    const int e = X.em_order[(int)(idx / S.n_chunks)], h = (int)(idx % S.n_chunks);
     const int64_t t = (int64_t)h * X.n_em + e;
     const int b = X.em_blocks[e];
     const int q = X.q_off[b + 1] - X.q_off[b], p = X.p_off[b + 1] - X.p_off[b];
     const int nc = (int)(S.chunk_off[h + 1] - S.chunk_off[h]);
     const int c = T.cnt[t];
     if (c == 0) {
-        T.tbytes[t] = 0; T.save[t] = 0;
+        T.tbytes[t] = 0;
         const int o = O.fixed_iter ? O.maxiter_x : 1;
         const int in = O.fixed_iter ? O.maxiter_x * O.maxiter_bt : 1;
         if (iters) { iters[2 * t] = o; iters[2 * t + 1] = in; }
@@ -300,26 +318,23 @@ __global__ void classify_kernel(XDev X, Sample S, Tasks T, int64_t n_tasks, EmOp
         atomicAdd(&stats[3], (unsigned long long)o * (q + p) * nc);
         return;
     }
-    int ncell = T.runs[t], ents = c;
-    if (X.poor[b]) { ncell += 1; ents = ncell * q; }      // dense records + the pseudo cell
-    if (X.poor[b] && q > 64) { atomicExch((int *)&T.counters[7], 1); }   // adjID is kept as a 64-bit mask
-    const bool small = (p <= kSmallP) && (q * p + p <= kStepSlot);
-    const int sv = state_bytes(q, p);
-    T.save[t] = sv;
-    T.tbytes[t] = sv + ncell * (16 + 8 * ppad_of(p)) + 16 * ents;
-    T.runs[t] = ncell;
-    if (small) T.small_list[atomicAdd(&T.counters[0], 1u)] = (int32_t)t;
-    else T.big_list[atomicAdd(&T.counters[2], 1u)] = (int32_t)t;
-    atomicAdd(&T.counters[3], 1u);
+    int n = T.runs[t], E = c;
+    if (X.poor[b]) { n += 1; E = n * q; }                 // dense records + the pseudo cell
+    if (X.poor[b] && q > 64) atomicExch(&T.counters[7], 1u);   // adjID is kept as a 64-bit mask
+    if (E > 65535 || n > 65535) { atomicExch(&T.counters[7], 2u); E = 0; n = 0; }   // u16 indices in the blob
+    T.runs[t] = n;
+    T.cnt[t] = E;
+    T.tbytes[t] = blob_layout(n, E).bytes;
+    if (n == 0) return;
+    const int need = slot_bytes_of(q, p, n, E);
+    int cls = kClasses - 1;
+    for (int k = kClasses - 2; k >= 0; k--)
+        if (n * p <= C.pairs[k] && need <= C.bytes[k]) cls = k;
+    atomicMax(&T.counters[5], (unsigned)need);
+    T.list[cls][atomicAdd(&T.counters[cls], 1u)] = (int32_t)t;
+    atomicAdd(&T.counters[4], 1u);
 }
 
-__global__ void cursor_init_kernel(Tasks T, int64_t n_tasks)
-{
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_tasks) return;
-    T.byte_cur[t] = T.toff[t] + T.save[t];
-    T.run_cur[t] = T.run_off[t];
-}
 // exclusive scan int32 -> int64, three phases (block sums, scan of sums, add back)
 constexpr int kScanThreads = 1024;
 constexpr int kScanItems = 4;
@@ -409,7 +424,7 @@ __global__ void task_scatter_kernel(XDev X, Sample S, Tasks T, double *__restric
         const int64_t cell = c0 + c;
         const int64_t s = S.y_start[cell];
         const int n = S.y_len[cell];
-        // phase A: place entries; the first entry of a run also writes the record header
+        // phase A: place entries; the first entry of a run also writes the record's cell id and start
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const int row = S.y_row[s + i];
             const double v = S.y_val[s + i];
@@ -420,37 +435,37 @@ __global__ void task_scatter_kernel(XDev X, Sample S, Tasks T, double *__restric
                 continue;
             }
             const int64_t t = tbase + e;
+            const int nrec = T.runs[t], E = T.cnt[t];
+            if (nrec == 0) continue;           // task rejected by classify (error flag is set)
             const int rl = row - X.q_off[b];
-            const int p = X.p_off[b + 1] - X.p_off[b];
             int head = i;
             while (head > 0 && X.row_block[S.y_row[s + head - 1]] == b) head--;
-            const int64_t pos = T.byte_cur[t];
-            char *rec = T.tdata + pos;
-            Ent *en = (Ent *)(rec + 16 + 8 * ppad_of(p));
+            const BlobLayout L = blob_layout(nrec, E);
+            char *blob = T.tdata + T.toff[t];
+            double *ey = (double *)blob;
+            uint32_t *rcell = (uint32_t *)(blob + L.off_cell);
+            uint16_t *eptr = (uint16_t *)(blob + L.off_ptr);
+            uint16_t *erow = (uint16_t *)(blob + L.off_row);
+            const int a = T.rec_cur[t], k0 = T.ent_cur[t];
             const bool is_head = (i == head);
-            int tail = i;
-            if (is_head) while (tail + 1 < n && X.row_block[S.y_row[s + tail + 1]] == b) tail++;
             if (X.poor[b]) {                   // dense record: every row of the block
                 const int q = X.q_off[b + 1] - X.q_off[b];
-                en[rl].y = v;
+                ey[k0 + rl] = v;
                 if (is_head) {
+                    int tail = i;
+                    while (tail + 1 < n && X.row_block[S.y_row[s + tail + 1]] == b) tail++;
                     int k = head;
                     for (int r = 0; r < q; r++) {
-                        en[r].row = r; en[r].pad = 0;
-                        if (k <= tail && S.y_row[s + k] - X.q_off[b] == r) k++; else en[r].y = 0.0;
+                        erow[k0 + r] = (uint16_t)r;
+                        if (k <= tail && S.y_row[s + k] - X.q_off[b] == r) k++; else ey[k0 + r] = 0.0;
                     }
-                    CellHdr hd; hd.lnorm = 0.0; hd.m = q; hd.cell = (uint32_t)c;
-                    *(CellHdr *)rec = hd;
-                    T.rec_pos[T.run_cur[t]] = pos;
+                    rcell[a] = (uint32_t)c;
+                    eptr[a] = (uint16_t)k0;
                 }
             } else {
-                Ent ev; ev.y = v; ev.row = rl; ev.pad = 0;
-                en[i - head] = ev;
-                if (is_head) {
-                    CellHdr hd; hd.lnorm = 0.0; hd.m = tail - head + 1; hd.cell = (uint32_t)c;
-                    *(CellHdr *)rec = hd;
-                    T.rec_pos[T.run_cur[t]] = pos;
-                }
+                ey[k0 + i - head] = v;
+                erow[k0 + i - head] = (uint16_t)rl;
+                if (is_head) { rcell[a] = (uint32_t)c; eptr[a] = (uint16_t)k0; }
             }
         }
         __syncthreads();
@@ -464,51 +479,33 @@ __global__ void task_scatter_kernel(XDev X, Sample S, Tasks T, double *__restric
             int head = i;
             while (head > 0 && X.row_block[S.y_row[s + head - 1]] == b) head--;
             const int64_t t = tbase + e;
-            const int p = X.p_off[b + 1] - X.p_off[b];
-            const int m = X.poor[b] ? (X.q_off[b + 1] - X.q_off[b]) : (i - head + 1);
-            T.byte_cur[t] += rec_bytes(p, m);
-            T.run_cur[t] += 1;
+            T.ent_cur[t] += X.poor[b] ? (X.q_off[b + 1] - X.q_off[b]) : (i - head + 1);
+            T.rec_cur[t] += 1;
         }
         __syncthreads();
     }
-    // pseudo cell of every non-empty poor task: all cells of the chunk without counts in the block
-    for (int k = threadIdx.x; k < X.n_poor; k += blockDim.x) {
-        const int e = X.poor_em[k];
+    // close every blob of the chunk (eptr[n] = E); poor tasks get their pseudo cell: all cells of
+    // the chunk without counts in the block
+    for (int e = threadIdx.x; e < X.n_em; e += blockDim.x) {
         const int64_t t = tbase + e;
-        if (T.cnt[t] == 0) continue;
+        const int nrec = T.runs[t], E = T.cnt[t];
+        if (nrec == 0) continue;
+        const BlobLayout L = blob_layout(nrec, E);
+        char *blob = T.tdata + T.toff[t];
+        uint16_t *eptr = (uint16_t *)(blob + L.off_ptr);
+        eptr[nrec] = (uint16_t)E;
         const int b = X.em_blocks[e];
-        const int q = X.q_off[b + 1] - X.q_off[b], p = X.p_off[b + 1] - X.p_off[b];
-        const int64_t pos = T.byte_cur[t];
-        char *rec = T.tdata + pos;
-        Ent *en = (Ent *)(rec + 16 + 8 * ppad_of(p));
-        for (int r = 0; r < q; r++) { Ent ev; ev.y = 0.0; ev.row = r; ev.pad = 0; en[r] = ev; }
-        CellHdr hd; hd.lnorm = 0.0; hd.m = q; hd.cell = kPseudo | (uint32_t)(nc - (T.runs[t] - 1));
-        *(CellHdr *)rec = hd;
-        T.rec_pos[T.run_cur[t]] = pos;
+        if (!X.poor[b]) continue;
+        const int q = X.q_off[b + 1] - X.q_off[b];
+        double *ey = (double *)blob;
+        uint32_t *rcell = (uint32_t *)(blob + L.off_cell);
+        uint16_t *erow = (uint16_t *)(blob + L.off_row);
+        const int a = nrec - 1, k0 = a * q;
+        for (int r = 0; r < q; r++) { ey[k0 + r] = 0.0; erow[k0 + r] = (uint16_t)r; }
+        rcell[a] = kPseudo | (uint32_t)(nc - a);
+        eptr[a] = (uint16_t)k0;
     }
 }
-// ------------------------------------------------------------------------------------------
-// Bulk-synchronous EM.  One ROUND = one estim.BETA iteration (Rsource:749-758) for every task
-// that is still running, executed as
-//     beta_pass_kernel   one thread per cell record: gamma (digamma + exp), mu = X gamma for the
-//                        rows with counts, the y/mu ratio and the X^T back-projection, fused;
-//                        writes beta in place and raises the task's fail flag
-//     task_step_kernel   one thread (small tasks) or one warp (big tasks) per task: reads the
-//                        flag = the chunk-wide max(err) < maxerr test; when estim.BETA is over it
-//                        runs estim.X.em (:898-922), the outer test (:1019-1020) and either
-//                        starts the next estim.BETA call or de-adjusts and writes the result.
-// Converged tasks drop out; the host compacts the task / record lists when half of them are gone.
-// Sums over cells run in record (= cell) order inside one thread, or as per-lane partial sums in
-// cell order plus a fixed xor tree inside one warp: the result does not depend on how tasks are
-// scheduled, listed or sharded over GPUs.
-struct alignas(16) TaskState {
-    int32_t alive, fail, outer, inner_it, inner_total, nadj;
-    int32_t ncell, pad0;
-    unsigned long long adjmask;
-    int32_t pad1[6];
-};  // 64 bytes, followed by Xc[qp] Xn[qp] cs[p] bts[p]
-static_assert(sizeof(TaskState) == 64, "TaskState layout");
-
 
 __device__ __forceinline__ void task_done_stats(int32_t *iters, unsigned long long *stats, int64_t t, int outer,
                                                 int inner_total, int q, int p, int nc, int ncell)
@@ -522,675 +519,6 @@ __device__ __forceinline__ void task_done_stats(int32_t *iters, unsigned long lo
     atomicAdd(&stats[5], (unsigned long long)ncell);
 }
 
-struct RoundArgs {
-    XDev X;
-    Sample S;
-    Tasks T;
-    EmOpts O;
-    double *out;
-    int32_t *iters;
-    unsigned long long *stats;
-    const int32_t *tlist;        // task ids (small or big list)
-    const unsigned int *tlist_n;
-    int32_t *alive_flags;        // [list length] written by the step kernels for the compaction
-    const int32_t *r_task;       // record list: task id / byte offset of the record
-    const int64_t *r_off;
-    int64_t n_rec;
-    int xcap, pcap, qcap;        // warp-per-task kernels: shared memory sizing (max q*p, p, q)
-};
-
-// per task: state header, X.est0 = X0, colSums(X); for poor blocks rowSums(Ymat), bestTx and adjID
-// (Rsource:989-1004).  One thread per listed task (poor blocks are narrow: p = 2).
-__global__ void task_init_kernel(RoundArgs A)
-{
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *A.tlist_n) return;
-    const XDev &X = A.X;
-    const Tasks &T = A.T;
-    const int64_t t = A.tlist[i];
-    const int e = (int)(t % X.n_em);
-    const int b = X.em_blocks[e];
-    const int q = X.q_off[b + 1] - X.q_off[b], p = X.p_off[b + 1] - X.p_off[b];
-    const int qp = q * p, ppad = ppad_of(p);
-    char *blob = T.tdata + T.toff[t];
-    TaskState *st = (TaskState *)blob;
-    double *Xc = (double *)(blob + 64), *cs = Xc + 2 * qp;
-    const double *X0 = X.x + X.x_off[b];
-    for (int k = 0; k < qp; k++) Xc[k] = X0[k];                       // X.est0 = X0  :1011
-    for (int j = 0; j < p; j++) {                                     // csum = colSums(X)  :731
-        double s = 0;
-        for (int r = 0; r < q; r++) s += X0[j * q + r];
-        cs[j] = s;
-    }
-    const int ncell = T.runs[t];
-    int nadj = 0;
-    unsigned long long adjmask = 0;
-    if (X.poor[b]) {
-        double *rs = Xc + qp;                                         // Xn as scratch
-        for (int r = 0; r < q; r++) rs[r] = 0.0;
-        const char *rec = blob + T.save[t];
-        for (int a = 0; a < ncell; a++) {
-            const CellHdr hd = *(const CellHdr *)rec;
-            const Ent *en = (const Ent *)(rec + 16 + 8 * ppad);
-            const double mult = (hd.cell & kPseudo) ? (double)(hd.cell & 0xffff) : 1.0;
-            for (int k = 0; k < hd.m; k++) rs[en[k].row] += mult * en[k].y;
-            rec += rec_bytes(p, hd.m);
-        }
-        double tot = 0;
-        for (int r = 0; r < q; r++) tot += rs[r];
-        int best = -1;
-        double bestv = -INFINITY;
-        for (int j = 0; j < p; j++) {                                 // which.max(cos_sim(X0[,j], rs/sum(rs)))  :991-995
-            double ab = 0, aa = 0, bb = 0;
-            for (int r = 0; r < q; r++) {
-                const double xv = X0[j * q + r], rv = rs[r] / tot;
-                ab += xv * rv; aa += xv * xv; bb += rv * rv;
-            }
-            const double sim = ab / sqrt(aa * bb);
-            if (sim == sim && sim > bestv) { bestv = sim; best = j; }
-        }
-        if (best >= 0)
-            for (int r = 0; r < q; r++)
-                if (X0[best * q + r] > 0) { adjmask |= 1ull << r; nadj++; }       // adjID  :997
-    }
-    TaskState s0;
-    s0.alive = 1; s0.fail = 0; s0.outer = 0; s0.inner_it = 0; s0.inner_total = 0; s0.nadj = nadj;
-    s0.ncell = ncell; s0.pad0 = 0; s0.adjmask = adjmask;
-    for (int k = 0; k < 6; k++) s0.pad1[k] = 0;
-    *st = s0;
-    A.alive_flags[i] = 1;
-}
-
-// per record: Ymat[adjID,] += adjust_esp (:1004), beta0 = Ysum / p (:1012-1013), logNorm (:732-733)
-__global__ void rec_init_kernel(RoundArgs A)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= A.n_rec) return;
-    const XDev &X = A.X;
-    const Tasks &T = A.T;
-    const int64_t t = A.r_task[i];
-    const int b = X.em_blocks[(int)(t % X.n_em)];
-    const int p = X.p_off[b + 1] - X.p_off[b];
-    const TaskState *st = (const TaskState *)(T.tdata + T.toff[t]);
-    const unsigned long long adjmask = st->adjmask;
-    char *rec = T.tdata + A.r_off[i];
-    const CellHdr hd = *(const CellHdr *)rec;
-    double *bt = (double *)(rec + 16);
-    Ent *en = (Ent *)(rec + 16 + 8 * ppad_of(p));
-    double ys = 0;
-    for (int k = 0; k < hd.m; k++) {
-        Ent ev = en[k];
-        if (adjmask >> ev.row & 1ull) { ev.y += A.O.adjust_esp; en[k].y = ev.y; }
-        ys += ev.y;
-    }
-    ((CellHdr *)rec)->lnorm = digamma_pos(ys + 0.00000001);
-    const double b0 = ys / p;
-    for (int j = 0; j < p; j++) bt[j] = b0;
-}
-
-// One estim.BETA iteration for one cell (fn1 + fn2, Rsource:736-747, and the err of :755).
-__global__ void __launch_bounds__(256) beta_pass_kernel(RoundArgs A)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= A.n_rec) return;
-    const XDev &X = A.X;
-    const Tasks &T = A.T;
-    const int64_t t = A.r_task[i];
-    char *blob = T.tdata + T.toff[t];
-    TaskState *st = (TaskState *)blob;
-    if (!st->alive) return;
-    const int b = X.em_blocks[(int)(t % X.n_em)];
-    const int q = X.q_off[b + 1] - X.q_off[b], p = X.p_off[b + 1] - X.p_off[b];
-    const int qp = q * p;
-    const double *Xc = (const double *)(blob + 64), *cs = Xc + 2 * qp;
-    const int64_t off = A.r_off[i];
-    char *rec = T.tdata + off;
-    const CellHdr hd = *(const CellHdr *)rec;
-    double *bt = (double *)(rec + 16);
-    const Ent *en = (const Ent *)(rec + 16 + 8 * ppad_of(p));
-    double *g = (double *)(T.scr + off + 16);                       // gamma0 of wide blocks
-    double *sa = (double *)(T.scr + off + 16 + 8 * ppad_of(p));     // wide blocks: one weight per entry (stride 2)
-    double g0 = 0, g1 = 0, acc0 = 0, acc1 = 0;                      // p <= 2 stays in registers
-    if (p <= 2) {
-        g0 = em_gamma(bt[0], hd.lnorm, A.O.modify);
-        if (p == 2) g1 = em_gamma(bt[1], hd.lnorm, A.O.modify);
-        for (int k = 0; k < hd.m; k++) {
-            const Ent ev = en[k];
-            const double x0 = Xc[ev.row], x1 = (p == 2) ? Xc[q + ev.row] : 0.0;
-            const double mu = x0 * g0 + x1 * g1;                    // rowSums(t(t(X)*gamma0))
-            const double w = ev.y / (mu > 0 ? mu : 1.0);
-            acc0 += x0 * w; acc1 += x1 * w;
-        }
-    } else {
-        for (int j = 0; j < p; j++) g[j] = em_gamma(bt[j], hd.lnorm, A.O.modify);
-        for (int k = 0; k < hd.m; k++) {
-            const Ent ev = en[k];
-            double mu = 0.0;
-            for (int j = 0; j < p; j++) mu += Xc[j * q + ev.row] * g[j];
-            sa[2 * k] = ev.y / (mu > 0 ? mu : 1.0);
-        }
-    }
-    bool fail = false;
-    for (int j = 0; j < p; j++) {
-        double s, gj;
-        if (p <= 2) { s = j ? acc1 : acc0; gj = j ? g1 : g0; }
-        else {
-            s = 0.0;
-            for (int k = 0; k < hd.m; k++) s += Xc[j * q + en[k].row] * sa[2 * k];
-            gj = g[j];
-        }
-        const double old = bt[j];
-        double nb = gj * s / cs[j];
-        if (nb != nb) nb = 0.0;                                      // :754
-        const double er = fabs(nb - old) / (old > A.O.lim ? old : A.O.lim);
-        if (!(er < A.O.maxerr)) fail = true;                         // :755-756
-        bt[j] = nb;
-    }
-    if (fail) st->fail = 1;                                          // every writer stores the same value
-}
-
-__device__ __forceinline__ void finish_task(const RoundArgs &A, int64_t t, int i, TaskState *st, int q, int p, int nc)
-{
-    st->alive = 0;
-    A.alive_flags[i] = 0;
-    task_done_stats(A.iters, A.stats, t, st->outer, st->inner_total, q, p, nc, st->ncell);
-    atomicSub(&A.T.counters[3], 1u);
-}
-
-// After a beta pass, per SMALL task (a tile of 8 lanes): estim.BETA's loop control, estim.X.em, the
-// outer loop control, the result.  Lanes split the task's records (lane l takes records l, l+8, ..),
-// keep private partial sums in shared memory, and the partials are added in lane order.
-constexpr int kTile = 8;
-__device__ __forceinline__ void write_cell(const RoundArgs &A, int64_t row, int64_t col0, const double *bt, int p,
-                                           int nadj, double deduct)
-{
-    double s = 0;
-    if (nadj > 0) for (int j = 0; j < p; j++) s += bt[j];
-    double *o = A.out + row * A.X.n_cols + col0;
-    for (int j = 0; j < p; j++) { double v = bt[j]; if (nadj > 0) v = v - deduct * (v / s); o[j] = v; }
-}
-
-__global__ void __launch_bounds__(128) task_step_small_kernel(RoundArgs A)
-{
-    extern __shared__ double sm[];
-    const int sub = threadIdx.x & (kTile - 1);
-    const int tile_in_cta = threadIdx.x / kTile;
-    double *mine = sm + (size_t)threadIdx.x * kStepSlot;              // this lane's partial sums: T[qp], BTsum[p]
-    double *tile0 = sm + (size_t)tile_in_cta * kTile * kStepSlot;     // lane 0's area: the reduced sums / X.est
-    const unsigned tmask = 0xffu << ((threadIdx.x & 31) & ~(kTile - 1));
-    const unsigned i = blockIdx.x * (blockDim.x / kTile) + tile_in_cta;
-    if (i >= *A.tlist_n) return;
-    const XDev &X = A.X;
-    const Tasks &T = A.T;
-    const EmOpts &O = A.O;
-    const int64_t t = A.tlist[i];
-    char *td = T.tdata;
-    char *blob = td + T.toff[t];
-    TaskState *st = (TaskState *)blob;
-    if (!st->alive) return;
-    const bool fail = st->fail != 0;
-    const int inner_it = st->inner_it + 1;
-    const int outer = st->outer + 1;
-    __syncwarp(tmask);
-    if (sub == 0) { st->inner_it = inner_it; st->inner_total += 1; st->fail = 0; }
-    if (!((!O.fixed_iter && !fail) || inner_it >= O.maxiter_bt)) return;         // next estim.BETA iteration  :756-757
-
-    const int e = (int)(t % X.n_em), h = (int)(t / X.n_em);
-    const int b = X.em_blocks[e];
-    const int q = X.q_off[b + 1] - X.q_off[b], p = X.p_off[b + 1] - X.p_off[b];
-    const int qp = q * p, ppad = ppad_of(p);
-    const int nc = (int)(A.S.chunk_off[h + 1] - A.S.chunk_off[h]);
-    double *Xc = (double *)(blob + 64), *cs = Xc + 2 * qp;
-    const int ncell = st->ncell;
-    const int64_t *rpos = T.rec_pos + T.run_off[t];
-
-    // ---- estim.X.em(X.est0, BT, Ymat)  :898-922
-    for (int k = 0; k < qp + p; k++) mine[k] = 0.0;
-    for (int a = sub; a < ncell; a += kTile) {
-        const char *rec = td + rpos[a];
-        const CellHdr hd = *(const CellHdr *)rec;
-        const double *bt = (const double *)(rec + 16);
-        const Ent *en = (const Ent *)(rec + 16 + 8 * ppad);
-        const double mult = (hd.cell & kPseudo) ? (double)(hd.cell & 0xffff) : 1.0;
-        for (int j = 0; j < p; j++) mine[qp + j] += mult * bt[j];                // BTsum = colSums(BETA)  :904
-        for (int k = 0; k < hd.m; k++) {
-            const Ent ev = en[k];
-            double mu = 0.0;                                                      // sumx1 = rowSums(x1)  :907
-            for (int j = 0; j < p; j++) mu += bt[j] * Xc[j * q + ev.row];
-            const double w = mult * ev.y / (mu > 0 ? mu : 0.1);                  // :908-910
-            for (int j = 0; j < p; j++) mine[j * q + ev.row] += bt[j] * Xc[j * q + ev.row] * w;
-        }
-    }
-    __syncwarp(tmask);
-    for (int k = sub; k < qp + p; k += kTile) {                                   // partials added in lane order
-        double s = 0;
-        for (int l = 0; l < kTile; l++) s += tile0[l * kStepSlot + k];
-        tile0[k] = s;                                                             // slot k is read and written by this lane only
-    }
-    __syncwarp(tmask);
-    bool xfail = false;
-    for (int j = sub; j < p; j += kTile) {
-        const double bs = tile0[qp + j];
-        const double d = bs > 0 ? bs : 0.1;                                       // :917
-        double csum = 0.0;
-        for (int r = 0; r < q; r++) { const double v = tile0[j * q + r] / d; tile0[j * q + r] = v; csum += v; }
-        const double d2 = csum > 0 ? csum : 0.1;                                  // :919
-        for (int r = 0; r < q; r++) {
-            double v = tile0[j * q + r] / d2;
-            const double x0 = Xc[j * q + r];
-            if (csum < 0.00001) v = x0;                                           // :920
-            tile0[j * q + r] = v;
-            const double er = fabs(v - x0) / (fabs(x0) > O.lim ? x0 : O.lim);    // :1019
-            if (!(er < O.maxerr)) xfail = true;
-        }
-    }
-    const bool any_x = __ballot_sync(tmask, xfail) != 0;
-    if (sub == 0) st->outer = outer;
-    if (!((!O.fixed_iter && !any_x) || outer >= O.maxiter_x)) {                   // :1020-1023: next estim.BETA call
-        for (int j = sub; j < p; j += kTile) {
-            double s = 0;
-            for (int r = 0; r < q; r++) { const double v = tile0[j * q + r]; Xc[j * q + r] = v; s += v; }
-            cs[j] = s;
-        }
-        if (sub == 0) st->inner_it = 0;
-        return;
-    }
-    // ---- de-adjust (:1027-1037) and write BT into the result (:1042)
-    const int nadj = st->nadj;
-    const double deduct = nadj * O.adjust_esp;
-    const int64_t cbase = A.S.chunk_off[h];
-    const int64_t col0 = X.p_off[b];
-    for (int a = sub; a < ncell; a += kTile) {
-        const char *rec = td + rpos[a];
-        const uint32_t cw = ((const CellHdr *)rec)->cell;
-        if (!(cw & kPseudo)) write_cell(A, cbase + (int64_t)cw, col0, (const double *)(rec + 16), p, nadj, deduct);
-    }
-    const uint32_t lastw = ((const CellHdr *)(td + rpos[ncell - 1]))->cell;
-    if ((lastw & kPseudo) && (lastw & 0xffff) != 0) {
-        // cells of the chunk without a record of their own take the pseudo cell's values; the real
-        // cells are listed in ascending order, so walk the gaps
-        const double *bt = (const double *)(td + rpos[ncell - 1] + 16);
-        for (int a = sub; a < ncell; a += kTile) {
-            const int lo = a == 0 ? 0 : (int)(((const CellHdr *)(td + rpos[a - 1]))->cell) + 1;
-            const int hi = a == ncell - 1 ? nc : (int)(((const CellHdr *)(td + rpos[a]))->cell);
-            for (int cc = lo; cc < hi; cc++) write_cell(A, cbase + cc, col0, bt, p, nadj, deduct);
-        }
-    }
-    __syncwarp(tmask);
-    if (sub == 0) finish_task(A, t, (int)i, st, q, p, nc);
-}
-
-// estim.X.em's sums for a WIDE block, one warp: lane = block row, cells visited in order.  Each lane
-// owns its row of the accumulator Xn and (for j = lane) its entry of colSums(BETA): no shuffles,
-// and every sum over cells runs in cell order.  ysm[q] is a per-warp scratch for one cell's counts.
-__device__ __forceinline__ void xupd_rows(const Tasks &T, const int64_t *rpos, int ncell, int q, int p, int ppad,
-                                          const double *Xc, double *Xn, double *bts, double *ysm, int lane)
-{
-    const char *td = T.tdata;
-    for (int k = lane; k < q * p; k += kWarp) Xn[k] = 0.0;
-    for (int j = lane; j < p; j += kWarp) bts[j] = 0.0;
-    __syncwarp();
-    for (int a = 0; a < ncell; a++) {
-        const int64_t off = rpos[a];
-        const CellHdr hd = *(const CellHdr *)(td + off);
-        const double *bt = (const double *)(td + off + 16);
-        const Ent *en = (const Ent *)(td + off + 16 + 8 * ppad);
-        const double mult = (hd.cell & kPseudo) ? (double)(hd.cell & 0xffff) : 1.0;
-        for (int r = lane; r < q; r += kWarp) ysm[r] = 0.0;
-        __syncwarp();
-        for (int k = lane; k < hd.m; k += kWarp) { const Ent ev = en[k]; ysm[ev.row] = ev.y; }
-        for (int j = lane; j < p; j += kWarp) bts[j] += mult * bt[j];            // BTsum = colSums(BETA)  :904
-        __syncwarp();
-        for (int r = lane; r < q; r += kWarp) {
-            const double y = ysm[r];
-            if (y != 0.0) {
-                double mu = 0.0;                                                  // sumx1 = rowSums(x1)  :907
-                for (int j = 0; j < p; j++) mu += bt[j] * Xc[j * q + r];
-                const double w = mult * y / (mu > 0 ? mu : 0.1);                 // :908-910
-                for (int j = 0; j < p; j++) Xn[j * q + r] += bt[j] * Xc[j * q + r] * w;
-            }
-        }
-        __syncwarp();
-    }
-}
-
-// The same per BIG task (wide block or many cells): one warp, lane = cell, row-by-row xor-tree sums.
-__global__ void __launch_bounds__(128) task_step_big_kernel(RoundArgs A)
-{
-    extern __shared__ double sm[];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    double *Xn = sm + (size_t)warp * (A.xcap + A.pcap + A.qcap);
-    double *bts = Xn + A.xcap;
-    double *ysm = bts + A.pcap;
-    const unsigned i = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (i >= *A.tlist_n) return;
-    const XDev &X = A.X;
-    const Tasks &T = A.T;
-    const EmOpts &O = A.O;
-    const int64_t t = A.tlist[i];
-    char *td = T.tdata;
-    char *blob = td + T.toff[t];
-    TaskState *st = (TaskState *)blob;
-    if (!st->alive) return;
-    const bool fail = st->fail != 0;
-    const int inner_it = st->inner_it + 1;
-    __syncwarp();
-    if (lane == 0) { st->inner_it = inner_it; st->inner_total += 1; st->fail = 0; }
-    if (!((!O.fixed_iter && !fail) || inner_it >= O.maxiter_bt)) return;
-
-    const int e = (int)(t % X.n_em), h = (int)(t / X.n_em);
-    const int b = X.em_blocks[e];
-    const int q = X.q_off[b + 1] - X.q_off[b], p = X.p_off[b + 1] - X.p_off[b];
-    const int qp = q * p, ppad = ppad_of(p);
-    const int nc = (int)(A.S.chunk_off[h + 1] - A.S.chunk_off[h]);
-    double *Xc = (double *)(blob + 64), *cs = Xc + 2 * qp;
-    const int ncell = st->ncell;
-    const int64_t *rpos = T.rec_pos + T.run_off[t];
-
-    xupd_rows(T, rpos, ncell, q, p, ppad, Xc, Xn, bts, ysm, lane);
-    for (int j = lane; j < p; j += kWarp) {
-        const double d = bts[j] > 0 ? bts[j] : 0.1;                  // :917
-        double csum = 0.0;
-        for (int r = 0; r < q; r++) { double v = Xn[j * q + r] / d; Xn[j * q + r] = v; csum += v; }
-        const double d2 = csum > 0 ? csum : 0.1;                     // :919
-        for (int r = 0; r < q; r++) Xn[j * q + r] /= d2;
-        if (csum < 0.00001)                                          // :920
-            for (int r = 0; r < q; r++) Xn[j * q + r] = Xc[j * q + r];
-    }
-    __syncwarp();
-    bool xfail = false;                                              // :1019
-    for (int k = lane; k < qp; k += kWarp) {
-        const double x0 = Xc[k];
-        const double er = fabs(Xn[k] - x0) / (fabs(x0) > O.lim ? x0 : O.lim);
-        if (!(er < O.maxerr)) xfail = true;
-    }
-    const bool any_x = __any_sync(kFull, xfail);
-    const int outer = st->outer + 1;
-    __syncwarp();
-    if (lane == 0) st->outer = outer;
-    if (!((!O.fixed_iter && !any_x) || outer >= O.maxiter_x)) {      // :1020-1023
-        for (int k = lane; k < qp; k += kWarp) Xc[k] = Xn[k];
-        __syncwarp();
-        for (int j = lane; j < p; j += kWarp) {
-            double s = 0;
-            for (int r = 0; r < q; r++) s += Xn[j * q + r];
-            cs[j] = s;
-        }
-        if (lane == 0) st->inner_it = 0;
-        return;
-    }
-    const int nadj = st->nadj;
-    const double deduct = nadj * O.adjust_esp;
-    const int64_t cbase = A.S.chunk_off[h];
-    const int64_t col0 = X.p_off[b];
-    for (int a = lane; a < ncell; a += kWarp) {
-        const int64_t off = rpos[a];
-        const CellHdr hd = *(const CellHdr *)(td + off);
-        const double *bt = (const double *)(td + off + 16);
-        double s = 0;
-        if (nadj > 0) for (int j = 0; j < p; j++) s += bt[j];
-        if (!(hd.cell & kPseudo)) {
-            double *o = A.out + (cbase + (int64_t)hd.cell) * X.n_cols + col0;
-            for (int j = 0; j < p; j++) { double v = bt[j]; if (nadj > 0) v = v - deduct * (v / s); o[j] = v; }
-        } else if ((hd.cell & 0xffff) != 0) {
-            int ai = 0;
-            uint32_t next_real = ((const CellHdr *)(td + rpos[0]))->cell;
-            for (int cc = 0; cc < nc; cc++) {
-                if (ai < ncell - 1 && next_real == (uint32_t)cc) {
-                    ai++;
-                    next_real = ((const CellHdr *)(td + rpos[ai]))->cell;
-                    continue;
-                }
-                double *o = A.out + (cbase + cc) * X.n_cols + col0;
-                for (int j = 0; j < p; j++) { double v = bt[j]; if (nadj > 0) v = v - deduct * (v / s); o[j] = v; }
-            }
-        }
-    }
-    __syncwarp();
-    if (lane == 0) finish_task(A, t, (int)i, st, q, p, nc);
-}
-
-// ------------------------------------------------------------------------------------------
-// Stragglers.  After the bulk rounds a few per cent of the tasks still iterate (slowly converging
-// blocks run hundreds of iterations); a global round per iteration would then cost a kernel launch
-// for a handful of cells.  This persistent kernel takes over: ONE WARP per task runs it to the end
-// from the state the rounds left (X.est0, counters in TaskState; beta, logNorm in the records).
-// gamma runs over the flattened (cell, transcript) pairs, the rest is lane = cell.
-__global__ void __launch_bounds__(128) em_finish_kernel(RoundArgs A, unsigned int *next_task)
-{
-    extern __shared__ double sm[];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int per_warp = 2 * A.xcap + 2 * A.pcap + A.qcap;
-    double *Xc = sm + (size_t)warp * per_warp;   // current X (X.est0), column-major
-    double *Xn = Xc + A.xcap;                    // estim.X.em result (X.est)
-    double *cs = Xn + A.xcap;                    // colSums(X)
-    double *bts = cs + A.pcap;                   // colSums(BETA)
-    double *ysm = bts + A.pcap;                  // one cell's counts by row (wide blocks)
-
-    const XDev &X = A.X;
-    const Tasks &T = A.T;
-    const EmOpts &O = A.O;
-    const unsigned total = *A.tlist_n;
-
-    for (;;) {
-        unsigned ti = 0;
-        if (lane == 0) ti = atomicAdd(next_task, 1u);
-        ti = __shfl_sync(kFull, ti, 0);
-        if (ti >= total) break;
-        const int64_t t = A.tlist[ti];
-        char *td = T.tdata, *sc = T.scr;
-        TaskState *st = (TaskState *)(td + T.toff[t]);
-        if (!st->alive) continue;
-        const int e = (int)(t % X.n_em), h = (int)(t / X.n_em);
-        const int b = X.em_blocks[e];
-        const int q = X.q_off[b + 1] - X.q_off[b];
-        const int p = X.p_off[b + 1] - X.p_off[b];
-        const int qp = q * p, ppad = ppad_of(p);
-        const int nc = (int)(A.S.chunk_off[h + 1] - A.S.chunk_off[h]);
-        const int ncell = st->ncell;
-        const int n_round = (ncell + 31) & ~31;
-        const int64_t *rpos = T.rec_pos + T.run_off[t];
-        int outer = st->outer, inner_total = st->inner_total, inner_it0 = st->inner_it;
-        const int nadj = st->nadj;
-        const double *sx = (const double *)(td + T.toff[t] + 64);
-        for (int k = lane; k < qp; k += kWarp) Xc[k] = sx[k];
-        __syncwarp();
-
-        for (;;) {
-            // ================= estim.BETA(X.est0, Ymat, beta0)  :726-761
-            for (int j = lane; j < p; j += kWarp) {                     // csum = colSums(X)
-                double s = 0;
-                for (int r = 0; r < q; r++) s += Xc[j * q + r];
-                cs[j] = s;
-            }
-            __syncwarp();
-            for (int it = inner_it0 + 1;; it++) {
-                // stage 1: gamma over the flattened (cell, transcript) pairs
-                const int npairs = ncell * p;
-                for (int idx = lane; idx < npairs; idx += kWarp) {
-                    const int a = idx / p, j = idx - a * p;
-                    const int64_t off = rpos[a];
-                    const double lnm = ((const CellHdr *)(td + off))->lnorm;
-                    const double bv = ((const double *)(td + off + 16))[j];
-                    ((double *)(sc + off + 16))[j] = em_gamma(bv, lnm, O.modify);
-                }
-                __syncwarp();
-                // stage 2: lane = cell
-                bool fail = false;
-                for (int a = lane; a < n_round; a += kWarp) {
-                    if (a < ncell) {
-                        const int64_t off = rpos[a];
-                        const CellHdr hd = *(const CellHdr *)(td + off);
-                        double *bt = (double *)(td + off + 16);
-                        const double *g = (const double *)(sc + off + 16);
-                        const Ent *en = (const Ent *)(td + off + 16 + 8 * ppad);
-                        double *w = (double *)(sc + off + 16 + 8 * ppad);     // one double per entry (stride 2)
-                        for (int k = 0; k < hd.m; k++) {
-                            const Ent ev = en[k];
-                            double mu = 0.0;
-                            for (int j = 0; j < p; j++) mu += Xc[j * q + ev.row] * g[j];
-                            w[2 * k] = ev.y / (mu > 0 ? mu : 1.0);
-                        }
-                        for (int j = 0; j < p; j++) {
-                            double s = 0.0;
-                            for (int k = 0; k < hd.m; k++) s += Xc[j * q + en[k].row] * w[2 * k];
-                            const double old = bt[j];
-                            double nb = g[j] * s / cs[j];
-                            if (nb != nb) nb = 0.0;                      // :754
-                            const double er = fabs(nb - old) / (old > O.lim ? old : O.lim);
-                            if (!(er < O.maxerr)) fail = true;
-                            bt[j] = nb;
-                        }
-                    }
-                }
-                inner_total++;
-                const bool any_fail = __any_sync(kFull, fail);
-                if ((!O.fixed_iter && !any_fail) || it >= O.maxiter_bt) break;
-            }
-            inner_it0 = 0;
-            __syncwarp();
-
-            // ================= estim.X.em(X.est0, BT, Ymat)  :898-922
-            if (p > kSmallP || qp + p > kStepSlot) {
-                xupd_rows(T, rpos, ncell, q, p, ppad, Xc, Xn, bts, ysm, lane);
-            } else {
-                for (int j = 0; j < p; j++) {                               // BTsum = colSums(BETA)
-                    double s = 0;
-                    for (int a = lane; a < ncell; a += kWarp) {
-                        const int64_t off = rpos[a];
-                        const uint32_t cw = ((const CellHdr *)(td + off))->cell;
-                        const double mult = (cw & kPseudo) ? (double)(cw & 0xffff) : 1.0;
-                        s += mult * ((const double *)(td + off + 16))[j];
-                    }
-                    s = warp_sum(s);
-                    if (lane == 0) bts[j] = s;
-                }
-                for (int i = lane; i < qp; i += kWarp) Xn[i] = 0.0;
-                __syncwarp();
-                for (int a0 = 0; a0 < ncell; a0 += kWarp) {
-                    const int a = a0 + lane;
-                    const bool valid = a < ncell;
-                    const double *bt = nullptr;
-                    const Ent *en = nullptr;
-                    int cur = 0, end = 0;
-                    double mult = 1.0;
-                    if (valid) {
-                        const int64_t off = rpos[a];
-                        const CellHdr hd = *(const CellHdr *)(td + off);
-                        bt = (const double *)(td + off + 16);
-                        en = (const Ent *)(td + off + 16 + 8 * ppad);
-                        end = hd.m;
-                        mult = (hd.cell & kPseudo) ? (double)(hd.cell & 0xffff) : 1.0;
-                    }
-                    for (int r = 0; r < q; r++) {
-                        const bool has = valid && cur < end && en[cur].row == r;
-                        if (!__any_sync(kFull, has)) continue;
-                        double w = 0.0;
-                        if (has) {
-                            const double y = en[cur++].y;
-                            double mu = 0.0;                                 // sumx1 = rowSums(x1)
-                            for (int j = 0; j < p; j++) mu += bt[j] * Xc[j * q + r];
-                            w = mult * y / (mu > 0 ? mu : 0.1);
-                        }
-                        for (int j = 0; j < p; j++) {
-                            const double xr = Xc[j * q + r];
-                            if (xr != 0.0) {                                 // uniform across the warp
-                                double v = has ? bt[j] * xr * w : 0.0;      // x2 * Y
-                                v = warp_sum(v);
-                                if (lane == 0) Xn[j * q + r] += v;
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-            }
-            for (int j = lane; j < p; j += kWarp) {
-                const double d = bts[j] > 0 ? bts[j] : 0.1;              // :917
-                double csum = 0.0;
-                for (int r = 0; r < q; r++) { double v = Xn[j * q + r] / d; Xn[j * q + r] = v; csum += v; }
-                const double d2 = csum > 0 ? csum : 0.1;                 // :919
-                for (int r = 0; r < q; r++) Xn[j * q + r] /= d2;
-                if (csum < 0.00001)                                      // :920
-                    for (int r = 0; r < q; r++) Xn[j * q + r] = Xc[j * q + r];
-            }
-            __syncwarp();
-            bool xfail = false;                                          // :1019
-            for (int i = lane; i < qp; i += kWarp) {
-                const double x0 = Xc[i];
-                const double er = fabs(Xn[i] - x0) / (fabs(x0) > O.lim ? x0 : O.lim);
-                if (!(er < O.maxerr)) xfail = true;
-            }
-            outer++;
-            const bool any_x = __any_sync(kFull, xfail);
-            if ((!O.fixed_iter && !any_x) || outer >= O.maxiter_x) break; // :1020
-            for (int i = lane; i < qp; i += kWarp) Xc[i] = Xn[i];        // X.est0 = X.est  :1022
-            __syncwarp();
-        }
-
-        // ---- de-adjust (:1027-1037) and scatter BT into the result (:1042)
-        const double deduct = nadj * O.adjust_esp;
-        const int64_t cbase = A.S.chunk_off[h];
-        const int64_t col0 = X.p_off[b];
-        for (int a = lane; a < ncell; a += kWarp) {
-            const int64_t off = rpos[a];
-            const CellHdr hd = *(const CellHdr *)(td + off);
-            const double *bt = (const double *)(td + off + 16);
-            double s = 0;
-            if (nadj > 0) for (int j = 0; j < p; j++) s += bt[j];
-            if (!(hd.cell & kPseudo)) {
-                double *o = A.out + (cbase + (int64_t)hd.cell) * X.n_cols + col0;
-                for (int j = 0; j < p; j++) { double v = bt[j]; if (nadj > 0) v = v - deduct * (v / s); o[j] = v; }
-            } else if ((hd.cell & 0xffff) != 0) {
-                int ai = 0;
-                uint32_t next_real = ((const CellHdr *)(td + rpos[0]))->cell;
-                for (int cc = 0; cc < nc; cc++) {
-                    if (ai < ncell - 1 && next_real == (uint32_t)cc) {
-                        ai++;
-                        next_real = ((const CellHdr *)(td + rpos[ai]))->cell;
-                        continue;
-                    }
-                    double *o = A.out + (cbase + cc) * X.n_cols + col0;
-                    for (int j = 0; j < p; j++) { double v = bt[j]; if (nadj > 0) v = v - deduct * (v / s); o[j] = v; }
-                }
-            }
-        }
-        if (lane == 0) {
-            st->alive = 0;
-            task_done_stats(A.iters, A.stats, t, outer, inner_total, q, p, nc, ncell);
-        }
-        __syncwarp();
-    }
-}
-
-// ---- list maintenance ---------------------------------------------------------------------
-__global__ void gather_ncell_kernel(Tasks T, const int32_t *tlist, const unsigned int *n, int32_t *ncell_out)
-{
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < *n) ncell_out[i] = T.runs[tlist[i]];
-}
-// record list of the listed tasks, in list order then record order
-__global__ void fill_records_kernel(Tasks T, const int32_t *tlist, const unsigned int *n, const int64_t *roff,
-                                    int64_t base, int32_t *r_task, int64_t *r_off)
-{
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *n) return;
-    const int64_t t = tlist[i];
-    const int ncell = T.runs[t];
-    const int64_t *rpos = T.rec_pos + T.run_off[t];
-    int64_t o = base + roff[i];
-    for (int a = 0; a < ncell; a++) { r_task[o + a] = (int32_t)t; r_off[o + a] = rpos[a]; }
-}
-// stable compaction of a task list by the alive flags: out[scan[i]] = in[i]
-__global__ void compact_list_kernel(const int32_t *in, const int32_t *alive, const int64_t *pos, const unsigned int *n,
-                                    int32_t *out, int32_t *alive_out)
-{
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *n) return;
-    if (alive[i]) { out[pos[i]] = in[i]; alive_out[pos[i]] = 1; }
-}
-__global__ void set_count_kernel(unsigned int *dst, const int64_t *src) { *dst = (unsigned int)*src; }
 // ------------------------------------------------------------------------------------------
 // Column sums over cells: the rowSums of step2:167 (rows with sum > 0 survive).  Grid = (tiles of
 // kTileCells cells) x (column slices).  A thread owns kFinPerThread fixed columns and adds them for
@@ -1290,3 +618,5 @@ __global__ void gene_direct_kernel(const double *__restrict__ iso, int64_t n_cel
 }
 
 }  // namespace scasa
+
+#include "scasa_em.cuh"

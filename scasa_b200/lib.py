@@ -40,13 +40,18 @@ class Crp(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("total_ms", C.c_float), ("pack_ms", C.c_float), ("tasks_ms", C.c_float), ("em_ms", C.c_float),
-                ("finish_ms", C.c_float), ("gene_ms", C.c_float), ("em_setup_ms", C.c_float), ("em_rounds_ms", C.c_float),
-                ("em_stragglers_ms", C.c_float), ("n_tasks", C.c_int64), ("n_entries", C.c_int64),
-                ("n_active", C.c_int64), ("n_handed_over", C.c_int64), ("inner_iters", C.c_int64), ("outer_iters", C.c_int64),
-                ("alg_bytes", C.c_double), ("launches", C.c_int32), ("rounds", C.c_int32), ("rebuilds", C.c_int32)]
+                ("finish_ms", C.c_float), ("gene_ms", C.c_float), ("em_class_ms", C.c_float * 4),
+                ("em_class_tasks", C.c_int64 * 4), ("n_tasks", C.c_int64), ("n_entries", C.c_int64),
+                ("n_active", C.c_int64), ("inner_iters", C.c_int64), ("outer_iters", C.c_int64),
+                ("alg_bytes", C.c_double), ("em_alg_bytes", C.c_double), ("launches", C.c_int32),
+                ("max_slot_bytes", C.c_int32)]
 
     def as_dict(self) -> dict:
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {}
+        for k, _ in self._fields_:
+            v = getattr(self, k)
+            d[k] = list(v) if hasattr(v, "__len__") else v
+        return d
 
 
 # every symbol include/scasa_cuda.h declares (tests check the library exports all of them)
