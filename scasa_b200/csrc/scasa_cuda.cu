@@ -89,10 +89,10 @@ struct scasa_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join[kClasses] = {}, ev_cls[kClasses][2] = {};
     // work classes of the EM kernel: warps per task, pairs and slot limits, resident CTAs per SM
     int cls_warps[kClasses] = {1, 2, 4, 8};
-    int cls_pairs[kClasses] = {32, 96, 256, 1 << 30};
-    int cls_bytes[kClasses] = {2048, 6144, 16384, 1 << 30};
-    int cls_cta_threads[kClasses] = {128, 128, 128, 256};
-    int cls_ctas_per_sm[kClasses] = {8, 4, 2, 1};
+    int cls_pairs[kClasses] = {96, 256, 512, 1 << 30};
+    int cls_bytes[kClasses] = {6144, 12288, 16384, 1 << 30};
+    int cls_cta_threads[kClasses] = {64, 128, 128, 256};
+    int cls_ctas_per_sm[kClasses] = {16, 8, 4, 2};
     DBuf<unsigned long long> d_stats;
     DBuf<int> d_flag;
 

@@ -129,7 +129,7 @@ template <int W> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs
         const uint16_t *eptr = (const uint16_t *)(slot + BL.off_ptr);
         const uint16_t *erow = (const uint16_t *)(slot + BL.off_row);
         double *ew = (double *)(slot + BL.bytes);
-        double *Xc = ew + E, *Xn = Xc + qp, *cs = Xn + qp, *bts = cs + p, *lnorm = bts + p;
+        double *Xc = ew + E, *Xn = Xc + qp, *rcs = Xn + qp, *bts = rcs + p, *nrm = bts + p, *lnorm = nrm + p;
         double *beta = lnorm + n, *gam = beta + np;
         uint16_t *erec = (uint16_t *)(gam + np), *rptr = erec + E, *perm = rptr + q + 1;
         int *cur = (int *)Xn;                        // q ints of scratch until the first X update
@@ -225,50 +225,61 @@ template <int W> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs
             G.sync();
         }
 
-        // ---- csum = colSums(X) (:731), logNorm (:732-733), beta0 = colSums(Ymat)/p (:1012-1013)
+        // ---- 1/colSums(X) (:731, :745), logNorm (:732-733), beta0 = colSums(Ymat)/p (:1012-1013)
         for (int j = gl; j < p; j += GT) {
             double s = 0;
+#pragma unroll 1
             for (int r = 0; r < q; r++) s += Xc[j * q + r];
-            cs[j] = s;
+            rcs[j] = 1.0 / s;
         }
         for (int a = gl; a < n; a += GT) {
             double ys = 0;
             const int k1 = eptr[a + 1];
+#pragma unroll 1
             for (int k = eptr[a]; k < k1; k++) ys += ey[k];
             lnorm[a] = digamma_pos(ys + 0.00000001);
             const double b0 = ys / p;
+#pragma unroll 1
             for (int j = 0; j < p; j++) beta[j * n + a] = b0;
         }
         G.sync();
 
-        // pair index idx = j*n + a walks in steps of GT
+        // the pair index idx = j*n + a and the X element index idx = j*q + r walk in steps of GT
         const int j_first = gl / n, a_first = gl - j_first * n;
         const int dj = GT / n, da = GT - dj * n;
+        const int xj_first = gl / q, xr_first = gl - xj_first * q;
+        const int dxj = GT / q, dxr = GT - dxj * q;
 
         int outer = 0, inner_total = 0;
         for (;;) {
             // ================= estim.BETA(X.est0, Ymat, beta0)  :726-761
             for (int it = 1;; it++) {
+#pragma unroll 1
                 for (int idx = gl, a = a_first; idx < np; idx += GT) {          // S1
                     gam[idx] = O.modify ? em_gamma_fast(beta[idx], lnorm[a]) : beta[idx];
                     a += da;
                     if (a >= n) a -= n;
                 }
                 G.sync();
+#pragma unroll 1
                 for (int k = gl; k < E; k += GT) {                               // S2
                     const int r = erow[k], a = erec[k];
                     double mu = 0.0;                                             // rowSums(t(t(X)*gamma0))  :739-740
+#pragma unroll 1
                     for (int j = 0; j < p; j++) mu += Xc[j * q + r] * gam[j * n + a];
                     ew[k] = ey[k] / (mu > 0 ? mu : 1.0);                         // :741
                 }
                 G.sync();
                 bool fail = false;
+#pragma unroll 1
                 for (int idx = gl, a = a_first, j = j_first; idx < np; idx += GT) {   // S3
                     double s = 0.0;
                     const int k1 = eptr[a + 1];
+#pragma unroll 1
                     for (int k = eptr[a]; k < k1; k++) s += Xc[j * q + erow[k]] * ew[k];
                     const double old = beta[idx];
-                    double nb = gam[idx] * s / cs[j];                            // :745
+                    const double gs = gam[idx] * s;
+                    double nb = gs == 0.0 ? 0.0 : gs * rcs[j];                   // :745 (division by csum as a reciprocal)
                     if (nb != nb) nb = 0.0;                                      // :754
                     const double den = old > O.lim ? old : O.lim;               // :755
                     if (!(fabs(nb - old) < O.maxerr * den)) fail = true;
@@ -284,58 +295,70 @@ template <int W> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs
             // ================= estim.X.em(X.est0, BT, Ymat)  :898-922
             for (int j = gl; j < p; j += GT) {                                   // BTsum = colSums(BETA)  :904
                 double s = 0;
+#pragma unroll 1
                 for (int a = 0; a < n; a++) {
                     const uint32_t cw = rcell[a];
                     s += ((cw & kPseudo) ? (double)(cw & 0xffff) : 1.0) * beta[j * n + a];
                 }
-                bts[j] = s;
+                bts[j] = s > 0 ? s : 0.1;                                        // :917 (may be denormal: no reciprocal)
             }
+#pragma unroll 1
             for (int k = gl; k < E; k += GT) {
                 const int r = erow[k], a = erec[k];
                 double mu = 0.0;                                                  // sumx1 = rowSums(x1)  :907
+#pragma unroll 1
                 for (int j = 0; j < p; j++) mu += beta[j * n + a] * Xc[j * q + r];
                 const uint32_t cw = rcell[a];
                 const double mult = (cw & kPseudo) ? (double)(cw & 0xffff) : 1.0;
                 ew[k] = mult * ey[k] / (mu > 0 ? mu : 0.1);                      // :908-910
             }
             G.sync();
-            for (int idx = gl; idx < qp; idx += GT) {                            // T = colSums(x2 * Y) per row  :911-914
-                const int j = idx / q, r = idx - j * q;
+#pragma unroll 1
+            for (int idx = gl, j = xj_first, r = xr_first; idx < qp; idx += GT) {   // X.est = colSums(x2 * Y) / BTsum  :911-917
                 const double x = Xc[idx];
                 double acc = 0.0;
                 const int i1 = rptr[r + 1];
+#pragma unroll 1
                 for (int i = rptr[r]; i < i1; i++) {
                     const int k = perm[i];
                     acc += beta[j * n + erec[k]] * x * ew[k];
                 }
-                Xn[idx] = acc;
+                Xn[idx] = acc == 0.0 ? 0.0 : acc / bts[j];                       // zero numerators would take the slow division path
+                r += dxr; j += dxj;
+                if (r >= q) { r -= q; j++; }
             }
             G.sync();
-            for (int j = gl; j < p; j += GT) {
-                const double d = bts[j] > 0 ? bts[j] : 0.1;                      // :917
+            for (int j = gl; j < p; j += GT) {                                   // csum = colSums(X.est)  :918
                 double csum = 0.0;
-                for (int r = 0; r < q; r++) { const double v = Xn[j * q + r] / d; Xn[j * q + r] = v; csum += v; }
-                const double d2 = csum > 0 ? csum : 0.1;                         // :919
-                for (int r = 0; r < q; r++) Xn[j * q + r] /= d2;
-                if (csum < 0.00001)                                              // :920
-                    for (int r = 0; r < q; r++) Xn[j * q + r] = Xc[j * q + r];
+#pragma unroll 1
+                for (int r = 0; r < q; r++) csum += Xn[j * q + r];
+                // :919-920: scale by 1/csum (0.1 when 0); a negative scale marks "revert to X.est0"
+                nrm[j] = csum < 0.00001 ? -1.0 : 1.0 / (csum > 0 ? csum : 0.1);
             }
             G.sync();
             bool xfail = false;                                                  // :1019
-            for (int idx = gl; idx < qp; idx += GT) {
-                const double x0 = Xc[idx];
-                const double er = fabs(Xn[idx] - x0) / (fabs(x0) > O.lim ? x0 : O.lim);
-                if (!(er < O.maxerr)) xfail = true;
+#pragma unroll 1
+            for (int idx = gl, j = xj_first, r = xr_first; idx < qp; idx += GT) {
+                const double x0 = Xc[idx], sc = nrm[j];
+                const double v = sc < 0 ? x0 : Xn[idx] * sc;
+                Xn[idx] = v;
+                const double num = fabs(v - x0), den = fabs(x0) > O.lim ? x0 : O.lim;
+                const bool ok = den > 0 ? (num < O.maxerr * den) : (num / den < O.maxerr);
+                if (!ok) xfail = true;
+                r += dxr; j += dxj;
+                if (r >= q) { r -= q; j++; }
             }
             outer++;
             const bool any_x = G.any(xfail);
             if ((!O.fixed_iter && !any_x) || outer >= O.maxiter_x) break;        // :1020
+#pragma unroll 1
             for (int idx = gl; idx < qp; idx += GT) Xc[idx] = Xn[idx];           // X.est0 = X.est  :1022
             G.sync();
-            for (int j = gl; j < p; j += GT) {                                   // csum of the next estim.BETA call
+            for (int j = gl; j < p; j += GT) {                                   // 1/csum of the next estim.BETA call
                 double s = 0;
+#pragma unroll 1
                 for (int r = 0; r < q; r++) s += Xc[j * q + r];
-                cs[j] = s;
+                rcs[j] = 1.0 / s;
             }
             G.sync();
         }

@@ -117,11 +117,11 @@ __host__ __device__ inline BlobLayout blob_layout(int n, int E)
     return L;
 }
 // shared memory one task needs in the EM kernel: blob image, then
-//     ew[E] Xc[qp] Xn[qp] cs[p] bts[p] lnorm[n] beta[p*n] gam[p*n]  (f64)
+//     ew[E] Xc[qp] Xn[qp] rcs[p] bts[p] nrm[p] lnorm[n] beta[p*n] gam[p*n]  (f64)
 //     erec[E] rptr[q+1] perm[E]                                     (u16)
 __host__ __device__ inline int slot_bytes_of(int q, int p, int n, int E)
 {
-    return blob_layout(n, E).bytes + 8 * (E + 2 * q * p + 2 * p + n + 2 * p * n) + align16(2 * (2 * E + q + 1));
+    return blob_layout(n, E).bytes + 8 * (E + 2 * q * p + 3 * p + n + 2 * p * n) + align16(2 * (2 * E + q + 1));
 }
 
 // work classes: W warps per task, a slot of at most kClassBytes[c] (the last class takes the rest)
