@@ -114,6 +114,11 @@ int scasa_stage_eqcounts(scasa_ctx *ctx, int64_t n_cells, int32_t n_chunks, cons
                          const int64_t *cell_ptr, const int32_t *eq_id, const int32_t *eq_count,
                          int64_t n_eq, const int32_t *eq_row);
 int scasa_run(scasa_ctx *ctx);   /* pack -> EM -> (gene sums); everything on the device */
+/* The two dense results travel zero-suppressed ((column, value) pairs, > 90 % of the matrices are
+ * zeros) and are re-expanded into the caller's buffer by host threads; the buffer ends up
+ * bit-identical to a plain copy.  scasa_set_host_threads: threads of that expansion, 0 = all cores,
+ * -1 = plain dense copy instead. */
+int scasa_set_host_threads(scasa_ctx *ctx, int32_t n_threads);
 int scasa_fetch_iso(scasa_ctx *ctx, double *iso_out);            /* n_cells x n_cols           */
 int scasa_fetch_iters(scasa_ctx *ctx, int32_t *iters_out);       /* [n_chunks][n_em_blocks][2] */
 int scasa_fetch_colsum(scasa_ctx *ctx, double *colsum /* [n_cols] */); /* rowSums of step2:167 */

@@ -149,6 +149,10 @@ class Scasa:
         self._ck(self._L.scasa_last_timing(self._ctx, C.byref(t)))
         return t.as_dict()
 
+    def set_host_threads(self, n: int) -> None:
+        """Threads that re-expand the zero-suppressed results on the host (0 = all cores, -1 = plain dense copy)."""
+        self._ck(self._L.scasa_set_host_threads(self._ctx, n))
+
     def fetch_iso(self, out: np.ndarray | None = None) -> np.ndarray:
         if out is None:
             out = np.empty((self.n_cells, self.n_cols), np.float64)

@@ -11,7 +11,9 @@
 #include <cstdlib>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
+#include <emmintrin.h>
 
 using namespace scasa;
 
@@ -98,6 +100,21 @@ struct scasa_ctx {
 
     // ---- results
     DBuf<double> d_iso, d_partial, d_colsum, d_gene;
+    // zero-suppressed fetch: two batches in flight (device pairs -> pinned staging -> threaded expansion)
+    struct FetchBuf {
+        DBuf<int32_t> d_cols, d_nnz;
+        DBuf<double> d_vals;
+        DBuf<int64_t> d_start;
+        DBuf<unsigned long long> d_cursor;
+        int32_t *h_cols = nullptr, *h_nnz = nullptr;
+        double *h_vals = nullptr;
+        int64_t *h_start = nullptr;
+        unsigned long long *h_cursor = nullptr;
+        size_t cap = 0, rows = 0;
+        cudaEvent_t done = nullptr;
+    } fb[2];
+    int host_threads = 0;        // 0 = hardware concurrency
+    int fetch_dense_copy = 0;    // 1 = plain dense D2H (SCASA_FETCH_DENSE)
     int n_genes = 0;
     DBuf<int32_t> d_gene_of_col, d_gene_ptr, d_gene_cols;
     scasa_timing_t timing{};
@@ -202,14 +219,16 @@ void launch_finish(scasa_ctx *c, int64_t n_cells, double *gene, int &launches)
     launches += 2;
     if (gene) {
         const size_t smem = (size_t)c->n_genes * sizeof(double);
-        const int grid = (int)std::min<int64_t>(n_cells, (int64_t)c->n_sm * 4);
-        if (smem <= 220 * 1024) {
+        if (smem <= 220 * 1024 && getenv("SCASA_GENE_SMEM")) {
             CK(cudaFuncSetAttribute(gene_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            gene_smem_kernel<<<std::min<int>(grid, c->n_sm), 1024, smem, s>>>(c->d_iso.p, n_cells, c->n_cols, c->d_gene_of_col.p,
-                                                                           c->d_gene_ptr.p, c->d_gene_cols.p, c->n_genes, gene);
+            const int grid = (int)std::min<int64_t>(n_cells, (int64_t)c->n_sm);
+            gene_smem_kernel<<<grid, 1024, smem, s>>>(c->d_iso.p, n_cells, c->n_cols, c->d_gene_of_col.p,
+                                                      c->d_gene_ptr.p, c->d_gene_cols.p, c->n_genes, gene);
         } else {
-            gene_direct_kernel<<<grid, 1024, 0, s>>>(c->d_iso.p, n_cells, c->n_cols, c->d_gene_ptr.p, c->d_gene_cols.p,
-                                                     c->n_genes, gene);
+            const int tiles = (c->n_genes + kGeneThreads * kGeneIlp - 1) / (kGeneThreads * kGeneIlp);
+            if (n_cells * tiles >= ((int64_t)1 << 31)) throw ArgErr{SCASA_ERR_UNSUPPORTED, "too many cells x genes for one launch"};
+            gene_gather_kernel<<<(unsigned)(n_cells * tiles), kGeneThreads, 0, s>>>(c->d_iso.p, n_cells, c->n_cols, c->d_gene_ptr.p,
+                                                                                   c->d_gene_cols.p, c->n_genes, tiles, gene);
         }
         launches++;
     }
@@ -254,6 +273,117 @@ template <int W> void launch_em(const EmArgs &A, unsigned grid, int threads, siz
 {
     CK(cudaFuncSetAttribute(em_task_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     em_task_kernel<W><<<grid, threads, smem, s>>>(A);
+}
+
+// ---- host side of the zero-suppressed fetch --------------------------------------------------
+// n doubles of zeros with non-temporal stores (the destination is written once and not read here)
+inline void stream_zero(double *p, int64_t n)
+{
+    while (n > 0 && ((uintptr_t)p & 15)) { _mm_stream_si64((long long *)p, 0); p++; n--; }
+    const __m128d z = _mm_setzero_pd();
+    for (; n >= 2; n -= 2, p += 2) _mm_stream_pd(p, z);
+    if (n) _mm_stream_si64((long long *)p, 0);
+}
+// rows [r0, r1) of a batch: pairs are in ascending column order inside a row
+void expand_rows(double *out, int64_t n_cols, int64_t r0, int64_t r1, const int64_t *start, const int32_t *nnz,
+                 const int32_t *cols, const double *vals)
+{
+    for (int64_t r = r0; r < r1; r++) {
+        double *o = out + r * n_cols;
+        const int32_t *c = cols + start[r];
+        const double *v = vals + start[r];
+        int64_t at = 0;
+        for (int32_t k = 0; k < nnz[r]; k++) {
+            const int64_t j = c[k];
+            stream_zero(o + at, j - at);
+            long long bits;
+            memcpy(&bits, v + k, 8);
+            _mm_stream_si64((long long *)(o + j), bits);
+            at = j + 1;
+        }
+        stream_zero(o + at, n_cols - at);
+    }
+    _mm_sfence();
+}
+
+void fetch_buf_ensure(scasa_ctx *c, scasa_ctx::FetchBuf &b, size_t rows, size_t cap)
+{
+    if (b.rows >= rows && b.cap >= cap) return;
+    if (b.h_cols) { cudaFreeHost(b.h_cols); cudaFreeHost(b.h_vals); cudaFreeHost(b.h_start); cudaFreeHost(b.h_nnz); cudaFreeHost(b.h_cursor); }
+    b.h_cols = nullptr; b.rows = 0; b.cap = 0;
+    b.d_cols.ensure(cap); b.d_vals.ensure(cap); b.d_start.ensure(rows); b.d_nnz.ensure(rows); b.d_cursor.ensure(1);
+    CK(cudaHostAlloc((void **)&b.h_cols, cap * sizeof(int32_t), cudaHostAllocDefault));
+    CK(cudaHostAlloc((void **)&b.h_vals, cap * sizeof(double), cudaHostAllocDefault));
+    CK(cudaHostAlloc((void **)&b.h_start, rows * sizeof(int64_t), cudaHostAllocDefault));
+    CK(cudaHostAlloc((void **)&b.h_nnz, rows * sizeof(int32_t), cudaHostAllocDefault));
+    CK(cudaHostAlloc((void **)&b.h_cursor, sizeof(unsigned long long), cudaHostAllocDefault));
+    if (!b.done) CK(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
+    b.rows = rows; b.cap = cap;
+}
+
+// Dense (n_rows x n_cols) device matrix -> dense host matrix, sent as (column, value) pairs in
+// batches of rows: while the host threads expand batch k, the GPU compacts and copies batch k+1.
+void fetch_dense(scasa_ctx *c, const double *d_mat, int64_t n_rows, int64_t n_cols, double *out)
+{
+    cudaStream_t s = c->stream;
+    if (c->fetch_dense_copy || c->host_threads < 0 || n_rows * n_cols < (1 << 20)) {
+        CK(cudaMemcpyAsync(out, d_mat, (size_t)(n_rows * n_cols) * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        return;
+    }
+    int nthr = c->host_threads > 0 ? c->host_threads : (int)std::thread::hardware_concurrency();
+    nthr = std::max(1, std::min(nthr, 256));
+    const int64_t batch = std::max<int64_t>(64, std::min<int64_t>(n_rows, ((int64_t)48 << 20) / n_cols));   // ~48 M cells of the matrix per batch
+    const size_t cap = (size_t)(batch * n_cols / 3 + 1024);
+    for (auto &b : c->fb) fetch_buf_ensure(c, b, (size_t)batch, cap);
+    const int64_t n_batches = (n_rows + batch - 1) / batch;
+    auto launch = [&](int64_t k) {
+        scasa_ctx::FetchBuf &b = c->fb[k & 1];
+        const int64_t r0 = k * batch, nr = std::min(batch, n_rows - r0);
+        CK(cudaMemsetAsync(b.d_cursor.p, 0, sizeof(unsigned long long), s));
+        const int grid = (int)std::min<int64_t>(nr, (int64_t)c->n_sm * 3);
+        compact_rows_kernel<<<grid, kCompThreads, 0, s>>>(d_mat + r0 * n_cols, nr, n_cols, b.d_cursor.p, (unsigned long long)b.cap,
+                                                         b.d_start.p, b.d_nnz.p, b.d_cols.p, b.d_vals.p);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(b.h_cursor, b.d_cursor.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(b.h_start, b.d_start.p, nr * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(b.h_nnz, b.d_nnz.p, nr * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));       // the pair count sizes the copy (the other batch is being expanded meanwhile)
+        const size_t used = (size_t)std::min<unsigned long long>(*b.h_cursor, b.cap);
+        if (used) {
+            CK(cudaMemcpyAsync(b.h_cols, b.d_cols.p, used * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(b.h_vals, b.d_vals.p, used * sizeof(double), cudaMemcpyDeviceToHost, s));
+        }
+        CK(cudaEventRecord(b.done, s));
+    };
+    // the expansion of batch k runs on worker threads while this thread drives the GPU for batch k+1
+    std::vector<std::thread> workers;
+    auto expand_async = [&](int64_t k) {
+        scasa_ctx::FetchBuf &b = c->fb[k & 1];
+        const int64_t r0 = k * batch, nr = std::min(batch, n_rows - r0);
+        double *dst = out + r0 * n_cols;
+        for (int t = 0; t < nthr; t++) {
+            const int64_t a = nr * t / nthr, e = nr * (t + 1) / nthr;
+            if (a < e) workers.emplace_back(expand_rows, dst, n_cols, a, e, b.h_start, b.h_nnz, b.h_cols, b.h_vals);
+        }
+    };
+    auto join_all = [&]() { for (auto &w : workers) w.join(); workers.clear(); };
+    struct Joiner { decltype(join_all) &j; ~Joiner() { j(); } } joiner{join_all};   // no detached threads on an exception
+    launch(0);
+    for (int64_t k = 0; k < n_batches; k++) {
+        scasa_ctx::FetchBuf &b = c->fb[k & 1];
+        CK(cudaEventSynchronize(b.done));
+        const int64_t r0 = k * batch, nr = std::min(batch, n_rows - r0);
+        bool overflow = false;
+        for (int64_t r = 0; r < nr; r++) if (b.h_nnz[r] < 0) { overflow = true; break; }
+        join_all();                                   // batch k-1 (it reads the other buffer, which launch(k+1) reuses)
+        if (overflow) {                               // denser than the staging buffer: plain copy of this batch
+            CK(cudaMemcpyAsync(out + r0 * n_cols, d_mat + r0 * n_cols, (size_t)(nr * n_cols) * sizeof(double), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+        } else expand_async(k);
+        if (k + 1 < n_batches) launch(k + 1);
+    }
+    join_all();
 }
 
 }  // namespace
@@ -353,6 +483,7 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
             std::stable_sort(c->em_order.begin(), c->em_order.end(),
                              [&](int32_t x, int32_t y) { return cost[(size_t)x] > cost[(size_t)y]; });
         }
+        if (getenv("SCASA_FETCH_DENSE")) c->fetch_dense_copy = 1;
         // EM work classes; SCASA_EM_CFG="warps:pairs:bytes:cta_threads:ctas_per_sm,..." overrides (tuning)
         if (const char *env = getenv("SCASA_EM_CFG")) {
             int k = 0;
@@ -426,6 +557,11 @@ void scasa_ctx_destroy(scasa_ctx *c)
     for (auto b : f64) b->release();
     c->d_poor.release(); c->d_next.release(); c->d_stats.release(); c->d_flag.release();
     c->d_tdata.release(); c->d_counters.release();
+    for (auto &b : c->fb) {
+        b.d_cols.release(); b.d_nnz.release(); b.d_vals.release(); b.d_start.release(); b.d_cursor.release();
+        if (b.h_cols) { cudaFreeHost(b.h_cols); cudaFreeHost(b.h_vals); cudaFreeHost(b.h_start); cudaFreeHost(b.h_nnz); cudaFreeHost(b.h_cursor); }
+        if (b.done) cudaEventDestroy(b.done);
+    }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (int k = 0; k < kClasses; k++) {
         if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
@@ -755,7 +891,9 @@ static int fetch(scasa_ctx *c, void *dst, const void *src, size_t bytes)
 
 int scasa_fetch_iso(scasa_ctx *c, double *out)
 {
-    return fetch(c, out, c ? c->d_iso.p : nullptr, c ? (size_t)(c->n_cells * c->n_cols) * sizeof(double) : 0);
+    if (!c || !out) return fail(c, SCASA_ERR_ARG, "null argument");
+    if (!c->ran) return fail(c, SCASA_ERR_STATE, "scasa_run has not completed");
+    return guarded(c, [&] { fetch_dense(c, c->d_iso.p, c->n_cells, c->n_cols, out); });
 }
 int scasa_fetch_iters(scasa_ctx *c, int32_t *out)
 {
@@ -767,8 +905,17 @@ int scasa_fetch_colsum(scasa_ctx *c, double *out)
 }
 int scasa_fetch_gene(scasa_ctx *c, double *out)
 {
-    if (c && c->n_genes <= 0) return fail(c, SCASA_ERR_STATE, "no gene map set");
-    return fetch(c, out, c ? c->d_gene.p : nullptr, c ? (size_t)c->n_cells * c->n_genes * sizeof(double) : 0);
+    if (!c || !out) return fail(c, SCASA_ERR_ARG, "null argument");
+    if (!c->ran) return fail(c, SCASA_ERR_STATE, "scasa_run has not completed");
+    if (c->n_genes <= 0) return fail(c, SCASA_ERR_STATE, "no gene map set");
+    return guarded(c, [&] { fetch_dense(c, c->d_gene.p, c->n_cells, c->n_genes, out); });
+}
+
+int scasa_set_host_threads(scasa_ctx *c, int32_t n_threads)
+{
+    if (!c || n_threads < -1) return fail(c, SCASA_ERR_ARG, "bad argument");
+    c->host_threads = n_threads;
+    return SCASA_OK;
 }
 
 int scasa_fetch_counts(scasa_ctx *c, int64_t *rowptr, int32_t *rowidx, double *val, int64_t cap, int64_t *nnz_out)

@@ -601,19 +601,106 @@ __global__ void __launch_bounds__(1024) gene_smem_kernel(const double *__restric
         __syncthreads();
     }
 }
-// any number of genes: one thread per gene row, members read straight from the isoform row
-__global__ void gene_direct_kernel(const double *__restrict__ iso, int64_t n_cells, int64_t n_cols,
-                                   const int32_t *__restrict__ gene_ptr, const int32_t *__restrict__ gene_cols,
-                                   int n_genes, double *__restrict__ gene)
+// scasa_genemat as a gather: one thread per (cell, gene), members read straight from the isoform row in
+// column order (step3:27).  Every isoform value is read exactly once, so HBM traffic is the two
+// matrices; the row being gathered sits in L2 (a few hundred KB per CTA row).  kGeneIlp genes per
+// thread keep that many gathers in flight.
+constexpr int kGeneThreads = 256;
+constexpr int kGeneIlp = 4;
+__global__ void __launch_bounds__(kGeneThreads) gene_gather_kernel(const double *__restrict__ iso, int64_t n_cells,
+                                                                   int64_t n_cols, const int32_t *__restrict__ gene_ptr,
+                                                                   const int32_t *__restrict__ gene_cols, int n_genes,
+                                                                   int tiles_per_cell, double *__restrict__ gene)
 {
-    for (int64_t c = blockIdx.x; c < n_cells; c += gridDim.x) {
-        const double *row = iso + c * n_cols;
-        double *out = gene + c * (int64_t)n_genes;
-        for (int g = threadIdx.x; g < n_genes; g += blockDim.x) {
-            double sum = 0;
-            for (int m = gene_ptr[g]; m < gene_ptr[g + 1]; m++) sum += row[gene_cols[m]];
-            out[g] = sum;
+    const int64_t c = blockIdx.x / tiles_per_cell;
+    const int tile = blockIdx.x - (int)(c * tiles_per_cell);
+    const double *row = iso + c * n_cols;
+    double *out = gene + c * (int64_t)n_genes;
+    const int g0 = tile * (kGeneThreads * kGeneIlp) + threadIdx.x;
+    int lo[kGeneIlp], hi[kGeneIlp];
+    double sum[kGeneIlp];
+#pragma unroll
+    for (int u = 0; u < kGeneIlp; u++) {
+        const int g = g0 + u * kGeneThreads;
+        lo[u] = g < n_genes ? gene_ptr[g] : 0;
+        hi[u] = g < n_genes ? gene_ptr[g + 1] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < kGeneIlp; u++) sum[u] = lo[u] < hi[u] ? row[gene_cols[lo[u]]] : 0.0;   // the copies (step3:39)
+#pragma unroll
+    for (int u = 0; u < kGeneIlp; u++)
+        for (int m = lo[u] + 1; m < hi[u]; m++) sum[u] += row[gene_cols[m]];                    // parasum (step3:24-30)
+#pragma unroll
+    for (int u = 0; u < kGeneIlp; u++) {
+        const int g = g0 + u * kGeneThreads;
+        if (g < n_genes) out[g] = sum[u];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Zero suppression for the trip to the host.  The reference's results are dense matrices that are
+// > 90 % zeros; the fetch entry points send (column, value) pairs instead of the dense rows and the
+// host re-expands them with streaming stores (scasa_cuda.cu: fetch_dense).  One CTA per row:
+// pass A counts the row's non-zeros and reserves its slice with one atomic, pass B (the row is in L2
+// by then) writes the pairs in ascending column order.  "Non-zero" is the bit pattern, so -0.0 and
+// NaN survive the round trip: the expanded matrix is bit-identical to the dense one.
+constexpr int kCompThreads = 512;
+constexpr int kCompPer = 8;
+__global__ void __launch_bounds__(kCompThreads) compact_rows_kernel(const double *__restrict__ dense, int64_t n_rows,
+                                                                    int64_t n_cols, unsigned long long *cursor,
+                                                                    unsigned long long cap, int64_t *__restrict__ row_start,
+                                                                    int32_t *__restrict__ row_nnz, int32_t *__restrict__ cols,
+                                                                    double *__restrict__ vals)
+{
+    __shared__ int wsum[kCompThreads / 32];
+    __shared__ unsigned long long s_base;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    constexpr int kTile = kCompThreads * kCompPer;
+    for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        const double *r = dense + row * n_cols;
+        // pass A
+        int cnt = 0;
+        for (int64_t j = tid; j < n_cols; j += kCompThreads) cnt += __double_as_longlong(r[j]) != 0;
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(kFull, cnt, o);
+        if (lane == 0) wsum[w] = cnt;
+        __syncthreads();
+        if (tid == 0) {
+            int total = 0;
+            for (int k = 0; k < kCompThreads / 32; k++) total += wsum[k];
+            unsigned long long base = atomicAdd(cursor, (unsigned long long)total);
+            if (base + (unsigned long long)total > cap) { base = ~0ull; total = -1; }   // does not fit: the host copies this batch densely
+            row_start[row] = (int64_t)base;
+            row_nnz[row] = total;
+            s_base = base;
         }
+        __syncthreads();
+        const unsigned long long base = s_base;
+        if (base == ~0ull) continue;
+        // pass B: thread owns kCompPer consecutive columns of each tile
+        unsigned long long running = base;
+        for (int64_t j0 = 0; j0 < n_cols; j0 += kTile) {
+            const int64_t jb = j0 + (int64_t)tid * kCompPer;
+            double v[kCompPer];
+            int c = 0;
+#pragma unroll
+            for (int u = 0; u < kCompPer; u++) {
+                v[u] = jb + u < n_cols ? r[jb + u] : 0.0;
+                c += __double_as_longlong(v[u]) != 0;
+            }
+            int inc = c;
+            for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += x; }
+            __syncthreads();                       // wsum of the previous tile / pass A has been read
+            if (lane == 31) wsum[w] = inc;
+            __syncthreads();
+            int before = 0, total = 0;
+            for (int k = 0; k < kCompThreads / 32; k++) { const int x = wsum[k]; if (k < w) before += x; total += x; }
+            unsigned long long pos = running + before + inc - c;
+#pragma unroll
+            for (int u = 0; u < kCompPer; u++)
+                if (__double_as_longlong(v[u]) != 0) { cols[pos] = (int32_t)(jb + u); vals[pos] = v[u]; pos++; }
+            running += total;
+        }
+        __syncthreads();
     }
 }
 

@@ -135,3 +135,28 @@ def test_hand_built_blocks_and_tie_break(oracle):
     finally:
         g.close()
     assert list(got) == [2, 1]            # pattern 001 -> row 101 by the median tie-break; 011 is an exact match
+
+
+def test_zero_suppressed_fetch_is_bit_identical(xm):
+    """scasa_fetch_iso / scasa_fetch_gene send (column, value) pairs and re-expand them on the host
+    (several batches, ragged last batch); the result must equal the plain dense copy bit for bit."""
+    from scasa_b200 import synth
+    from scasa_b200.api import Scasa, chunk_split
+    n = 3100                                     # > 2 batches of ~1435 rows
+    rowptr, rows, vals = synth.CellGenerator(xm, seed=5).counts_csr(0, n)
+    g = Scasa(xm, device=0, with_crp=False, fixed_iter=1, maxiter_x=2, maxiter_bt=2)
+    n_genes = len(xm.gene_names)
+    g.set_gene_map(np.asarray(xm.gene_of_col, np.int32), n_genes)
+    g.stage_counts(chunk_split(n, 4), rowptr, rows, vals)
+    g.run()
+    g.set_host_threads(-1)
+    iso_d, gene_d = g.fetch_iso(), g.fetch_gene()
+    for thr in (0, 3):
+        g.set_host_threads(thr)
+        iso_s = np.full((n, g.n_cols), 7.0)
+        gene_s = np.full((n, n_genes), 7.0)
+        g.fetch_iso(iso_s)
+        g.fetch_gene(gene_s)
+        assert np.array_equal(iso_s.view(np.int64), iso_d.view(np.int64))
+        assert np.array_equal(gene_s.view(np.int64), gene_d.view(np.int64))
+    g.close()
