@@ -244,15 +244,22 @@ def main():
         h_iso = _l.pinned_empty((ne, xm.n_cols), np.float64)
         h_gene = _l.pinned_empty((ne, n_genes), np.float64)
 
+        parts = {"eqclass_map_s": 0.0, "stage_h2d_s": 0.0, "run_s": 0.0, "fetch_iso_s": 0.0, "fetch_gene_s": 0.0}
+
         def e2e_step():
-            row = g.eqclass_map(ed.eq_off, ed.eq_tx, nthreads)
-            g.stage_eqcounts(chunks_e, h_ptr, h_id, h_cnt, row)
-            g.run()
-            g.fetch_iso(h_iso)
-            g.fetch_gene(h_gene)
+            t = [time.perf_counter()]
+            row = g.eqclass_map(ed.eq_off, ed.eq_tx, nthreads); t.append(time.perf_counter())
+            g.stage_eqcounts(chunks_e, h_ptr, h_id, h_cnt, row); t.append(time.perf_counter())
+            g.run(); t.append(time.perf_counter())
+            g.fetch_iso(h_iso); t.append(time.perf_counter())
+            g.fetch_gene(h_gene); t.append(time.perf_counter())
+            for k, name in enumerate(parts):
+                parts[name] += t[k + 1] - t[k]
             return float(h_iso[0].sum() + h_gene[-1].sum())
 
         e2e_step()
+        for name in parts:
+            parts[name] = 0.0
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
@@ -266,7 +273,9 @@ def main():
         e2e = {"value": ne * world / te, "unit": "cells/s", "cells_per_gpu": ne, "s_per_step": te,
                "h2d_bytes_per_step": int(h_ptr.nbytes + h_id.nbytes + h_cnt.nbytes + eq_row.nbytes),
                "d2h_bytes_per_step": int(h_iso.nbytes + h_gene.nbytes),
-               "includes": "host eqclass->row map, H2D counts, pack+EM+gene kernels, D2H isoform+gene matrices"}
+               "includes": "host eqclass->row map, H2D counts, pack+EM+gene kernels, D2H isoform+gene matrices "
+                           "(zero-suppressed on the wire, dense in the caller's pinned buffers)",
+               "parts_s_per_step": {k: v / args.e2e_steps for k, v in parts.items()}, "host_threads": os.cpu_count()}
         for a in (h_ptr, h_id, h_cnt, h_iso, h_gene):
             _l.pinned_free(a)
 

@@ -119,6 +119,10 @@ int scasa_run(scasa_ctx *ctx);   /* pack -> EM -> (gene sums); everything on the
  * bit-identical to a plain copy.  scasa_set_host_threads: threads of that expansion, 0 = all cores,
  * -1 = plain dense copy instead. */
 int scasa_set_host_threads(scasa_ctx *ctx, int32_t n_threads);
+/* The host half of that, usable on its own (no GPU, no context): rows of (column, value) pairs,
+ * columns strictly ascending inside a row, -> dense n_rows x n_cols matrix; every element written. */
+int scasa_expand_pairs(double *out, int64_t n_rows, int64_t n_cols, const int64_t *row_start, const int32_t *row_nnz,
+                       const int32_t *cols, const double *vals, int32_t n_threads);
 int scasa_fetch_iso(scasa_ctx *ctx, double *iso_out);            /* n_cells x n_cols           */
 int scasa_fetch_iters(scasa_ctx *ctx, int32_t *iters_out);       /* [n_chunks][n_em_blocks][2] */
 int scasa_fetch_colsum(scasa_ctx *ctx, double *colsum /* [n_cols] */); /* rowSums of step2:167 */

@@ -5,6 +5,10 @@
 #include "scasa_host.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -13,7 +17,6 @@
 #include <string>
 #include <thread>
 #include <vector>
-#include <emmintrin.h>
 
 using namespace scasa;
 
@@ -275,36 +278,73 @@ template <int W> void launch_em(const EmArgs &A, unsigned grid, int threads, siz
     em_task_kernel<W><<<grid, threads, smem, s>>>(A);
 }
 
-// ---- host side of the zero-suppressed fetch --------------------------------------------------
-// n doubles of zeros with non-temporal stores (the destination is written once and not read here)
-inline void stream_zero(double *p, int64_t n)
-{
-    while (n > 0 && ((uintptr_t)p & 15)) { _mm_stream_si64((long long *)p, 0); p++; n--; }
-    const __m128d z = _mm_setzero_pd();
-    for (; n >= 2; n -= 2, p += 2) _mm_stream_pd(p, z);
-    if (n) _mm_stream_si64((long long *)p, 0);
-}
-// rows [r0, r1) of a batch: pairs are in ascending column order inside a row
-void expand_rows(double *out, int64_t n_cols, int64_t r0, int64_t r1, const int64_t *start, const int32_t *nnz,
-                 const int32_t *cols, const double *vals)
-{
-    for (int64_t r = r0; r < r1; r++) {
-        double *o = out + r * n_cols;
-        const int32_t *c = cols + start[r];
-        const double *v = vals + start[r];
-        int64_t at = 0;
-        for (int32_t k = 0; k < nnz[r]; k++) {
-            const int64_t j = c[k];
-            stream_zero(o + at, j - at);
-            long long bits;
-            memcpy(&bits, v + k, 8);
-            _mm_stream_si64((long long *)(o + j), bits);
-            at = j + 1;
-        }
-        stream_zero(o + at, n_cols - at);
+// ---- host side of the zero-suppressed fetch: expand_rows() is in scasa_host.cpp -------------------
+// Worker threads of the expansion.  Jobs (batches) are posted one after the other; every worker
+// visits every job in order and claims rows of it in chunks, so a batch is balanced across threads
+// whatever its rows look like.  At most two jobs are in flight (the two staging buffers).
+class ExpandPool {
+public:
+    explicit ExpandPool(int n_threads)
+    {
+        for (int t = 0; t < n_threads; t++) th_.emplace_back([this] { work(); });
     }
-    _mm_sfence();
-}
+    ~ExpandPool()
+    {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+        cv_work_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    void post(double *dst, int64_t n_cols, int64_t n_rows, const int64_t *start, const int32_t *nnz, const int32_t *cols,
+              const double *vals)
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        Job &j = job_[posted_ & 1];
+        j.dst = dst; j.n_cols = n_cols; j.n_rows = n_rows; j.start = start; j.nnz = nnz; j.cols = cols; j.vals = vals;
+        j.next.store(0); j.finished = 0;
+        posted_++;
+        cv_work_.notify_all();
+    }
+    void wait_all()       // every posted job is complete
+    {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_done_.wait(lk, [&] { return completed_ == posted_; });
+    }
+
+private:
+    struct Job {
+        double *dst; int64_t n_cols, n_rows; const int64_t *start; const int32_t *nnz; const int32_t *cols; const double *vals;
+        std::atomic<int64_t> next{0};
+        int64_t finished = 0;
+    } job_[2];
+    std::mutex m_;
+    std::condition_variable cv_work_, cv_done_;
+    int64_t posted_ = 0, completed_ = 0;
+    bool stop_ = false;
+    std::vector<std::thread> th_;
+    void work()
+    {
+        int64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(m_);
+            cv_work_.wait(lk, [&] { return stop_ || posted_ > seen; });
+            if (posted_ <= seen) return;
+            Job &j = job_[seen & 1];
+            seen++;
+            lk.unlock();
+            int64_t mine = 0;
+            for (;;) {
+                const int64_t r = j.next.fetch_add(8);
+                if (r >= j.n_rows) break;
+                const int64_t e = std::min(r + 8, j.n_rows);
+                scasa::expand_rows(j.dst, j.n_cols, r, e, j.start, j.nnz, j.cols, j.vals);
+                mine += e - r;
+            }
+            lk.lock();
+            j.finished += mine;
+            if (mine > 0 && j.finished == j.n_rows) { completed_++; cv_done_.notify_all(); }
+        }
+    }
+};
 
 void fetch_buf_ensure(scasa_ctx *c, scasa_ctx::FetchBuf &b, size_t rows, size_t cap)
 {
@@ -356,34 +396,49 @@ void fetch_dense(scasa_ctx *c, const double *d_mat, int64_t n_rows, int64_t n_co
         }
         CK(cudaEventRecord(b.done, s));
     };
-    // the expansion of batch k runs on worker threads while this thread drives the GPU for batch k+1
-    std::vector<std::thread> workers;
+    // the expansion of batch k runs on a pool of worker threads (rows claimed in small chunks) while
+    // this thread drives the GPU for batch k+1
+    ExpandPool pool(nthr);
     auto expand_async = [&](int64_t k) {
         scasa_ctx::FetchBuf &b = c->fb[k & 1];
         const int64_t r0 = k * batch, nr = std::min(batch, n_rows - r0);
-        double *dst = out + r0 * n_cols;
-        for (int t = 0; t < nthr; t++) {
-            const int64_t a = nr * t / nthr, e = nr * (t + 1) / nthr;
-            if (a < e) workers.emplace_back(expand_rows, dst, n_cols, a, e, b.h_start, b.h_nnz, b.h_cols, b.h_vals);
-        }
+        pool.post(out + r0 * n_cols, n_cols, nr, b.h_start, b.h_nnz, b.h_cols, b.h_vals);
     };
-    auto join_all = [&]() { for (auto &w : workers) w.join(); workers.clear(); };
-    struct Joiner { decltype(join_all) &j; ~Joiner() { j(); } } joiner{join_all};   // no detached threads on an exception
+    auto join_all = [&]() { pool.wait_all(); };
+    const bool trace = getenv("SCASA_FETCH_TRACE") != nullptr;
+    double t_wait_gpu = 0, t_join = 0, t_launch = 0;
+    unsigned long long pairs = 0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now();
     launch(0);
+    t_launch += now() - t0;
     for (int64_t k = 0; k < n_batches; k++) {
         scasa_ctx::FetchBuf &b = c->fb[k & 1];
+        t0 = now();
         CK(cudaEventSynchronize(b.done));
+        t_wait_gpu += now() - t0;
+        pairs += *b.h_cursor;
         const int64_t r0 = k * batch, nr = std::min(batch, n_rows - r0);
         bool overflow = false;
         for (int64_t r = 0; r < nr; r++) if (b.h_nnz[r] < 0) { overflow = true; break; }
+        t0 = now();
         join_all();                                   // batch k-1 (it reads the other buffer, which launch(k+1) reuses)
+        t_join += now() - t0;
         if (overflow) {                               // denser than the staging buffer: plain copy of this batch
             CK(cudaMemcpyAsync(out + r0 * n_cols, d_mat + r0 * n_cols, (size_t)(nr * n_cols) * sizeof(double), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
         } else expand_async(k);
+        t0 = now();
         if (k + 1 < n_batches) launch(k + 1);
+        t_launch += now() - t0;
     }
+    t0 = now();
     join_all();
+    t_join += now() - t0;
+    if (trace)
+        fprintf(stderr, "[scasa fetch] %lld x %lld, %lld batches of %lld rows, %llu pairs (%.1f per row): launch+compact %.3f s, "
+                        "wait copy %.3f s, wait expansion %.3f s, %d threads\n", (long long)n_rows, (long long)n_cols,
+                (long long)n_batches, (long long)batch, pairs, (double)pairs / (double)n_rows, t_launch, t_wait_gpu, t_join, nthr);
 }
 
 }  // namespace
@@ -909,6 +964,33 @@ int scasa_fetch_gene(scasa_ctx *c, double *out)
     if (!c->ran) return fail(c, SCASA_ERR_STATE, "scasa_run has not completed");
     if (c->n_genes <= 0) return fail(c, SCASA_ERR_STATE, "no gene map set");
     return guarded(c, [&] { fetch_dense(c, c->d_gene.p, c->n_cells, c->n_genes, out); });
+}
+
+int scasa_expand_pairs(double *out, int64_t n_rows, int64_t n_cols, const int64_t *row_start, const int32_t *row_nnz,
+                       const int32_t *cols, const double *vals, int32_t n_threads)
+{
+    if (!out || n_rows < 0 || n_cols <= 0 || !row_start || !row_nnz || (!cols && n_rows > 0) || (!vals && n_rows > 0))
+        return fail(nullptr, SCASA_ERR_ARG, "bad argument");
+    for (int64_t r = 0; r < n_rows; r++) {
+        if (row_nnz[r] < 0 || row_nnz[r] > n_cols || row_start[r] < 0) return fail(nullptr, SCASA_ERR_ARG, "bad row extent");
+        const int32_t *c = cols + row_start[r];
+        for (int32_t k = 0; k < row_nnz[r]; k++)
+            if (c[k] < 0 || c[k] >= n_cols || (k > 0 && c[k] <= c[k - 1]))
+                return fail(nullptr, SCASA_ERR_ARG, "columns must be strictly ascending inside a row and < n_cols");
+    }
+    int nthr = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nthr = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(nthr, 256), n_rows));
+    try {
+        std::vector<std::thread> workers;
+        for (int t = 0; t < nthr; t++) {
+            const int64_t a = n_rows * t / nthr, e = n_rows * (t + 1) / nthr;
+            if (a < e) workers.emplace_back(scasa::expand_rows, out, n_cols, a, e, row_start, row_nnz, cols, vals);
+        }
+        for (auto &w : workers) w.join();
+    } catch (const std::exception &e) {
+        return fail(nullptr, SCASA_ERR_NOMEM, e.what());
+    }
+    return SCASA_OK;
 }
 
 int scasa_set_host_threads(scasa_ctx *c, int32_t n_threads)

@@ -10,6 +10,8 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <immintrin.h>
+#include <cstdint>
 
 namespace scasa {
 
@@ -259,4 +261,88 @@ void CrpIndex::map(int64_t n_eq, const int64_t *eq_off, const int32_t *eq_tx, in
     for (auto &t : th) t.join();
 }
 
+// ------------------------------------------------------------------------------------------
+// Expansion of zero-suppressed result rows (see fetch_dense in scasa_cuda.cu).  The destination is
+// written once and not read here, so all stores are non-temporal; the row is produced in aligned
+// blocks: an empty block is one store of zeros, a block with values is assembled on the stack.
+namespace {
+
+inline void put1(double *p, double x)
+{
+    long long bits;
+    memcpy(&bits, &x, 8);
+    _mm_stream_si64((long long *)p, bits);
+}
+
+void expand_row_sse2(double *o, int64_t n_cols, const int32_t *c, const double *v, int nnz)
+{
+    int64_t at = 0;
+    int k = 0;
+    if (n_cols > 0 && ((uintptr_t)o & 15)) { double x = 0; if (k < nnz && c[k] == 0) x = v[k++]; put1(o, x); at = 1; }
+    const __m128d z = _mm_setzero_pd();
+    int64_t next = k < nnz ? c[k] : INT64_MAX;
+    for (; at + 2 <= n_cols; at += 2) {
+        if (next >= at + 2) { _mm_stream_pd(o + at, z); continue; }
+        alignas(16) double t[2] = {0, 0};
+        do { t[next - at] = v[k]; k++; next = k < nnz ? c[k] : INT64_MAX; } while (next < at + 2);
+        _mm_stream_pd(o + at, _mm_load_pd(t));
+    }
+    for (; at < n_cols; at++) { double x = 0; if (k < nnz && c[k] == at) x = v[k++]; put1(o + at, x); }
+}
+
+__attribute__((target("avx2"))) void expand_row_avx2(double *o, int64_t n_cols, const int32_t *c, const double *v, int nnz)
+{
+    int64_t at = 0;
+    int k = 0;
+    while (at < n_cols && ((uintptr_t)(o + at) & 31)) { double x = 0; if (k < nnz && c[k] == at) x = v[k++]; put1(o + at, x); at++; }
+    const __m256d z = _mm256_setzero_pd();
+    int64_t next = k < nnz ? c[k] : INT64_MAX;
+    for (; at + 4 <= n_cols; at += 4) {
+        if (next >= at + 4) { _mm256_stream_pd(o + at, z); continue; }
+        alignas(32) double t[4] = {0, 0, 0, 0};
+        do { t[next - at] = v[k]; k++; next = k < nnz ? c[k] : INT64_MAX; } while (next < at + 4);
+        _mm256_stream_pd(o + at, _mm256_load_pd(t));
+    }
+    for (; at < n_cols; at++) { double x = 0; if (k < nnz && c[k] == at) x = v[k++]; put1(o + at, x); }
+}
+
+__attribute__((target("avx512f"))) void expand_row_avx512(double *o, int64_t n_cols, const int32_t *c, const double *v, int nnz)
+{
+    int64_t at = 0;
+    int k = 0;
+    while (at < n_cols && ((uintptr_t)(o + at) & 63)) { double x = 0; if (k < nnz && c[k] == at) x = v[k++]; put1(o + at, x); at++; }
+    const __m512d z = _mm512_setzero_pd();
+    int64_t next = k < nnz ? c[k] : INT64_MAX;
+    for (; at + 8 <= n_cols; at += 8) {
+        if (next >= at + 8) { _mm512_stream_pd(o + at, z); continue; }
+        alignas(64) double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        do { t[next - at] = v[k]; k++; next = k < nnz ? c[k] : INT64_MAX; } while (next < at + 8);
+        _mm512_stream_pd(o + at, _mm512_load_pd(t));
+    }
+    for (; at < n_cols; at++) { double x = 0; if (k < nnz && c[k] == at) x = v[k++]; put1(o + at, x); }
+}
+
+using ExpandRow = void (*)(double *, int64_t, const int32_t *, const double *, int);
+ExpandRow pick_expand()
+{
+    if (const char *env = getenv("SCASA_EXPAND")) {          // testing: force a code path
+        if (!strcmp(env, "sse2")) return expand_row_sse2;
+        if (!strcmp(env, "avx2") && __builtin_cpu_supports("avx2")) return expand_row_avx2;
+    }
+    if (__builtin_cpu_supports("avx512f")) return expand_row_avx512;
+    if (__builtin_cpu_supports("avx2")) return expand_row_avx2;
+    return expand_row_sse2;
+}
+
+}  // namespace
+
+void expand_rows(double *out, int64_t n_cols, int64_t r0, int64_t r1, const int64_t *start, const int32_t *nnz,
+                 const int32_t *cols, const double *vals)
+{
+    static const ExpandRow fn = pick_expand();
+    for (int64_t r = r0; r < r1; r++) fn(out + r * n_cols, n_cols, cols + start[r], vals + start[r], nnz[r]);
+    _mm_sfence();
+}
+
 }  // namespace scasa
+

@@ -38,4 +38,10 @@ private:
 // each element is read back as, and whether its text is exactly "0" (see SURVEY.md §9 Q1).
 void r_format_roundtrip(const double *v, int n, double *back, uint8_t *is_zero_text);
 
+// Rows [r0, r1) of a zero-suppressed batch -> dense rows of `out` (row stride n_cols).  Pairs are in
+// ascending column order inside a row; every element of the rows is written exactly once with
+// non-temporal stores (64-byte blocks with AVX-512, 32-byte with AVX2, else SSE2; chosen at run time).
+void expand_rows(double *out, int64_t n_cols, int64_t r0, int64_t r1, const int64_t *start, const int32_t *nnz,
+                 const int32_t *cols, const double *vals);
+
 }  // namespace scasa

@@ -61,7 +61,7 @@ SYMBOLS = (
     "scasa_chunk_split", "scasa_estimate", "scasa_stage_counts", "scasa_stage_eqcounts", "scasa_run",
     "scasa_fetch_iso", "scasa_fetch_iters", "scasa_fetch_colsum", "scasa_fetch_counts", "scasa_set_gene_map",
     "scasa_fetch_gene", "scasa_gene_sum", "scasa_eqclass_map", "scasa_last_timing", "scasa_host_alloc",
-    "scasa_host_free", "scasa_device_count", "scasa_version", "scasa_set_host_threads",
+    "scasa_host_free", "scasa_device_count", "scasa_version", "scasa_set_host_threads", "scasa_expand_pairs",
 )
 
 
@@ -113,6 +113,7 @@ def load():
     L.scasa_eqclass_map.argtypes = [vp, C.c_int64, i64p, i32p, i32p, C.c_int32]
     L.scasa_last_timing.argtypes = [vp, C.POINTER(Timing)]
     L.scasa_set_host_threads.argtypes = [vp, C.c_int32]
+    L.scasa_expand_pairs.argtypes = [f64p, C.c_int64, C.c_int64, i64p, i32p, i32p, f64p, C.c_int32]
     L.scasa_host_alloc.restype = vp
     L.scasa_host_alloc.argtypes = [C.c_int64]
     L.scasa_host_free.argtypes = [vp]

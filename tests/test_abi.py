@@ -74,3 +74,41 @@ def test_shard_chunks_partitions_contiguously():
     cell_ptr = np.arange(3956) * 7
     c0, c1, loc, e0, e1 = local_problem(chunks, cell_ptr, shard_chunks(chunks, 4)[2])
     assert loc[0] == 0 and loc[-1] == c1 - c0 and (e0, e1) == (c0 * 7, c1 * 7)
+
+
+def _expand_case(seed, n_rows, n_cols, offset):
+    import ctypes as C
+    from scasa_b200 import lib as _l
+    L = _l.load()
+    rng = np.random.default_rng(seed)
+    dense = rng.normal(size=(n_rows, n_cols)) * (rng.random((n_rows, n_cols)) < 0.08)
+    dense[0] = 0                                   # an empty row
+    dense[1] = rng.normal(size=n_cols)             # a full row
+    dense[2, 0] = -0.0
+    dense[3, -1] = np.nan
+    mask = dense.view(np.int64) != 0               # bit pattern, like the device kernel
+    nnz = mask.sum(1).astype(np.int32)
+    start = np.concatenate([[0], np.cumsum(nnz)[:-1]]).astype(np.int64)
+    rows, cols = np.nonzero(mask)
+    vals = dense[rows, cols]
+    buf = np.full(n_rows * n_cols + offset + 8, 7.0)     # offset: 8-byte aligned but not 64-byte aligned rows
+    out = buf[offset:offset + n_rows * n_cols]
+    rc = L.scasa_expand_pairs(_l.ptr(out, C.c_double), n_rows, n_cols, _l.ptr(start, C.c_int64), _l.ptr(nnz, C.c_int32),
+                              _l.ptr(cols.astype(np.int32), C.c_int32), _l.ptr(np.ascontiguousarray(vals), C.c_double), 3)
+    assert rc == 0
+    assert np.array_equal(out.view(np.int64), dense.reshape(-1).view(np.int64))
+    assert buf[offset - 1] == 7.0 if offset else True
+    assert buf[offset + n_rows * n_cols] == 7.0        # nothing written past the end
+
+
+def test_expand_pairs_all_code_paths():
+    """Host half of the zero-suppressed fetch: bit-exact dense rows, ragged widths and alignments,
+    on the widest instruction set of this machine and on the forced AVX2 / SSE2 paths."""
+    import subprocess, sys
+    for n_cols, off in ((1, 0), (7, 1), (64, 0), (129, 3), (1000, 5)):
+        _expand_case(n_cols, 9, n_cols, off)
+    code = ("import sys; sys.path.insert(0, %r); from tests.test_abi import _expand_case\n"
+            "for n_cols, off in ((1, 0), (7, 1), (64, 0), (129, 3), (1000, 5)): _expand_case(n_cols, 9, n_cols, off)" % ROOT)
+    for path in ("sse2", "avx2"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SCASA_EXPAND=path), capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
