@@ -236,7 +236,6 @@ def main():
         while ne > 1000 and out_bytes(ne) > 0.5 * avail:
             ne //= 2
         ne = min(ne, n)
-        chunks_e = chunk_split(ne, 4)
         nnz_e = int(cell_ptr[ne])
         h_ptr = _l.pinned_empty(ne + 1, np.int64); h_ptr[:] = cell_ptr[: ne + 1]
         h_id = _l.pinned_empty(nnz_e, np.int32); h_id[:] = eq_id[:nnz_e]
@@ -244,22 +243,15 @@ def main():
         h_iso = _l.pinned_empty((ne, xm.n_cols), np.float64)
         h_gene = _l.pinned_empty((ne, n_genes), np.float64)
 
-        parts = {"eqclass_map_s": 0.0, "stage_h2d_s": 0.0, "run_s": 0.0, "fetch_iso_s": 0.0, "fetch_gene_s": 0.0}
+        g.set_host_threads(nthreads)
 
         def e2e_step():
-            t = [time.perf_counter()]
-            row = g.eqclass_map(ed.eq_off, ed.eq_tx, nthreads); t.append(time.perf_counter())
-            g.stage_eqcounts(chunks_e, h_ptr, h_id, h_cnt, row); t.append(time.perf_counter())
-            g.run(); t.append(time.perf_counter())
-            g.fetch_iso(h_iso); t.append(time.perf_counter())
-            g.fetch_gene(h_gene); t.append(time.perf_counter())
-            for k, name in enumerate(parts):
-                parts[name] += t[k + 1] - t[k]
-            return float(h_iso[0].sum() + h_gene[-1].sum())
+            # the call a user makes: host eqclass counts in, dense host matrices out
+            r = g.quant(h_ptr, h_id, h_cnt, ed.eq_off, ed.eq_tx, core=4, n_threads=nthreads, iso_out=h_iso,
+                        gene_out=h_gene, want_iters=False)
+            return float(r.iso[0].sum() + r.gene[-1].sum() + r.colsum[0])
 
         e2e_step()
-        for name in parts:
-            parts[name] = 0.0
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
@@ -275,7 +267,8 @@ def main():
                "d2h_bytes_per_step": int(h_iso.nbytes + h_gene.nbytes),
                "includes": "host eqclass->row map, H2D counts, pack+EM+gene kernels, D2H isoform+gene matrices "
                            "(zero-suppressed on the wire, dense in the caller's pinned buffers)",
-               "parts_s_per_step": {k: v / args.e2e_steps for k, v in parts.items()}, "host_threads": os.cpu_count()}
+               "api": "scasa_b200.api.Scasa.quant -> scasa_quant (chunks in slices, two contexts: transfer of one slice "
+                      "overlaps the computation of the next)", "host_threads": nthreads}
         for a in (h_ptr, h_id, h_cnt, h_iso, h_gene):
             _l.pinned_free(a)
 

@@ -105,6 +105,17 @@ int scasa_estimate(scasa_ctx *ctx, int64_t n_cells, int32_t n_chunks, const int6
                    const int64_t *y_rowptr, const int32_t *y_rowidx, const double *y_val,
                    double *iso_out, int32_t *iters_out);
 
+/* ---- the body of step2 (:88-136) + step3 (:48) for a whole sample in one call ---------------
+ * eqclass-level counts in (see scasa_stage_eqcounts), dense matrices out, all host buffers.
+ * The chunks are processed in n_slices slices (0 = automatic) that alternate between two
+ * contexts on the GPU, so the transfer and host-side expansion of one slice's results overlap
+ * the computation of the next; device memory is sized by the slice.  gene_out (needs
+ * scasa_set_gene_map), colsum_out and iters_out may be NULL. */
+int scasa_quant(scasa_ctx *ctx, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off,
+                const int64_t *cell_ptr, const int32_t *eq_id, const int32_t *eq_count, int64_t n_eq,
+                const int32_t *eq_row, double *iso_out, double *gene_out, double *colsum_out,
+                int32_t *iters_out, int32_t n_slices);
+
 /* ---- the same in resident stages (what scasa_estimate is made of) ----------------------- */
 int scasa_stage_counts(scasa_ctx *ctx, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off,
                        const int64_t *y_rowptr, const int32_t *y_rowidx, const double *y_val);

@@ -243,17 +243,31 @@ class Scasa:
         return out
 
     def quant(self, cell_ptr, eq_id, eq_count, eq_off, eq_tx, core: int = 4, gene_of_col=None, n_genes: int = 0,
-              n_threads: int = 8) -> QuantResult:
-        """step2's two foreach bodies (+ step3's gene sums) for a whole sample."""
+              n_threads: int = 8, n_slices: int = 0, iso_out=None, gene_out=None, want_iters: bool = True) -> QuantResult:
+        """step2's two foreach bodies (+ step3's gene sums) for a whole sample: one scasa_quant call
+        (host buffers in and out; chunks processed in slices that overlap compute and transfer)."""
+        cell_ptr = np.ascontiguousarray(cell_ptr, np.int64)
+        eq_id = np.ascontiguousarray(eq_id, np.int32)
+        eq_count = np.ascontiguousarray(eq_count, np.int32)
         n_cells = len(cell_ptr) - 1
         chunks = chunk_split(n_cells, core)
         eq_row = self.eqclass_map(eq_off, eq_tx, n_threads)
-        self.stage_eqcounts(chunks, cell_ptr, eq_id, eq_count, eq_row)
         if gene_of_col is not None:
             self.set_gene_map(gene_of_col, n_genes)
-        t = self.run()
-        return QuantResult(self.fetch_iso(), self.fetch_gene() if self.n_genes else None, self.fetch_colsum(),
-                           self.fetch_iters(), t)
+        self.n_cells, self.n_chunks = n_cells, len(chunks) - 1
+        iso = iso_out if iso_out is not None else np.empty((n_cells, self.n_cols), np.float64)
+        gene = None
+        if self.n_genes:
+            gene = gene_out if gene_out is not None else np.empty((n_cells, self.n_genes), np.float64)
+        colsum = np.empty(self.n_cols, np.float64)
+        iters = np.empty((self.n_chunks, self.n_em, 2), np.int32) if want_iters else None
+        self._ck(self._L.scasa_quant(self._ctx, n_cells, self.n_chunks, _l.ptr(chunks, C.c_int64), _l.ptr(cell_ptr, C.c_int64),
+                                     _l.ptr(eq_id, C.c_int32), _l.ptr(eq_count, C.c_int32), len(eq_row),
+                                     _l.ptr(eq_row, C.c_int32), _l.ptr(iso, C.c_double),
+                                     _l.ptr(gene, C.c_double) if gene is not None else None,
+                                     _l.ptr(colsum, C.c_double), _l.ptr(iters, C.c_int32) if iters is not None else None,
+                                     n_slices))
+        return QuantResult(iso, gene, colsum, iters, {"n_slices": n_slices})
 
 
 def dense_to_csr(y_dense: np.ndarray):

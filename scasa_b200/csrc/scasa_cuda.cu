@@ -116,6 +116,8 @@ struct scasa_ctx {
         size_t cap = 0, rows = 0;
         cudaEvent_t done = nullptr;
     } fb[2];
+    scasa_ctx *twin = nullptr;   // second context on the same device: scasa_quant overlaps its slices on the two
+    std::vector<int32_t> gene_of_col_host;
     int host_threads = 0;        // 0 = hardware concurrency
     int fetch_dense_copy = 0;    // 1 = plain dense D2H (SCASA_FETCH_DENSE)
     int n_genes = 0;
@@ -597,6 +599,7 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
 void scasa_ctx_destroy(scasa_ctx *c)
 {
     if (!c) return;
+    if (c->twin) { scasa_ctx_destroy(c->twin); c->twin = nullptr; }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DBuf<int32_t> *i32[] = {&c->d_q_off, &c->d_p_off, &c->d_row_block, &c->d_em_index, &c->d_em_blocks, &c->d_poor_em, &c->d_em_order,
@@ -735,7 +738,7 @@ int scasa_set_gene_map(scasa_ctx *c, const int32_t *gene_of_col, int32_t n_genes
 {
     if (!c) return fail(c, SCASA_ERR_ARG, "null context");
     return guarded(c, [&] {
-        if (!gene_of_col || n_genes <= 0) { c->n_genes = 0; return; }
+        if (!gene_of_col || n_genes <= 0) { c->n_genes = 0; c->gene_of_col_host.clear(); return; }
         std::vector<int32_t> ptr((size_t)n_genes + 1, 0), cols;
         for (int64_t j = 0; j < c->n_cols; j++) {
             int g = gene_of_col[j];
@@ -751,6 +754,7 @@ int scasa_set_gene_map(scasa_ctx *c, const int32_t *gene_of_col, int32_t n_genes
         }
         c->n_genes = n_genes;
         std::vector<int32_t> goc(gene_of_col, gene_of_col + c->n_cols);
+        c->gene_of_col_host = goc;
         // per column: >= 0 copy into that gene row; <= -2 first member of gene -(a+2): sum; -1 nothing
         std::vector<int32_t> action((size_t)c->n_cols, -1);
         for (int64_t j = 0; j < c->n_cols; j++) {
@@ -1041,6 +1045,85 @@ int scasa_estimate(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const int64_
     if (rc) return rc;
     if (iters_out) rc = scasa_fetch_iters(c, iters_out);
     return rc;
+}
+
+// One call for a whole sample, host buffers in and out: the chunks are cut into slices and the
+// slices alternate between this context and a twin on the same GPU, each driven by its own host
+// thread: while one slice's results are expanded into the caller's matrices (host-memory bound)
+// the next slice is staged and computed.  Chunks are independent, so slicing changes no result;
+// device memory is sized by the slice, not by the sample.
+int scasa_quant(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off, const int64_t *cell_ptr,
+                const int32_t *eq_id, const int32_t *eq_count, int64_t n_eq, const int32_t *eq_row, double *iso_out,
+                double *gene_out, double *colsum_out, int32_t *iters_out, int32_t n_slices)
+{
+    if (!c) return fail(c, SCASA_ERR_ARG, "null context");
+    if (n_cells <= 0 || n_chunks <= 0 || !chunk_off || !cell_ptr || !eq_id || !eq_count || !eq_row || !iso_out)
+        return fail(c, SCASA_ERR_ARG, "bad argument");
+    if (chunk_off[0] != 0 || chunk_off[n_chunks] != n_cells) return fail(c, SCASA_ERR_ARG, "chunk_off must cover [0, n_cells]");
+    if (gene_out && c->n_genes <= 0) return fail(c, SCASA_ERR_STATE, "no gene map set");
+    if (n_slices <= 0) n_slices = std::max(2, std::min(8, n_chunks / 128));   // measured: 4-8 slices of >= 100 chunks are best
+    n_slices = std::max(1, std::min(n_slices, n_chunks));
+    if (n_slices > 1 && !c->twin) {
+        scasa_xmat_t m;
+        m.n_blocks = c->B; m.q_off = c->q_off.data(); m.p_off = c->p_off.data(); m.x_off = c->x_off.data(); m.x = c->x.data();
+        int rc = scasa_ctx_create(&m, nullptr, &c->opts, c->device, &c->twin);
+        if (rc) return fail(c, rc, std::string("twin context: ") + scasa_last_error(nullptr));
+    }
+    scasa_ctx *ctxs[2] = {c, n_slices > 1 ? c->twin : c};
+    if (n_slices > 1) {
+        scasa_ctx *t = c->twin;
+        t->opts = c->opts; t->host_threads = c->host_threads; t->fetch_dense_copy = c->fetch_dense_copy;
+        for (int k = 0; k < kClasses; k++) {
+            t->cls_warps[k] = c->cls_warps[k]; t->cls_pairs[k] = c->cls_pairs[k]; t->cls_bytes[k] = c->cls_bytes[k];
+            t->cls_cta_threads[k] = c->cls_cta_threads[k]; t->cls_ctas_per_sm[k] = c->cls_ctas_per_sm[k];
+        }
+        if (c->n_genes > 0 && (t->n_genes != c->n_genes || t->gene_of_col_host != c->gene_of_col_host)) {
+            int rc = scasa_set_gene_map(t, c->gene_of_col_host.data(), c->n_genes);
+            if (rc) return fail(c, rc, std::string("twin context: ") + scasa_last_error(t));
+        } else if (c->n_genes <= 0) t->n_genes = 0;
+    }
+    std::vector<double> colsum_parts;
+    if (colsum_out) colsum_parts.assign((size_t)n_slices * c->n_cols, 0.0);
+    int rcs[2] = {SCASA_OK, SCASA_OK};
+    auto drive = [&](int which) {
+        scasa_ctx *x = ctxs[which];
+        std::vector<int64_t> ptr, coff;
+        for (int sl = which; sl < n_slices; sl += 2) {
+            const int h0 = (int)((int64_t)n_chunks * sl / n_slices), h1 = (int)((int64_t)n_chunks * (sl + 1) / n_slices);
+            if (h1 <= h0) continue;
+            const int64_t c0 = chunk_off[h0], c1 = chunk_off[h1];
+            coff.resize((size_t)(h1 - h0) + 1);
+            for (int h = h0; h <= h1; h++) coff[(size_t)(h - h0)] = chunk_off[h] - c0;
+            ptr.resize((size_t)(c1 - c0) + 1);
+            const int64_t e0 = cell_ptr[c0];
+            for (int64_t i = c0; i <= c1; i++) ptr[(size_t)(i - c0)] = cell_ptr[i] - e0;
+            int rc = scasa_stage_eqcounts(x, c1 - c0, h1 - h0, coff.data(), ptr.data(), eq_id + e0, eq_count + e0, n_eq, eq_row);
+            if (!rc) rc = scasa_run(x);
+            if (!rc) rc = scasa_fetch_iso(x, iso_out + c0 * c->n_cols);
+            if (!rc && gene_out) rc = scasa_fetch_gene(x, gene_out + c0 * (int64_t)c->n_genes);
+            if (!rc && colsum_out) rc = scasa_fetch_colsum(x, colsum_parts.data() + (size_t)sl * c->n_cols);
+            if (!rc && iters_out) rc = scasa_fetch_iters(x, iters_out + (int64_t)h0 * c->n_em * 2);
+            if (rc) { rcs[which] = rc; return; }
+        }
+    };
+    if (n_slices > 1) {
+        try {
+            std::thread other(drive, 1);
+            drive(0);
+            other.join();
+        } catch (const std::exception &e) {
+            return fail(c, SCASA_ERR_NOMEM, e.what());
+        }
+    } else drive(0);
+    if (rcs[0]) return rcs[0];
+    if (rcs[1]) return fail(c, rcs[1], std::string("twin context: ") + scasa_last_error(c->twin));
+    if (colsum_out)                                   // slices added in order: a fixed sequence for a given n_slices
+        for (int64_t j = 0; j < c->n_cols; j++) {
+            double acc = 0;
+            for (int sl = 0; sl < n_slices; sl++) acc += colsum_parts[(size_t)sl * c->n_cols + j];
+            colsum_out[j] = acc;
+        }
+    return SCASA_OK;
 }
 
 int scasa_gene_sum(scasa_ctx *c, const int32_t *gene_of_col, int32_t n_genes, const double *iso, int64_t n_cells,

@@ -101,7 +101,7 @@ def test_quant_from_eqclasses_equals_estimate_from_counts(gpu, xm, eqdata):
     from scasa_b200.api import chunk_split
     ed, cell_ptr, eq_id, eq_cnt = eqdata
     gpu.set_opts()
-    r = gpu.quant(cell_ptr, eq_id, eq_cnt, ed.eq_off, ed.eq_tx, core=4)
+    r = gpu.quant(cell_ptr, eq_id, eq_cnt, ed.eq_off, ed.eq_tx, core=4, n_slices=1)
     rowptr, idx, val = gpu.fetch_counts()
     iso2, it2 = gpu.estimate(chunk_split(200, 4), rowptr, idx, val)
     assert np.array_equal(r.iso, iso2)
@@ -160,3 +160,28 @@ def test_zero_suppressed_fetch_is_bit_identical(xm):
         assert np.array_equal(iso_s.view(np.int64), iso_d.view(np.int64))
         assert np.array_equal(gene_s.view(np.int64), gene_d.view(np.int64))
     g.close()
+
+
+def test_sliced_quant_is_bitwise_the_unsliced_one(xm):
+    """scasa_quant cuts the chunks into slices that alternate between two contexts (compute of one
+    overlaps the transfer of the other).  Chunks are independent: any slicing gives the same bits."""
+    from scasa_b200 import synth
+    from scasa_b200.api import Scasa
+    n = 730                                       # 7 chunks, ragged
+    rowptr, rows, vals = synth.CellGenerator(xm, seed=9).counts_csr(0, n)
+    ed = synth.eqclass_dictionary(xm, 9)
+    cell_ptr, eq_id, eq_cnt = synth.counts_to_eqcounts(rowptr, rows, vals, 9)
+    n_genes = len(xm.gene_names)
+    goc = np.asarray(xm.gene_of_col, np.int32)
+    g = Scasa(xm, device=0)
+    try:
+        ref = g.quant(cell_ptr, eq_id, eq_cnt, ed.eq_off, ed.eq_tx, gene_of_col=goc, n_genes=n_genes, n_slices=1)
+        for ns in (2, 3, 7, 0):
+            r = g.quant(cell_ptr, eq_id, eq_cnt, ed.eq_off, ed.eq_tx, gene_of_col=goc, n_genes=n_genes, n_slices=ns)
+            assert np.array_equal(r.iso.view(np.int64), ref.iso.view(np.int64)), ns
+            assert np.array_equal(r.gene.view(np.int64), ref.gene.view(np.int64)), ns
+            assert np.array_equal(r.iters, ref.iters), ns
+            assert np.allclose(r.colsum, ref.colsum, rtol=1e-12, atol=0)
+            assert np.array_equal(r.colsum > 0, ref.colsum > 0)
+    finally:
+        g.close()
