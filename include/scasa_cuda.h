@@ -120,7 +120,8 @@ int scasa_quant(scasa_ctx *ctx, int64_t n_cells, int32_t n_chunks, const int64_t
 int scasa_stage_counts(scasa_ctx *ctx, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off,
                        const int64_t *y_rowptr, const int32_t *y_rowidx, const double *y_val);
 /* eqclass-level counts (the crpcount_td input): per cell (eqclass id, UMI count) plus the
- * eqclass -> global row map from scasa_eqclass_map (row < 0: dropped). */
+ * eqclass -> global row map from scasa_eqclass_map (row < 0: dropped).  Counts <= 0 are ignored
+ * (alevin's count is the number of UMIs, >= 1). */
 int scasa_stage_eqcounts(scasa_ctx *ctx, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off,
                          const int64_t *cell_ptr, const int32_t *eq_id, const int32_t *eq_count,
                          int64_t n_eq, const int32_t *eq_row);

@@ -69,7 +69,9 @@ struct scasa_ctx {
     std::vector<double> x;
     std::vector<uint8_t> poor;
     int64_t poor_rows = 0;           // sum of q over poor blocks
-    DBuf<int32_t> d_q_off, d_p_off, d_row_block, d_em_index, d_em_blocks, d_poor_em, d_em_order;
+    DBuf<int32_t> d_q_off, d_p_off, d_row_block, d_em_index, d_em_blocks, d_poor_em, d_em_order, d_row_col;
+    DBuf<int2> d_row_info;
+    DBuf<uint32_t> d_scatter_scratch;
     DBuf<int64_t> d_x_off;
     DBuf<double> d_x;
     DBuf<uint8_t> d_poor;
@@ -86,12 +88,12 @@ struct scasa_ctx {
     int64_t max_cell_entries = 0;
 
     // ---- task arrays
-    DBuf<int32_t> d_cnt, d_runs, d_tbytes, d_iters, d_rec_cur, d_ent_cur, d_list[kClasses];
+    DBuf<int32_t> d_cnt, d_runs, d_tbytes, d_iters, d_list[kClasses];
     DBuf<int64_t> d_toff, d_scan_sums, d_totals;
     DBuf<char> d_tdata;
     DBuf<unsigned int> d_next, d_counters;
     cudaStream_t cls_stream[kClasses] = {};
-    cudaEvent_t ev_fork = nullptr, ev_join[kClasses] = {}, ev_cls[kClasses][2] = {};
+    cudaEvent_t ev_fork = nullptr, ev_fill = nullptr, ev_join[kClasses] = {}, ev_cls[kClasses][2] = {};
     // work classes of the EM kernel: warps per task, pairs and slot limits, resident CTAs per SM
     int cls_warps[kClasses] = {1, 2, 4, 8};
     int cls_pairs[kClasses] = {96, 256, 512, 1 << 30};
@@ -178,7 +180,7 @@ XDev xdev(scasa_ctx *c)
     X.q_off = c->d_q_off.p; X.p_off = c->d_p_off.p; X.x_off = c->d_x_off.p; X.x = c->d_x.p;
     X.row_block = c->d_row_block.p; X.em_index = c->d_em_index.p; X.em_blocks = c->d_em_blocks.p;
     X.poor = c->d_poor.p; X.poor_em = c->d_poor_em.p; X.n_poor = (int)c->poor_em.size();
-    X.em_order = c->d_em_order.p;
+    X.em_order = c->d_em_order.p; X.row_info = c->d_row_info.p; X.row_col = c->d_row_col.p;
     return X;
 }
 Sample sdev(scasa_ctx *c)
@@ -193,7 +195,7 @@ Tasks tdev(scasa_ctx *c)
 {
     Tasks T;
     T.cnt = c->d_cnt.p; T.runs = c->d_runs.p; T.tbytes = c->d_tbytes.p;
-    T.toff = c->d_toff.p; T.rec_cur = c->d_rec_cur.p; T.ent_cur = c->d_ent_cur.p;
+    T.toff = c->d_toff.p;
     T.tdata = c->d_tdata.p;
     for (int k = 0; k < kClasses; k++) T.list[k] = c->d_list[k].p;
     T.counters = c->d_counters.p;
@@ -565,6 +567,7 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
             CK(cudaEventCreate(&c->ev_cls[k][1]));
         }
         CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_fill, cudaEventDisableTiming));
 
         c->d_q_off.upload(c->q_off, c->stream);
         c->d_p_off.upload(c->p_off, c->stream);
@@ -578,6 +581,17 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
         c->d_poor_em.upload(c->poor_em, c->stream);
         c->d_em_order.ensure(c->em_order.size() + 1);
         c->d_em_order.upload(c->em_order, c->stream);
+        {
+            std::vector<int2> info((size_t)c->n_rows);
+            std::vector<int32_t> rcol((size_t)c->n_rows);
+            for (int k = 0; k < B; k++)
+                for (int r = c->q_off[k]; r < c->q_off[k + 1]; r++) {
+                    info[(size_t)r] = make_int2(c->em_index[k], r - c->q_off[k]);
+                    rcol[(size_t)r] = c->p_off[k];
+                }
+            c->d_row_info.upload(info, c->stream);
+            c->d_row_col.upload(rcol, c->stream);
+        }
         c->d_next.ensure(16); c->d_counters.ensure(8); c->d_stats.ensure(8); c->d_totals.ensure(4); c->d_flag.ensure(1);
         CK(cudaStreamSynchronize(c->stream));
 
@@ -604,7 +618,7 @@ void scasa_ctx_destroy(scasa_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     DBuf<int32_t> *i32[] = {&c->d_q_off, &c->d_p_off, &c->d_row_block, &c->d_em_index, &c->d_em_blocks, &c->d_poor_em, &c->d_em_order,
                             &c->d_cell_chunk, &c->d_y_len, &c->d_y_row, &c->d_eq_id, &c->d_eq_count, &c->d_eq_row,
-                            &c->d_cnt, &c->d_runs, &c->d_tbytes, &c->d_iters, &c->d_rec_cur, &c->d_ent_cur,
+                            &c->d_cnt, &c->d_runs, &c->d_tbytes, &c->d_iters, &c->d_row_col,
                             &c->d_list[0], &c->d_list[1], &c->d_list[2], &c->d_list[3],
                             &c->d_gene_of_col, &c->d_gene_ptr, &c->d_gene_cols};
     for (auto b : i32) b->release();
@@ -614,13 +628,14 @@ void scasa_ctx_destroy(scasa_ctx *c)
                            &c->d_colsum, &c->d_gene};
     for (auto b : f64) b->release();
     c->d_poor.release(); c->d_next.release(); c->d_stats.release(); c->d_flag.release();
-    c->d_tdata.release(); c->d_counters.release();
+    c->d_tdata.release(); c->d_counters.release(); c->d_row_info.release(); c->d_scatter_scratch.release();
     for (auto &b : c->fb) {
         b.d_cols.release(); b.d_nnz.release(); b.d_vals.release(); b.d_start.release(); b.d_cursor.release();
         if (b.h_cols) { cudaFreeHost(b.h_cols); cudaFreeHost(b.h_vals); cudaFreeHost(b.h_start); cudaFreeHost(b.h_nnz); cudaFreeHost(b.h_cursor); }
         if (b.done) cudaEventDestroy(b.done);
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_fill) cudaEventDestroy(c->ev_fill);
     for (int k = 0; k < kClasses; k++) {
         if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
         for (auto &e : c->ev_cls[k]) if (e) cudaEventDestroy(e);
@@ -784,16 +799,12 @@ int scasa_run(scasa_ctx *c)
         c->d_iso.ensure((size_t)iso_elems);
         c->d_cnt.ensure((size_t)n_tasks + 1); c->d_runs.ensure((size_t)n_tasks + 1);
         c->d_tbytes.ensure((size_t)n_tasks + 1); c->d_toff.ensure((size_t)n_tasks + 1);
-        c->d_rec_cur.ensure((size_t)n_tasks + 1); c->d_ent_cur.ensure((size_t)n_tasks + 1);
         for (int k = 0; k < kClasses; k++) c->d_list[k].ensure((size_t)n_tasks + 1);
         c->d_iters.ensure((size_t)n_tasks * 2 + 2);
 
         CK(cudaEventRecord(c->ev[0], s));
-        CK(cudaMemsetAsync(c->d_iso.p, 0, iso_elems * sizeof(double), s));
         CK(cudaMemsetAsync(c->d_cnt.p, 0, (n_tasks + 1) * sizeof(int32_t), s));
         CK(cudaMemsetAsync(c->d_runs.p, 0, (n_tasks + 1) * sizeof(int32_t), s));
-        CK(cudaMemsetAsync(c->d_rec_cur.p, 0, (n_tasks + 1) * sizeof(int32_t), s));
-        CK(cudaMemsetAsync(c->d_ent_cur.p, 0, (n_tasks + 1) * sizeof(int32_t), s));
         CK(cudaMemsetAsync(c->d_stats.p, 0, 8 * sizeof(unsigned long long), s));
         CK(cudaMemsetAsync(c->d_next.p, 0, 16 * sizeof(unsigned int), s));
         CK(cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(unsigned int), s));
@@ -801,14 +812,13 @@ int scasa_run(scasa_ctx *c)
 
         // ---- pack: eqclass counts -> Y
         if (c->have_eq) {
-            int seg = (int)((c->n_rows + 511) / 512);
-            seg |= 1;                                             // odd segment length: conflict-free strided reads
-            const size_t dense_smem = (size_t)seg * 512 * sizeof(int);
+            const int wpt = (int)((c->n_rows + 32 * 512 - 1) / (32 * 512));      // bitmap words per thread
+            const size_t dense_smem = (size_t)wpt * 512 * 33 * sizeof(int);       // int32 histogram + touched-row bitmap
             if (dense_smem <= 200 * 1024 && !getenv("SCASA_PACK_SORT")) {
                 CK(cudaFuncSetAttribute(pack_cells_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_smem));
                 int grid = (int)std::min<int64_t>(c->n_cells, (int64_t)c->n_sm);
                 pack_cells_dense_kernel<<<grid, 512, dense_smem, s>>>(c->n_cells, c->d_cell_ptr.p, c->d_eq_id.p, c->d_eq_count.p,
-                                                                      c->d_eq_row.p, c->n_eq, (int)c->n_rows, seg, c->d_y_row.p,
+                                                                      c->d_eq_row.p, c->n_eq, (int)c->n_rows, wpt, c->d_y_row.p,
                                                                       c->d_y_val.p, c->d_y_len.p);
             } else {
                 int cap = 32;
@@ -824,6 +834,19 @@ int scasa_run(scasa_ctx *c)
             launches++;
         }
         CK(cudaEventRecord(c->ev[1], s));
+
+        // ---- result rows: zeros + pass-through blocks, on a side stream next to the task build
+        {
+            cudaStream_t fs = c->cls_stream[0];
+            CK(cudaStreamWaitEvent(fs, c->ev[1], 0));
+            const size_t smem = (size_t)kFillTile * sizeof(double);
+            CK(cudaFuncSetAttribute(iso_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int grid = (int)std::min<int64_t>(c->n_cells, (int64_t)c->n_sm * 3);
+            iso_fill_kernel<<<grid, kFillThreads, smem, fs>>>(xdev(c), sdev(c), c->d_iso.p);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(c->ev_fill, fs));
+            launches++;
+        }
 
         // ---- task extents, work classes, blobs
         XDev X = xdev(c);
@@ -853,9 +876,18 @@ int scasa_run(scasa_ctx *c)
             T = tdev(c);
             c->timing.n_entries = tot[0];
         }
-        task_scatter_kernel<<<c->n_chunks, 256, 0, s>>>(X, S, T, c->d_iso.p);
-        CK(cudaGetLastError());
-        launches++;
+        if (c->n_em > 0) {
+            const size_t st_bytes = (size_t)3 * c->n_em * sizeof(uint32_t);
+            uint32_t *scratch = nullptr;
+            if (st_bytes > 160 * 1024) {           // too many EM blocks for shared memory: cursors in HBM
+                c->d_scatter_scratch.ensure((size_t)c->n_chunks * 3 * c->n_em);
+                scratch = c->d_scatter_scratch.p;
+            } else CK(cudaFuncSetAttribute(task_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_bytes));
+            task_scatter_kernel<<<c->n_chunks, kScatterThreads, scratch ? 0 : st_bytes, s>>>(X, S, T, scratch);
+            CK(cudaGetLastError());
+            launches++;
+        }
+        CK(cudaStreamWaitEvent(s, c->ev_fill, 0));
         CK(cudaEventRecord(c->ev[2], s));
 
         // ---- EM: one persistent kernel per work class, side by side on their own streams

@@ -83,6 +83,8 @@ struct XDev {                 // resident X-matrix (DM0) and its derived index m
     const uint8_t *poor;      // [n_blocks] poorCondX (Rsource:957-971)
     const int32_t *poor_em;   // [n_poor]  EM indices of the poor blocks
     const int32_t *em_order;  // [n_em]    EM indices, most expensive block shape first (work-queue order)
+    const int2 *row_info;     // [n_rows]  {EM index of the row's block or -1, row index inside the block}
+    const int32_t *row_col;   // [n_rows]  first DM0 column of the row's block
     int n_poor;
 };
 
@@ -133,7 +135,6 @@ struct Tasks {                // task t = chunk * n_em + em index
     int32_t *runs;            // [n_tasks] cells with counts; after classify: records n (incl. the pseudo cell)
     int32_t *tbytes;          // [n_tasks] blob bytes
     int64_t *toff;            // [n_tasks+1] exclusive scan of tbytes
-    int32_t *rec_cur, *ent_cur;   // [n_tasks] cursors of the scatter (zeroed)
     char *tdata;              // blobs
     int32_t *list[kClasses];  // task ids per work class, expensive block shapes first
     unsigned int *counters;   // [0..3] list lengths [4] non-empty tasks [5] largest slot need [7] error flag
@@ -149,13 +150,16 @@ __global__ void __launch_bounds__(512) pack_cells_dense_kernel(int64_t n_cells, 
                                                                const int32_t *__restrict__ eq_id,
                                                                const int32_t *__restrict__ eq_count,
                                                                const int32_t *__restrict__ eq_row, int64_t n_eq, int n_rows,
-                                                               int seg, int32_t *__restrict__ y_row,
+                                                               int words_per_thread, int32_t *__restrict__ y_row,
                                                                double *__restrict__ y_val, int32_t *__restrict__ y_len)
 {
-    extern __shared__ int hist[];
+    extern __shared__ int pack_sm[];
+    const int n_words = words_per_thread * (int)blockDim.x;       // >= ceil(n_rows / 32)
+    int *hist = pack_sm;                                          // [n_words * 32] counts by row
+    unsigned *bits = (unsigned *)(pack_sm + (size_t)n_words * 32);   // [n_words] rows touched by this cell
     __shared__ int wsum[16];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    for (int i = tid; i < seg * (int)blockDim.x; i += blockDim.x) hist[i] = 0;
+    for (int i = tid; i < n_words * 33; i += blockDim.x) pack_sm[i] = 0;
     __syncthreads();
     for (int64_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
         const int64_t s = cell_ptr[cell];
@@ -164,13 +168,13 @@ __global__ void __launch_bounds__(512) pack_cells_dense_kernel(int64_t n_cells, 
             const int e = eq_id[s + i];
             const int r = (e >= 0 && e < n_eq) ? eq_row[e] : -1;
             const int c = eq_count[s + i];
-            if (r >= 0 && r < n_rows && c != 0) atomicAdd(&hist[r], c);
+            if (r >= 0 && r < n_rows && c > 0) { atomicAdd(&hist[r], c); atomicOr(&bits[r >> 5], 1u << (r & 31)); }   // UMI counts are >= 1
         }
         __syncthreads();
-        const int r0 = tid * seg;
+        // thread owns words [tid*wpt, (tid+1)*wpt): rows in ascending order across threads
+        const int w0 = tid * words_per_thread;
         int cnt = 0;
-        for (int k = 0; k < seg; k++) cnt += hist[r0 + k] != 0;
-        // block-wide exclusive scan of cnt
+        for (int k = 0; k < words_per_thread; k++) cnt += __popc(bits[w0 + k]);
         int inc = cnt;
         for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += v; }
         if (lane == 31) wsum[w] = inc;
@@ -179,9 +183,16 @@ __global__ void __launch_bounds__(512) pack_cells_dense_kernel(int64_t n_cells, 
         for (int k = 0; k < (int)(blockDim.x >> 5); k++) { int v = wsum[k]; if (k < w) base += v; total += v; }
         int o = base + inc - cnt;
         if (cnt)
-            for (int k = 0; k < seg; k++) {
-                const int v = hist[r0 + k];
-                if (v != 0) { y_row[s + o] = r0 + k; y_val[s + o] = (double)v; o++; hist[r0 + k] = 0; }
+            for (int k = 0; k < words_per_thread; k++) {
+                unsigned m = bits[w0 + k];
+                bits[w0 + k] = 0;
+                while (m) {
+                    const int r = ((w0 + k) << 5) + __ffs(m) - 1;
+                    m &= m - 1;
+                    const int v = hist[r];
+                    hist[r] = 0;
+                    y_row[s + o] = r; y_val[s + o] = (double)v; o++;
+                }
             }
         if (tid == 0) y_len[cell] = total;
         __syncthreads();
@@ -213,7 +224,7 @@ __global__ void pack_cells_kernel(int64_t n_cells, const int64_t *__restrict__ c
                 int e = eq_id[s + i];
                 int r = (e >= 0 && e < n_eq) ? eq_row[e] : -1;
                 int c = eq_count[s + i];
-                if (r >= 0 && c != 0) k = ((unsigned long long)(unsigned)r << 32) | (unsigned)c;
+                if (r >= 0 && c > 0) k = ((unsigned long long)(unsigned)r << 32) | (unsigned)c;   // UMI counts are >= 1
             }
             sm_keys[i] = k;
         }
@@ -278,11 +289,10 @@ __global__ void task_count_kernel(XDev X, Sample S, Tasks T)
     const int n = S.y_len[cell];
     const int64_t tbase = (int64_t)S.cell_chunk[cell] * X.n_em;
     for (int i = lane; i < n; i += kWarp) {
-        int b = X.row_block[S.y_row[s + i]];
-        int e = X.em_index[b];
+        const int e = X.row_info[S.y_row[s + i]].x;
         if (e < 0) continue;
         atomicAdd(&T.cnt[tbase + e], 1);
-        bool head = (i == 0) || (X.row_block[S.y_row[s + i - 1]] != b);
+        const bool head = (i == 0) || (X.row_info[S.y_row[s + i - 1]].x != e);
         if (head) atomicAdd(&T.runs[tbase + e], 1);
     }
 }
@@ -299,40 +309,63 @@ struct EmOpts {
 __global__ void classify_kernel(XDev X, Sample S, Tasks T, int64_t n_tasks, EmOpts O, ClassCfg C, int32_t *iters,
                                 unsigned long long *stats)
 {
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_tasks) return;
-    const int e = X.em_order[(int)(idx / S.n_chunks)], h = (int)(idx % S.n_chunks);
-    const int64_t t = (int64_t)h * X.n_em + e;
-    const int b = X.em_blocks[e];
-    const int q = X.q_off[b + 1] - X.q_off[b], p = X.p_off[b + 1] - X.p_off[b];
-    const int nc = (int)(S.chunk_off[h + 1] - S.chunk_off[h]);
-    const int c = T.cnt[t];
-    if (c == 0) {
-        T.tbytes[t] = 0;
-        const int o = O.fixed_iter ? O.maxiter_x : 1;
-        const int in = O.fixed_iter ? O.maxiter_x * O.maxiter_bt : 1;
-        if (iters) { iters[2 * t] = o; iters[2 * t + 1] = in; }
-        atomicAdd(&stats[0], (unsigned long long)in);
-        atomicAdd(&stats[1], (unsigned long long)o);
-        atomicAdd(&stats[2], (unsigned long long)in * (q + 2 * p) * nc);
-        atomicAdd(&stats[3], (unsigned long long)o * (q + p) * nc);
-        return;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    // what this thread adds to the run statistics / which list its task joins (warp-aggregated below)
+    unsigned long long a_in = 0, a_out = 0, a_bin = 0, a_bout = 0;
+    int cls = -1;
+    unsigned need = 0;
+    int64_t t = 0;
+    if (idx < n_tasks) {
+        const int e = X.em_order[(int)(idx / S.n_chunks)], h = (int)(idx % S.n_chunks);
+        t = (int64_t)h * X.n_em + e;
+        const int b = X.em_blocks[e];
+        const int q = X.q_off[b + 1] - X.q_off[b], p = X.p_off[b + 1] - X.p_off[b];
+        const int nc = (int)(S.chunk_off[h + 1] - S.chunk_off[h]);
+        const int c = T.cnt[t];
+        if (c == 0) {
+            T.tbytes[t] = 0;
+            const int o = O.fixed_iter ? O.maxiter_x : 1;
+            const int in = O.fixed_iter ? O.maxiter_x * O.maxiter_bt : 1;
+            if (iters) { iters[2 * t] = o; iters[2 * t + 1] = in; }
+            a_in = (unsigned long long)in; a_out = (unsigned long long)o;
+            a_bin = (unsigned long long)in * (q + 2 * p) * nc; a_bout = (unsigned long long)o * (q + p) * nc;
+        } else {
+            int n = T.runs[t], E = c;
+            if (X.poor[b]) { n += 1; E = n * q; }                 // dense records + the pseudo cell
+            if (X.poor[b] && q > 64) atomicExch(&T.counters[7], 1u);   // adjID is kept as a 64-bit mask
+            if (E > 65535 || n > 65535) { atomicExch(&T.counters[7], 2u); E = 0; n = 0; }   // u16 indices in the blob
+            T.runs[t] = n;
+            T.cnt[t] = E;
+            T.tbytes[t] = blob_layout(n, E).bytes;
+            if (n > 0) {
+                need = (unsigned)slot_bytes_of(q, p, n, E);
+                cls = kClasses - 1;
+                for (int k = kClasses - 2; k >= 0; k--)
+                    if (n * p <= C.pairs[k] && (int)need <= C.bytes[k]) cls = k;
+            }
+        }
     }
-    int n = T.runs[t], E = c;
-    if (X.poor[b]) { n += 1; E = n * q; }                 // dense records + the pseudo cell
-    if (X.poor[b] && q > 64) atomicExch(&T.counters[7], 1u);   // adjID is kept as a 64-bit mask
-    if (E > 65535 || n > 65535) { atomicExch(&T.counters[7], 2u); E = 0; n = 0; }   // u16 indices in the blob
-    T.runs[t] = n;
-    T.cnt[t] = E;
-    T.tbytes[t] = blob_layout(n, E).bytes;
-    if (n == 0) return;
-    const int need = slot_bytes_of(q, p, n, E);
-    int cls = kClasses - 1;
-    for (int k = kClasses - 2; k >= 0; k--)
-        if (n * p <= C.pairs[k] && need <= C.bytes[k]) cls = k;
-    atomicMax(&T.counters[5], (unsigned)need);
-    T.list[cls][atomicAdd(&T.counters[cls], 1u)] = (int32_t)t;
-    atomicAdd(&T.counters[4], 1u);
+    // one atomic per warp and counter instead of one per task
+    for (int o = 16; o > 0; o >>= 1) {
+        a_in += __shfl_xor_sync(kFull, a_in, o); a_out += __shfl_xor_sync(kFull, a_out, o);
+        a_bin += __shfl_xor_sync(kFull, a_bin, o); a_bout += __shfl_xor_sync(kFull, a_bout, o);
+        need = max(need, __shfl_xor_sync(kFull, need, o));
+    }
+    if (lane == 0) {
+        if (a_in) { atomicAdd(&stats[0], a_in); atomicAdd(&stats[1], a_out); atomicAdd(&stats[2], a_bin); atomicAdd(&stats[3], a_bout); }
+        if (need) atomicMax(&T.counters[5], need);
+    }
+    const unsigned nonempty = __ballot_sync(kFull, cls >= 0);
+    if (lane == 0 && nonempty) atomicAdd(&T.counters[4], (unsigned)__popc(nonempty));
+    for (int k = 0; k < kClasses; k++) {
+        const unsigned m = __ballot_sync(kFull, cls == k);
+        if (!m) continue;
+        unsigned base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(&T.counters[k], (unsigned)__popc(m));
+        base = __shfl_sync(kFull, base, __ffs(m) - 1);
+        if (cls == k) T.list[k][base + __popc(m & ((1u << lane) - 1u))] = (int32_t)t;
+    }
 }
 
 // exclusive scan int32 -> int64, three phases (block sums, scan of sums, add back)
@@ -410,15 +443,79 @@ __global__ void scan_add_back(const int32_t *__restrict__ in, int64_t n, const i
 }
 
 // ------------------------------------------------------------------------------------------
+// The dense result rows, first pass: zeros everywhere and, for the blocks with a single row
+// (nrow(X0) == 1, Scasa_Rsource.R:979-983), the count itself as the estimate.  One CTA per cell
+// assembles the row tile by tile in shared memory and writes it out coalesced, so the 26.7 GB
+// matrix (100k cells) is written exactly once here; the EM kernel later fills in its columns.
+constexpr int kFillThreads = 512;
+constexpr int kFillTile = 8192;     // doubles per tile (64 KB)
+constexpr int kFillKeep = 8;        // Y entries a thread keeps in registers across the tiles of a row
+__global__ void __launch_bounds__(kFillThreads) iso_fill_kernel(XDev X, Sample S, double *__restrict__ out)
+{
+    extern __shared__ double fill_tile[];
+    const int tid = threadIdx.x;
+    for (int64_t cell = blockIdx.x; cell < S.n_cells; cell += gridDim.x) {
+        const int64_t s = S.y_start[cell];
+        const int n = S.y_len[cell];
+        double *row = out + cell * X.n_cols;
+        int col[kFillKeep];
+        double val[kFillKeep];
+#pragma unroll
+        for (int u = 0; u < kFillKeep; u++) {
+            const int i = tid + u * kFillThreads;
+            col[u] = -1; val[u] = 0.0;
+            if (i < n) {
+                const int r = S.y_row[s + i];
+                if (X.row_info[r].x < 0) { col[u] = X.row_col[r]; val[u] = S.y_val[s + i]; }
+            }
+        }
+        for (int64_t t0 = 0; t0 < X.n_cols; t0 += kFillTile) {
+            const int tn = (int)min((int64_t)kFillTile, X.n_cols - t0);
+            for (int i = tid; i < tn; i += kFillThreads) fill_tile[i] = 0.0;
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < kFillKeep; u++)
+                if (col[u] >= t0 && col[u] < t0 + tn) fill_tile[col[u] - t0] = val[u];
+            for (int i = tid + kFillKeep * kFillThreads; i < n; i += kFillThreads) {     // cells with very many entries
+                const int r = S.y_row[s + i];
+                if (X.row_info[r].x < 0) {
+                    const int c = X.row_col[r];
+                    if (c >= t0 && c < t0 + tn) fill_tile[c - t0] = S.y_val[s + i];
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < tn; i += kFillThreads) __stcs(row + t0 + i, fill_tile[i]);
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Scatter Y into the task blobs.  One CTA per chunk; cells are visited in order so the records
 // of a task are sorted by cell (and their entries by row) without atomics — the order of every
 // later floating-point sum is therefore fixed (same chunk => same bits on any GPU count).
-__global__ void task_scatter_kernel(XDev X, Sample S, Tasks T, double *__restrict__ out)
+// The chunk's per-task cursors, extents and blob offsets live in shared memory (st[]: 3 words per
+// EM block), or in a global scratch area when the X-matrix has too many EM blocks for that.
+constexpr int kScatterThreads = 512;
+__global__ void __launch_bounds__(kScatterThreads) task_scatter_kernel(XDev X, Sample S, Tasks T, uint32_t *scratch)
 {
+    extern __shared__ uint32_t scatter_sm[];
     const int h = blockIdx.x;
     const int64_t c0 = S.chunk_off[h], c1 = S.chunk_off[h + 1];
     const int nc = (int)(c1 - c0);
     const int64_t tbase = (int64_t)h * X.n_em;
+    uint32_t *st = scratch ? scratch + (size_t)h * 3 * X.n_em : scatter_sm;
+    uint32_t *cur = st;                  // records placed << 16 | entries placed
+    uint32_t *ext = st + X.n_em;         // records << 16 | entries of the task
+    uint32_t *boff = st + 2 * X.n_em;    // blob offset inside the chunk's blob area, in 16-byte units
+    const int64_t chunk_base = T.toff[tbase];
+    char *cdata = T.tdata + chunk_base;
+    for (int e = threadIdx.x; e < X.n_em; e += blockDim.x) {
+        cur[e] = 0;
+        ext[e] = ((uint32_t)T.runs[tbase + e] << 16) | (uint32_t)T.cnt[tbase + e];
+        boff[e] = (uint32_t)((T.toff[tbase + e] - chunk_base) >> 4);
+    }
+    __syncthreads();
 
     for (int c = 0; c < nc; c++) {
         const int64_t cell = c0 + c;
@@ -426,38 +523,36 @@ __global__ void task_scatter_kernel(XDev X, Sample S, Tasks T, double *__restric
         const int n = S.y_len[cell];
         // phase A: place entries; the first entry of a run also writes the record's cell id and start
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const int row = S.y_row[s + i];
-            const double v = S.y_val[s + i];
-            const int b = X.row_block[row];
-            const int e = X.em_index[b];
-            if (e < 0) {                       // nrow(X0) == 1: the count is the estimate (Rsource:979-983)
-                out[cell * X.n_cols + X.p_off[b]] = v;
-                continue;
-            }
-            const int64_t t = tbase + e;
-            const int nrec = T.runs[t], E = T.cnt[t];
+            const int2 info = X.row_info[S.y_row[s + i]];
+            const int e = info.x;
+            if (e < 0) continue;               // pass-through block: written by iso_fill_kernel
+            const uint32_t x = ext[e];
+            const int nrec = (int)(x >> 16), E = (int)(x & 0xffff);
             if (nrec == 0) continue;           // task rejected by classify (error flag is set)
-            const int rl = row - X.q_off[b];
+            const double v = S.y_val[s + i];
+            const int rl = info.y;
             int head = i;
-            while (head > 0 && X.row_block[S.y_row[s + head - 1]] == b) head--;
+            while (head > 0 && X.row_info[S.y_row[s + head - 1]].x == e) head--;
             const BlobLayout L = blob_layout(nrec, E);
-            char *blob = T.tdata + T.toff[t];
+            char *blob = cdata + ((size_t)boff[e] << 4);
             double *ey = (double *)blob;
             uint32_t *rcell = (uint32_t *)(blob + L.off_cell);
             uint16_t *eptr = (uint16_t *)(blob + L.off_ptr);
             uint16_t *erow = (uint16_t *)(blob + L.off_row);
-            const int a = T.rec_cur[t], k0 = T.ent_cur[t];
+            const uint32_t cu = cur[e];
+            const int a = (int)(cu >> 16), k0 = (int)(cu & 0xffff);
             const bool is_head = (i == head);
+            const int b = X.em_blocks[e];
             if (X.poor[b]) {                   // dense record: every row of the block
                 const int q = X.q_off[b + 1] - X.q_off[b];
                 ey[k0 + rl] = v;
                 if (is_head) {
                     int tail = i;
-                    while (tail + 1 < n && X.row_block[S.y_row[s + tail + 1]] == b) tail++;
+                    while (tail + 1 < n && X.row_info[S.y_row[s + tail + 1]].x == e) tail++;
                     int k = head;
                     for (int r = 0; r < q; r++) {
                         erow[k0 + r] = (uint16_t)r;
-                        if (k <= tail && S.y_row[s + k] - X.q_off[b] == r) k++; else ey[k0 + r] = 0.0;
+                        if (k <= tail && X.row_info[S.y_row[s + k]].y == r) k++; else ey[k0 + r] = 0.0;
                     }
                     rcell[a] = (uint32_t)c;
                     eptr[a] = (uint16_t)k0;
@@ -471,27 +566,26 @@ __global__ void task_scatter_kernel(XDev X, Sample S, Tasks T, double *__restric
         __syncthreads();
         // phase B: the last entry of each run advances the task's cursors
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const int b = X.row_block[S.y_row[s + i]];
-            const int e = X.em_index[b];
+            const int e = X.row_info[S.y_row[s + i]].x;
             if (e < 0) continue;
-            const bool tail = (i == n - 1) || (X.row_block[S.y_row[s + i + 1]] != b);
+            const bool tail = (i == n - 1) || (X.row_info[S.y_row[s + i + 1]].x != e);
             if (!tail) continue;
             int head = i;
-            while (head > 0 && X.row_block[S.y_row[s + head - 1]] == b) head--;
-            const int64_t t = tbase + e;
-            T.ent_cur[t] += X.poor[b] ? (X.q_off[b + 1] - X.q_off[b]) : (i - head + 1);
-            T.rec_cur[t] += 1;
+            while (head > 0 && X.row_info[S.y_row[s + head - 1]].x == e) head--;
+            const int b = X.em_blocks[e];
+            const int m = X.poor[b] ? (X.q_off[b + 1] - X.q_off[b]) : (i - head + 1);
+            cur[e] += (1u << 16) + (uint32_t)m;
         }
         __syncthreads();
     }
     // close every blob of the chunk (eptr[n] = E); poor tasks get their pseudo cell: all cells of
     // the chunk without counts in the block
     for (int e = threadIdx.x; e < X.n_em; e += blockDim.x) {
-        const int64_t t = tbase + e;
-        const int nrec = T.runs[t], E = T.cnt[t];
+        const uint32_t x = ext[e];
+        const int nrec = (int)(x >> 16), E = (int)(x & 0xffff);
         if (nrec == 0) continue;
         const BlobLayout L = blob_layout(nrec, E);
-        char *blob = T.tdata + T.toff[t];
+        char *blob = cdata + ((size_t)boff[e] << 4);
         uint16_t *eptr = (uint16_t *)(blob + L.off_ptr);
         eptr[nrec] = (uint16_t)E;
         const int b = X.em_blocks[e];
