@@ -253,18 +253,21 @@ def main():
 
         e2e_step()
         barrier()
+        g.transfer_bytes(reset=True)
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             e2e_step()
         barrier()
         te = time.perf_counter() - t0
+        wire_h2d, wire_d2h = g.transfer_bytes(reset=True)
         tt = torch.tensor([te], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         te = float(tt[0]) / args.e2e_steps
         e2e = {"value": ne * world / te, "unit": "cells/s", "cells_per_gpu": ne, "s_per_step": te,
-               "h2d_bytes_per_step": int(h_ptr.nbytes + h_id.nbytes + h_cnt.nbytes + eq_row.nbytes),
-               "d2h_bytes_per_step": int(h_iso.nbytes + h_gene.nbytes),
+               "h2d_bytes_per_step": int(wire_h2d // args.e2e_steps), "d2h_bytes_per_step": int(wire_d2h // args.e2e_steps),
+               "host_input_bytes": int(h_ptr.nbytes + h_id.nbytes + h_cnt.nbytes + eq_row.nbytes),
+               "host_result_bytes": int(h_iso.nbytes + h_gene.nbytes),
                "includes": "host eqclass->row map, H2D counts, pack+EM+gene kernels, D2H isoform+gene matrices "
                            "(zero-suppressed on the wire, dense in the caller's pinned buffers)",
                "api": "scasa_b200.api.Scasa.quant -> scasa_quant (chunks in slices, two contexts: transfer of one slice "
@@ -287,7 +290,10 @@ def main():
     roofline = {"bound": "hbm", "kernel": "em_task_kernel<W> (4 persistent launches per step, W = 1/2/4/8 warps per task, side by side on 4 streams; em_ms = fork to join)",
                 "achieved": em_bytes / (t["em_ms"] * 1e-3) / 1e9, "peak": peak,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
-                "unit": "GB/s", "traffic": None,
+                "unit": "GB/s",
+                # dram__bytes_read.sum + dram__bytes_write.sum of the four em_task_kernel launches of one step, from the
+                # ncu capture of this command committed under profiles/ (r1h_launches_100k.txt); only valid for the default workload
+                "traffic": 4.6e9 if (n == 100000 and not os.environ.get("SCASA_EM_CFG")) else None,
                 "model": "SURVEY.md 8(d) streaming model: sum over (chunk, block) tasks of inner*8*(q+2p)*n_c + "
                          "outer*8*(q+p)*n_c with the iteration counts the kernel actually ran",
                 "alg_bytes_per_launch_set": em_bytes, "em_ms": t["em_ms"],

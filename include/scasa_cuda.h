@@ -173,6 +173,9 @@ typedef struct {
 } scasa_timing_t;
 int scasa_last_timing(scasa_ctx *ctx, scasa_timing_t *out);
 
+/* bytes this context (and its scasa_quant twin) moved over PCIe since the last reset */
+int scasa_transfer_bytes(scasa_ctx *ctx, int64_t *h2d, int64_t *d2h, int32_t reset);
+
 void *scasa_host_alloc(int64_t bytes); /* pinned host memory for fast H2D/D2H */
 void scasa_host_free(void *p);
 int scasa_device_count(void);

@@ -149,6 +149,12 @@ class Scasa:
         self._ck(self._L.scasa_last_timing(self._ctx, C.byref(t)))
         return t.as_dict()
 
+    def transfer_bytes(self, reset: bool = True):
+        """(host->device, device->host) bytes moved over PCIe since the last reset."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._ck(self._L.scasa_transfer_bytes(self._ctx, C.byref(a), C.byref(b), int(reset)))
+        return a.value, b.value
+
     def set_host_threads(self, n: int) -> None:
         """Threads that re-expand the zero-suppressed results on the host (0 = all cores, -1 = plain dense copy)."""
         self._ck(self._L.scasa_set_host_threads(self._ctx, n))

@@ -120,6 +120,7 @@ struct scasa_ctx {
     } fb[2];
     scasa_ctx *twin = nullptr;   // second context on the same device: scasa_quant overlaps its slices on the two
     std::vector<int32_t> gene_of_col_host;
+    std::atomic<long long> wire_h2d{0}, wire_d2h{0};   // bytes that crossed PCIe since the last scasa_transfer_bytes(reset)
     int host_threads = 0;        // 0 = hardware concurrency
     int fetch_dense_copy = 0;    // 1 = plain dense D2H (SCASA_FETCH_DENSE)
     int n_genes = 0;
@@ -373,6 +374,7 @@ void fetch_dense(scasa_ctx *c, const double *d_mat, int64_t n_rows, int64_t n_co
     if (c->fetch_dense_copy || c->host_threads < 0 || n_rows * n_cols < (1 << 20)) {
         CK(cudaMemcpyAsync(out, d_mat, (size_t)(n_rows * n_cols) * sizeof(double), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
+        c->wire_d2h += (long long)(n_rows * n_cols) * 8;
         return;
     }
     int nthr = c->host_threads > 0 ? c->host_threads : (int)std::thread::hardware_concurrency();
@@ -398,6 +400,7 @@ void fetch_dense(scasa_ctx *c, const double *d_mat, int64_t n_rows, int64_t n_co
             CK(cudaMemcpyAsync(b.h_cols, b.d_cols.p, used * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
             CK(cudaMemcpyAsync(b.h_vals, b.d_vals.p, used * sizeof(double), cudaMemcpyDeviceToHost, s));
         }
+        c->wire_d2h += (long long)(used * 12 + (size_t)nr * 12 + 8);
         CK(cudaEventRecord(b.done, s));
     };
     // the expansion of batch k runs on a pool of worker threads (rows claimed in small chunks) while
@@ -431,6 +434,7 @@ void fetch_dense(scasa_ctx *c, const double *d_mat, int64_t n_rows, int64_t n_co
         if (overflow) {                               // denser than the staging buffer: plain copy of this batch
             CK(cudaMemcpyAsync(out + r0 * n_cols, d_mat + r0 * n_cols, (size_t)(nr * n_cols) * sizeof(double), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
+            c->wire_d2h += (long long)(nr * n_cols) * 8;
         } else expand_async(k);
         t0 = now();
         if (k + 1 < n_batches) launch(k + 1);
@@ -711,6 +715,7 @@ int scasa_stage_counts(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const in
             CK(cudaMemcpyAsync(c->d_y_val.p, y_val, nnz * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         }
         CK(cudaStreamSynchronize(c->stream));
+        c->wire_h2d += (long long)(n_cells * 12 + nnz * 12 + (n_chunks + 1) * 8 + n_cells * 4);
     });
 }
 
@@ -746,6 +751,7 @@ int scasa_stage_eqcounts(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const 
         }
         CK(cudaMemcpyAsync(c->d_eq_row.p, eq_row, n_eq * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
         CK(cudaStreamSynchronize(c->stream));
+        c->wire_h2d += (long long)((n_cells + 1) * 8 + n_cells * 8 + nnz * 8 + n_eq * 4 + (n_chunks + 1) * 8 + n_cells * 4);
     });
 }
 
@@ -977,6 +983,7 @@ static int fetch(scasa_ctx *c, void *dst, const void *src, size_t bytes)
     return guarded(c, [&] {
         CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
+        c->wire_d2h += (long long)bytes;
     });
 }
 
@@ -1026,6 +1033,17 @@ int scasa_expand_pairs(double *out, int64_t n_rows, int64_t n_cols, const int64_
     } catch (const std::exception &e) {
         return fail(nullptr, SCASA_ERR_NOMEM, e.what());
     }
+    return SCASA_OK;
+}
+
+int scasa_transfer_bytes(scasa_ctx *c, int64_t *h2d, int64_t *d2h, int32_t reset)
+{
+    if (!c) return fail(c, SCASA_ERR_ARG, "null context");
+    long long a = c->wire_h2d.load(), b = c->wire_d2h.load();
+    if (c->twin) { a += c->twin->wire_h2d.load(); b += c->twin->wire_d2h.load(); }
+    if (h2d) *h2d = a;
+    if (d2h) *d2h = b;
+    if (reset) { c->wire_h2d = 0; c->wire_d2h = 0; if (c->twin) { c->twin->wire_h2d = 0; c->twin->wire_d2h = 0; } }
     return SCASA_OK;
 }
 

@@ -143,6 +143,11 @@ template <int W> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs
             for (int k = gl; k < qp; k += GT) Xc[k] = X0[k];
         }
         G.sync();
+        // a poor task's last record is the pseudo cell: all pmult cells of the chunk without counts in the block
+        const uint32_t last_cw = rcell[n - 1];
+        const int ap = (last_cw & kPseudo) ? n - 1 : -1;
+        const double pmult = (last_cw & kPseudo) ? (double)(last_cw & 0xffff) : 0.0;
+        const int n_real = ap >= 0 ? n - 1 : n;
         for (int a = gl; a < n; a += GT) {
             const int k1 = eptr[a + 1];
             for (int k = eptr[a]; k < k1; k++) erec[k] = (uint16_t)a;
@@ -195,8 +200,7 @@ template <int W> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs
                 const int i1 = rptr[r + 1];
                 for (int i = rptr[r]; i < i1; i++) {
                     const int k = perm[i];
-                    const uint32_t cw = rcell[erec[k]];
-                    s += ((cw & kPseudo) ? (double)(cw & 0xffff) : 1.0) * ey[k];
+                    s += (erec[k] == ap ? pmult : 1.0) * ey[k];
                 }
                 rs[r] = s;
             }
@@ -296,10 +300,8 @@ template <int W> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs
             for (int j = gl; j < p; j += GT) {                                   // BTsum = colSums(BETA)  :904
                 double s = 0;
 #pragma unroll 1
-                for (int a = 0; a < n; a++) {
-                    const uint32_t cw = rcell[a];
-                    s += ((cw & kPseudo) ? (double)(cw & 0xffff) : 1.0) * beta[j * n + a];
-                }
+                for (int a = 0; a < n_real; a++) s += beta[j * n + a];
+                if (ap >= 0) s += pmult * beta[j * n + ap];                      // the pseudo cell stands for pmult cells
                 bts[j] = s > 0 ? s : 0.1;                                        // :917 (may be denormal: no reciprocal)
             }
 #pragma unroll 1
@@ -308,8 +310,7 @@ template <int W> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs
                 double mu = 0.0;                                                  // sumx1 = rowSums(x1)  :907
 #pragma unroll 1
                 for (int j = 0; j < p; j++) mu += beta[j * n + a] * Xc[j * q + r];
-                const uint32_t cw = rcell[a];
-                const double mult = (cw & kPseudo) ? (double)(cw & 0xffff) : 1.0;
+                const double mult = a == ap ? pmult : 1.0;
                 ew[k] = mult * ey[k] / (mu > 0 ? mu : 0.1);                      // :908-910
             }
             G.sync();
@@ -333,7 +334,14 @@ template <int W> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs
 #pragma unroll 1
                 for (int r = 0; r < q; r++) csum += Xn[j * q + r];
                 // :919-920: scale by 1/csum (0.1 when 0); a negative scale marks "revert to X.est0"
-                nrm[j] = csum < 0.00001 ? -1.0 : 1.0 / (csum > 0 ? csum : 0.1);
+                const double sc = csum < 0.00001 ? -1.0 : 1.0 / (csum > 0 ? csum : 0.1);
+                nrm[j] = sc;
+                if (sc >= 0) {                                                   // 1/colSums of the normalised column, for the next estim.BETA call
+                    double s2 = 0;
+#pragma unroll 1
+                    for (int r = 0; r < q; r++) s2 += Xn[j * q + r] * sc;
+                    rcs[j] = 1.0 / s2;
+                }
             }
             G.sync();
             bool xfail = false;                                                  // :1019
@@ -341,7 +349,7 @@ template <int W> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs
             for (int idx = gl, j = xj_first, r = xr_first; idx < qp; idx += GT) {
                 const double x0 = Xc[idx], sc = nrm[j];
                 const double v = sc < 0 ? x0 : Xn[idx] * sc;
-                Xn[idx] = v;
+                Xc[idx] = v;                                                     // X.est0 = X.est (:1022); unused if the loop ends here
                 const double num = fabs(v - x0), den = fabs(x0) > O.lim ? x0 : O.lim;
                 const bool ok = den > 0 ? (num < O.maxerr * den) : (num / den < O.maxerr);
                 if (!ok) xfail = true;
@@ -351,16 +359,6 @@ template <int W> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs
             outer++;
             const bool any_x = G.any(xfail);
             if ((!O.fixed_iter && !any_x) || outer >= O.maxiter_x) break;        // :1020
-#pragma unroll 1
-            for (int idx = gl; idx < qp; idx += GT) Xc[idx] = Xn[idx];           // X.est0 = X.est  :1022
-            G.sync();
-            for (int j = gl; j < p; j += GT) {                                   // 1/csum of the next estim.BETA call
-                double s = 0;
-#pragma unroll 1
-                for (int r = 0; r < q; r++) s += Xc[j * q + r];
-                rcs[j] = 1.0 / s;
-            }
-            G.sync();
         }
 
         // ---- de-adjust (:1027-1037) and scatter BT into the result (:1042)
