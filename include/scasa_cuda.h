@@ -155,6 +155,34 @@ int scasa_gene_sum(scasa_ctx *ctx, const int32_t *gene_of_col, int32_t n_genes, 
 int scasa_eqclass_map(scasa_ctx *ctx, int64_t n_eq, const int64_t *eq_off, const int32_t *eq_tx,
                       int32_t *eq_row, int32_t n_threads);
 
+/* ---- alevin bfh.txt -> quant inputs (host only; replaces scasa_quant_step1_1_v1.0.0.R:16-68 and
+ * the ordering of scasa_quant_step2_v1.0.0.R:59-60) --------------------------------------------
+ * Cells are the barcodes that occur in some eqclass, in byte order of their sequences
+ * (data.table::setorder); per cell the (eqclass, count) pairs in ascending eqclass id, count =
+ * number of UMIs; per eqclass its transcript indices into the file's own transcript list (map the
+ * names to the ids used in scasa_crp_t.col_tx before calling scasa_eqclass_map). */
+typedef struct scasa_bfh scasa_bfh;
+int scasa_bfh_open(const char *path, int32_t n_threads /* 0 = all cores */, scasa_bfh **out);
+void scasa_bfh_close(scasa_bfh *f);
+int scasa_bfh_sizes(const scasa_bfh *f, int64_t *n_tx, int64_t *n_cells, int64_t *n_eq, int64_t *n_pairs,
+                    int64_t *n_eq_tx, int64_t *tx_name_bytes, int64_t *barcode_bytes);
+/* names are written one per line ('\n'-terminated, sizes from scasa_bfh_sizes); any pointer may be NULL */
+int scasa_bfh_read(const scasa_bfh *f, char *tx_names, char *barcodes, int64_t *eq_off /* [n_eq+1] */,
+                   int32_t *eq_tx /* [n_eq_tx] */, int64_t *cell_ptr /* [n_cells+1] */, int32_t *eq_id /* [n_pairs], 0-based line */,
+                   int32_t *eq_count /* [n_pairs] */);
+
+/* ---- the two text outputs (host only) ----------------------------------------------------------
+ * write.table(t(result)[keep, ], file, quote = F, row.names = T, sep = "\t") as at
+ * scasa_quant_step2_v1.0.0.R:165-170 and scasa_quant_step3_v1.0.0.R:52: mat is the library's
+ * cell-major matrix (n_cells x n_cols); the file has a header of cell names (one field fewer than
+ * the data lines) and one line per column j with keep[j] != 0 (keep == NULL: all): its name, then
+ * its value in every cell, formatted like R's writetable does (15 significant digits at most).
+ * row_names / cell_names: one name per line, '\n'-terminated. */
+int scasa_write_table(const char *path, const double *mat, int64_t n_cells, int64_t n_cols, const uint8_t *keep,
+                      const char *row_names, const char *cell_names, int32_t n_threads);
+/* the text R's write.table gives one number; returns its length (buf needs 32 bytes) */
+int scasa_format_real15(double x, char *buf, int32_t cap);
+
 /* ---- measurement ---------------------------------------------------------------------------
  * device time (CUDA events on the library's stream) of the last scasa_run, per phase */
 typedef struct {

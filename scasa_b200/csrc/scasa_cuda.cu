@@ -24,6 +24,10 @@ namespace {
 
 thread_local std::string g_err;   // errors raised before a context exists
 
+}  // namespace
+void scasa::set_global_error(const std::string &m) { g_err = m; }
+namespace {
+
 struct CudaErr { cudaError_t e; const char *what; };
 #define CK(call)                                                       \
     do {                                                               \

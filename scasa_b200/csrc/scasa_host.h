@@ -7,6 +7,7 @@
 // work becomes an integer scatter-add on the GPU (pack_cells_kernel).
 #pragma once
 #include <cstdint>
+#include <string>
 #include <unordered_map>
 #include <vector>
 
@@ -43,5 +44,8 @@ void r_format_roundtrip(const double *v, int n, double *back, uint8_t *is_zero_t
 // non-temporal stores (64-byte blocks with AVX-512, 32-byte with AVX2, else SSE2; chosen at run time).
 void expand_rows(double *out, int64_t n_cols, int64_t r0, int64_t r1, const int64_t *start, const int32_t *nnz,
                  const int32_t *cols, const double *vals);
+
+// message returned by scasa_last_error(NULL) on the calling thread (for the host-only entry points)
+void set_global_error(const std::string &m);
 
 }  // namespace scasa

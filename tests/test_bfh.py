@@ -1,0 +1,71 @@
+"""N1 (SURVEY.md §8 f): the bfh.txt reader against the literal restatement of step1_1 + step2:59-60."""
+import os
+
+import numpy as np
+import pytest
+
+
+def _write_bfh(path, rng, n_tx=40, n_cb=30, n_eq=120, crlf=False, trailing_newline=True):
+    tx = [f"NM_{1000 + i}.{i % 3}" for i in range(n_tx)]
+    cb = ["".join(rng.choice(list("ACGT"), 16)) for _ in range(n_cb)]
+    cb[3] = cb[7]                                  # a repeated sequence: one cell in R (unique(Barcode))
+    lines = [str(n_tx), str(n_cb), str(n_eq)] + tx + cb
+    for _ in range(n_eq):
+        k = int(rng.integers(1, 6))
+        tids = sorted(rng.choice(n_tx, k, replace=False).tolist())
+        nb = int(rng.integers(1, 5))
+        bcs = rng.choice(n_cb - 2, nb, replace=False).tolist()      # the last two barcodes never occur
+        f = [str(k)] + [str(t) for t in tids]
+        body, total = [], 0
+        for b in bcs:
+            numi = int(rng.integers(1, 4))
+            body += [str(b), str(numi)]
+            for _u in range(numi):
+                c = int(rng.integers(1, 9))
+                total += c
+                body += ["".join(rng.choice(list("ACGT"), 10)), str(c)]
+        f += [str(total), str(nb)] + body
+        lines.append("\t".join(f))
+    nl = "\r\n" if crlf else "\n"
+    with open(path, "w", newline="") as fh:
+        fh.write(nl.join(lines) + (nl if trailing_newline else ""))
+    return tx, cb
+
+
+@pytest.mark.parametrize("crlf,trailing", [(False, True), (True, True), (False, False)])
+def test_bfh_reader_equals_literal_restatement(tmp_path, crlf, trailing):
+    from scasa_b200.bfh import read_bfh
+    from oracle import bfh_literal
+    rng = np.random.default_rng(11)
+    path = str(tmp_path / "bfh.txt")
+    _write_bfh(path, rng, crlf=crlf, trailing_newline=trailing)
+    tx_all, cells, per_cell, eq_tx = bfh_literal.quant_inputs(path)
+    for threads in (1, 3):
+        b = read_bfh(path, threads)
+        assert b.tx_names == tx_all
+        assert b.barcodes == cells
+        assert b.barcodes == sorted(set(b.barcodes), key=str.encode)
+        assert len(b.cell_ptr) == len(cells) + 1 and b.cell_ptr[-1] == len(b.eq_id)
+        for c, bc in enumerate(cells):
+            ids = b.eq_id[b.cell_ptr[c]:b.cell_ptr[c + 1]] + 1          # R's eqClass is the 1-based line
+            cnt = b.eq_count[b.cell_ptr[c]:b.cell_ptr[c + 1]]
+            want = sorted(per_cell[bc].items())
+            assert list(ids) == [e for e, _ in want]
+            assert list(cnt) == [v for _, v in want]
+        for e, txs in eq_tx.items():
+            got = [b.tx_names[t] for t in b.eq_tx[b.eq_off[e - 1]:b.eq_off[e]]]
+            assert got == txs
+
+
+def test_bfh_errors(tmp_path):
+    from scasa_b200 import lib
+    from scasa_b200.bfh import read_bfh
+    p = str(tmp_path / "bad.txt")
+    open(p, "w").write("2\n1\n1\nA\nB\nACGT\n1\t5\t3\t1\t0\t1\tACGT\t3\n")       # transcript index 5 of 2
+    with pytest.raises(lib.ScasaError):
+        read_bfh(p)
+    with pytest.raises(lib.ScasaError):
+        read_bfh(str(tmp_path / "missing.txt"))
+    open(p, "w").write("2\n1\n3\nA\nB\nACGT\n")                                  # shorter than the header says
+    with pytest.raises(lib.ScasaError):
+        read_bfh(p)

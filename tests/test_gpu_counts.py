@@ -185,3 +185,48 @@ def test_sliced_quant_is_bitwise_the_unsliced_one(xm):
             assert np.array_equal(r.colsum > 0, ref.colsum > 0)
     finally:
         g.close()
+
+
+def test_bfh_file_to_quant_equals_arrays(xm, tmp_path):
+    """N1 end to end: a bfh.txt written from the synthetic eqclass counts, read back by scasa_bfh_*,
+    gives bitwise the isoform matrix of the run that was handed the arrays directly."""
+    from scasa_b200 import synth
+    from scasa_b200.api import Scasa
+    from scasa_b200.bfh import read_bfh
+    n = 120
+    rowptr, rows, vals = synth.CellGenerator(xm, seed=21).counts_csr(0, n)
+    ed = synth.eqclass_dictionary(xm, 21)
+    cell_ptr, eq_id, eq_cnt = synth.counts_to_eqcounts(rowptr, rows, vals, 21)
+    cell_ptr, eq_id, eq_cnt = np.asarray(cell_ptr), np.asarray(eq_id), np.asarray(eq_cnt)
+    keep = eq_cnt > 0
+    bcs = synth.barcodes(n, 21)
+    assert bcs == sorted(bcs)
+    n_eq = len(ed.eq_off) - 1
+    cell_of = np.repeat(np.arange(n), np.diff(cell_ptr))
+    order = np.argsort(eq_id[keep], kind="stable")
+    e_sorted, c_sorted, k_sorted = eq_id[keep][order], cell_of[keep][order], eq_cnt[keep][order]
+    starts = np.searchsorted(e_sorted, np.arange(n_eq + 1))
+    path = str(tmp_path / "bfh.txt")
+    with open(path, "w") as fh:
+        fh.write(f"{len(xm.tx_names)}\n{n}\n{n_eq}\n")
+        fh.write("\n".join(xm.tx_names) + "\n")
+        fh.write("\n".join(bcs) + "\n")
+        for e in range(n_eq):
+            tx = ed.eq_tx[ed.eq_off[e]:ed.eq_off[e + 1]]
+            a, b = starts[e], starts[e + 1]
+            f = [str(len(tx))] + [str(int(t)) for t in tx] + [str(int(k_sorted[a:b].sum())), str(b - a)]
+            for c, k in zip(c_sorted[a:b], k_sorted[a:b]):
+                f += [str(int(c)), str(int(k))]
+                for u in range(int(k)):
+                    f += ["ACGTACGTAC"[u % 7:] + "G" * (u % 7), "1"]
+            fh.write("\t".join(f) + "\n")
+    bf = read_bfh(path)
+    assert bf.barcodes == bcs
+    g = Scasa(xm, device=0)
+    try:
+        r1 = g.quant(bf.cell_ptr, bf.eq_id, bf.eq_count, bf.eq_off, bf.tx_ids(xm), n_slices=1)
+        r0 = g.quant(cell_ptr, eq_id, eq_cnt, ed.eq_off, ed.eq_tx, n_slices=1)
+    finally:
+        g.close()
+    assert np.array_equal(r1.iso.view(np.int64), r0.iso.view(np.int64))
+    assert np.array_equal(r1.iters, r0.iters)

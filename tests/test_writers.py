@@ -1,0 +1,95 @@
+"""N2 (SURVEY.md §8 f): write.table-compatible text output (step2:170, step3:52)."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+# R session facts (R >= 3.x, write.table / format(x, digits = 15) on single values)
+R_KNOWN = [
+    (1.0, "1"), (1.5, "1.5"), (0.1, "0.1"), (1 / 3, "0.333333333333333"), (2 / 3, "0.666666666666667"),
+    (1e5, "1e+05"), (123456.0, "123456"), (1e-4, "1e-04"), (0.001, "0.001"), (0.00012345, "0.00012345"),
+    (1e15, "1e+15"), (123456789012.0, "123456789012"), (100.0, "100"), (1e-15, "1e-15"), (0.5, "0.5"),
+    (-2.5, "-2.5"), (math.pi, "3.14159265358979"), (math.e, "2.71828182845905"), (1e300, "1e+300"),
+    (0.1 + 0.2, "0.3"), (100000.5, "100000.5"), (1234567.1, "1234567.1"), (3e-10, "3e-10"),
+    (1.25e-7, "1.25e-07"), (-1e-300, "-1e-300"), (2.0 ** 52, "4503599627370496"), (0.0, "0"), (-0.0, "0"),
+    (float("inf"), "Inf"), (float("-inf"), "-Inf"), (float("nan"), "NaN"), (17.0, "17"), (99999.0, "99999"),
+    (1e22, "1e+22"), (123456.7890123, "123456.7890123"),
+]
+
+
+def py_format15(x: float) -> str:
+    """Independent restatement with correctly rounded decimal conversion (Python's %e) instead of
+    R's long double arithmetic: formatReal for one value with digits = 15."""
+    if x == 0:
+        return "0"
+    if math.isnan(x):
+        return "NaN"
+    if math.isinf(x):
+        return "Inf" if x > 0 else "-Inf"
+    neg = 1 if x < 0 else 0
+    r = abs(x)
+    mant, exp = ("%.14e" % r).split("e")
+    kp = int(exp)
+    digits = mant.replace(".", "").rstrip("0")
+    nsig = max(len(digits), 1)
+    widens = 0 < kp <= 22 and r < float(10 ** kp)
+    left = kp + 1 - (1 if widens else 0)
+    sleft = neg + (1 if left <= 0 else left)
+    rgt = min(max(nsig - left, 0), 22)
+    wF = sleft + rgt + (1 if rgt else 0)
+    e = 2 if (kp >= 100 or kp <= -99) else 1
+    d = nsig - 1
+    wE = neg + (1 if d > 0 else 0) + d + 4 + e
+    if wF <= wE:
+        return "%.*f" % (rgt, x)
+    return "%.*e" % (d, x)
+
+
+def test_format_real15_known_r_outputs():
+    from scasa_b200.writers import format_real15
+    for x, want in R_KNOWN:
+        assert format_real15(x) == want, (x, format_real15(x), want)
+        assert py_format15(x) == want, (x, py_format15(x), want)
+
+
+def test_format_real15_random_values_agree_with_independent_restatement():
+    from scasa_b200.writers import format_real15
+    rng = np.random.default_rng(3)
+    xs = np.concatenate([
+        rng.normal(size=4000) * 10.0 ** rng.integers(-12, 13, 4000),
+        rng.integers(1, 10 ** 9, 2000).astype(float),
+        rng.integers(1, 2000, 2000) / 8.0,
+        rng.gamma(0.5, 3.0, 3000),
+        np.round(rng.gamma(2.0, 40.0, 2000), 3),
+        10.0 ** rng.integers(-30, 30, 200),
+    ])
+    for x in xs:
+        a = format_real15(float(x))
+        assert a == py_format15(float(x)), (repr(float(x)), a, py_format15(float(x)))
+        if np.isfinite(x) and x != 0:
+            assert abs(float(a) - x) <= 5e-15 * abs(x)          # 15 significant digits are kept
+
+
+@pytest.mark.parametrize("threads", [1, 3])
+def test_write_table_layout(tmp_path, threads):
+    from scasa_b200.writers import write_table
+    rng = np.random.default_rng(5)
+    n_cells, n_cols = 9, 75                                    # > 2 blocks of 32 lines
+    mat = rng.gamma(0.4, 5.0, (n_cells, n_cols)) * (rng.random((n_cells, n_cols)) < 0.3)
+    mat[2, 5] = 1e-7
+    mat[3, 6] = 123456789.25
+    keep = mat.sum(0) > 0
+    keep[11] = False
+    rows = [f"NM_{i} NM_{i + 1}" if i % 7 == 0 else f"NM_{i}" for i in range(n_cols)]     # merged names contain a space
+    cells = [f"ACGT{i:04d}" for i in range(n_cells)]
+    path = str(tmp_path / "t.txt")
+    write_table(path, mat, rows, cells, keep=keep, n_threads=threads)
+    got = open(path, "rb").read().decode()
+    want = ["\t".join(cells)]
+    for j in range(n_cols):
+        if keep[j]:
+            want.append("\t".join([rows[j]] + [py_format15(float(v)) for v in mat[:, j]]))
+    assert got == "\n".join(want) + "\n"
+    write_table(path, mat, rows, cells, n_threads=threads)      # no filter: every column
+    assert len(open(path).read().split("\n")) == n_cols + 2
