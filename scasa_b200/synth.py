@@ -181,3 +181,38 @@ def counts_to_eqcounts(rowptr, rowidx, val, seed: int, device="cpu"):
     per_cell = torch.zeros(len(rowptr) - 1, dtype=torch.int64, device=device).index_add_(0, cells, per_entry)
     cell_ptr = np.concatenate([[0], torch.cumsum(per_cell, 0).cpu().numpy()]).astype(np.int64)
     return cell_ptr, ids[keep].to(torch.int32).cpu().numpy(), cnt[keep].to(torch.int32).cpu().numpy()
+
+
+# --------------------------------------------------------------------------------------------
+def resample_xmatrix(xm: XMatrix, n_blocks: int, seed: int, min_q: int = 1, min_p: int = 1) -> XMatrix:
+    """A synthetic X-matrix of ``n_blocks`` blocks drawn with replacement from the shipped ones
+    (SURVEY.md §8 d: config C3 = "GRCh38.106-like", ≈ 93k blocks; config C5 = heavy multimapping,
+    ``min_q = 8, min_p = 4``).  CRP and DM0 pieces are carried along; every drawn block gets fresh
+    transcript ids, so blocks share no transcript."""
+    rng = np.random.default_rng(seed + 32452843)
+    q_all = np.diff(xm.q_off)
+    p_all = np.diff(xm.dm0_p_off)
+    pool = np.nonzero((q_all >= min_q) & (p_all >= min_p))[0]
+    pick = pool[rng.integers(0, len(pool), n_blocks)]
+    q = q_all[pick]
+    pd = p_all[pick]
+    pc = np.diff(xm.crp_p_off)[pick]
+    q_off = np.concatenate([[0], np.cumsum(q)]).astype(np.int32)
+    dm0_p_off = np.concatenate([[0], np.cumsum(pd)]).astype(np.int32)
+    crp_p_off = np.concatenate([[0], np.cumsum(pc)]).astype(np.int32)
+    dm0_x_off = np.concatenate([[0], np.cumsum(q.astype(np.int64) * pd)]).astype(np.int64)
+    crp_x_off = np.concatenate([[0], np.cumsum(q.astype(np.int64) * pc)]).astype(np.int64)
+    dm0_x = np.empty(dm0_x_off[-1])
+    crp_x = np.empty(crp_x_off[-1])
+    crp_pat = np.empty(crp_x_off[-1], np.uint8)
+    crp_member = np.empty(crp_p_off[-1], np.int32)
+    for i, k in enumerate(pick):
+        dm0_x[dm0_x_off[i]:dm0_x_off[i + 1]] = xm.dm0_x[xm.dm0_x_off[k]:xm.dm0_x_off[k + 1]]
+        crp_x[crp_x_off[i]:crp_x_off[i + 1]] = xm.crp_x[xm.crp_x_off[k]:xm.crp_x_off[k + 1]]
+        crp_pat[crp_x_off[i]:crp_x_off[i + 1]] = xm.crp_pat[xm.crp_x_off[k]:xm.crp_x_off[k + 1]]
+        m = xm.crp_member[xm.crp_p_off[k]:xm.crp_p_off[k + 1]]
+        crp_member[crp_p_off[i]:crp_p_off[i + 1]] = np.where(m >= 0, m - xm.dm0_p_off[k] + dm0_p_off[i], -1)
+    crp_tx = np.arange(crp_p_off[-1], dtype=np.int32)
+    tx_names = [f"TX{t}" for t in range(crp_p_off[-1])]
+    return XMatrix(q_off, crp_p_off, crp_x_off, crp_x, crp_tx, crp_pat, dm0_p_off, dm0_x_off, dm0_x, crp_member,
+                   np.arange(n_blocks, dtype=np.int32), tx_names)

@@ -165,3 +165,76 @@ def test_colsum_and_gene_sums(gpu, xm, oracle, c1):
     gpu.set_gene_map(goc, len(names))
     gpu.run()
     assert np.array_equal(gpu.fetch_gene(), got)
+
+
+def test_large_resampled_xmatrix_uses_the_general_paths(xm, oracle):
+    """Config C3's shape ("GRCh38.106-like": more blocks than the shipped X-matrix).  With 110k
+    blocks the row histogram no longer fits in shared memory (pack_cells_kernel, the sort path) and
+    the scatter keeps its cursors in HBM; both must give what the shared-memory paths give:
+    Y bit-exact against the oracle's crpcount, estimates <= 1e-6 in fixed-iteration mode."""
+    from scasa_b200 import synth
+    from scasa_b200.api import Scasa
+    big = synth.resample_xmatrix(xm, 110000, seed=106)
+    assert big.n_rows > 49152                                   # beyond the histogram kernel
+    n = 230                                                     # 2 chunks of 115
+    rowptr, rows, vals = synth.CellGenerator(big, seed=3).counts_csr(0, n)
+    ed = synth.eqclass_dictionary(big, 3)
+    cell_ptr, eq_id, eq_cnt = synth.counts_to_eqcounts(rowptr, rows, vals, 3)
+    g = Scasa(big, device=0, fixed_iter=1, maxiter_x=3, maxiter_bt=4)
+    try:
+        assert g.n_em * 12 > 160 * 1024                          # scatter cursors in HBM
+        r = g.quant(cell_ptr, eq_id, eq_cnt, ed.eq_off, ed.eq_tx, n_slices=1)
+        yp, yi, yv = g.fetch_counts()
+    finally:
+        g.close()
+    h = oracle.CrpHandle(big)
+    y = oracle.crpcount_cells(h, ed.eq_off, ed.eq_tx, cell_ptr, eq_id, eq_cnt, nthreads=4)
+    assert np.array_equal(synth.csr_to_dense(yp, yi, yv, big.n_rows), y)
+    from scasa_b200.api import chunk_split
+    chunks = chunk_split(n, 4)
+    ref, ref_it = oracle.estim_chunks(big, y, chunks, oracle.Opts.make(fixed_iter=1, maxiter_x=3, maxiter_bt=4), nthreads=4)
+    q = np.diff(big.q_off)
+    poor_blocks = np.zeros(big.n_blocks, bool)
+    g2 = Scasa(big, device=0, with_crp=False)
+    try:
+        poor_blocks = g2.poor_blocks()
+    finally:
+        g2.close()
+    poor = np.repeat(poor_blocks, np.diff(big.dm0_p_off))
+    pt = np.repeat(q == 1, np.diff(big.dm0_p_off))
+    assert np.array_equal(r.iso[:, pt], ref[:, pt])
+    assert rel_err(r.iso[:, ~poor], ref[:, ~poor]) < RTOL
+    assert np.max(np.abs(r.iso[:, poor] - ref[:, poor])) < 1e-6
+
+
+def test_heavy_multimapping_tight_tolerance(xm, oracle):
+    """Config C5's shape: only wide blocks (p >= 4, q >= 8), library x4, maxerr 1e-6: the 8-warp
+    class of the EM kernel does most of the work and tasks run into the iteration caps."""
+    from scasa_b200 import synth
+    from scasa_b200.api import Scasa, chunk_split
+    wide = synth.resample_xmatrix(xm, 60, seed=5, min_q=8, min_p=4)
+    n = 200
+    rowptr, rows, vals = synth.CellGenerator(wide, seed=5, lib_scale=4.0).counts_csr(0, n)
+    # the generator spreads a 4000-read library over 60 blocks only: scale to ~40 reads per block and cell
+    vals = np.minimum(vals, 200.0)
+    chunks = chunk_split(n, 4)
+    y = synth.csr_to_dense(rowptr, rows, vals, wide.n_rows)
+    g = Scasa(wide, device=0, with_crp=False, maxerr=1e-6, maxiter_x=60, maxiter_bt=60)
+    try:
+        iso, iters = g.estimate(chunks, rowptr, rows, vals)
+    finally:
+        g.close()
+    ref, ref_it = oracle.estim_chunks(wide, y, chunks, oracle.Opts.make(maxerr=1e-6, maxiter_x=60, maxiter_bt=60), nthreads=4)
+    ref_it = ref_it[:, wide.em_blocks(), :]
+    same = np.all(iters == ref_it, axis=2)
+    assert same.mean() >= 0.9, same.mean()
+    assert iters[..., 0].max() == 60                             # some tasks hit the outer cap
+    p_off = wide.dm0_p_off
+    worst = 0.0
+    for hh in range(len(chunks) - 1):
+        cs = slice(chunks[hh], chunks[hh + 1])
+        for e, k in enumerate(wide.em_blocks()):
+            if same[hh, e]:
+                worst = max(worst, rel_err(iso[cs, p_off[k]:p_off[k + 1]], ref[cs, p_off[k]:p_off[k + 1]], floor=1e-6))
+    assert worst < RTOL, worst
+    assert np.all(np.isfinite(iso))
