@@ -126,6 +126,10 @@ int scasa_stage_eqcounts(scasa_ctx *ctx, int64_t n_cells, int32_t n_chunks, cons
                          const int64_t *cell_ptr, const int32_t *eq_id, const int32_t *eq_count,
                          int64_t n_eq, const int32_t *eq_row);
 int scasa_run(scasa_ctx *ctx);   /* pack -> EM -> (gene sums); everything on the device */
+/* Experimental: scasa_run can cut the staged chunks into n_parts ranges that alternate between two
+ * sets of streams (EM kernels of one range next to the bandwidth-bound kernels of another).
+ * 0 / 1 = one range (default: on B200 the split measured slower).  No result depends on it. */
+int scasa_set_run_parts(scasa_ctx *ctx, int32_t n_parts);
 /* The two dense results travel zero-suppressed ((column, value) pairs, > 90 % of the matrices are
  * zeros) and are re-expanded into the caller's buffer by host threads; the buffer ends up
  * bit-identical to a plain copy.  scasa_set_host_threads: threads of that expansion, 0 = all cores,
@@ -198,6 +202,8 @@ typedef struct {
     double em_alg_bytes;    /* ... of the EM kernels alone (per-iteration terms) */
     int32_t launches;       /* kernels launched by the last run             */
     int32_t max_slot_bytes; /* largest shared-memory slot a task needed     */
+    int32_t run_parts;      /* ranges of chunks the run was cut into; with more than one the phase times above are
+                               sums over ranges that ran side by side (they exceed total_ms) */
 } scasa_timing_t;
 int scasa_last_timing(scasa_ctx *ctx, scasa_timing_t *out);
 

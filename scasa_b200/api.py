@@ -155,6 +155,10 @@ class Scasa:
         self._ck(self._L.scasa_transfer_bytes(self._ctx, C.byref(a), C.byref(b), int(reset)))
         return a.value, b.value
 
+    def set_run_parts(self, n: int) -> None:
+        """Ranges of chunks scasa_run overlaps on two stream sets (0 = automatic, 1 = no overlap)."""
+        self._ck(self._L.scasa_set_run_parts(self._ctx, n))
+
     def set_host_threads(self, n: int) -> None:
         """Threads that re-expand the zero-suppressed results on the host (0 = all cores, -1 = plain dense copy)."""
         self._ck(self._L.scasa_set_host_threads(self._ctx, n))

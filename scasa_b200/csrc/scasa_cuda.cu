@@ -108,7 +108,8 @@ struct scasa_ctx {
     DBuf<int> d_flag;
 
     // ---- results
-    DBuf<double> d_iso, d_partial, d_colsum, d_gene;
+    DBuf<double> d_iso, d_partial, d_colsum, d_colsum_parts, d_gene;
+    int run_parts = 0;           // ranges scasa_run cuts the sample into (0 = automatic)
     // zero-suppressed fetch: two batches in flight (device pairs -> pinned staging -> threaded expansion)
     struct FetchBuf {
         DBuf<int32_t> d_cols, d_nnz;
@@ -188,11 +189,14 @@ XDev xdev(scasa_ctx *c)
     X.em_order = c->d_em_order.p; X.row_info = c->d_row_info.p; X.row_col = c->d_row_col.p;
     return X;
 }
-Sample sdev(scasa_ctx *c)
+// chunks [h0, h1) of the sample staged in c
+Sample sdev(scasa_ctx *c, int h0, int h1)
 {
+    const int64_t c0 = c->chunk_off[(size_t)h0], c1 = c->chunk_off[(size_t)h1];
     Sample S;
-    S.n_cells = c->n_cells; S.n_chunks = c->n_chunks; S.chunk_off = c->d_chunk_off.p;
-    S.cell_chunk = c->d_cell_chunk.p; S.y_start = c->d_y_start.p; S.y_len = c->d_y_len.p;
+    S.n_cells = c1 - c0; S.n_chunks = h1 - h0; S.cell_base = c0; S.chunk_base = h0;
+    S.chunk_off = c->d_chunk_off.p + h0;
+    S.cell_chunk = c->d_cell_chunk.p + c0; S.y_start = c->d_y_start.p + c0; S.y_len = c->d_y_len.p + c0;
     S.y_row = c->d_y_row.p; S.y_val = c->d_y_val.p;
     return S;
 }
@@ -219,28 +223,29 @@ void exclusive_scan(scasa_ctx *c, const int32_t *in, int64_t n, int64_t *out, in
 }
 
 // column sums (+ gene sums) of a resident isoform matrix
-void launch_finish(scasa_ctx *c, int64_t n_cells, double *gene, int &launches)
+// column sums (+ gene sums) of n_cells rows of an isoform matrix resident at iso; w supplies the
+// stream, the scratch for the tile sums and the gene map
+void launch_finish(scasa_ctx *w, const double *iso, int64_t n_cells, double *gene, double *colsum, int &launches)
 {
-    cudaStream_t s = c->stream;
+    cudaStream_t s = w->stream;
     const int n_tiles = (int)((n_cells + kTileCells - 1) / kTileCells);
-    c->d_partial.ensure((size_t)n_tiles * c->n_cols);
-    c->d_colsum.ensure((size_t)c->n_cols);
-    colsum_kernel<<<dim3(n_tiles, (unsigned)((c->n_cols + kFinCols - 1) / kFinCols)), kFinThreads, 0, s>>>(
-        c->d_iso.p, n_cells, c->n_cols, c->d_partial.p);
-    colsum_reduce<<<(unsigned)((c->n_cols + 255) / 256), 256, 0, s>>>(c->d_partial.p, n_tiles, c->n_cols, c->d_colsum.p);
+    w->d_partial.ensure((size_t)n_tiles * w->n_cols);
+    colsum_kernel<<<dim3(n_tiles, (unsigned)((w->n_cols + kFinCols - 1) / kFinCols)), kFinThreads, 0, s>>>(
+        iso, n_cells, w->n_cols, w->d_partial.p);
+    colsum_reduce<<<(unsigned)((w->n_cols + 255) / 256), 256, 0, s>>>(w->d_partial.p, n_tiles, w->n_cols, colsum);
     launches += 2;
     if (gene) {
-        const size_t smem = (size_t)c->n_genes * sizeof(double);
+        const size_t smem = (size_t)w->n_genes * sizeof(double);
         if (smem <= 220 * 1024 && getenv("SCASA_GENE_SMEM")) {
             CK(cudaFuncSetAttribute(gene_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const int grid = (int)std::min<int64_t>(n_cells, (int64_t)c->n_sm);
-            gene_smem_kernel<<<grid, 1024, smem, s>>>(c->d_iso.p, n_cells, c->n_cols, c->d_gene_of_col.p,
-                                                      c->d_gene_ptr.p, c->d_gene_cols.p, c->n_genes, gene);
+            const int grid = (int)std::min<int64_t>(n_cells, (int64_t)w->n_sm);
+            gene_smem_kernel<<<grid, 1024, smem, s>>>(iso, n_cells, w->n_cols, w->d_gene_of_col.p,
+                                                      w->d_gene_ptr.p, w->d_gene_cols.p, w->n_genes, gene);
         } else {
-            const int tiles = (c->n_genes + kGeneThreads * kGeneIlp - 1) / (kGeneThreads * kGeneIlp);
+            const int tiles = (w->n_genes + kGeneThreads * kGeneIlp - 1) / (kGeneThreads * kGeneIlp);
             if (n_cells * tiles >= ((int64_t)1 << 31)) throw ArgErr{SCASA_ERR_UNSUPPORTED, "too many cells x genes for one launch"};
-            gene_gather_kernel<<<(unsigned)(n_cells * tiles), kGeneThreads, 0, s>>>(c->d_iso.p, n_cells, c->n_cols, c->d_gene_ptr.p,
-                                                                                   c->d_gene_cols.p, c->n_genes, tiles, gene);
+            gene_gather_kernel<<<(unsigned)(n_cells * tiles), kGeneThreads, 0, s>>>(iso, n_cells, w->n_cols, w->d_gene_ptr.p,
+                                                                                   w->d_gene_cols.p, w->n_genes, tiles, gene);
         }
         launches++;
     }
@@ -551,6 +556,7 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
                              [&](int32_t x, int32_t y) { return cost[(size_t)x] > cost[(size_t)y]; });
         }
         if (getenv("SCASA_FETCH_DENSE")) c->fetch_dense_copy = 1;
+        if (const char *env = getenv("SCASA_RUN_PARTS")) c->run_parts = std::max(0, atoi(env));
         // EM work classes; SCASA_EM_CFG="warps:pairs:bytes:cta_threads:ctas_per_sm,..." overrides (tuning)
         if (const char *env = getenv("SCASA_EM_CFG")) {
             int k = 0;
@@ -633,7 +639,7 @@ void scasa_ctx_destroy(scasa_ctx *c)
     DBuf<int64_t> *i64[] = {&c->d_x_off, &c->d_chunk_off, &c->d_y_start, &c->d_cell_ptr, &c->d_toff, &c->d_scan_sums, &c->d_totals};
     for (auto b : i64) b->release();
     DBuf<double> *f64[] = {&c->d_x, &c->d_y_val, &c->d_iso, &c->d_partial,
-                           &c->d_colsum, &c->d_gene};
+                           &c->d_colsum, &c->d_colsum_parts, &c->d_gene};
     for (auto b : f64) b->release();
     c->d_poor.release(); c->d_next.release(); c->d_stats.release(); c->d_flag.release();
     c->d_tdata.release(); c->d_counters.release(); c->d_row_info.release(); c->d_scatter_scratch.release();
@@ -797,179 +803,294 @@ int scasa_set_gene_map(scasa_ctx *c, const int32_t *gene_of_col, int32_t n_genes
     });
 }
 
-int scasa_run(scasa_ctx *c)
+// What one range of chunks contributed to the run statistics.
+struct RangeStats {
+    float pack_ms = 0, tasks_ms = 0, em_ms = 0, finish_ms = 0, cls_ms[kClasses] = {0, 0, 0, 0};
+    unsigned long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned int cnts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t blob_bytes = 0;
+    int launches = 0;
+};
+
+// Chunks [h0, h1) of the sample staged in c: pack -> tasks -> EM -> column / gene sums, with w's
+// work buffers, streams and X-matrix tables (w is c itself or its twin).  Results go into c's matrices.
+static void run_range(scasa_ctx *w, scasa_ctx *c, int h0, int h1, int part, RangeStats &rs)
 {
-    if (!c) return fail(c, SCASA_ERR_ARG, "null context");
+    cudaStream_t s = w->stream;
+    int launches = 0;
+    const int n_chunks = h1 - h0;
+    const int64_t c0 = c->chunk_off[(size_t)h0], n_cells = c->chunk_off[(size_t)h1] - c0;
+    const int64_t n_tasks = (int64_t)n_chunks * w->n_em;
+    double *iso = c->d_iso.p + c0 * c->n_cols;
+    w->d_cnt.ensure((size_t)n_tasks + 1); w->d_runs.ensure((size_t)n_tasks + 1);
+    w->d_tbytes.ensure((size_t)n_tasks + 1); w->d_toff.ensure((size_t)n_tasks + 1);
+    for (int k = 0; k < kClasses; k++) w->d_list[k].ensure((size_t)n_tasks + 1);
+
+    CK(cudaEventRecord(w->ev[0], s));
+    CK(cudaMemsetAsync(w->d_cnt.p, 0, (n_tasks + 1) * sizeof(int32_t), s));
+    CK(cudaMemsetAsync(w->d_runs.p, 0, (n_tasks + 1) * sizeof(int32_t), s));
+    CK(cudaMemsetAsync(w->d_stats.p, 0, 8 * sizeof(unsigned long long), s));
+    CK(cudaMemsetAsync(w->d_next.p, 0, 16 * sizeof(unsigned int), s));
+    CK(cudaMemsetAsync(w->d_counters.p, 0, 8 * sizeof(unsigned int), s));
+    CK(cudaMemsetAsync(w->d_flag.p, 0, sizeof(int), s));
+
+    // ---- pack: eqclass counts -> Y
+    if (c->have_eq) {
+        const int wpt = (int)((c->n_rows + 32 * 512 - 1) / (32 * 512));      // bitmap words per thread
+        const size_t dense_smem = (size_t)wpt * 512 * 33 * sizeof(int);       // int32 histogram + touched-row bitmap
+        if (dense_smem <= 200 * 1024 && !getenv("SCASA_PACK_SORT")) {
+            CK(cudaFuncSetAttribute(pack_cells_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_smem));
+            int grid = (int)std::min<int64_t>(n_cells, (int64_t)w->n_sm);
+            pack_cells_dense_kernel<<<grid, 512, dense_smem, s>>>(n_cells, c->d_cell_ptr.p + c0, c->d_eq_id.p, c->d_eq_count.p,
+                                                                  c->d_eq_row.p, c->n_eq, (int)c->n_rows, wpt, c->d_y_row.p,
+                                                                  c->d_y_val.p, c->d_y_len.p + c0);
+        } else {
+            int cap = 32;
+            while (cap < c->max_cell_entries) cap <<= 1;
+            size_t smem = (size_t)cap * sizeof(unsigned long long);
+            CK(cudaFuncSetAttribute(pack_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int grid = (int)std::min<int64_t>(n_cells, (int64_t)w->n_sm * 8);
+            pack_cells_kernel<<<grid, 256, smem, s>>>(n_cells, c->d_cell_ptr.p + c0, c->d_eq_id.p, c->d_eq_count.p,
+                                                      c->d_eq_row.p, c->n_eq, cap, c->d_y_row.p, c->d_y_val.p,
+                                                      c->d_y_len.p + c0, w->d_flag.p);
+        }
+        CK(cudaGetLastError());
+        launches++;
+    }
+    CK(cudaEventRecord(w->ev[1], s));
+
+    XDev X = xdev(w);
+    Sample S = sdev(c, h0, h1);
+    // ---- result rows: zeros + pass-through blocks, on a side stream next to the task build
+    {
+        cudaStream_t fs = w->cls_stream[0];
+        CK(cudaStreamWaitEvent(fs, w->ev[1], 0));
+        const size_t smem = (size_t)kFillTile * sizeof(double);
+        CK(cudaFuncSetAttribute(iso_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = (int)std::min<int64_t>(n_cells, (int64_t)w->n_sm * 3);
+        iso_fill_kernel<<<grid, kFillThreads, smem, fs>>>(X, S, iso);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(w->ev_fill, fs));
+        launches++;
+    }
+
+    // ---- task extents, work classes, blobs
+    Tasks T = tdev(w);
+    EmOpts O;
+    O.maxiter_x = c->opts.maxiter_x; O.maxiter_bt = c->opts.maxiter_bt; O.modify = c->opts.modify;
+    O.fixed_iter = c->opts.fixed_iter;
+    O.maxerr = c->opts.maxerr; O.lim = c->opts.lim; O.adjust_esp = c->opts.adjust_esp;
+    ClassCfg CC;
+    for (int k = 0; k < kClasses; k++) { CC.pairs[k] = c->cls_pairs[k]; CC.bytes[k] = c->cls_bytes[k]; }
+    int32_t *iters = c->d_iters.p + (int64_t)h0 * w->n_em * 2;
+    int64_t tot[2] = {0, 0};
+    unsigned int *cnts = rs.cnts;
+    if (w->n_em > 0) {
+        const int wpb = 8;
+        task_count_kernel<<<(unsigned)((n_cells + wpb - 1) / wpb), wpb * 32, 0, s>>>(X, S, T);
+        classify_kernel<<<(unsigned)((n_tasks + 255) / 256), 256, 0, s>>>(X, S, T, n_tasks, O, CC, iters, w->d_stats.p);
+        launches += 2;
+        exclusive_scan(w, w->d_tbytes.p, n_tasks, w->d_toff.p, w->d_totals.p + 0, launches);
+        CK(cudaMemcpyAsync(tot, w->d_totals.p, sizeof tot, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(cnts, w->d_counters.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (cnts[7] == 1) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a poor-condition (2-column) block may have at most 64 rows"};
+        if (cnts[7] == 2) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a (chunk, block) task may hold at most 65535 cells-with-counts and 65535 count entries"};
+        if (cnts[5] > 200 * 1024) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a (chunk, block) task needs more than 200 KB of shared memory (chunk too large for this block)"};
+        w->d_tdata.ensure((size_t)tot[0] + 64);
+        T = tdev(w);
+        rs.blob_bytes = tot[0];
+        const size_t st_bytes = (size_t)3 * w->n_em * sizeof(uint32_t);
+        uint32_t *scratch = nullptr;
+        if (st_bytes > 160 * 1024) {           // too many EM blocks for shared memory: cursors in HBM
+            w->d_scatter_scratch.ensure((size_t)n_chunks * 3 * w->n_em);
+            scratch = w->d_scatter_scratch.p;
+        } else CK(cudaFuncSetAttribute(task_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_bytes));
+        task_scatter_kernel<<<n_chunks, kScatterThreads, scratch ? 0 : st_bytes, s>>>(X, S, T, scratch);
+        CK(cudaGetLastError());
+        launches++;
+    }
+    CK(cudaStreamWaitEvent(s, w->ev_fill, 0));
+    CK(cudaEventRecord(w->ev[2], s));
+
+    // ---- EM: one persistent kernel per work class, side by side on their own streams
+    bool ran_cls[kClasses] = {false, false, false, false};
+    if (w->n_em > 0 && cnts[4] > 0) {
+        CK(cudaEventRecord(w->ev_fork, s));
+        for (int k = kClasses - 1; k >= 0; k--) {          // long tasks first
+            const unsigned n = cnts[k];
+            if (n == 0) continue;
+            const int W = c->cls_warps[k];
+            const int threads = c->cls_cta_threads[k];
+            const int groups = threads / (32 * W);
+            int slot = (k == kClasses - 1) ? (int)cnts[5] : std::min<int>(c->cls_bytes[k], (int)cnts[5]);
+            slot = (slot + 15) & ~15;
+            const size_t smem = (size_t)slot * groups;
+            if (smem > 220 * 1024) throw ArgErr{SCASA_ERR_UNSUPPORTED, "EM work class needs more shared memory than an SM has"};
+            EmArgs A;
+            A.X = X; A.S = S; A.T = T; A.O = O; A.out = iso; A.iters = iters; A.stats = w->d_stats.p;
+            A.list = w->d_list[k].p; A.list_n = w->d_counters.p + k; A.next = w->d_next.p + k; A.slot_bytes = slot;
+            const unsigned grid = (unsigned)std::min<int64_t>((int64_t)w->n_sm * c->cls_ctas_per_sm[k], ((int64_t)n + groups - 1) / groups);
+            cudaStream_t cs = w->cls_stream[k];
+            CK(cudaStreamWaitEvent(cs, w->ev_fork, 0));
+            CK(cudaEventRecord(w->ev_cls[k][0], cs));
+            switch (W) {
+            case 1: launch_em<1>(A, grid, threads, smem, cs); break;
+            case 2: launch_em<2>(A, grid, threads, smem, cs); break;
+            case 4: launch_em<4>(A, grid, threads, smem, cs); break;
+            default: launch_em<8>(A, grid, threads, smem, cs); break;
+            }
+            CK(cudaEventRecord(w->ev_cls[k][1], cs));
+            CK(cudaEventRecord(w->ev_join[k], cs));
+            CK(cudaStreamWaitEvent(s, w->ev_join[k], 0));
+            ran_cls[k] = true;
+            launches++;
+        }
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(w->ev[3], s));
+
+    // ---- column sums (+ gene sums)
+    double *gene = c->n_genes > 0 ? c->d_gene.p + c0 * (int64_t)c->n_genes : nullptr;
+    launch_finish(w, iso, n_cells, gene, c->d_colsum_parts.p + (size_t)part * c->n_cols, launches);
+    CK(cudaEventRecord(w->ev[4], s));
+
+    int flag = 0;
+    CK(cudaMemcpyAsync(rs.st, w->d_stats.p, sizeof rs.st, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&flag, w->d_flag.p, sizeof flag, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (flag) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a cell exceeded the eqclass capacity of the pack kernel"};
+    CK(cudaEventElapsedTime(&rs.pack_ms, w->ev[0], w->ev[1]));
+    CK(cudaEventElapsedTime(&rs.tasks_ms, w->ev[1], w->ev[2]));
+    CK(cudaEventElapsedTime(&rs.em_ms, w->ev[2], w->ev[3]));
+    CK(cudaEventElapsedTime(&rs.finish_ms, w->ev[3], w->ev[4]));
+    for (int k = 0; k < kClasses; k++)
+        if (ran_cls[k]) CK(cudaEventElapsedTime(&rs.cls_ms[k], w->ev_cls[k][0], w->ev_cls[k][1]));
+    rs.launches = launches;
+}
+
+// make the twin context (second set of streams and work buffers on the same GPU) match c
+static int sync_twin(scasa_ctx *c)
+{
+    if (!c->twin) {
+        scasa_xmat_t m;
+        m.n_blocks = c->B; m.q_off = c->q_off.data(); m.p_off = c->p_off.data(); m.x_off = c->x_off.data(); m.x = c->x.data();
+        int rc = scasa_ctx_create(&m, nullptr, &c->opts, c->device, &c->twin);
+        if (rc) return fail(c, rc, std::string("twin context: ") + scasa_last_error(nullptr));
+    }
+    scasa_ctx *t = c->twin;
+    t->opts = c->opts; t->host_threads = c->host_threads; t->fetch_dense_copy = c->fetch_dense_copy;
+    for (int k = 0; k < kClasses; k++) {
+        t->cls_warps[k] = c->cls_warps[k]; t->cls_pairs[k] = c->cls_pairs[k]; t->cls_bytes[k] = c->cls_bytes[k];
+        t->cls_cta_threads[k] = c->cls_cta_threads[k]; t->cls_ctas_per_sm[k] = c->cls_ctas_per_sm[k];
+    }
+    if (c->n_genes > 0 && (t->n_genes != c->n_genes || t->gene_of_col_host != c->gene_of_col_host)) {
+        int rc = scasa_set_gene_map(t, c->gene_of_col_host.data(), c->n_genes);
+        if (rc) return fail(c, rc, std::string("twin context: ") + scasa_last_error(t));
+    } else if (c->n_genes <= 0) t->n_genes = 0;
+    return SCASA_OK;
+}
+
+// The staged sample is cut into ranges of chunks that alternate between this context and its twin,
+// each driven by its own host thread: the instruction-bound EM kernels of one range run next to
+// the bandwidth-bound pack / row-fill / gene kernels of another.  Chunks are independent, so the
+// cut changes no result.  `allow_split = false` (scasa_quant's slices, which already alternate on
+// the two contexts) runs everything as one range on c.
+static int run_staged(scasa_ctx *c, bool allow_split)
+{
     if (!c->staged) return fail(c, SCASA_ERR_STATE, "nothing staged: call scasa_stage_counts / scasa_stage_eqcounts first");
+    int parts = 1;
+    if (allow_split) {
+        parts = c->run_parts > 0 ? c->run_parts : 1;   // measured: no gain (the persistent EM kernels fill the SMs' registers
+                                                        // and shared memory, the other range's kernels queue behind them)
+        parts = std::max(1, std::min(parts, c->n_chunks));
+    }
+    if (parts > 1) { int rc = sync_twin(c); if (rc) return rc; }
+    // range boundaries: the first and last ranges are half-size so that the two workers fall out of phase
+    std::vector<int> cut((size_t)parts + 1, 0);
+    {
+        std::vector<double> wgt((size_t)parts, 1.0);
+        if (parts >= 4) { wgt[0] = 0.5; wgt[(size_t)parts - 1] = 0.5; }
+        double tot = 0, acc = 0;
+        for (double x : wgt) tot += x;
+        for (int k = 0; k < parts; k++) {
+            acc += wgt[(size_t)k];
+            cut[(size_t)k + 1] = std::max(cut[(size_t)k] + 1, (int)std::llround(c->n_chunks * acc / tot));
+        }
+        cut[(size_t)parts] = c->n_chunks;
+        for (int k = parts - 1; k > 0; k--) cut[(size_t)k] = std::min(cut[(size_t)k], cut[(size_t)k + 1] - 1);
+    }
+    std::vector<RangeStats> rs((size_t)parts);
+    int rcs[2] = {SCASA_OK, SCASA_OK};
+    int rc0 = guarded(c, [&] {
+        const int64_t n_tasks = (int64_t)c->n_chunks * c->n_em;
+        c->d_iso.ensure((size_t)(c->n_cells * c->n_cols));
+        c->d_iters.ensure((size_t)n_tasks * 2 + 2);
+        c->d_colsum.ensure((size_t)c->n_cols);
+        c->d_colsum_parts.ensure((size_t)parts * c->n_cols);
+        if (c->n_genes > 0) c->d_gene.ensure((size_t)c->n_cells * c->n_genes);
+        CK(cudaEventRecord(c->ev[6], c->stream));
+    });
+    if (rc0) return rc0;
+    auto drive = [&](int which) {
+        scasa_ctx *w = which ? c->twin : c;
+        for (int k = which; k < parts; k += 2) {
+            int rc = guarded(w, [&] { run_range(w, c, cut[(size_t)k], cut[(size_t)k + 1], k, rs[(size_t)k]); });
+            if (rc) { rcs[which] = rc; return; }
+        }
+    };
+    if (parts > 1) {
+        try {
+            std::thread other(drive, 1);
+            drive(0);
+            other.join();
+        } catch (const std::exception &e) {
+            return fail(c, SCASA_ERR_NOMEM, e.what());
+        }
+    } else drive(0);
+    if (rcs[0]) return rcs[0];
+    if (rcs[1]) return fail(c, rcs[1], std::string("twin context: ") + scasa_last_error(c->twin));
     return guarded(c, [&] {
         cudaStream_t s = c->stream;
-        int launches = 0;
-        const int64_t n_tasks = (int64_t)c->n_chunks * c->n_em;
-        const int64_t iso_elems = c->n_cells * c->n_cols;
-        c->d_iso.ensure((size_t)iso_elems);
-        c->d_cnt.ensure((size_t)n_tasks + 1); c->d_runs.ensure((size_t)n_tasks + 1);
-        c->d_tbytes.ensure((size_t)n_tasks + 1); c->d_toff.ensure((size_t)n_tasks + 1);
-        for (int k = 0; k < kClasses; k++) c->d_list[k].ensure((size_t)n_tasks + 1);
-        c->d_iters.ensure((size_t)n_tasks * 2 + 2);
-
-        CK(cudaEventRecord(c->ev[0], s));
-        CK(cudaMemsetAsync(c->d_cnt.p, 0, (n_tasks + 1) * sizeof(int32_t), s));
-        CK(cudaMemsetAsync(c->d_runs.p, 0, (n_tasks + 1) * sizeof(int32_t), s));
-        CK(cudaMemsetAsync(c->d_stats.p, 0, 8 * sizeof(unsigned long long), s));
-        CK(cudaMemsetAsync(c->d_next.p, 0, 16 * sizeof(unsigned int), s));
-        CK(cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(unsigned int), s));
-        CK(cudaMemsetAsync(c->d_flag.p, 0, sizeof(int), s));
-
-        // ---- pack: eqclass counts -> Y
-        if (c->have_eq) {
-            const int wpt = (int)((c->n_rows + 32 * 512 - 1) / (32 * 512));      // bitmap words per thread
-            const size_t dense_smem = (size_t)wpt * 512 * 33 * sizeof(int);       // int32 histogram + touched-row bitmap
-            if (dense_smem <= 200 * 1024 && !getenv("SCASA_PACK_SORT")) {
-                CK(cudaFuncSetAttribute(pack_cells_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_smem));
-                int grid = (int)std::min<int64_t>(c->n_cells, (int64_t)c->n_sm);
-                pack_cells_dense_kernel<<<grid, 512, dense_smem, s>>>(c->n_cells, c->d_cell_ptr.p, c->d_eq_id.p, c->d_eq_count.p,
-                                                                      c->d_eq_row.p, c->n_eq, (int)c->n_rows, wpt, c->d_y_row.p,
-                                                                      c->d_y_val.p, c->d_y_len.p);
-            } else {
-                int cap = 32;
-                while (cap < c->max_cell_entries) cap <<= 1;
-                size_t smem = (size_t)cap * sizeof(unsigned long long);
-                CK(cudaFuncSetAttribute(pack_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                int grid = (int)std::min<int64_t>(c->n_cells, (int64_t)c->n_sm * 8);
-                pack_cells_kernel<<<grid, 256, smem, s>>>(c->n_cells, c->d_cell_ptr.p, c->d_eq_id.p, c->d_eq_count.p,
-                                                          c->d_eq_row.p, c->n_eq, cap, c->d_y_row.p, c->d_y_val.p,
-                                                          c->d_y_len.p, c->d_flag.p);
-            }
-            CK(cudaGetLastError());
-            launches++;
-        }
-        CK(cudaEventRecord(c->ev[1], s));
-
-        // ---- result rows: zeros + pass-through blocks, on a side stream next to the task build
-        {
-            cudaStream_t fs = c->cls_stream[0];
-            CK(cudaStreamWaitEvent(fs, c->ev[1], 0));
-            const size_t smem = (size_t)kFillTile * sizeof(double);
-            CK(cudaFuncSetAttribute(iso_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const int grid = (int)std::min<int64_t>(c->n_cells, (int64_t)c->n_sm * 3);
-            iso_fill_kernel<<<grid, kFillThreads, smem, fs>>>(xdev(c), sdev(c), c->d_iso.p);
-            CK(cudaGetLastError());
-            CK(cudaEventRecord(c->ev_fill, fs));
-            launches++;
-        }
-
-        // ---- task extents, work classes, blobs
-        XDev X = xdev(c);
-        Sample S = sdev(c);
-        Tasks T = tdev(c);
-        EmOpts O;
-        O.maxiter_x = c->opts.maxiter_x; O.maxiter_bt = c->opts.maxiter_bt; O.modify = c->opts.modify;
-        O.fixed_iter = c->opts.fixed_iter;
-        O.maxerr = c->opts.maxerr; O.lim = c->opts.lim; O.adjust_esp = c->opts.adjust_esp;
-        ClassCfg CC;
-        for (int k = 0; k < kClasses; k++) { CC.pairs[k] = c->cls_pairs[k]; CC.bytes[k] = c->cls_bytes[k]; }
-        int64_t tot[2] = {0, 0};
-        unsigned int cnts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (c->n_em > 0) {
-            const int wpb = 8;
-            task_count_kernel<<<(unsigned)((c->n_cells + wpb - 1) / wpb), wpb * 32, 0, s>>>(X, S, T);
-            classify_kernel<<<(unsigned)((n_tasks + 255) / 256), 256, 0, s>>>(X, S, T, n_tasks, O, CC, c->d_iters.p, c->d_stats.p);
-            launches += 2;
-            exclusive_scan(c, c->d_tbytes.p, n_tasks, c->d_toff.p, c->d_totals.p + 0, launches);
-            CK(cudaMemcpyAsync(tot, c->d_totals.p, sizeof tot, cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(cnts, c->d_counters.p, sizeof cnts, cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
-            if (cnts[7] == 1) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a poor-condition (2-column) block may have at most 64 rows"};
-            if (cnts[7] == 2) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a (chunk, block) task may hold at most 65535 cells-with-counts and 65535 count entries"};
-            if (cnts[5] > 200 * 1024) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a (chunk, block) task needs more than 200 KB of shared memory (chunk too large for this block)"};
-            c->d_tdata.ensure((size_t)tot[0] + 64);
-            T = tdev(c);
-            c->timing.n_entries = tot[0];
-        }
-        if (c->n_em > 0) {
-            const size_t st_bytes = (size_t)3 * c->n_em * sizeof(uint32_t);
-            uint32_t *scratch = nullptr;
-            if (st_bytes > 160 * 1024) {           // too many EM blocks for shared memory: cursors in HBM
-                c->d_scatter_scratch.ensure((size_t)c->n_chunks * 3 * c->n_em);
-                scratch = c->d_scatter_scratch.p;
-            } else CK(cudaFuncSetAttribute(task_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_bytes));
-            task_scatter_kernel<<<c->n_chunks, kScatterThreads, scratch ? 0 : st_bytes, s>>>(X, S, T, scratch);
-            CK(cudaGetLastError());
-            launches++;
-        }
-        CK(cudaStreamWaitEvent(s, c->ev_fill, 0));
-        CK(cudaEventRecord(c->ev[2], s));
-
-        // ---- EM: one persistent kernel per work class, side by side on their own streams
-        bool ran_cls[kClasses] = {false, false, false, false};
-        if (c->n_em > 0 && cnts[4] > 0) {
-            CK(cudaEventRecord(c->ev_fork, s));
-            for (int k = kClasses - 1; k >= 0; k--) {          // long tasks first
-                const unsigned n = cnts[k];
-                if (n == 0) continue;
-                const int W = c->cls_warps[k];
-                const int threads = c->cls_cta_threads[k];
-                const int groups = threads / (32 * W);
-                int slot = (k == kClasses - 1) ? (int)cnts[5] : std::min<int>(c->cls_bytes[k], (int)cnts[5]);
-                slot = (slot + 15) & ~15;
-                const size_t smem = (size_t)slot * groups;
-                if (smem > 220 * 1024) throw ArgErr{SCASA_ERR_UNSUPPORTED, "EM work class needs more shared memory than an SM has"};
-                EmArgs A;
-                A.X = X; A.S = S; A.T = T; A.O = O; A.out = c->d_iso.p; A.iters = c->d_iters.p; A.stats = c->d_stats.p;
-                A.list = c->d_list[k].p; A.list_n = c->d_counters.p + k; A.next = c->d_next.p + k; A.slot_bytes = slot;
-                const unsigned grid = (unsigned)std::min<int64_t>((int64_t)c->n_sm * c->cls_ctas_per_sm[k], ((int64_t)n + groups - 1) / groups);
-                cudaStream_t cs = c->cls_stream[k];
-                CK(cudaStreamWaitEvent(cs, c->ev_fork, 0));
-                CK(cudaEventRecord(c->ev_cls[k][0], cs));
-                switch (W) {
-                case 1: launch_em<1>(A, grid, threads, smem, cs); break;
-                case 2: launch_em<2>(A, grid, threads, smem, cs); break;
-                case 4: launch_em<4>(A, grid, threads, smem, cs); break;
-                default: launch_em<8>(A, grid, threads, smem, cs); break;
-                }
-                CK(cudaEventRecord(c->ev_cls[k][1], cs));
-                CK(cudaEventRecord(c->ev_join[k], cs));
-                CK(cudaStreamWaitEvent(s, c->ev_join[k], 0));
-                ran_cls[k] = true;
-                launches++;
-            }
-            CK(cudaGetLastError());
-        }
-        CK(cudaEventRecord(c->ev[3], s));
-
-        // ---- column sums (+ gene sums)
-        double *gene = nullptr;
-        if (c->n_genes > 0) { c->d_gene.ensure((size_t)c->n_cells * c->n_genes); gene = c->d_gene.p; }
-        launch_finish(c, c->n_cells, gene, launches);
-        CK(cudaEventRecord(c->ev[4], s));
-
-        unsigned long long st[8];
-        int flag = 0;
-        CK(cudaMemcpyAsync(st, c->d_stats.p, sizeof st, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(&flag, c->d_flag.p, sizeof flag, cudaMemcpyDeviceToHost, s));
+        colsum_combine<<<(unsigned)((c->n_cols + 255) / 256), 256, 0, s>>>(c->d_colsum_parts.p, parts, c->n_cols, c->d_colsum.p);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(c->ev[7], s));
         CK(cudaStreamSynchronize(s));
-        if (flag) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a cell exceeded the eqclass capacity of the pack kernel"};
         scasa_timing_t &tm = c->timing;
-        CK(cudaEventElapsedTime(&tm.total_ms, c->ev[0], c->ev[4]));
-        CK(cudaEventElapsedTime(&tm.pack_ms, c->ev[0], c->ev[1]));
-        CK(cudaEventElapsedTime(&tm.tasks_ms, c->ev[1], c->ev[2]));
-        CK(cudaEventElapsedTime(&tm.em_ms, c->ev[2], c->ev[3]));
-        CK(cudaEventElapsedTime(&tm.finish_ms, c->ev[3], c->ev[4]));
-        for (int k = 0; k < kClasses; k++) {
-            tm.em_class_ms[k] = 0.f;
-            tm.em_class_tasks[k] = cnts[k];
-            if (ran_cls[k]) CK(cudaEventElapsedTime(&tm.em_class_ms[k], c->ev_cls[k][0], c->ev_cls[k][1]));
+        memset(&tm, 0, sizeof tm);
+        CK(cudaEventElapsedTime(&tm.total_ms, c->ev[6], c->ev[7]));
+        unsigned long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (const RangeStats &r : rs) {
+            tm.pack_ms += r.pack_ms; tm.tasks_ms += r.tasks_ms; tm.em_ms += r.em_ms; tm.finish_ms += r.finish_ms;
+            for (int k = 0; k < kClasses; k++) { tm.em_class_ms[k] += r.cls_ms[k]; tm.em_class_tasks[k] += r.cnts[k]; }
+            for (int k = 0; k < 8; k++) st[k] += r.st[k];
+            tm.n_entries += r.blob_bytes;
+            tm.launches += r.launches;
+            tm.max_slot_bytes = std::max<int32_t>(tm.max_slot_bytes, (int32_t)r.cnts[5]);
         }
+        tm.launches += 1;
+        tm.run_parts = parts;
         tm.gene_ms = c->n_genes > 0 ? tm.finish_ms : 0.f;
         tm.inner_iters = (int64_t)st[0]; tm.outer_iters = (int64_t)st[1];
         tm.n_tasks = (int64_t)st[4]; tm.n_active = (int64_t)st[5];
-        tm.max_slot_bytes = (int32_t)cnts[5];
         // sum_tasks [in*8*(q+2p)*n_c + out*8*(q+p)*n_c] + n_cells*8*(sum q + sum p)
         tm.em_alg_bytes = 8.0 * ((double)st[2] + (double)st[3]);
         tm.alg_bytes = tm.em_alg_bytes + (double)c->n_cells * 8.0 * (double)(c->n_rows + c->n_cols);
-        tm.launches = launches;
         c->ran = true;
     });
+}
+
+int scasa_run(scasa_ctx *c)
+{
+    if (!c) return fail(c, SCASA_ERR_ARG, "null context");
+    return run_staged(c, true);
+}
+
+int scasa_set_run_parts(scasa_ctx *c, int32_t n_parts)
+{
+    if (!c || n_parts < 0) return fail(c, SCASA_ERR_ARG, "bad argument");
+    c->run_parts = n_parts;
+    return SCASA_OK;
 }
 
 int scasa_last_timing(scasa_ctx *c, scasa_timing_t *out)
@@ -1117,25 +1238,8 @@ int scasa_quant(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const int64_t *
     if (gene_out && c->n_genes <= 0) return fail(c, SCASA_ERR_STATE, "no gene map set");
     if (n_slices <= 0) n_slices = std::max(2, std::min(8, n_chunks / 128));   // measured: 4-8 slices of >= 100 chunks are best
     n_slices = std::max(1, std::min(n_slices, n_chunks));
-    if (n_slices > 1 && !c->twin) {
-        scasa_xmat_t m;
-        m.n_blocks = c->B; m.q_off = c->q_off.data(); m.p_off = c->p_off.data(); m.x_off = c->x_off.data(); m.x = c->x.data();
-        int rc = scasa_ctx_create(&m, nullptr, &c->opts, c->device, &c->twin);
-        if (rc) return fail(c, rc, std::string("twin context: ") + scasa_last_error(nullptr));
-    }
+    if (n_slices > 1) { int rc = sync_twin(c); if (rc) return rc; }
     scasa_ctx *ctxs[2] = {c, n_slices > 1 ? c->twin : c};
-    if (n_slices > 1) {
-        scasa_ctx *t = c->twin;
-        t->opts = c->opts; t->host_threads = c->host_threads; t->fetch_dense_copy = c->fetch_dense_copy;
-        for (int k = 0; k < kClasses; k++) {
-            t->cls_warps[k] = c->cls_warps[k]; t->cls_pairs[k] = c->cls_pairs[k]; t->cls_bytes[k] = c->cls_bytes[k];
-            t->cls_cta_threads[k] = c->cls_cta_threads[k]; t->cls_ctas_per_sm[k] = c->cls_ctas_per_sm[k];
-        }
-        if (c->n_genes > 0 && (t->n_genes != c->n_genes || t->gene_of_col_host != c->gene_of_col_host)) {
-            int rc = scasa_set_gene_map(t, c->gene_of_col_host.data(), c->n_genes);
-            if (rc) return fail(c, rc, std::string("twin context: ") + scasa_last_error(t));
-        } else if (c->n_genes <= 0) t->n_genes = 0;
-    }
     std::vector<double> colsum_parts;
     if (colsum_out) colsum_parts.assign((size_t)n_slices * c->n_cols, 0.0);
     int rcs[2] = {SCASA_OK, SCASA_OK};
@@ -1152,7 +1256,7 @@ int scasa_quant(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const int64_t *
             const int64_t e0 = cell_ptr[c0];
             for (int64_t i = c0; i <= c1; i++) ptr[(size_t)(i - c0)] = cell_ptr[i] - e0;
             int rc = scasa_stage_eqcounts(x, c1 - c0, h1 - h0, coff.data(), ptr.data(), eq_id + e0, eq_count + e0, n_eq, eq_row);
-            if (!rc) rc = scasa_run(x);
+            if (!rc) rc = run_staged(x, false);
             if (!rc) rc = scasa_fetch_iso(x, iso_out + c0 * c->n_cols);
             if (!rc && gene_out) rc = scasa_fetch_gene(x, gene_out + c0 * (int64_t)c->n_genes);
             if (!rc && colsum_out) rc = scasa_fetch_colsum(x, colsum_parts.data() + (size_t)sl * c->n_cols);
@@ -1192,7 +1296,8 @@ int scasa_gene_sum(scasa_ctx *c, const int32_t *gene_of_col, int32_t n_genes, co
         c->d_gene.ensure((size_t)n_cells * n_genes);
         CK(cudaMemcpyAsync(c->d_iso.p, iso, n_cells * c->n_cols * sizeof(double), cudaMemcpyHostToDevice, s));
         int launches = 0;
-        launch_finish(c, n_cells, c->d_gene.p, launches);
+        c->d_colsum.ensure((size_t)c->n_cols);
+        launch_finish(c, c->d_iso.p, n_cells, c->d_gene.p, c->d_colsum.p, launches);
         CK(cudaMemcpyAsync(gene_out, c->d_gene.p, (size_t)n_cells * n_genes * sizeof(double), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
     });

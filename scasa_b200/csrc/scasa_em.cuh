@@ -363,7 +363,7 @@ template <int W> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs
 
         // ---- de-adjust (:1027-1037) and scatter BT into the result (:1042)
         const double deduct = nadj * O.adjust_esp;
-        const int64_t cbase = A.S.chunk_off[h];
+        const int64_t cbase = A.S.chunk_off[h] - A.S.cell_base;
         const int64_t col0 = X.p_off[b];
         for (int a = gl; a < n; a += GT) {
             const uint32_t cw = rcell[a];

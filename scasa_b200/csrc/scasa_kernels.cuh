@@ -88,9 +88,11 @@ struct XDev {                 // resident X-matrix (DM0) and its derived index m
     int n_poor;
 };
 
-struct Sample {               // what is staged for one scasa_run
-    int64_t n_cells;
+struct Sample {               // the cells [cell_base, cell_base + n_cells) = chunks [chunk_base, chunk_base + n_chunks)
+    int64_t n_cells;          // of the staged sample; every per-cell / per-chunk pointer below is already offset to the range
     int n_chunks;
+    int64_t cell_base;        // chunk_off and cell_chunk hold sample-wide values: subtract these
+    int chunk_base;
     const int64_t *chunk_off;   // [n_chunks+1]
     const int32_t *cell_chunk;  // [n_cells]
     const int64_t *y_start;     // [n_cells]  first Y entry of the cell
@@ -287,7 +289,7 @@ __global__ void task_count_kernel(XDev X, Sample S, Tasks T)
     const int lane = threadIdx.x & 31;
     const int64_t s = S.y_start[cell];
     const int n = S.y_len[cell];
-    const int64_t tbase = (int64_t)S.cell_chunk[cell] * X.n_em;
+    const int64_t tbase = (int64_t)(S.cell_chunk[cell] - S.chunk_base) * X.n_em;
     for (int i = lane; i < n; i += kWarp) {
         const int e = X.row_info[S.y_row[s + i]].x;
         if (e < 0) continue;
@@ -501,7 +503,7 @@ __global__ void __launch_bounds__(kScatterThreads) task_scatter_kernel(XDev X, S
 {
     extern __shared__ uint32_t scatter_sm[];
     const int h = blockIdx.x;
-    const int64_t c0 = S.chunk_off[h], c1 = S.chunk_off[h + 1];
+    const int64_t c0 = S.chunk_off[h] - S.cell_base, c1 = S.chunk_off[h + 1] - S.cell_base;
     const int nc = (int)(c1 - c0);
     const int64_t tbase = (int64_t)h * X.n_em;
     uint32_t *st = scratch ? scratch + (size_t)h * 3 * X.n_em : scatter_sm;
@@ -652,6 +654,16 @@ __global__ void colsum_reduce(const double *__restrict__ partial, int n_tiles, i
     if (j >= n_cols) return;
     double s = 0;
     for (int t = 0; t < n_tiles; t++) s += partial[(int64_t)t * n_cols + j];
+    colsum[j] = s;
+}
+
+// column sums of a run that was cut into ranges: the ranges' sums added in range order
+__global__ void colsum_combine(const double *__restrict__ parts, int n_parts, int64_t n_cols, double *__restrict__ colsum)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_cols) return;
+    double s = 0;
+    for (int k = 0; k < n_parts; k++) s += parts[(int64_t)k * n_cols + j];
     colsum[j] = s;
 }
 

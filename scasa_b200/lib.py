@@ -44,7 +44,7 @@ class Timing(C.Structure):
                 ("em_class_tasks", C.c_int64 * 4), ("n_tasks", C.c_int64), ("n_entries", C.c_int64),
                 ("n_active", C.c_int64), ("inner_iters", C.c_int64), ("outer_iters", C.c_int64),
                 ("alg_bytes", C.c_double), ("em_alg_bytes", C.c_double), ("launches", C.c_int32),
-                ("max_slot_bytes", C.c_int32)]
+                ("max_slot_bytes", C.c_int32), ("run_parts", C.c_int32)]
 
     def as_dict(self) -> dict:
         d = {}
@@ -61,7 +61,7 @@ SYMBOLS = (
     "scasa_chunk_split", "scasa_estimate", "scasa_stage_counts", "scasa_stage_eqcounts", "scasa_run",
     "scasa_fetch_iso", "scasa_fetch_iters", "scasa_fetch_colsum", "scasa_fetch_counts", "scasa_set_gene_map",
     "scasa_fetch_gene", "scasa_gene_sum", "scasa_eqclass_map", "scasa_last_timing", "scasa_host_alloc",
-    "scasa_host_free", "scasa_device_count", "scasa_version", "scasa_set_host_threads", "scasa_expand_pairs", "scasa_quant", "scasa_transfer_bytes", "scasa_bfh_open", "scasa_bfh_close", "scasa_bfh_sizes", "scasa_bfh_read", "scasa_write_table", "scasa_format_real15",
+    "scasa_host_free", "scasa_device_count", "scasa_version", "scasa_set_host_threads", "scasa_expand_pairs", "scasa_quant", "scasa_transfer_bytes", "scasa_bfh_open", "scasa_bfh_close", "scasa_bfh_sizes", "scasa_bfh_read", "scasa_write_table", "scasa_format_real15", "scasa_set_run_parts",
 )
 
 
@@ -103,6 +103,7 @@ def load():
     L.scasa_stage_counts.argtypes = [vp, C.c_int64, C.c_int32, i64p, i64p, i32p, f64p]
     L.scasa_stage_eqcounts.argtypes = [vp, C.c_int64, C.c_int32, i64p, i64p, i32p, i32p, C.c_int64, i32p]
     L.scasa_run.argtypes = [vp]
+    L.scasa_set_run_parts.argtypes = [vp, C.c_int32]
     L.scasa_write_table.argtypes = [C.c_char_p, f64p, C.c_int64, C.c_int64, u8p, C.c_char_p, C.c_char_p, C.c_int32]
     L.scasa_format_real15.argtypes = [C.c_double, C.c_char_p, C.c_int32]
     L.scasa_bfh_open.argtypes = [C.c_char_p, C.c_int32, C.POINTER(vp)]

@@ -230,3 +230,33 @@ def test_bfh_file_to_quant_equals_arrays(xm, tmp_path):
         g.close()
     assert np.array_equal(r1.iso.view(np.int64), r0.iso.view(np.int64))
     assert np.array_equal(r1.iters, r0.iters)
+
+
+def test_run_parts_do_not_change_results(xm):
+    """scasa_run cuts the staged chunks into ranges that run side by side on two stream sets
+    (EM kernels of one range next to the bandwidth-bound kernels of another): bitwise the same."""
+    from scasa_b200 import synth
+    from scasa_b200.api import Scasa, chunk_split
+    n = 730
+    rowptr, rows, vals = synth.CellGenerator(xm, seed=9).counts_csr(0, n)
+    ed = synth.eqclass_dictionary(xm, 9)
+    cell_ptr, eq_id, eq_cnt = synth.counts_to_eqcounts(rowptr, rows, vals, 9)
+    g = Scasa(xm, device=0)
+    try:
+        g.set_gene_map(np.asarray(xm.gene_of_col, np.int32), len(xm.gene_names))
+        eq_row = g.eqclass_map(ed.eq_off, ed.eq_tx, 4)
+        g.stage_eqcounts(chunk_split(n, 4), cell_ptr, eq_id, eq_cnt, eq_row)
+        out = {}
+        for parts in (1, 2, 5, 7):
+            g.set_run_parts(parts)
+            t = g.run()
+            assert t["run_parts"] == parts
+            out[parts] = (g.fetch_iso(), g.fetch_gene(), g.fetch_iters(), g.fetch_colsum(), g.fetch_counts())
+        for parts in (2, 5, 7):
+            for a, b in zip(out[parts][:3], out[1][:3]):
+                assert np.array_equal(a.view(np.int64) if a.dtype == np.float64 else a, b.view(np.int64) if b.dtype == np.float64 else b), parts
+            assert np.allclose(out[parts][3], out[1][3], rtol=1e-12, atol=0)
+            for a, b in zip(out[parts][4], out[1][4]):
+                assert np.array_equal(a, b)
+    finally:
+        g.close()
