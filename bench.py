@@ -236,13 +236,29 @@ def main():
         while ne > 1000 and out_bytes(ne) > 0.5 * avail:
             ne //= 2
         ne = min(ne, n)
-        nnz_e = int(cell_ptr[ne])
-        h_ptr = _l.pinned_empty(ne + 1, np.int64); h_ptr[:] = cell_ptr[: ne + 1]
-        h_id = _l.pinned_empty(nnz_e, np.int32); h_id[:] = eq_id[:nnz_e]
-        h_cnt = _l.pinned_empty(nnz_e, np.int32); h_cnt[:] = eq_cnt[:nnz_e]
-        h_iso = _l.pinned_empty((ne, xm.n_cols), np.float64)
-        h_gene = _l.pinned_empty((ne, n_genes), np.float64)
-
+        # pinned host buffers for the inputs, pageable ones for the two dense results; if the box cannot hold
+        # that much (several ranks share one host) fall back to a smaller sample rather than to no number
+        while True:
+            bufs = []
+            try:
+                nnz_e = int(cell_ptr[ne])
+                h_ptr = _l.pinned_empty(ne + 1, np.int64); bufs.append(h_ptr)
+                h_id = _l.pinned_empty(nnz_e, np.int32); bufs.append(h_id)
+                h_cnt = _l.pinned_empty(nnz_e, np.int32); bufs.append(h_cnt)
+                # the results are written by host threads (zero-suppressed transfer), so the caller's matrices
+                # need not be pinned: plain pageable memory, like the R matrices of the reference
+                h_iso = np.empty((ne, xm.n_cols), np.float64)
+                h_gene = np.empty((ne, n_genes), np.float64)
+                break
+            except Exception:
+                for a_ in bufs:
+                    _l.pinned_free(a_)
+                if ne <= 1000:
+                    raise
+                ne //= 2
+        h_ptr[:] = cell_ptr[: ne + 1]
+        h_id[:] = eq_id[:nnz_e]
+        h_cnt[:] = eq_cnt[:nnz_e]
         g.set_host_threads(nthreads)
 
         def e2e_step():
@@ -269,11 +285,12 @@ def main():
                "host_input_bytes": int(h_ptr.nbytes + h_id.nbytes + h_cnt.nbytes + eq_row.nbytes),
                "host_result_bytes": int(h_iso.nbytes + h_gene.nbytes),
                "includes": "host eqclass->row map, H2D counts, pack+EM+gene kernels, D2H isoform+gene matrices "
-                           "(zero-suppressed on the wire, dense in the caller's pinned buffers)",
+                           "(zero-suppressed on the wire, dense in the caller's pageable buffers)",
                "api": "scasa_b200.api.Scasa.quant -> scasa_quant (chunks in slices, two contexts: transfer of one slice "
                       "overlaps the computation of the next)", "host_threads": nthreads}
-        for a in (h_ptr, h_id, h_cnt, h_iso, h_gene):
+        for a in (h_ptr, h_id, h_cnt):
             _l.pinned_free(a)
+        del h_iso, h_gene
 
     if rank != 0:
         if world > 1:
@@ -287,8 +304,11 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     em_bytes = t["em_alg_bytes"]
+    em_ms = float(np.mean([x["em_ms"] for x in tms]))          # average launch duration over the timed steps
+    fin_ms = float(np.mean([x["finish_ms"] for x in tms]))
+    fin_bytes = n * (xm.n_cols * 8 * 2 + n_genes * 8)           # colsum reads iso; gene_gather reads iso and writes genes
     roofline = {"bound": "hbm", "kernel": "em_task_kernel<W> (4 persistent launches per step, W = 1/2/4/8 warps per task, side by side on 4 streams; em_ms = fork to join)",
-                "achieved": em_bytes / (t["em_ms"] * 1e-3) / 1e9, "peak": peak,
+                "achieved": em_bytes / (em_ms * 1e-3) / 1e9, "peak": peak,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
                 "unit": "GB/s",
                 # dram__bytes_read.sum + dram__bytes_write.sum of the four em_task_kernel launches of one step, from the
@@ -296,7 +316,12 @@ def main():
                 "traffic": 4.6e9 if (n == 100000 and not os.environ.get("SCASA_EM_CFG")) else None,
                 "model": "SURVEY.md 8(d) streaming model: sum over (chunk, block) tasks of inner*8*(q+2p)*n_c + "
                          "outer*8*(q+p)*n_c with the iteration counts the kernel actually ran",
-                "alg_bytes_per_launch_set": em_bytes, "em_ms": t["em_ms"],
+                "alg_bytes_per_launch_set": em_bytes, "em_ms": em_ms,
+                "note": "a task stays in shared memory for all its iterations, so the kernel moves `traffic` bytes, not the "
+                        "streaming-model bytes: frac > 1 is expected; ncu shows it instruction-issue bound (DESIGN.md 4-5)",
+                "hbm_phase": {"kernels": "colsum_kernel + colsum_reduce + gene_gather_kernel (stream the result matrices)",
+                              "bytes": fin_bytes, "ms": fin_ms, "achieved": fin_bytes / (fin_ms * 1e-3) / 1e9,
+                              "frac": fin_bytes / (fin_ms * 1e-3) / 1e9 / peak},
                 "whole_step": {"alg_bytes": t["alg_bytes"], "ms": t["total_ms"],
                                "achieved": t["alg_bytes"] / (t["total_ms"] * 1e-3) / 1e9},
                 "compulsory": {"bytes": n * B_IO, "achieved": n * B_IO / (t["total_ms"] * 1e-3) / 1e9}}
