@@ -73,7 +73,7 @@ struct scasa_ctx {
     std::vector<double> x;
     std::vector<uint8_t> poor;
     int64_t poor_rows = 0;           // sum of q over poor blocks
-    DBuf<int32_t> d_q_off, d_p_off, d_row_block, d_em_index, d_em_blocks, d_poor_em, d_em_order, d_row_col;
+    DBuf<int32_t> d_q_off, d_p_off, d_em_blocks, d_em_order, d_row_col;
     DBuf<int2> d_row_info;
     DBuf<uint32_t> d_scatter_scratch;
     DBuf<int64_t> d_x_off;
@@ -129,7 +129,7 @@ struct scasa_ctx {
     int host_threads = 0;        // 0 = hardware concurrency
     int fetch_dense_copy = 0;    // 1 = plain dense D2H (SCASA_FETCH_DENSE)
     int n_genes = 0;
-    DBuf<int32_t> d_gene_of_col, d_gene_ptr, d_gene_cols;
+    DBuf<int32_t> d_gene_ptr, d_gene_cols;
     scasa_timing_t timing{};
 };
 
@@ -184,8 +184,8 @@ XDev xdev(scasa_ctx *c)
     XDev X;
     X.n_blocks = c->B; X.n_em = c->n_em; X.n_rows = c->n_rows; X.n_cols = c->n_cols;
     X.q_off = c->d_q_off.p; X.p_off = c->d_p_off.p; X.x_off = c->d_x_off.p; X.x = c->d_x.p;
-    X.row_block = c->d_row_block.p; X.em_index = c->d_em_index.p; X.em_blocks = c->d_em_blocks.p;
-    X.poor = c->d_poor.p; X.poor_em = c->d_poor_em.p; X.n_poor = (int)c->poor_em.size();
+    X.em_blocks = c->d_em_blocks.p;
+    X.poor = c->d_poor.p;
     X.em_order = c->d_em_order.p; X.row_info = c->d_row_info.p; X.row_col = c->d_row_col.p;
     return X;
 }
@@ -235,18 +235,10 @@ void launch_finish(scasa_ctx *w, const double *iso, int64_t n_cells, double *gen
     colsum_reduce<<<(unsigned)((w->n_cols + 255) / 256), 256, 0, s>>>(w->d_partial.p, n_tiles, w->n_cols, colsum);
     launches += 2;
     if (gene) {
-        const size_t smem = (size_t)w->n_genes * sizeof(double);
-        if (smem <= 220 * 1024 && getenv("SCASA_GENE_SMEM")) {
-            CK(cudaFuncSetAttribute(gene_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const int grid = (int)std::min<int64_t>(n_cells, (int64_t)w->n_sm);
-            gene_smem_kernel<<<grid, 1024, smem, s>>>(iso, n_cells, w->n_cols, w->d_gene_of_col.p,
-                                                      w->d_gene_ptr.p, w->d_gene_cols.p, w->n_genes, gene);
-        } else {
-            const int tiles = (w->n_genes + kGeneThreads * kGeneIlp - 1) / (kGeneThreads * kGeneIlp);
-            if (n_cells * tiles >= ((int64_t)1 << 31)) throw ArgErr{SCASA_ERR_UNSUPPORTED, "too many cells x genes for one launch"};
-            gene_gather_kernel<<<(unsigned)(n_cells * tiles), kGeneThreads, 0, s>>>(iso, n_cells, w->n_cols, w->d_gene_ptr.p,
-                                                                                   w->d_gene_cols.p, w->n_genes, tiles, gene);
-        }
+        const int tiles = (w->n_genes + kGeneThreads * kGeneIlp - 1) / (kGeneThreads * kGeneIlp);
+        if (n_cells * tiles >= ((int64_t)1 << 31)) throw ArgErr{SCASA_ERR_UNSUPPORTED, "too many cells x genes for one launch"};
+        gene_gather_kernel<<<(unsigned)(n_cells * tiles), kGeneThreads, 0, s>>>(iso, n_cells, w->n_cols, w->d_gene_ptr.p,
+                                                                               w->d_gene_cols.p, w->n_genes, tiles, gene);
         launches++;
     }
     CK(cudaGetLastError());
@@ -587,12 +579,8 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
         c->d_p_off.upload(c->p_off, c->stream);
         c->d_x_off.upload(c->x_off, c->stream);
         c->d_x.upload(c->x, c->stream);
-        c->d_row_block.upload(c->row_block, c->stream);
-        c->d_em_index.upload(c->em_index, c->stream);
         c->d_em_blocks.upload(c->em_blocks, c->stream);
         c->d_poor.upload(c->poor, c->stream);
-        c->d_poor_em.ensure(c->poor_em.size() + 1);
-        c->d_poor_em.upload(c->poor_em, c->stream);
         c->d_em_order.ensure(c->em_order.size() + 1);
         c->d_em_order.upload(c->em_order, c->stream);
         {
@@ -630,11 +618,11 @@ void scasa_ctx_destroy(scasa_ctx *c)
     if (c->twin) { scasa_ctx_destroy(c->twin); c->twin = nullptr; }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    DBuf<int32_t> *i32[] = {&c->d_q_off, &c->d_p_off, &c->d_row_block, &c->d_em_index, &c->d_em_blocks, &c->d_poor_em, &c->d_em_order,
+    DBuf<int32_t> *i32[] = {&c->d_q_off, &c->d_p_off, &c->d_em_blocks, &c->d_em_order,
                             &c->d_cell_chunk, &c->d_y_len, &c->d_y_row, &c->d_eq_id, &c->d_eq_count, &c->d_eq_row,
                             &c->d_cnt, &c->d_runs, &c->d_tbytes, &c->d_iters, &c->d_row_col,
                             &c->d_list[0], &c->d_list[1], &c->d_list[2], &c->d_list[3],
-                            &c->d_gene_of_col, &c->d_gene_ptr, &c->d_gene_cols};
+                            &c->d_gene_ptr, &c->d_gene_cols};
     for (auto b : i32) b->release();
     DBuf<int64_t> *i64[] = {&c->d_x_off, &c->d_chunk_off, &c->d_y_start, &c->d_cell_ptr, &c->d_toff, &c->d_scan_sums, &c->d_totals};
     for (auto b : i64) b->release();
@@ -786,16 +774,6 @@ int scasa_set_gene_map(scasa_ctx *c, const int32_t *gene_of_col, int32_t n_genes
         c->n_genes = n_genes;
         std::vector<int32_t> goc(gene_of_col, gene_of_col + c->n_cols);
         c->gene_of_col_host = goc;
-        // per column: >= 0 copy into that gene row; <= -2 first member of gene -(a+2): sum; -1 nothing
-        std::vector<int32_t> action((size_t)c->n_cols, -1);
-        for (int64_t j = 0; j < c->n_cols; j++) {
-            int g = goc[(size_t)j];
-            if (g < 0) continue;
-            int k0 = ptr[(size_t)g], k1 = ptr[(size_t)g + 1];
-            if (k1 - k0 == 1) action[(size_t)j] = g;
-            else if (cols[(size_t)k0] == (int32_t)j) action[(size_t)j] = -(g + 2);
-        }
-        c->d_gene_of_col.upload(action, c->stream);
         c->d_gene_ptr.upload(ptr, c->stream);
         c->d_gene_cols.ensure(cols.size() + 1);
         c->d_gene_cols.upload(cols, c->stream);

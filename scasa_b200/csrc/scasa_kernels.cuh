@@ -77,15 +77,11 @@ struct XDev {                 // resident X-matrix (DM0) and its derived index m
     const int32_t *q_off, *p_off;
     const int64_t *x_off;
     const double *x;
-    const int32_t *row_block; // [n_rows]  block of a global row
-    const int32_t *em_index;  // [n_blocks] index among EM blocks, -1 for pass-through
     const int32_t *em_blocks; // [n_em]    block id
     const uint8_t *poor;      // [n_blocks] poorCondX (Rsource:957-971)
-    const int32_t *poor_em;   // [n_poor]  EM indices of the poor blocks
     const int32_t *em_order;  // [n_em]    EM indices, most expensive block shape first (work-queue order)
     const int2 *row_info;     // [n_rows]  {EM index of the row's block or -1, row index inside the block}
     const int32_t *row_col;   // [n_rows]  first DM0 column of the row's block
-    int n_poor;
 };
 
 struct Sample {               // the cells [cell_base, cell_base + n_cells) = chunks [chunk_base, chunk_base + n_chunks)
@@ -213,7 +209,6 @@ __global__ void pack_cells_kernel(int64_t n_cells, const int64_t *__restrict__ c
                                   int32_t *__restrict__ y_len, int *__restrict__ err_flag)
 {
     extern __shared__ unsigned long long sm_keys[];   // (row << 32) | count, cap entries (power of two)
-    __shared__ int s_heads;
     for (int64_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
         const int64_t s = cell_ptr[cell];
         const int n = (int)(cell_ptr[cell + 1] - s);
@@ -230,7 +225,6 @@ __global__ void pack_cells_kernel(int64_t n_cells, const int64_t *__restrict__ c
             }
             sm_keys[i] = k;
         }
-        if (threadIdx.x == 0) s_heads = 0;
         __syncthreads();
         for (int k = 2; k <= m; k <<= 1)
             for (int j = k >> 1; j > 0; j >>= 1) {
@@ -667,46 +661,6 @@ __global__ void colsum_combine(const double *__restrict__ parts, int n_parts, in
     colsum[j] = s;
 }
 
-// scasa_genemat (step3:32-46).  One CTA walks cells; per cell the isoform row is read coalesced,
-// every column puts its value where its gene row is — a single-isoform gene is a copy (step3:39),
-// the first isoform of a multi-isoform gene sums the members in column order (step3:27) — into a
-// shared-memory image of the gene row, which is then written out coalesced.
-// col_action[j]: >= 0 copy to that gene row; <= -2 first member of gene -(a+2); -1 nothing.
-__global__ void __launch_bounds__(1024) gene_smem_kernel(const double *__restrict__ iso, int64_t n_cells, int64_t n_cols,
-                                                         const int32_t *__restrict__ col_action,
-                                                         const int32_t *__restrict__ gene_ptr,
-                                                         const int32_t *__restrict__ gene_cols, int n_genes,
-                                                         double *__restrict__ gene)
-{
-    extern __shared__ double grow[];
-    for (int64_t c = blockIdx.x; c < n_cells; c += gridDim.x) {
-        const double *row = iso + c * n_cols;
-        for (int64_t jb = threadIdx.x; jb < n_cols; jb += 4 * (int64_t)blockDim.x) {
-            int a[4];
-            double v[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {                     // independent loads first
-                const int64_t j = jb + (int64_t)u * blockDim.x;
-                a[u] = j < n_cols ? col_action[j] : -1;
-                v[u] = j < n_cols ? row[j] : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (a[u] >= 0) grow[a[u]] = v[u];
-                else if (a[u] <= -2) {
-                    const int g = -(a[u] + 2);
-                    double sum = v[u];                        // the first member is this column
-                    for (int m = gene_ptr[g] + 1; m < gene_ptr[g + 1]; m++) sum += row[gene_cols[m]];
-                    grow[g] = sum;
-                }
-            }
-        }
-        __syncthreads();
-        double *out = gene + c * (int64_t)n_genes;
-        for (int g = threadIdx.x; g < n_genes; g += blockDim.x) out[g] = grow[g];
-        __syncthreads();
-    }
-}
 // scasa_genemat as a gather: one thread per (cell, gene), members read straight from the isoform row in
 // column order (step3:27).  Every isoform value is read exactly once, so HBM traffic is the two
 // matrices; the row being gathered sits in L2 (a few hundred KB per CTA row).  kGeneIlp genes per
