@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--fp32", action="store_true", help="EM iterates in fp32 (scasa_opts_t.fp32); the default and the parity path is fp64")
     return ap.parse_args()
 
 
@@ -192,7 +193,7 @@ def main():
     goc, n_genes = gene_map(xm)
     chunks = chunk_split(n, 4)
 
-    g = Scasa(xm, device=local)
+    g = Scasa(xm, device=local, fp32=1 if args.fp32 else 0)
     g.set_gene_map(goc, n_genes)
     nthreads = max(1, (os.cpu_count() or 8) // max(world, 1))
     eq_row = g.eqclass_map(ed.eq_off, ed.eq_tx, nthreads)
@@ -328,7 +329,7 @@ def main():
     roofline["frac"] = roofline["achieved"] / peak
     line = {"metric": "cells/sec EM quant (2QUANT hot path)", "value": n * world / step_s, "unit": "cells/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_s * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.fp32 else "f64", "data": "synthetic",
             "config": {"workload": "C4: 100k-cell synthetic atlas on the shipped hg38 alevin X-matrix "
                                    "(29,351 blocks, 3,960 EM blocks), reference convergence options",
                        "cells_per_gpu": n, "chunks_per_gpu": len(chunks) - 1, "seed": args.seed,

@@ -52,7 +52,7 @@ typedef struct {
     double adjust_esp;    /* 2     pseudo count for poor 2-column blocks  Rsource:973  */
     int32_t hamming_dist; /* 1                                            Rsource:534  */
     int32_t fixed_iter;   /* 0     1 = never break: exactly maxiter_x x maxiter_bt iterations (parity mode) */
-    int32_t fp32;         /* 0     reserved (fp32 arithmetic); must be 0 in this version */
+    int32_t fp32;         /* 0     1 = the EM iterates in fp32 (counts and results stay fp64): ~1e-4 relative to the fp64 path */
 } scasa_opts_t;
 
 /* A block list (R list of small dense matrices) flattened; blocks column-major like R. */

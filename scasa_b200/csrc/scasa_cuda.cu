@@ -278,10 +278,14 @@ void stage_common(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const int64_t
     c->staged = true; c->ran = false;
 }
 
-template <int W> void launch_em(const EmArgs &A, unsigned grid, int threads, size_t smem, cudaStream_t s)
+template <int W, typename R> void launch_em_t(const EmArgs &A, unsigned grid, int threads, size_t smem, cudaStream_t s)
 {
-    CK(cudaFuncSetAttribute(em_task_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    em_task_kernel<W><<<grid, threads, smem, s>>>(A);
+    CK(cudaFuncSetAttribute(em_task_kernel<W, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    em_task_kernel<W, R><<<grid, threads, smem, s>>>(A);
+}
+template <int W> void launch_em(const EmArgs &A, unsigned grid, int threads, size_t smem, cudaStream_t s, bool fp32)
+{
+    if (fp32) launch_em_t<W, float>(A, grid, threads, smem, s); else launch_em_t<W, double>(A, grid, threads, smem, s);
 }
 
 // ---- host side of the zero-suppressed fetch: expand_rows() is in scasa_host.cpp -------------------
@@ -478,7 +482,7 @@ int scasa_set_opts(scasa_ctx *c, const scasa_opts_t *o)
 {
     if (!c || !o) return fail(c, SCASA_ERR_ARG, "null argument");
     if (o->maxiter_x < 1 || o->maxiter_bt < 1) return fail(c, SCASA_ERR_ARG, "iteration caps must be >= 1");
-    if (o->fp32) return fail(c, SCASA_ERR_UNSUPPORTED, "fp32 arithmetic is not available in this version");
+    if (o->fp32 != 0 && o->fp32 != 1) return fail(c, SCASA_ERR_ARG, "fp32 must be 0 or 1");
     c->opts = *o;
     return SCASA_OK;
 }
@@ -860,6 +864,7 @@ static void run_range(scasa_ctx *w, scasa_ctx *c, int h0, int h1, int part, Rang
     O.maxerr = c->opts.maxerr; O.lim = c->opts.lim; O.adjust_esp = c->opts.adjust_esp;
     ClassCfg CC;
     for (int k = 0; k < kClasses; k++) { CC.pairs[k] = c->cls_pairs[k]; CC.bytes[k] = c->cls_bytes[k]; }
+    CC.real_bytes = c->opts.fp32 ? 4 : 8;
     int32_t *iters = c->d_iters.p + (int64_t)h0 * w->n_em * 2;
     int64_t tot[2] = {0, 0};
     unsigned int *cnts = rs.cnts;
@@ -913,10 +918,10 @@ static void run_range(scasa_ctx *w, scasa_ctx *c, int h0, int h1, int part, Rang
             CK(cudaStreamWaitEvent(cs, w->ev_fork, 0));
             CK(cudaEventRecord(w->ev_cls[k][0], cs));
             switch (W) {
-            case 1: launch_em<1>(A, grid, threads, smem, cs); break;
-            case 2: launch_em<2>(A, grid, threads, smem, cs); break;
-            case 4: launch_em<4>(A, grid, threads, smem, cs); break;
-            default: launch_em<8>(A, grid, threads, smem, cs); break;
+            case 1: launch_em<1>(A, grid, threads, smem, cs, c->opts.fp32 != 0); break;
+            case 2: launch_em<2>(A, grid, threads, smem, cs, c->opts.fp32 != 0); break;
+            case 4: launch_em<4>(A, grid, threads, smem, cs, c->opts.fp32 != 0); break;
+            default: launch_em<8>(A, grid, threads, smem, cs, c->opts.fp32 != 0); break;
             }
             CK(cudaEventRecord(w->ev_cls[k][1], cs));
             CK(cudaEventRecord(w->ev_join[k], cs));

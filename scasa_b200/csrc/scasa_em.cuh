@@ -25,29 +25,31 @@ namespace scasa {
 //   digamma(x) = log(xs) - 1/(2 xs) - series(1/xs^2) - sum_{i<9} 1/(x+i),   xs = x + 9 for x < 9
 //   => exp(digamma(x) - L) = xs * exp(-(1/(2 xs) + series + rec + L)),
 // one division serving both 1/xs and the folded reciprocal sum (see digamma_pos).
-__device__ __forceinline__ double em_gamma_fast(double beta, double lnorm)
+template <typename R> __device__ __forceinline__ R em_gamma_fast(R beta, R lnorm)
 {
-    const double x = beta + 0.00000001;
-    double xs = x, num = 0.0, den = 1.0;
-    if (x < 9.0) {
-        const double u = x * (x + 8.0);
-        const double a = u + 7.0, b = u + 12.0, c = u + 15.0;
-        const double bc = b * c;
-        const double D = u * a * bc;
-        const double N = a * bc + u * (bc + a * (b + c));
-        const double x4 = x + 4.0;
-        num = (2.0 * x + 8.0) * N * x4 + D;
+    const R x = beta + R(0.00000001);
+    R xs = x, num = R(0), den = R(1);
+    if (x < R(9)) {
+        const R u = x * (x + R(8));
+        const R a = u + R(7), b = u + R(12), c = u + R(15);
+        const R bc = b * c;
+        const R D = u * a * bc;
+        const R N = a * bc + u * (bc + a * (b + c));
+        const R x4 = x + R(4);
+        num = (R(2) * x + R(8)) * N * x4 + D;
         den = D * x4;
-        xs = x + 9.0;
+        xs = x + R(9);
     }
-    const double inv = 1.0 / (xs * den);
-    const double r = den * inv;
-    const double rec = num * xs * inv;
-    const double r2 = r * r;
-    const double s = r2 * (1.0 / 12.0 - r2 * (1.0 / 120.0 - r2 * (1.0 / 252.0 - r2 * (1.0 / 240.0 -
-                     r2 * (1.0 / 132.0 - r2 * (691.0 / 32760.0 - r2 * (1.0 / 12.0)))))));
-    return xs * exp(-(0.5 * r + s + rec + lnorm));
+    const R inv = R(1) / (xs * den);
+    const R r = den * inv;
+    const R rec = num * xs * inv;
+    const R r2 = r * r;
+    const R s = r2 * (R(1.0 / 12.0) - r2 * (R(1.0 / 120.0) - r2 * (R(1.0 / 252.0) - r2 * (R(1.0 / 240.0) -
+                r2 * (R(1.0 / 132.0) - r2 * (R(691.0 / 32760.0) - r2 * R(1.0 / 12.0)))))));
+    return xs * exp(-(R(0.5) * r + s + rec + lnorm));
 }
+__device__ __forceinline__ double rabs(double x) { return fabs(x); }
+__device__ __forceinline__ float rabs(float x) { return fabsf(x); }
 
 struct EmArgs {
     XDev X;
@@ -83,7 +85,9 @@ template <int W> struct Group {
     }
 };
 
-template <int W> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs A)
+// R = double: the parity path.  R = float (scasa_opts_t.fp32): shared-memory state and arithmetic in
+// fp32, counts and results still fp64 in HBM; estimates agree with the fp64 path to ~1e-4 relative.
+template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs A)
 {
     extern __shared__ __align__(16) unsigned char em_smem[];
     constexpr int GT = 32 * W;
@@ -128,9 +132,9 @@ template <int W> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs
         const uint32_t *rcell = (const uint32_t *)(slot + BL.off_cell);
         const uint16_t *eptr = (const uint16_t *)(slot + BL.off_ptr);
         const uint16_t *erow = (const uint16_t *)(slot + BL.off_row);
-        double *ew = (double *)(slot + BL.bytes);
-        double *Xc = ew + E, *Xn = Xc + qp, *rcs = Xn + qp, *bts = rcs + p, *nrm = bts + p, *lnorm = nrm + p;
-        double *beta = lnorm + n, *gam = beta + np;
+        R *ew = (R *)(slot + BL.bytes);
+        R *Xc = ew + E, *Xn = Xc + qp, *rcs = Xn + qp, *bts = rcs + p, *nrm = bts + p, *lnorm = nrm + p;
+        R *beta = lnorm + n, *gam = beta + np;
         uint16_t *erec = (uint16_t *)(gam + np), *rptr = erec + E, *perm = rptr + q + 1;
         int *cur = (int *)Xn;                        // q ints of scratch until the first X update
 
@@ -140,13 +144,13 @@ template <int W> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs
             uint4 *dst = (uint4 *)slot;
             for (int i = gl; i < (BL.bytes >> 4); i += GT) dst[i] = __ldcs(src + i);
             const double *X0 = X.x + X.x_off[b];
-            for (int k = gl; k < qp; k += GT) Xc[k] = X0[k];
+            for (int k = gl; k < qp; k += GT) Xc[k] = (R)X0[k];
         }
         G.sync();
         // a poor task's last record is the pseudo cell: all pmult cells of the chunk without counts in the block
         const uint32_t last_cw = rcell[n - 1];
         const int ap = (last_cw & kPseudo) ? n - 1 : -1;
-        const double pmult = (last_cw & kPseudo) ? (double)(last_cw & 0xffff) : 0.0;
+        const R pmult = (last_cw & kPseudo) ? (R)(last_cw & 0xffff) : R(0);
         const int n_real = ap >= 0 ? n - 1 : n;
         for (int a = gl; a < n; a += GT) {
             const int k1 = eptr[a + 1];
@@ -194,26 +198,26 @@ template <int W> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs
         // ---- poor blocks: rowSums(Ymat), bestTx, adjID, Ymat[adjID,] += adjust_esp (:989-1004)
         int nadj = 0;
         if (poor) {
-            double *rs = Xn;
+            R *rs = Xn;
             for (int r = gl; r < q; r += GT) {
                 double s = 0;
                 const int i1 = rptr[r + 1];
                 for (int i = rptr[r]; i < i1; i++) {
                     const int k = perm[i];
-                    s += (erec[k] == ap ? pmult : 1.0) * ey[k];
+                    s += (erec[k] == ap ? (double)pmult : 1.0) * ey[k];
                 }
-                rs[r] = s;
+                rs[r] = (R)s;
             }
             G.sync();
             const double *X0 = X.x + X.x_off[b];
             double tot = 0;
-            for (int r = 0; r < q; r++) tot += rs[r];
+            for (int r = 0; r < q; r++) tot += (double)rs[r];
             int best = -1;
             double bestv = -INFINITY;
             for (int j = 0; j < p; j++) {                               // which.max(cos_sim(X0[,j], rs/sum(rs)))  :991-995
                 double ab = 0, aa = 0, bb = 0;
                 for (int r = 0; r < q; r++) {
-                    const double xv = X0[j * q + r], rv = rs[r] / tot;
+                    const double xv = X0[j * q + r], rv = (double)rs[r] / tot;
                     ab += xv * rv; aa += xv * xv; bb += rv * rv;
                 }
                 const double sim = ab / sqrt(aa * bb);
@@ -231,18 +235,19 @@ template <int W> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs
 
         // ---- 1/colSums(X) (:731, :745), logNorm (:732-733), beta0 = colSums(Ymat)/p (:1012-1013)
         for (int j = gl; j < p; j += GT) {
-            double s = 0;
+            R s = 0;
 #pragma unroll 1
             for (int r = 0; r < q; r++) s += Xc[j * q + r];
-            rcs[j] = 1.0 / s;
+            rcs[j] = R(1) / s;
         }
+        const R lim = (R)O.lim, maxerr = (R)O.maxerr;
         for (int a = gl; a < n; a += GT) {
             double ys = 0;
             const int k1 = eptr[a + 1];
 #pragma unroll 1
             for (int k = eptr[a]; k < k1; k++) ys += ey[k];
-            lnorm[a] = digamma_pos(ys + 0.00000001);
-            const double b0 = ys / p;
+            lnorm[a] = (R)digamma_pos(ys + 0.00000001);
+            const R b0 = (R)(ys / p);
 #pragma unroll 1
             for (int j = 0; j < p; j++) beta[j * n + a] = b0;
         }
@@ -260,7 +265,7 @@ template <int W> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs
             for (int it = 1;; it++) {
 #pragma unroll 1
                 for (int idx = gl, a = a_first; idx < np; idx += GT) {          // S1
-                    gam[idx] = O.modify ? em_gamma_fast(beta[idx], lnorm[a]) : beta[idx];
+                    gam[idx] = O.modify ? em_gamma_fast<R>(beta[idx], lnorm[a]) : beta[idx];
                     a += da;
                     if (a >= n) a -= n;
                 }
@@ -268,25 +273,25 @@ template <int W> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs
 #pragma unroll 1
                 for (int k = gl; k < E; k += GT) {                               // S2
                     const int r = erow[k], a = erec[k];
-                    double mu = 0.0;                                             // rowSums(t(t(X)*gamma0))  :739-740
+                    R mu = 0;                                                    // rowSums(t(t(X)*gamma0))  :739-740
 #pragma unroll 1
                     for (int j = 0; j < p; j++) mu += Xc[j * q + r] * gam[j * n + a];
-                    ew[k] = ey[k] / (mu > 0 ? mu : 1.0);                         // :741
+                    ew[k] = (R)ey[k] / (mu > 0 ? mu : R(1));                     // :741
                 }
                 G.sync();
                 bool fail = false;
 #pragma unroll 1
                 for (int idx = gl, a = a_first, j = j_first; idx < np; idx += GT) {   // S3
-                    double s = 0.0;
+                    R s = 0;
                     const int k1 = eptr[a + 1];
 #pragma unroll 1
                     for (int k = eptr[a]; k < k1; k++) s += Xc[j * q + erow[k]] * ew[k];
-                    const double old = beta[idx];
-                    const double gs = gam[idx] * s;
-                    double nb = gs == 0.0 ? 0.0 : gs * rcs[j];                   // :745 (division by csum as a reciprocal)
-                    if (nb != nb) nb = 0.0;                                      // :754
-                    const double den = old > O.lim ? old : O.lim;               // :755
-                    if (!(fabs(nb - old) < O.maxerr * den)) fail = true;
+                    const R old = beta[idx];
+                    const R gs = gam[idx] * s;
+                    R nb = gs == R(0) ? R(0) : gs * rcs[j];                      // :745 (division by csum as a reciprocal)
+                    if (nb != nb) nb = R(0);                                     // :754
+                    const R den = old > lim ? old : lim;                         // :755
+                    if (!(rabs(nb - old) < maxerr * den)) fail = true;
                     beta[idx] = nb;
                     a += da; j += dj;
                     if (a >= n) { a -= n; j++; }
@@ -298,60 +303,60 @@ template <int W> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs
 
             // ================= estim.X.em(X.est0, BT, Ymat)  :898-922
             for (int j = gl; j < p; j += GT) {                                   // BTsum = colSums(BETA)  :904
-                double s = 0;
+                R s = 0;
 #pragma unroll 1
                 for (int a = 0; a < n_real; a++) s += beta[j * n + a];
                 if (ap >= 0) s += pmult * beta[j * n + ap];                      // the pseudo cell stands for pmult cells
-                bts[j] = s > 0 ? s : 0.1;                                        // :917 (may be denormal: no reciprocal)
+                bts[j] = s > 0 ? s : R(0.1);                                     // :917 (may be denormal: no reciprocal)
             }
 #pragma unroll 1
             for (int k = gl; k < E; k += GT) {
                 const int r = erow[k], a = erec[k];
-                double mu = 0.0;                                                  // sumx1 = rowSums(x1)  :907
+                R mu = 0;                                                         // sumx1 = rowSums(x1)  :907
 #pragma unroll 1
                 for (int j = 0; j < p; j++) mu += beta[j * n + a] * Xc[j * q + r];
-                const double mult = a == ap ? pmult : 1.0;
-                ew[k] = mult * ey[k] / (mu > 0 ? mu : 0.1);                      // :908-910
+                const R mult = a == ap ? pmult : R(1);
+                ew[k] = mult * (R)ey[k] / (mu > 0 ? mu : R(0.1));                // :908-910
             }
             G.sync();
 #pragma unroll 1
             for (int idx = gl, j = xj_first, r = xr_first; idx < qp; idx += GT) {   // X.est = colSums(x2 * Y) / BTsum  :911-917
-                const double x = Xc[idx];
-                double acc = 0.0;
+                const R x = Xc[idx];
+                R acc = 0;
                 const int i1 = rptr[r + 1];
 #pragma unroll 1
                 for (int i = rptr[r]; i < i1; i++) {
                     const int k = perm[i];
                     acc += beta[j * n + erec[k]] * x * ew[k];
                 }
-                Xn[idx] = acc == 0.0 ? 0.0 : acc / bts[j];                       // zero numerators would take the slow division path
+                Xn[idx] = acc == R(0) ? R(0) : acc / bts[j];                     // zero numerators would take the slow division path
                 r += dxr; j += dxj;
                 if (r >= q) { r -= q; j++; }
             }
             G.sync();
             for (int j = gl; j < p; j += GT) {                                   // csum = colSums(X.est)  :918
-                double csum = 0.0;
+                R csum = 0;
 #pragma unroll 1
                 for (int r = 0; r < q; r++) csum += Xn[j * q + r];
                 // :919-920: scale by 1/csum (0.1 when 0); a negative scale marks "revert to X.est0"
-                const double sc = csum < 0.00001 ? -1.0 : 1.0 / (csum > 0 ? csum : 0.1);
+                const R sc = csum < R(0.00001) ? R(-1) : R(1) / (csum > 0 ? csum : R(0.1));
                 nrm[j] = sc;
                 if (sc >= 0) {                                                   // 1/colSums of the normalised column, for the next estim.BETA call
-                    double s2 = 0;
+                    R s2 = 0;
 #pragma unroll 1
                     for (int r = 0; r < q; r++) s2 += Xn[j * q + r] * sc;
-                    rcs[j] = 1.0 / s2;
+                    rcs[j] = R(1) / s2;
                 }
             }
             G.sync();
             bool xfail = false;                                                  // :1019
 #pragma unroll 1
             for (int idx = gl, j = xj_first, r = xr_first; idx < qp; idx += GT) {
-                const double x0 = Xc[idx], sc = nrm[j];
-                const double v = sc < 0 ? x0 : Xn[idx] * sc;
+                const R x0 = Xc[idx], sc = nrm[j];
+                const R v = sc < 0 ? x0 : Xn[idx] * sc;
                 Xc[idx] = v;                                                     // X.est0 = X.est (:1022); unused if the loop ends here
-                const double num = fabs(v - x0), den = fabs(x0) > O.lim ? x0 : O.lim;
-                const bool ok = den > 0 ? (num < O.maxerr * den) : (num / den < O.maxerr);
+                const R num = rabs(v - x0), den = rabs(x0) > lim ? x0 : lim;
+                const bool ok = den > 0 ? (num < maxerr * den) : (num / den < maxerr);
                 if (!ok) xfail = true;
                 r += dxr; j += dxj;
                 if (r >= q) { r -= q; j++; }
@@ -368,10 +373,10 @@ template <int W> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs
         for (int a = gl; a < n; a += GT) {
             const uint32_t cw = rcell[a];
             double s = 0;
-            if (nadj > 0) for (int j = 0; j < p; j++) s += beta[j * n + a];
+            if (nadj > 0) for (int j = 0; j < p; j++) s += (double)beta[j * n + a];
             if (!(cw & kPseudo)) {
                 double *o = A.out + (cbase + (int64_t)cw) * X.n_cols + col0;
-                for (int j = 0; j < p; j++) { double v = beta[j * n + a]; if (nadj > 0) v = v - deduct * (v / s); o[j] = v; }
+                for (int j = 0; j < p; j++) { double v = (double)beta[j * n + a]; if (nadj > 0) v = v - deduct * (v / s); o[j] = v; }
             }
         }
         if (n > 0 && (rcell[n - 1] & kPseudo) && (rcell[n - 1] & 0xffff) != 0) {
@@ -379,13 +384,13 @@ template <int W> __global__ void __launch_bounds__(256, 4) em_task_kernel(EmArgs
             // cells are listed in ascending order, so walk the gaps
             const int ap = n - 1;
             double s = 0;
-            if (nadj > 0) for (int j = 0; j < p; j++) s += beta[j * n + ap];
+            if (nadj > 0) for (int j = 0; j < p; j++) s += (double)beta[j * n + ap];
             for (int a = gl; a < n; a += GT) {
                 const int lo = a == 0 ? 0 : (int)rcell[a - 1] + 1;
                 const int hi = a == n - 1 ? nc : (int)rcell[a];
                 for (int cc = lo; cc < hi; cc++) {
                     double *o = A.out + (cbase + cc) * X.n_cols + col0;
-                    for (int j = 0; j < p; j++) { double v = beta[j * n + ap]; if (nadj > 0) v = v - deduct * (v / s); o[j] = v; }
+                    for (int j = 0; j < p; j++) { double v = (double)beta[j * n + ap]; if (nadj > 0) v = v - deduct * (v / s); o[j] = v; }
                 }
             }
         }

@@ -117,16 +117,17 @@ __host__ __device__ inline BlobLayout blob_layout(int n, int E)
     return L;
 }
 // shared memory one task needs in the EM kernel: blob image, then
-//     ew[E] Xc[qp] Xn[qp] rcs[p] bts[p] nrm[p] lnorm[n] beta[p*n] gam[p*n]  (f64)
+//     ew[E] Xc[qp] Xn[qp] rcs[p] bts[p] nrm[p] lnorm[n] beta[p*n] gam[p*n]  (f64, or f32)
 //     erec[E] rptr[q+1] perm[E]                                     (u16)
-__host__ __device__ inline int slot_bytes_of(int q, int p, int n, int E)
+// rb = bytes of the arithmetic type (8, or 4 with scasa_opts_t.fp32)
+__host__ __device__ inline int slot_bytes_of(int q, int p, int n, int E, int rb)
 {
-    return blob_layout(n, E).bytes + 8 * (E + 2 * q * p + 3 * p + n + 2 * p * n) + align16(2 * (2 * E + q + 1));
+    return blob_layout(n, E).bytes + align16(rb * (E + 2 * q * p + 3 * p + n + 2 * p * n)) + align16(2 * (2 * E + q + 1));
 }
 
 // work classes: W warps per task, a slot of at most kClassBytes[c] (the last class takes the rest)
 constexpr int kClasses = 4;
-struct ClassCfg { int pairs[kClasses]; int bytes[kClasses]; };
+struct ClassCfg { int pairs[kClasses]; int bytes[kClasses]; int real_bytes; };
 
 struct Tasks {                // task t = chunk * n_em + em index
     int32_t *cnt;             // [n_tasks] Y entries; after classify: stored entries E (dense for poor blocks)
@@ -335,7 +336,7 @@ __global__ void classify_kernel(XDev X, Sample S, Tasks T, int64_t n_tasks, EmOp
             T.cnt[t] = E;
             T.tbytes[t] = blob_layout(n, E).bytes;
             if (n > 0) {
-                need = (unsigned)slot_bytes_of(q, p, n, E);
+                need = (unsigned)slot_bytes_of(q, p, n, E, C.real_bytes);
                 cls = kClasses - 1;
                 for (int k = kClasses - 2; k >= 0; k--)
                     if (n * p <= C.pairs[k] && (int)need <= C.bytes[k]) cls = k;

@@ -11,7 +11,8 @@ xm = XMatrix.load_npz(os.path.join(ROOT, "tests", "golden", "xmatrix_hg38_alevin
 rowptr, rows, vals = synth.CellGenerator(xm, seed=1).counts_csr(0, 200)
 chunks = chunk_split(200, 4)
 mx, mb = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (4, 8)
-g = Scasa(xm, device=0, fixed_iter=1, maxiter_x=mx, maxiter_bt=mb)
+fp32 = int(os.environ.get('FP32', '0'))
+g = Scasa(xm, device=0, fixed_iter=1, maxiter_x=mx, maxiter_bt=mb, fp32=fp32)
 iso, iters = g.estimate(chunks, rowptr, rows, vals)
 ref, _ = O.estim_chunks(xm, synth.csr_to_dense(rowptr, rows, vals, xm.n_rows), chunks,
                         O.Opts.make(fixed_iter=1, maxiter_x=mx, maxiter_bt=mb), nthreads=4)
@@ -22,7 +23,15 @@ err[:, poorcol] = np.abs(iso - ref)[:, poorcol]
 err = np.nan_to_num(err, nan=9.0)
 bad = np.argwhere(err > 1e-6)
 print("bad entries", len(bad), "max", err.max())
+for fl in (1e-9, 1e-6, 1e-3):
+    e2 = np.abs(iso - ref) / np.maximum(np.abs(ref), fl); e2[:, poorcol] = 0
+    print("floor", fl, "max rel err non-poor", np.nanmax(e2), " poor abs max", np.nanmax(np.abs(iso - ref)[:, poorcol]))
 col_block = np.repeat(np.arange(xm.n_blocks), np.diff(xm.dm0_p_off))
+e3 = np.abs(iso - ref) / np.maximum(np.abs(ref), 1e-3); e3[:, poorcol] = 0
+worst = np.dstack(np.unravel_index(np.argsort(-e3, axis=None)[:8], e3.shape))[0]
+for c, j in worst:
+    k = col_block[j]
+    print(f"worst non-poor: err {e3[c, j]:.3e} block {k} q={xm.q(k)} p={xm.p(k)} cell {c} col {j - xm.dm0_p_off[k]} gpu {iso[c, j]!r} ref {ref[c, j]!r}")
 seen = set()
 for c, j in bad[:400]:
     k = col_block[j]
