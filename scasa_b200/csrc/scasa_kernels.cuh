@@ -445,12 +445,24 @@ __global__ void scan_add_back(const int32_t *__restrict__ in, int64_t n, const i
 // assembles the row tile by tile in shared memory and writes it out coalesced, so the 26.7 GB
 // matrix (100k cells) is written exactly once here; the EM kernel later fills in its columns.
 constexpr int kFillThreads = 512;
-constexpr int kFillTile = 8192;     // doubles per tile (64 KB)
+constexpr int kFillTile = 4096;     // doubles per tile (32 KB); two tiles in flight
 constexpr int kFillKeep = 8;        // Y entries a thread keeps in registers across the tiles of a row
-__global__ void __launch_bounds__(kFillThreads) iso_fill_kernel(XDev X, Sample S, double *__restrict__ out)
+
+// TMA bulk store of a shared-memory tile (cp.async.bulk, UBLKCP in SASS): one thread hands the whole
+// tile to the copy engine; the CTA goes on to build the next tile in the other buffer.
+__device__ __forceinline__ void bulk_store_tile(double *dst, const double *tile, int n_doubles)
 {
-    extern __shared__ double fill_tile[];
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(tile);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(s), "r"(n_doubles * 8) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+// use_bulk: rows are 16-byte aligned (n_cols even), which the bulk copy needs; otherwise plain stores.
+__global__ void __launch_bounds__(kFillThreads) iso_fill_kernel(XDev X, Sample S, double *__restrict__ out, int use_bulk)
+{
+    extern __shared__ __align__(128) double fill_tile[];      // 2 x kFillTile
     const int tid = threadIdx.x;
+    int buf = 0;
     for (int64_t cell = blockIdx.x; cell < S.n_cells; cell += gridDim.x) {
         const int64_t s = S.y_start[cell];
         const int n = S.y_len[cell];
@@ -468,23 +480,37 @@ __global__ void __launch_bounds__(kFillThreads) iso_fill_kernel(XDev X, Sample S
         }
         for (int64_t t0 = 0; t0 < X.n_cols; t0 += kFillTile) {
             const int tn = (int)min((int64_t)kFillTile, X.n_cols - t0);
-            for (int i = tid; i < tn; i += kFillThreads) fill_tile[i] = 0.0;
+            double *tile = fill_tile + buf * kFillTile;
+            // the store that last read this buffer (two tiles ago) must have finished reading it
+            if (use_bulk) {
+                if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncthreads();
+            }
+            for (int i = tid; i < tn; i += kFillThreads) tile[i] = 0.0;
             __syncthreads();
 #pragma unroll
             for (int u = 0; u < kFillKeep; u++)
-                if (col[u] >= t0 && col[u] < t0 + tn) fill_tile[col[u] - t0] = val[u];
+                if (col[u] >= t0 && col[u] < t0 + tn) tile[col[u] - t0] = val[u];
             for (int i = tid + kFillKeep * kFillThreads; i < n; i += kFillThreads) {     // cells with very many entries
                 const int r = S.y_row[s + i];
                 if (X.row_info[r].x < 0) {
                     const int c = X.row_col[r];
-                    if (c >= t0 && c < t0 + tn) fill_tile[c - t0] = S.y_val[s + i];
+                    if (c >= t0 && c < t0 + tn) tile[c - t0] = S.y_val[s + i];
                 }
             }
-            __syncthreads();
-            for (int i = tid; i < tn; i += kFillThreads) __stcs(row + t0 + i, fill_tile[i]);
-            __syncthreads();
+            if (use_bulk) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the copy engine
+                __syncthreads();
+                if (tid == 0) bulk_store_tile(row + t0, tile, tn);
+                buf ^= 1;
+            } else {
+                __syncthreads();
+                for (int i = tid; i < tn; i += kFillThreads) __stcs(row + t0 + i, tile[i]);
+                __syncthreads();
+            }
         }
     }
+    if (use_bulk && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------
