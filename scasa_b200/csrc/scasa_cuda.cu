@@ -8,6 +8,8 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <deque>
+#include <memory>
 #include <mutex>
 #include <cmath>
 #include <cstdio>
@@ -56,6 +58,81 @@ template <class T> struct DBuf {   // grow-only device buffer
 };
 
 }  // namespace
+
+// Worker threads of the expansion: one pool per context pair (a context and its scasa_quant twin
+// share it, so the two never oversubscribe the cores), kept alive between calls.  Jobs (batches of
+// rows) queue up first-in first-out; the workers claim rows of the job at the head in small chunks,
+// so a batch is balanced across threads whatever its rows look like.
+class ExpandPool {
+public:
+    struct Job {
+        double *dst; int64_t n_cols, n_rows; const int64_t *start; const int32_t *nnz; const int32_t *cols; const double *vals;
+        std::atomic<int64_t> next{0};
+        int64_t finished = 0;
+        bool done = false;
+    };
+    explicit ExpandPool(int n_threads) : n_threads_(n_threads)
+    {
+        for (int t = 0; t < n_threads; t++) th_.emplace_back([this] { work(); });
+    }
+    ~ExpandPool()
+    {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+        cv_work_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    int threads() const { return n_threads_; }
+    std::shared_ptr<Job> post(double *dst, int64_t n_cols, int64_t n_rows, const int64_t *start, const int32_t *nnz,
+                              const int32_t *cols, const double *vals)
+    {
+        auto j = std::make_shared<Job>();
+        j->dst = dst; j->n_cols = n_cols; j->n_rows = n_rows; j->start = start; j->nnz = nnz; j->cols = cols; j->vals = vals;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            queue_.push_back(j);
+        }
+        cv_work_.notify_all();
+        return j;
+    }
+    void wait(const std::shared_ptr<Job> &j)
+    {
+        if (!j) return;
+        std::unique_lock<std::mutex> lk(m_);
+        cv_done_.wait(lk, [&] { return j->done; });
+    }
+
+private:
+    std::mutex m_;
+    std::condition_variable cv_work_, cv_done_;
+    std::deque<std::shared_ptr<Job>> queue_;
+    bool stop_ = false;
+    int n_threads_;
+    std::vector<std::thread> th_;
+    void work()
+    {
+        for (;;) {
+            std::shared_ptr<Job> j;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_work_.wait(lk, [&] { return stop_ || !queue_.empty(); });
+                if (queue_.empty()) return;
+                j = queue_.front();
+            }
+            int64_t mine = 0;
+            for (;;) {
+                const int64_t r = j->next.fetch_add(8);
+                if (r >= j->n_rows) break;
+                const int64_t e = std::min(r + 8, j->n_rows);
+                scasa::expand_rows(j->dst, j->n_cols, r, e, j->start, j->nnz, j->cols, j->vals);
+                mine += e - r;
+            }
+            std::lock_guard<std::mutex> lk(m_);
+            if (!queue_.empty() && queue_.front() == j) queue_.pop_front();      // exhausted: the next job becomes the head
+            j->finished += mine;
+            if (j->finished == j->n_rows && !j->done) { j->done = true; cv_done_.notify_all(); }
+        }
+    }
+};
 
 struct scasa_ctx {
     int device = 0;
@@ -124,6 +201,9 @@ struct scasa_ctx {
         cudaEvent_t done = nullptr;
     } fb[2];
     scasa_ctx *twin = nullptr;   // second context on the same device: scasa_quant overlaps its slices on the two
+    scasa_ctx *pool_owner = nullptr;                            // a twin expands with its parent's worker pool
+    std::unique_ptr<ExpandPool> pool;                           // host threads of the zero-suppressed fetch
+    std::mutex pool_mutex;
     std::vector<int32_t> gene_of_col_host;
     std::atomic<long long> wire_h2d{0}, wire_d2h{0};   // bytes that crossed PCIe since the last scasa_transfer_bytes(reset)
     int host_threads = 0;        // 0 = hardware concurrency
@@ -289,72 +369,14 @@ template <int W> void launch_em(const EmArgs &A, unsigned grid, int threads, siz
 }
 
 // ---- host side of the zero-suppressed fetch: expand_rows() is in scasa_host.cpp -------------------
-// Worker threads of the expansion.  Jobs (batches) are posted one after the other; every worker
-// visits every job in order and claims rows of it in chunks, so a batch is balanced across threads
-// whatever its rows look like.  At most two jobs are in flight (the two staging buffers).
-class ExpandPool {
-public:
-    explicit ExpandPool(int n_threads)
-    {
-        for (int t = 0; t < n_threads; t++) th_.emplace_back([this] { work(); });
-    }
-    ~ExpandPool()
-    {
-        { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
-        cv_work_.notify_all();
-        for (auto &t : th_) t.join();
-    }
-    void post(double *dst, int64_t n_cols, int64_t n_rows, const int64_t *start, const int32_t *nnz, const int32_t *cols,
-              const double *vals)
-    {
-        std::lock_guard<std::mutex> lk(m_);
-        Job &j = job_[posted_ & 1];
-        j.dst = dst; j.n_cols = n_cols; j.n_rows = n_rows; j.start = start; j.nnz = nnz; j.cols = cols; j.vals = vals;
-        j.next.store(0); j.finished = 0;
-        posted_++;
-        cv_work_.notify_all();
-    }
-    void wait_all()       // every posted job is complete
-    {
-        std::unique_lock<std::mutex> lk(m_);
-        cv_done_.wait(lk, [&] { return completed_ == posted_; });
-    }
-
-private:
-    struct Job {
-        double *dst; int64_t n_cols, n_rows; const int64_t *start; const int32_t *nnz; const int32_t *cols; const double *vals;
-        std::atomic<int64_t> next{0};
-        int64_t finished = 0;
-    } job_[2];
-    std::mutex m_;
-    std::condition_variable cv_work_, cv_done_;
-    int64_t posted_ = 0, completed_ = 0;
-    bool stop_ = false;
-    std::vector<std::thread> th_;
-    void work()
-    {
-        int64_t seen = 0;
-        for (;;) {
-            std::unique_lock<std::mutex> lk(m_);
-            cv_work_.wait(lk, [&] { return stop_ || posted_ > seen; });
-            if (posted_ <= seen) return;
-            Job &j = job_[seen & 1];
-            seen++;
-            lk.unlock();
-            int64_t mine = 0;
-            for (;;) {
-                const int64_t r = j.next.fetch_add(8);
-                if (r >= j.n_rows) break;
-                const int64_t e = std::min(r + 8, j.n_rows);
-                scasa::expand_rows(j.dst, j.n_cols, r, e, j.start, j.nnz, j.cols, j.vals);
-                mine += e - r;
-            }
-            lk.lock();
-            j.finished += mine;
-            if (mine > 0 && j.finished == j.n_rows) { completed_++; cv_done_.notify_all(); }
-        }
-    }
-};
+// the pool of a context: its own, or its parent's when it is a scasa_quant twin
+ExpandPool &expand_pool(scasa_ctx *c, int nthr)
+{
+    scasa_ctx *owner = c->pool_owner ? c->pool_owner : c;
+    std::lock_guard<std::mutex> lk(owner->pool_mutex);
+    if (!owner->pool || owner->pool->threads() != nthr) owner->pool.reset(new ExpandPool(nthr));
+    return *owner->pool;
+}
 
 void fetch_buf_ensure(scasa_ctx *c, scasa_ctx::FetchBuf &b, size_t rows, size_t cap)
 {
@@ -408,15 +430,17 @@ void fetch_dense(scasa_ctx *c, const double *d_mat, int64_t n_rows, int64_t n_co
         c->wire_d2h += (long long)(used * 12 + (size_t)nr * 12 + 8);
         CK(cudaEventRecord(b.done, s));
     };
-    // the expansion of batch k runs on a pool of worker threads (rows claimed in small chunks) while
+    // the expansion of batch k runs on the pool of worker threads (rows claimed in small chunks) while
     // this thread drives the GPU for batch k+1
-    ExpandPool pool(nthr);
+    ExpandPool &pool = expand_pool(c, nthr);
+    std::shared_ptr<ExpandPool::Job> pending;           // the batch being expanded (it reads the other staging buffer)
     auto expand_async = [&](int64_t k) {
         scasa_ctx::FetchBuf &b = c->fb[k & 1];
         const int64_t r0 = k * batch, nr = std::min(batch, n_rows - r0);
-        pool.post(out + r0 * n_cols, n_cols, nr, b.h_start, b.h_nnz, b.h_cols, b.h_vals);
+        pending = pool.post(out + r0 * n_cols, n_cols, nr, b.h_start, b.h_nnz, b.h_cols, b.h_vals);
     };
-    auto join_all = [&]() { pool.wait_all(); };
+    auto join_all = [&]() { pool.wait(pending); pending.reset(); };
+    struct Joiner { decltype(join_all) &j; ~Joiner() { j(); } } joiner{join_all};   // an exception must not leave a job reading freed buffers
     const bool trace = getenv("SCASA_FETCH_TRACE") != nullptr;
     double t_wait_gpu = 0, t_join = 0, t_launch = 0;
     unsigned long long pairs = 0;
@@ -963,6 +987,7 @@ static int sync_twin(scasa_ctx *c)
         if (rc) return fail(c, rc, std::string("twin context: ") + scasa_last_error(nullptr));
     }
     scasa_ctx *t = c->twin;
+    t->pool_owner = c;
     t->opts = c->opts; t->host_threads = c->host_threads; t->fetch_dense_copy = c->fetch_dense_copy;
     for (int k = 0; k < kClasses; k++) {
         t->cls_warps[k] = c->cls_warps[k]; t->cls_pairs[k] = c->cls_pairs[k]; t->cls_bytes[k] = c->cls_bytes[k];

@@ -277,3 +277,38 @@ def test_fp32_option_close_to_fp64(xm, oracle, c1):
         assert np.all(np.isfinite(iso2))
     finally:
         g.close()
+
+
+def test_c2_size_sampled_chunks_match_oracle(xm, oracle):
+    """Config C2 (3,955 cells = 40 chunks of 98-99, step2:64-68) in the reference's convergence mode:
+    the whole sample goes through scasa_quant (sliced), three of its chunks are re-run by the oracle."""
+    from scasa_b200 import synth
+    from scasa_b200.api import Scasa, chunk_split
+    n = 3955
+    chunks = chunk_split(n, 4)
+    assert len(chunks) - 1 == 40 and set(np.diff(chunks)) <= {98, 99}
+    rowptr, rows, vals = synth.CellGenerator(xm, seed=2).counts_csr(0, n)
+    g = Scasa(xm, device=0, with_crp=False)
+    try:
+        iso, iters = g.estimate(chunks, rowptr, rows, vals)
+        poor_b = g.poor_blocks()
+        em = g.em_blocks
+    finally:
+        g.close()
+    assert np.all(np.isfinite(iso))
+    p_off = xm.dm0_p_off
+    for h in (0, 17, 39):
+        c0, c1 = int(chunks[h]), int(chunks[h + 1])
+        sub_ptr = rowptr[c0:c1 + 1] - rowptr[c0]
+        sl = slice(rowptr[c0], rowptr[c1])
+        y = synth.csr_to_dense(sub_ptr, rows[sl], vals[sl], xm.n_rows)
+        ref, ref_it = oracle.estim_chunks(xm, y, np.array([0, c1 - c0]), None, nthreads=4)
+        same = np.all(iters[h] == ref_it[0][em], axis=1)
+        assert same.mean() >= 0.995, (h, same.mean())
+        worst = 0.0
+        for e, k in enumerate(em):
+            if same[e] and not poor_b[k]:
+                worst = max(worst, rel_err(iso[c0:c1, p_off[k]:p_off[k + 1]], ref[:, p_off[k]:p_off[k + 1]]))
+        assert worst < RTOL, (h, worst)
+        pt = np.repeat(np.diff(xm.q_off) == 1, np.diff(p_off))
+        assert np.array_equal(iso[c0:c1][:, pt], ref[:, pt])
