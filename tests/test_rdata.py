@@ -54,3 +54,28 @@ def test_reads_a_matrix_with_dimnames_and_altrep(tmp_path):
     assert np.array_equal(m.as_matrix(), [[0.6, 0.0], [0.4, 1.0]])       # column-major payload
     assert list(ws["seq"].value) == [1, 2, 3, 4, 5]
     assert ws["dim"].value == ["again"]                                  # tag resolved through the reference table
+
+
+def test_bustools_xmatrix_loads_through_the_same_reader():
+    """N4 (SURVEY.md §8 f): the kallisto/bustools X-matrix is the same RDX3 layout; reader and packing are
+    generic.  Sizes are the ones the survey measured (29,088 blocks, 4,563 EM blocks, sum q_em 18,507,
+    sum p_em 9,475, largest block 57 x 21).  Runs only where the reference tree is present."""
+    import os
+    import pytest
+    ref = "/root/reference/scasa/REFERENCE"
+    if not os.path.exists(os.path.join(ref, "Xmatrix_hg38_bustools.RData")):
+        pytest.skip("reference tree not present (GPU box)")
+    from scasa_b200.xmatrix import XMatrix
+    xm = XMatrix.from_rdata(os.path.join(ref, "Xmatrix_hg38_bustools.RData"),
+                            os.path.join(ref, "isoform_groups_UCSC_hg38_bustools.RData"))
+    q, p = np.diff(xm.q_off), np.diff(xm.dm0_p_off)
+    em = q > 1
+    assert (xm.n_blocks, int(em.sum()), int(q[em].sum()), int(p[em].sum())) == (29088, 4563, 18507, 9475)
+    assert (int(q.max()), int(p.max())) == (57, 21)
+    cs = np.concatenate([xm.dm0_block(k).sum(0) for k in range(0, xm.n_blocks, 7)])
+    assert np.allclose(cs, 1.0, atol=1e-12)                              # DM0 columns are stochastic (K3/K4)
+    assert xm.gene_of_col is not None and (np.asarray(xm.gene_of_col) >= 0).all()   # every column has a gene (K7)
+    # row patterns: 0/1, as many columns as the CRP block (K2)
+    for k in (0, 100, 20000):
+        pat = xm.crp_patterns(k)
+        assert pat.shape == (xm.q(k), xm.p_crp(k)) and set(np.unique(pat)) <= {0, 1}
