@@ -873,7 +873,8 @@ static void run_range(scasa_ctx *w, scasa_ctx *c, int h0, int h1, int part, Rang
         CK(cudaStreamWaitEvent(fs, w->ev[1], 0));
         const size_t smem = (size_t)2 * kFillTile * sizeof(double);
         CK(cudaFuncSetAttribute(iso_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int grid = (int)std::min<int64_t>(n_cells, (int64_t)w->n_sm * 3);
+        const int fill_ctas = getenv("SCASA_FILL_CTAS") ? std::max(1, atoi(getenv("SCASA_FILL_CTAS"))) : 2;
+        const int grid = (int)std::min<int64_t>(n_cells, (int64_t)w->n_sm * fill_ctas);
         const int use_bulk = (c->n_cols % 2 == 0) && ((uintptr_t)iso % 16 == 0) && !getenv("SCASA_FILL_PLAIN");
         iso_fill_kernel<<<grid, kFillThreads, smem, fs>>>(X, S, iso, use_bulk);
         CK(cudaGetLastError());
