@@ -260,3 +260,50 @@ def test_run_parts_do_not_change_results(xm):
                 assert np.array_equal(a, b)
     finally:
         g.close()
+
+
+def test_error_behaviour_through_the_abi(xm):
+    """Malformed input and wrong call order come back as error codes with a message (the R shim turns
+    them into stop()); nothing crashes, and the context stays usable afterwards."""
+    from scasa_b200 import lib, synth
+    from scasa_b200.api import Scasa, chunk_split
+    g = Scasa(xm, device=0, with_crp=False)
+    try:
+        with pytest.raises(lib.ScasaError) as e:
+            g.run()                                                    # nothing staged
+        assert e.value.code == -5
+        rowptr, rows, vals = synth.CellGenerator(xm, seed=1).counts_csr(0, 120)
+        chunks = chunk_split(120, 4)
+        bad = rows.copy()
+        bad[[0, 1]] = bad[[1, 0]]                                      # rows not ascending inside a cell
+        with pytest.raises(lib.ScasaError) as e:
+            g.stage_counts(chunks, rowptr, bad, vals)
+        assert e.value.code == -1
+        bad = rows.copy()
+        bad[5] = xm.n_rows                                             # row out of range
+        with pytest.raises(lib.ScasaError):
+            g.stage_counts(chunks, rowptr, bad, vals)
+        with pytest.raises(lib.ScasaError):
+            g.stage_counts([0, 60, 119], rowptr, rows, vals)            # chunks do not cover the cells
+        with pytest.raises(lib.ScasaError):
+            g.set_opts(maxiter_x=0)
+        with pytest.raises(lib.ScasaError):
+            g.eqclass_map([0, 1], [0], 1)                               # context created without CRP
+        g.stage_counts(chunks, rowptr, rows, vals)
+        with pytest.raises(lib.ScasaError) as e:
+            g.fetch_iso()                                               # staged but not run
+        assert e.value.code == -5
+        g.run()
+        with pytest.raises(lib.ScasaError):
+            g.fetch_gene()                                              # no gene map set
+        iso = g.fetch_iso()                                             # and the context still works
+        assert np.isfinite(iso).all() and iso.sum() > 0
+        # a chunk too large for a block's task (u16 indices / shared memory): documented limit, not a crash
+        big = 70000
+        rp = np.arange(big + 1, dtype=np.int64)
+        em_row = int(xm.q_off[xm.em_blocks()[0]])
+        with pytest.raises(lib.ScasaError) as e:
+            g.stage_counts([0, big], rp, np.full(big, em_row, np.int32), np.ones(big))
+        assert e.value.code == -4
+    finally:
+        g.close()
