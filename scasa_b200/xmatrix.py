@@ -101,6 +101,29 @@ class XMatrix:
         return [" ".join(self.tx_names[t] for t in self.crp_tx[self.crp_p_off[k]:self.crp_p_off[k + 1]])
                 for k in range(self.n_blocks)]
 
+    def dm0_is_ccrpfun_fixed_point(self, clim: float = 30.0, blocks=None) -> bool:
+        """N3 (SURVEY.md §8 f): can ``DM0 <- lapply(CRP, ccrpfun, clim)`` (scasa_quant_step2_v1.0.0.R:127,
+        serial minutes of svd + kmeans in the R master) be skipped in favour of the shipped ``CCRP``?
+        True when, for every block (or the given ones), DM0 is what ccrpfun's loop (Scasa_Rsource.R:168-193)
+        stops at: the zero-sum CRP columns are gone (:171-172), every DM0 column is the mean of its member
+        CRP columns (kmeans centres, :186-187) and all condition numbers max(sval)/sval are < clim (:175-179),
+        so ccrpfun applied to it again returns it unchanged."""
+        ks = range(self.n_blocks) if blocks is None else blocks
+        for k in ks:
+            crp, dm0 = self.crp_block(k), self.dm0_block(k)
+            mem = self.crp_member[self.crp_p_off[k]:self.crp_p_off[k + 1]]
+            if not np.array_equal(crp.sum(axis=0) > 0, mem >= 0):
+                return False
+            mem = mem - self.dm0_p_off[k]
+            for j in range(dm0.shape[1]):
+                if not (mem == j).any() or np.max(np.abs(crp[:, mem == j].mean(axis=1) - dm0[:, j])) > 1e-15:
+                    return False
+            if dm0.shape[1] >= 2:
+                sv = np.linalg.svd(dm0, compute_uv=False)
+                if not np.all(np.abs(sv.max() / sv) < clim):
+                    return False
+        return True
+
     def em_blocks(self) -> np.ndarray:
         """Blocks that go through the AEM loop: nrow(X0) > 1 (Scasa_Rsource.R:979)."""
         return np.nonzero(np.diff(self.q_off) > 1)[0].astype(np.int32)

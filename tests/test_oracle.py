@@ -204,6 +204,9 @@ def test_shipped_xmatrix_relations(xm):
             sv = np.linalg.svd(dm0, compute_uv=False)
             worst = max(worst, sv.max() / sv.min())
     assert worst < 30                                                                                 # K6: clim = 30
+    sample = np.random.default_rng(1).choice(xm.n_blocks, 3000, replace=False)
+    assert xm.dm0_is_ccrpfun_fixed_point(30.0, sample)                                                # N3: the recompute can be skipped
+    assert not xm.dm0_is_ccrpfun_fixed_point(1.5, xm.em_blocks()[:400])                               # ... but not for a stricter clim
     assert (xm.gene_of_col >= 0).all()                                                                # K7
     assert sum(" " in n for n in xm.dm0_colnames()) == 12140                                          # K8
 
