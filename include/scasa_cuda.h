@@ -175,6 +175,15 @@ int scasa_bfh_read(const scasa_bfh *f, char *tx_names, char *barcodes, int64_t *
                    int32_t *eq_tx /* [n_eq_tx] */, int64_t *cell_ptr /* [n_cells+1] */, int32_t *eq_id /* [n_pairs], 0-based line */,
                    int32_t *eq_count /* [n_pairs] */);
 
+/* ---- kallisto | bustools -> quant inputs (host only; replaces scasa_quant_step1_2_v1.0.0.R) -------
+ * bus_txt = output.correct.sort.bus.final.txt (barcode, UMI, eqclass, count, barcode+UMI; tab separated),
+ * matrix_ec and transcripts_txt as kallisto bus writes them.  Cells = barcodes with more than
+ * libsize_thres records (the wrapper passes 200); repeated (barcode, UMI) pairs are resolved as the
+ * script does; the count of a (cell, eqclass) is its number of kept molecules.  The handle is read
+ * and closed with scasa_bfh_sizes / scasa_bfh_read / scasa_bfh_close (eq_id = line of matrix.ec). */
+int scasa_bus_open(const char *bus_txt, const char *matrix_ec, const char *transcripts_txt, int64_t libsize_thres,
+                   scasa_bfh **out);
+
 /* ---- the two text outputs (host only) ----------------------------------------------------------
  * write.table(t(result)[keep, ], file, quote = F, row.names = T, sep = "\t") as at
  * scasa_quant_step2_v1.0.0.R:165-170 and scasa_quant_step3_v1.0.0.R:52: mat is the library's

@@ -32,12 +32,27 @@ class Bfh:
         return table[self.eq_tx]
 
 
+def read_bus(bus_txt: str, matrix_ec: str, transcripts_txt: str, libsize_thres: int = 200) -> Bfh:
+    """kallisto | bustools output -> the same arrays (replaces scasa_quant_step1_2_v1.0.0.R):
+    ``eq_id`` indexes the lines of matrix.ec, ``eq_count`` is the number of kept molecules."""
+    L = _l.load()
+    h = C.c_void_p()
+    rc = L.scasa_bus_open(bus_txt.encode(), matrix_ec.encode(), transcripts_txt.encode(), libsize_thres, C.byref(h))
+    if rc:
+        raise _l.ScasaError(rc, L.scasa_last_error(None).decode())
+    return _collect(L, h)
+
+
 def read_bfh(path: str, n_threads: int = 0) -> Bfh:
     L = _l.load()
     h = C.c_void_p()
     rc = L.scasa_bfh_open(path.encode(), n_threads, C.byref(h))
     if rc:
         raise _l.ScasaError(rc, L.scasa_last_error(None).decode())
+    return _collect(L, h)
+
+
+def _collect(L, h) -> Bfh:
     try:
         s = [C.c_int64(0) for _ in range(7)]
         L.scasa_bfh_sizes(h, *[C.byref(x) for x in s])

@@ -17,6 +17,7 @@
 // transcript indices into the file's transcript list.  Host-only: no CUDA here.
 #include "scasa_cuda.h"
 #include "scasa_host.h"
+#include "scasa_reads.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -29,18 +30,6 @@
 #include <thread>
 #include <vector>
 
-struct scasa_bfh {
-    std::vector<char> text;                    // the whole file
-    std::vector<const char *> line;            // line starts; line[k+1] - line[k] spans line k incl. its newline
-    int64_t n_tx = 0, n_cb = 0, n_eq = 0;
-    std::vector<int64_t> eq_off;               // [n_eq+1]
-    std::vector<int32_t> eq_tx;
-    std::vector<int32_t> cell_of_cb;           // [n_cb] rank among the barcodes that occur, -1 otherwise
-    std::vector<int32_t> cells;                // barcode index of each cell, in byte order of the sequences
-    std::vector<int64_t> cell_ptr;             // [n_cells+1]
-    std::vector<int32_t> eq_id, eq_count;
-};
-
 namespace {
 
 struct Span { const char *b, *e; };
@@ -50,6 +39,17 @@ inline Span line_span(const scasa_bfh &f, int64_t k)
     if (e > b && e[-1] == '\n') e--;
     if (e > b && e[-1] == '\r') e--;
     return {b, e};
+}
+// names: lines of the bfh file, or the strings a bustools read collected
+inline Span tx_name(const scasa_bfh &f, int64_t k)
+{
+    if (!f.tx_names_v.empty()) { const std::string &s = f.tx_names_v[(size_t)k]; return {s.data(), s.data() + s.size()}; }
+    return line_span(f, 3 + k);
+}
+inline Span cell_name(const scasa_bfh &f, int64_t i)
+{
+    if (!f.cell_names_v.empty()) { const std::string &s = f.cell_names_v[(size_t)i]; return {s.data(), s.data() + s.size()}; }
+    return line_span(f, 3 + f.n_tx + f.cells[(size_t)i]);
 }
 // next tab-separated field of [p, end); returns false at the end of the line
 inline bool next_field(const char *&p, const char *end, Span &out)
@@ -265,12 +265,12 @@ int scasa_bfh_sizes(const scasa_bfh *f, int64_t *n_tx, int64_t *n_cells, int64_t
     if (n_eq_tx) *n_eq_tx = (int64_t)f->eq_tx.size();
     if (tx_name_bytes) {
         int64_t b = 0;
-        for (int64_t k = 0; k < f->n_tx; k++) { Span s = line_span(*f, 3 + k); b += (s.e - s.b) + 1; }
+        for (int64_t k = 0; k < f->n_tx; k++) { Span s = tx_name(*f, k); b += (s.e - s.b) + 1; }
         *tx_name_bytes = b;
     }
     if (barcode_bytes) {
         int64_t b = 0;
-        for (int32_t cb : f->cells) { Span s = line_span(*f, 3 + f->n_tx + cb); b += (s.e - s.b) + 1; }
+        for (int64_t i = 0; i < (int64_t)f->cells.size(); i++) { Span s = cell_name(*f, i); b += (s.e - s.b) + 1; }
         *barcode_bytes = b;
     }
     return SCASA_OK;
@@ -282,14 +282,14 @@ int scasa_bfh_read(const scasa_bfh *f, char *tx_names, char *barcodes, int64_t *
     if (!f) return bfh_fail(SCASA_ERR_ARG, "null argument");
     if (tx_names)
         for (int64_t k = 0; k < f->n_tx; k++) {
-            Span s = line_span(*f, 3 + k);
+            Span s = tx_name(*f, k);
             memcpy(tx_names, s.b, (size_t)(s.e - s.b));
             tx_names += s.e - s.b;
             *tx_names++ = '\n';
         }
     if (barcodes)
-        for (int32_t cb : f->cells) {
-            Span s = line_span(*f, 3 + f->n_tx + cb);
+        for (int64_t i = 0; i < (int64_t)f->cells.size(); i++) {
+            Span s = cell_name(*f, i);
             memcpy(barcodes, s.b, (size_t)(s.e - s.b));
             barcodes += s.e - s.b;
             *barcodes++ = '\n';

@@ -61,7 +61,7 @@ SYMBOLS = (
     "scasa_chunk_split", "scasa_estimate", "scasa_stage_counts", "scasa_stage_eqcounts", "scasa_run",
     "scasa_fetch_iso", "scasa_fetch_iters", "scasa_fetch_colsum", "scasa_fetch_counts", "scasa_set_gene_map",
     "scasa_fetch_gene", "scasa_gene_sum", "scasa_eqclass_map", "scasa_last_timing", "scasa_host_alloc",
-    "scasa_host_free", "scasa_device_count", "scasa_version", "scasa_set_host_threads", "scasa_expand_pairs", "scasa_quant", "scasa_transfer_bytes", "scasa_bfh_open", "scasa_bfh_close", "scasa_bfh_sizes", "scasa_bfh_read", "scasa_write_table", "scasa_format_real15", "scasa_set_run_parts",
+    "scasa_host_free", "scasa_device_count", "scasa_version", "scasa_set_host_threads", "scasa_expand_pairs", "scasa_quant", "scasa_transfer_bytes", "scasa_bfh_open", "scasa_bfh_close", "scasa_bfh_sizes", "scasa_bfh_read", "scasa_bus_open", "scasa_write_table", "scasa_format_real15", "scasa_set_run_parts",
 )
 
 
@@ -108,6 +108,7 @@ def load():
     L.scasa_format_real15.argtypes = [C.c_double, C.c_char_p, C.c_int32]
     L.scasa_bfh_open.argtypes = [C.c_char_p, C.c_int32, C.POINTER(vp)]
     L.scasa_bfh_close.argtypes = [vp]
+    L.scasa_bus_open.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64, C.POINTER(vp)]
     L.scasa_bfh_close.restype = None
     L.scasa_bfh_sizes.argtypes = [vp] + [i64p] * 7
     L.scasa_bfh_read.argtypes = [vp, C.c_char_p, C.c_char_p, i64p, i32p, i64p, i32p, i32p]

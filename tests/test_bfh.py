@@ -69,3 +69,55 @@ def test_bfh_errors(tmp_path):
     open(p, "w").write("2\n1\n3\nA\nB\nACGT\n")                                  # shorter than the header says
     with pytest.raises(lib.ScasaError):
         read_bfh(p)
+
+
+def _write_bus(tmp_path, rng, n_tx=30, n_ec=60, n_cells=12, sort=True):
+    tx = [f"ENST{i:05d}.{i % 4}" for i in range(n_tx)]
+    (tmp_path / "transcripts.txt").write_text("\n".join(tx) + "\n")
+    ecs = []
+    for e in range(n_ec):
+        k = 1 if e < n_tx // 2 else int(rng.integers(2, 6))
+        ecs.append(sorted(rng.choice(n_tx, k, replace=False).tolist()))
+    (tmp_path / "matrix.ec").write_text("".join(f"{e}\t{','.join(map(str, t))}\n" for e, t in enumerate(ecs)))
+    recs = []
+    for c in range(n_cells):
+        bc = "".join(rng.choice(list("ACGT"), 16))
+        n_mol = int(rng.integers(3, 40))                          # some cells fall under the library-size threshold
+        for _m in range(n_mol):
+            umi = "".join(rng.choice(list("ACGT"), 6))            # short UMIs: collisions happen
+            kind = rng.random()
+            if kind < 0.6:
+                recs.append((bc, umi, int(rng.integers(0, n_ec)), int(rng.integers(1, 5))))
+            elif kind < 0.8:                                      # several records, unique largest count
+                es = rng.choice(n_ec, 3, replace=False)
+                for i, e in enumerate(es):
+                    recs.append((bc, umi, int(e), 5 - i))
+            else:                                                 # tie on the count: the eqclass size decides, or nothing does
+                es = rng.choice(n_ec, 3, replace=False)
+                for e in es:
+                    recs.append((bc, umi, int(e), 2))
+    recs = sorted(set(recs)) if sort else [recs[i] for i in rng.permutation(len(recs))]
+    (tmp_path / "bus.txt").write_text("".join(f"{b}\t{u}\t{e}\t{c}\t{b}{u}\n" for b, u, e, c in recs))
+    return str(tmp_path / "bus.txt"), str(tmp_path / "matrix.ec"), str(tmp_path / "transcripts.txt")
+
+
+@pytest.mark.parametrize("sort", [True, False])
+def test_bustools_front_end_equals_literal_restatement(tmp_path, sort):
+    """N4: step1_2's library-size filter, duplicated (barcode, UMI) rules and per-cell eqclass counts."""
+    from scasa_b200.bfh import read_bus
+    from oracle import bus_literal
+    rng = np.random.default_rng(23)
+    paths = _write_bus(tmp_path, rng, sort=sort)
+    for thres in (0, 10, 25):
+        ref, cells, per_cell, eq_tx = bus_literal.quant_inputs(*paths, thres)
+        b = read_bus(*paths, libsize_thres=thres)
+        assert b.tx_names == ref
+        assert b.barcodes == cells, thres
+        for c, bc in enumerate(cells):
+            ids = b.eq_id[b.cell_ptr[c]:b.cell_ptr[c + 1]]
+            cnt = b.eq_count[b.cell_ptr[c]:b.cell_ptr[c + 1]]
+            want = sorted(per_cell[bc].items())
+            assert list(ids) == [e for e, _ in want] and list(cnt) == [v for _, v in want], (thres, bc)
+        for e, txs in eq_tx.items():
+            assert [b.tx_names[t] for t in b.eq_tx[b.eq_off[e]:b.eq_off[e + 1]]] == txs
+    assert len(read_bus(*paths, libsize_thres=10 ** 6).barcodes) == 0
