@@ -6,11 +6,13 @@
 //   Y --task_count_kernel--> entries / cells-with-counts per (chunk, EM block) "task"
 //     --classify_kernel--> blob size, shared-memory need and work class per task; a scan gives
 //                          the blob offsets
-//   Y --task_scatter_kernel--> one compact blob per task (counts by cell, rows, cell ids);
-//        pass-through blocks (nrow == 1, Scasa_Rsource.R:979-983) go straight into the result
-//   blobs --em_task_kernel<W>--> the alternating EM (estim_chunk's loop, Rsource:1010-1042): W warps
+//   Y --task_scatter_kernel--> one compact blob per task (counts by cell, rows, cell ids)
+//   Y --iso_fill_kernel--> the dense result rows: zeros, and for pass-through blocks (nrow == 1,
+//        Scasa_Rsource.R:979-983) the count itself; tiles built in shared memory, TMA bulk stores
+//   blobs --em_task_kernel<W, R>--> the alternating EM (estim_chunk's loop, Rsource:1010-1042): W warps
 //        stage one task in shared memory and run it to the end; persistent, atomic work queue
 //   result --colsum / gene kernels--> per-column sums (step2:167) and gene sums (step3:32-46)
+//   result --compact_rows_kernel--> (column, value) pairs for the zero-suppressed trip to the host
 //
 // Why sparse: a cell with no counts in a block keeps beta = 0 through every iteration of
 // estim.BETA and contributes 0 to every sum of estim.X.em, so only (cell, block) pairs with
