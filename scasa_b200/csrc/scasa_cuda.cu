@@ -407,7 +407,7 @@ void fetch_dense(scasa_ctx *c, const double *d_mat, int64_t n_rows, int64_t n_co
     int nthr = c->host_threads > 0 ? c->host_threads : (int)std::thread::hardware_concurrency();
     nthr = std::max(1, std::min(nthr, 256));
     const int64_t batch = std::max<int64_t>(64, std::min<int64_t>(n_rows, ((int64_t)48 << 20) / n_cols));   // ~48 M cells of the matrix per batch
-    const size_t cap = (size_t)(batch * n_cols / 3 + 1024);
+    const size_t cap = (size_t)(batch * n_cols / 8 + 1024);     // pairs per batch: 12 % density fits (the results are ~6 % dense); denser batches are copied plainly
     for (auto &b : c->fb) fetch_buf_ensure(c, b, (size_t)batch, cap);
     const int64_t n_batches = (n_rows + batch - 1) / batch;
     auto launch = [&](int64_t k) {
