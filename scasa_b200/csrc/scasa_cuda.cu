@@ -179,8 +179,8 @@ struct scasa_ctx {
     int cls_warps[kClasses] = {1, 2, 4, 8};
     int cls_pairs[kClasses] = {96, 256, 512, 1 << 30};
     int cls_bytes[kClasses] = {6144, 12288, 16384, 1 << 30};
-    int cls_cta_threads[kClasses] = {64, 128, 128, 256};
-    int cls_ctas_per_sm[kClasses] = {16, 8, 4, 2};
+    int cls_cta_threads[kClasses] = {128, 256, 256, 256};
+    int cls_ctas_per_sm[kClasses] = {8, 4, 2, 2};
     DBuf<unsigned long long> d_stats;
     DBuf<int> d_flag;
 
