@@ -595,7 +595,13 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
         }
         c->cls_pairs[kClasses - 1] = 1 << 30; c->cls_bytes[kClasses - 1] = 1 << 30;
         for (int k = 0; k < kClasses; k++) {
-            CK(cudaStreamCreateWithFlags(&c->cls_stream[k], cudaStreamNonBlocking));
+            {   // the classes with few, long tasks get scheduling priority: their CTAs go first when an SM has room,
+                // the many-small-tasks class fills what is left and takes over when they are done
+                int lo_p = 0, hi_p = 0;
+                CK(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+                const int prio = (k == 0 || getenv("SCASA_EM_NOPRIO")) ? lo_p : hi_p;
+                CK(cudaStreamCreateWithPriority(&c->cls_stream[k], cudaStreamNonBlocking, prio));
+            }
             CK(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
             CK(cudaEventCreate(&c->ev_cls[k][0]));
             CK(cudaEventCreate(&c->ev_cls[k][1]));
