@@ -338,7 +338,8 @@ def main():
                        "parallelism": f"cells sharded by chunk over {world} GPU(s), no collective"},
             "device_ms_per_step": dev_max * 1e3 / args.steps,
             "phases_ms": {k: t[k] for k in ("pack_ms", "tasks_ms", "em_ms", "finish_ms")},
-            "em_class_ms": t["em_class_ms"], "em_class_tasks": t["em_class_tasks"], "max_slot_bytes": t["max_slot_bytes"],
+            "em_class_ms": t["em_class_ms"], "em_class_tasks": t["em_class_tasks"],
+            "em_pair_ms": t["em_pair_ms"], "em_pair_tasks": t["em_pair_tasks"], "max_slot_bytes": t["max_slot_bytes"],
             "work": {"tasks": t["n_tasks"], "active_cell_blocks": t["n_active"], "em_entries": t["n_entries"],
                      "inner_iters": t["inner_iters"], "outer_iters": t["outer_iters"]},
             "gpu_launches": int(sum(x["launches"] for x in tms)),

@@ -213,6 +213,8 @@ typedef struct {
     int32_t max_slot_bytes; /* largest shared-memory slot a task needed     */
     int32_t run_parts;      /* ranges of chunks the run was cut into; with more than one the phase times above are
                                sums over ranges that ran side by side (they exceed total_ms) */
+    float em_pair_ms;       /* EM kernel time of the tiny-task kernel (two tasks per warp); overlaps the classes above */
+    int64_t em_pair_tasks;  /* tasks it ran (not counted in em_class_tasks) */
 } scasa_timing_t;
 int scasa_last_timing(scasa_ctx *ctx, scasa_timing_t *out);
 

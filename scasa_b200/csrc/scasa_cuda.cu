@@ -169,18 +169,20 @@ struct scasa_ctx {
     int64_t max_cell_entries = 0;
 
     // ---- task arrays
-    DBuf<int32_t> d_cnt, d_runs, d_tbytes, d_iters, d_list[kClasses];
+    DBuf<int32_t> d_cnt, d_runs, d_tbytes, d_iters, d_list[kLists];
     DBuf<int64_t> d_toff, d_scan_sums, d_totals;
     DBuf<char> d_tdata;
     DBuf<unsigned int> d_next, d_counters;
-    cudaStream_t cls_stream[kClasses] = {};
-    cudaEvent_t ev_fork = nullptr, ev_fill = nullptr, ev_join[kClasses] = {}, ev_cls[kClasses][2] = {};
+    cudaStream_t cls_stream[kLists] = {};
+    cudaEvent_t ev_fork = nullptr, ev_fill = nullptr, ev_join[kLists] = {}, ev_cls[kLists][2] = {};
     // work classes of the EM kernel: warps per task, pairs and slot limits, resident CTAs per SM
     int cls_warps[kClasses] = {1, 2, 4, 8};
     int cls_pairs[kClasses] = {96, 256, 512, 1 << 30};
     int cls_bytes[kClasses] = {6144, 12288, 16384, 1 << 30};
     int cls_cta_threads[kClasses] = {128, 256, 256, 256};
     int cls_ctas_per_sm[kClasses] = {8, 4, 2, 2};
+    int pair_max = 16;                // tiny tasks two per warp (em_pair_kernel); SCASA_EM_PAIR=0 turns it off
+    int pair_ctas_per_sm = 8;
     DBuf<unsigned long long> d_stats;
     DBuf<int> d_flag;
 
@@ -286,7 +288,7 @@ Tasks tdev(scasa_ctx *c)
     T.cnt = c->d_cnt.p; T.runs = c->d_runs.p; T.tbytes = c->d_tbytes.p;
     T.toff = c->d_toff.p;
     T.tdata = c->d_tdata.p;
-    for (int k = 0; k < kClasses; k++) T.list[k] = c->d_list[k].p;
+    for (int k = 0; k < kLists; k++) T.list[k] = c->d_list[k].p;
     T.counters = c->d_counters.p;
     return T;
 }
@@ -594,12 +596,18 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
             }
         }
         c->cls_pairs[kClasses - 1] = 1 << 30; c->cls_bytes[kClasses - 1] = 1 << 30;
-        for (int k = 0; k < kClasses; k++) {
+        if (const char *env = getenv("SCASA_EM_PAIR")) {      // "max[:ctas_per_sm]"
+            int m = 16, cps = 8;
+            const int got = sscanf(env, "%d:%d", &m, &cps);
+            if (got >= 1) c->pair_max = std::max(0, std::min(16, m));
+            if (got >= 2 && cps >= 1) c->pair_ctas_per_sm = cps;
+        }
+        for (int k = 0; k < kLists; k++) {
             {   // the classes with few, long tasks get scheduling priority: their CTAs go first when an SM has room,
                 // the many-small-tasks class fills what is left and takes over when they are done
                 int lo_p = 0, hi_p = 0;
                 CK(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
-                const int prio = (k == 0 || getenv("SCASA_EM_NOPRIO")) ? lo_p : hi_p;
+                const int prio = (k == 0 || k == kPairList || getenv("SCASA_EM_NOPRIO")) ? lo_p : hi_p;
                 CK(cudaStreamCreateWithPriority(&c->cls_stream[k], cudaStreamNonBlocking, prio));
             }
             CK(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
@@ -655,7 +663,7 @@ void scasa_ctx_destroy(scasa_ctx *c)
     DBuf<int32_t> *i32[] = {&c->d_q_off, &c->d_p_off, &c->d_em_blocks, &c->d_em_order,
                             &c->d_cell_chunk, &c->d_y_len, &c->d_y_row, &c->d_eq_id, &c->d_eq_count, &c->d_eq_row,
                             &c->d_cnt, &c->d_runs, &c->d_tbytes, &c->d_iters, &c->d_row_col,
-                            &c->d_list[0], &c->d_list[1], &c->d_list[2], &c->d_list[3],
+                            &c->d_list[0], &c->d_list[1], &c->d_list[2], &c->d_list[3], &c->d_list[4],
                             &c->d_gene_ptr, &c->d_gene_cols};
     for (auto b : i32) b->release();
     DBuf<int64_t> *i64[] = {&c->d_x_off, &c->d_chunk_off, &c->d_y_start, &c->d_cell_ptr, &c->d_toff, &c->d_scan_sums, &c->d_totals};
@@ -672,7 +680,7 @@ void scasa_ctx_destroy(scasa_ctx *c)
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_fill) cudaEventDestroy(c->ev_fill);
-    for (int k = 0; k < kClasses; k++) {
+    for (int k = 0; k < kLists; k++) {
         if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
         for (auto &e : c->ev_cls[k]) if (e) cudaEventDestroy(e);
         if (c->cls_stream[k]) cudaStreamDestroy(c->cls_stream[k]);
@@ -817,7 +825,7 @@ int scasa_set_gene_map(scasa_ctx *c, const int32_t *gene_of_col, int32_t n_genes
 
 // What one range of chunks contributed to the run statistics.
 struct RangeStats {
-    float pack_ms = 0, tasks_ms = 0, em_ms = 0, finish_ms = 0, cls_ms[kClasses] = {0, 0, 0, 0};
+    float pack_ms = 0, tasks_ms = 0, em_ms = 0, finish_ms = 0, cls_ms[kLists] = {0, 0, 0, 0, 0};
     unsigned long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     unsigned int cnts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int64_t blob_bytes = 0;
@@ -836,7 +844,7 @@ static void run_range(scasa_ctx *w, scasa_ctx *c, int h0, int h1, int part, Rang
     double *iso = c->d_iso.p + c0 * c->n_cols;
     w->d_cnt.ensure((size_t)n_tasks + 1); w->d_runs.ensure((size_t)n_tasks + 1);
     w->d_tbytes.ensure((size_t)n_tasks + 1); w->d_toff.ensure((size_t)n_tasks + 1);
-    for (int k = 0; k < kClasses; k++) w->d_list[k].ensure((size_t)n_tasks + 1);
+    for (int k = 0; k < kLists; k++) w->d_list[k].ensure((size_t)n_tasks + 1);
 
     CK(cudaEventRecord(w->ev[0], s));
     CK(cudaMemsetAsync(w->d_cnt.p, 0, (n_tasks + 1) * sizeof(int32_t), s));
@@ -897,6 +905,7 @@ static void run_range(scasa_ctx *w, scasa_ctx *c, int h0, int h1, int part, Rang
     ClassCfg CC;
     for (int k = 0; k < kClasses; k++) { CC.pairs[k] = c->cls_pairs[k]; CC.bytes[k] = c->cls_bytes[k]; }
     CC.real_bytes = c->opts.fp32 ? 4 : 8;
+    CC.pair_max = c->pair_max;
     int32_t *iters = c->d_iters.p + (int64_t)h0 * w->n_em * 2;
     int64_t tot[2] = {0, 0};
     unsigned int *cnts = rs.cnts;
@@ -929,7 +938,7 @@ static void run_range(scasa_ctx *w, scasa_ctx *c, int h0, int h1, int part, Rang
     CK(cudaEventRecord(w->ev[2], s));
 
     // ---- EM: one persistent kernel per work class, side by side on their own streams
-    bool ran_cls[kClasses] = {false, false, false, false};
+    bool ran_cls[kLists] = {false, false, false, false, false};
     if (w->n_em > 0 && cnts[4] > 0) {
         CK(cudaEventRecord(w->ev_fork, s));
         for (int k = kClasses - 1; k >= 0; k--) {          // long tasks first
@@ -961,6 +970,36 @@ static void run_range(scasa_ctx *w, scasa_ctx *c, int h0, int h1, int part, Rang
             ran_cls[k] = true;
             launches++;
         }
+        if (cnts[kPairCounter] > 0) {                        // tiny tasks, two per warp
+            const int k = kPairList, threads = 128, halves = threads / 16;
+            const int rb = c->opts.fp32 ? 4 : 8, pm = c->pair_max;
+            int slot = 16;
+            for (int p = 1; p <= pm; p++)
+                for (int q = 1; q * p <= pm; q++)
+                    for (int n = 1; n * p <= pm; n++) slot = std::max(slot, slot_bytes_of(q, p, n, std::min(pm, n * q), rb));
+            slot = (slot + 15) & ~15;
+            const size_t smem = (size_t)slot * halves;
+            const unsigned n = cnts[kPairCounter];
+            EmArgs A;
+            A.X = X; A.S = S; A.T = T; A.O = O; A.out = iso; A.iters = iters; A.stats = w->d_stats.p;
+            A.list = w->d_list[k].p; A.list_n = w->d_counters.p + kPairCounter; A.next = w->d_next.p + k; A.slot_bytes = slot;
+            const unsigned grid = (unsigned)std::min<int64_t>((int64_t)w->n_sm * c->pair_ctas_per_sm, ((int64_t)n + halves - 1) / halves);
+            cudaStream_t cs = w->cls_stream[k];
+            CK(cudaStreamWaitEvent(cs, w->ev_fork, 0));
+            CK(cudaEventRecord(w->ev_cls[k][0], cs));
+            if (c->opts.fp32) {
+                CK(cudaFuncSetAttribute(em_pair_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                em_pair_kernel<float><<<grid, threads, smem, cs>>>(A);
+            } else {
+                CK(cudaFuncSetAttribute(em_pair_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                em_pair_kernel<double><<<grid, threads, smem, cs>>>(A);
+            }
+            CK(cudaEventRecord(w->ev_cls[k][1], cs));
+            CK(cudaEventRecord(w->ev_join[k], cs));
+            CK(cudaStreamWaitEvent(s, w->ev_join[k], 0));
+            ran_cls[k] = true;
+            launches++;
+        }
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(w->ev[3], s));
@@ -979,7 +1018,7 @@ static void run_range(scasa_ctx *w, scasa_ctx *c, int h0, int h1, int part, Rang
     CK(cudaEventElapsedTime(&rs.tasks_ms, w->ev[1], w->ev[2]));
     CK(cudaEventElapsedTime(&rs.em_ms, w->ev[2], w->ev[3]));
     CK(cudaEventElapsedTime(&rs.finish_ms, w->ev[3], w->ev[4]));
-    for (int k = 0; k < kClasses; k++)
+    for (int k = 0; k < kLists; k++)
         if (ran_cls[k]) CK(cudaEventElapsedTime(&rs.cls_ms[k], w->ev_cls[k][0], w->ev_cls[k][1]));
     rs.launches = launches;
 }
@@ -1000,6 +1039,7 @@ static int sync_twin(scasa_ctx *c)
         t->cls_warps[k] = c->cls_warps[k]; t->cls_pairs[k] = c->cls_pairs[k]; t->cls_bytes[k] = c->cls_bytes[k];
         t->cls_cta_threads[k] = c->cls_cta_threads[k]; t->cls_ctas_per_sm[k] = c->cls_ctas_per_sm[k];
     }
+    t->pair_max = c->pair_max; t->pair_ctas_per_sm = c->pair_ctas_per_sm;
     if (c->n_genes > 0 && (t->n_genes != c->n_genes || t->gene_of_col_host != c->gene_of_col_host)) {
         int rc = scasa_set_gene_map(t, c->gene_of_col_host.data(), c->n_genes);
         if (rc) return fail(c, rc, std::string("twin context: ") + scasa_last_error(t));
@@ -1079,6 +1119,7 @@ static int run_staged(scasa_ctx *c, bool allow_split)
         for (const RangeStats &r : rs) {
             tm.pack_ms += r.pack_ms; tm.tasks_ms += r.tasks_ms; tm.em_ms += r.em_ms; tm.finish_ms += r.finish_ms;
             for (int k = 0; k < kClasses; k++) { tm.em_class_ms[k] += r.cls_ms[k]; tm.em_class_tasks[k] += r.cnts[k]; }
+            tm.em_pair_ms += r.cls_ms[kPairList]; tm.em_pair_tasks += r.cnts[kPairCounter];
             for (int k = 0; k < 8; k++) st[k] += r.st[k];
             tm.n_entries += r.blob_bytes;
             tm.launches += r.launches;

@@ -399,4 +399,207 @@ template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_k
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Tiny tasks (not poor, n*p <= 16, E <= 16, q*p <= 16: more than half of all tasks) two per warp.
+// Each half-warp owns a task and a shared-memory slot; every stage fits one pass of its 16 lanes.
+// The warp runs a loop whose body is LOAD / one estim.BETA iteration / estim.X.em / OUT, each guarded
+// by the half's own phase: halves in the same phase execute it together (the common case for the
+// inner iteration), a half in another phase waits at the end of the block.  Same arithmetic, in
+// the same order, as em_task_kernel: a task's result does not depend on which kernel ran it.
+template <typename R> __global__ void __launch_bounds__(128, 8) em_pair_kernel(EmArgs A)
+{
+    extern __shared__ __align__(16) unsigned char em_smem[];
+    enum { LOAD = 0, INNER = 1, XUPD = 2, OUT = 3, DONE = 4 };
+    const int lane = threadIdx.x & 31;
+    const int hl = lane & 15;                                  // lane inside the half
+    const unsigned hmask = (lane & 16) ? 0xffff0000u : 0x0000ffffu;
+    const int hlead = lane & 16;                               // first lane of the half
+    unsigned char *slot = em_smem + (size_t)(threadIdx.x >> 4) * A.slot_bytes;
+    const XDev &X = A.X;
+    const EmOpts &O = A.O;
+    const unsigned n_list = *A.list_n;
+    const R lim = (R)O.lim, maxerr = (R)O.maxerr;
+
+    int phase = LOAD;
+    int64_t t = 0;
+    int b = 0, q = 1, p = 1, n = 1, E = 1, np = 1, qp = 1, nc = 0, h = 0;
+    int outer = 0, inner_total = 0, it = 0;
+    // slot arrays (set in LOAD)
+    double *ey = nullptr;
+    const uint32_t *rcell = nullptr;
+    const uint16_t *eptr = nullptr, *erow = nullptr;
+    R *ew = nullptr, *Xc = nullptr, *Xn = nullptr, *rcs = nullptr, *bts = nullptr, *nrm = nullptr, *lnorm = nullptr, *beta = nullptr,
+      *gam = nullptr;
+    uint16_t *erec = nullptr, *rptr = nullptr, *perm = nullptr;
+
+    for (;;) {
+        // ================= LOAD: next task of the queue into this half's slot
+        if (phase == LOAD) {
+            unsigned ti = 0;
+            if (hl == 0) ti = atomicAdd(A.next, 1u);
+            ti = __shfl_sync(hmask, ti, hlead);
+            if (ti >= n_list) phase = DONE;
+            else {
+                t = A.list[ti];
+                const int e = (int)(t % X.n_em);
+                h = (int)(t / X.n_em);
+                b = X.em_blocks[e];
+                q = X.q_off[b + 1] - X.q_off[b]; p = X.p_off[b + 1] - X.p_off[b];
+                qp = q * p;
+                n = A.T.runs[t]; E = A.T.cnt[t];
+                np = n * p;
+                nc = (int)(A.S.chunk_off[h + 1] - A.S.chunk_off[h]);
+                const BlobLayout BL = blob_layout(n, E);
+                ey = (double *)slot;
+                rcell = (const uint32_t *)(slot + BL.off_cell);
+                eptr = (const uint16_t *)(slot + BL.off_ptr);
+                erow = (const uint16_t *)(slot + BL.off_row);
+                ew = (R *)(slot + BL.bytes);
+                Xc = ew + E; Xn = Xc + qp; rcs = Xn + qp; bts = rcs + p; nrm = bts + p; lnorm = nrm + p;
+                beta = lnorm + n; gam = beta + np;
+                erec = (uint16_t *)(gam + np); rptr = erec + E; perm = rptr + q + 1;
+                {
+                    const uint4 *src = (const uint4 *)(A.T.tdata + A.T.toff[t]);
+                    uint4 *dst = (uint4 *)slot;
+                    for (int i = hl; i < (BL.bytes >> 4); i += 16) dst[i] = __ldcs(src + i);
+                    const double *X0 = X.x + X.x_off[b];
+                    if (hl < qp) Xc[hl] = (R)X0[hl];
+                }
+                __syncwarp(hmask);
+                if (hl < n) {
+                    const int k1 = eptr[hl + 1];
+                    for (int k = eptr[hl]; k < k1; k++) erec[k] = (uint16_t)hl;
+                }
+                // entries by row, stable in cell order: rank of an entry = entries with a smaller (row, index)
+                {
+                    const int myrow = hl < E ? erow[hl] : 0x7fffffff;
+                    int rank = 0, below = 0;
+                    for (int k = 0; k < E; k++) {
+                        const int rk = __shfl_sync(hmask, myrow, hlead + k);
+                        rank += (rk < myrow) || (rk == myrow && k < hl);
+                        below += rk < hl;                                   // entries in rows before row hl (for rptr)
+                    }
+                    if (hl < E) perm[rank] = (uint16_t)hl;
+                    if (hl < q) rptr[hl] = (uint16_t)below;
+                    if (hl == 0) rptr[q] = (uint16_t)E;
+                }
+                if (hl < p) {                                               // 1/colSums(X)  :731, :745
+                    R s0 = 0;
+                    for (int r = 0; r < q; r++) s0 += Xc[hl * q + r];
+                    rcs[hl] = R(1) / s0;
+                }
+                if (hl < n) {                                               // logNorm :732-733, beta0 :1012-1013
+                    double ys = 0;
+                    const int k1 = eptr[hl + 1];
+                    for (int k = eptr[hl]; k < k1; k++) ys += ey[k];
+                    lnorm[hl] = (R)digamma_pos(ys + 0.00000001);
+                    const R b0 = (R)(ys / p);
+                    for (int j = 0; j < p; j++) beta[j * n + hl] = b0;
+                }
+                __syncwarp(hmask);
+                outer = 0; inner_total = 0; it = 0;
+                phase = INNER;
+            }
+        }
+        if (__all_sync(kFull, phase == DONE)) break;
+
+        // ================= one iteration of estim.BETA  :726-761
+        if (phase == INNER) {
+            const int pj = hl / n, pa = hl - pj * n;                        // pair hl = (transcript pj, cell pa)
+            if (hl < np) gam[hl] = O.modify ? em_gamma_fast<R>(beta[hl], lnorm[pa]) : beta[hl];      // S1
+            __syncwarp(hmask);
+            if (hl < E) {                                                    // S2
+                const int r = erow[hl], a = erec[hl];
+                R mu = 0;
+                for (int j = 0; j < p; j++) mu += Xc[j * q + r] * gam[j * n + a];
+                ew[hl] = (R)ey[hl] / (mu > 0 ? mu : R(1));
+            }
+            __syncwarp(hmask);
+            bool fail = false;
+            if (hl < np) {                                                   // S3
+                R s0 = 0;
+                const int k1 = eptr[pa + 1];
+                for (int k = eptr[pa]; k < k1; k++) s0 += Xc[pj * q + erow[k]] * ew[k];
+                const R old = beta[hl];
+                const R gs = gam[hl] * s0;
+                R nb = gs == R(0) ? R(0) : gs * rcs[pj];
+                if (nb != nb) nb = R(0);
+                const R den = old > lim ? old : lim;
+                if (!(rabs(nb - old) < maxerr * den)) fail = true;
+                beta[hl] = nb;
+            }
+            it++;
+            inner_total++;
+            const bool any_fail = __any_sync(hmask, fail);
+            if ((!O.fixed_iter && !any_fail) || it >= O.maxiter_bt) phase = XUPD;
+        }
+
+        // ================= estim.X.em  :898-922, outer test :1019-1020
+        if (phase == XUPD) {
+            if (hl < p) {                                                    // BTsum  :904, :917
+                R s0 = 0;
+                for (int a = 0; a < n; a++) s0 += beta[hl * n + a];
+                bts[hl] = s0 > 0 ? s0 : R(0.1);
+            }
+            if (hl < E) {
+                const int r = erow[hl], a = erec[hl];
+                R mu = 0;
+                for (int j = 0; j < p; j++) mu += beta[j * n + a] * Xc[j * q + r];
+                ew[hl] = (R)ey[hl] / (mu > 0 ? mu : R(0.1));                 // mult = 1: no pseudo cell here
+            }
+            __syncwarp(hmask);
+            const int xj = hl / q, xr = hl - xj * q;                         // element hl = (row xr, transcript xj)
+            if (hl < qp) {
+                const R x = Xc[hl];
+                R acc = 0;
+                const int i1 = rptr[xr + 1];
+                for (int i = rptr[xr]; i < i1; i++) {
+                    const int k = perm[i];
+                    acc += beta[xj * n + erec[k]] * x * ew[k];
+                }
+                Xn[hl] = acc == R(0) ? R(0) : acc / bts[xj];
+            }
+            __syncwarp(hmask);
+            if (hl < p) {
+                R csum = 0;
+                for (int r = 0; r < q; r++) csum += Xn[hl * q + r];
+                const R sc = csum < R(0.00001) ? R(-1) : R(1) / (csum > 0 ? csum : R(0.1));
+                nrm[hl] = sc;
+                if (sc >= 0) {
+                    R s2 = 0;
+                    for (int r = 0; r < q; r++) s2 += Xn[hl * q + r] * sc;
+                    rcs[hl] = R(1) / s2;
+                }
+            }
+            __syncwarp(hmask);
+            bool xfail = false;
+            if (hl < qp) {
+                const R x0 = Xc[hl], sc = nrm[xj];
+                const R v = sc < 0 ? x0 : Xn[hl] * sc;
+                Xc[hl] = v;
+                const R num = rabs(v - x0), den = rabs(x0) > lim ? x0 : lim;
+                const bool ok = den > 0 ? (num < maxerr * den) : (num / den < maxerr);
+                if (!ok) xfail = true;
+            }
+            outer++;
+            const bool any_x = __any_sync(hmask, xfail);
+            if ((!O.fixed_iter && !any_x) || outer >= O.maxiter_x) phase = OUT;
+            else { it = 0; phase = INNER; }
+        }
+
+        // ================= BT into the result  :1042
+        if (phase == OUT) {
+            const int64_t cbase = A.S.chunk_off[h] - A.S.cell_base;
+            const int64_t col0 = X.p_off[b];
+            if (hl < n) {
+                double *o = A.out + (cbase + (int64_t)rcell[hl]) * X.n_cols + col0;
+                for (int j = 0; j < p; j++) o[j] = (double)beta[j * n + hl];
+            }
+            if (hl == 0) task_done_stats(A.iters, A.stats, t, outer, inner_total, q, p, nc, n);
+            __syncwarp(hmask);
+            phase = LOAD;
+        }
+    }
+}
+
 }  // namespace scasa

@@ -129,7 +129,12 @@ __host__ __device__ inline int slot_bytes_of(int q, int p, int n, int E, int rb)
 
 // work classes: W warps per task, a slot of at most kClassBytes[c] (the last class takes the rest)
 constexpr int kClasses = 4;
-struct ClassCfg { int pairs[kClasses]; int bytes[kClasses]; int real_bytes; };
+// one more list for tiny tasks, run two per warp by em_pair_kernel: not poor, and records*columns,
+// entries and rows*columns all <= pair_max (<= 16 = lanes of a half-warp; 0 turns the list off)
+constexpr int kLists = kClasses + 1;
+constexpr int kPairList = kClasses;
+constexpr int kPairCounter = 6;
+struct ClassCfg { int pairs[kClasses]; int bytes[kClasses]; int real_bytes; int pair_max; };
 
 struct Tasks {                // task t = chunk * n_em + em index
     int32_t *cnt;             // [n_tasks] Y entries; after classify: stored entries E (dense for poor blocks)
@@ -137,8 +142,8 @@ struct Tasks {                // task t = chunk * n_em + em index
     int32_t *tbytes;          // [n_tasks] blob bytes
     int64_t *toff;            // [n_tasks+1] exclusive scan of tbytes
     char *tdata;              // blobs
-    int32_t *list[kClasses];  // task ids per work class, expensive block shapes first
-    unsigned int *counters;   // [0..3] list lengths [4] non-empty tasks [5] largest slot need [7] error flag
+    int32_t *list[kLists];    // task ids per work class (+ the tiny-task list), expensive block shapes first
+    unsigned int *counters;   // [0..3] list lengths [4] non-empty tasks [5] largest slot need [6] tiny-task list length [7] error flag
 };
 // ------------------------------------------------------------------------------------------
 // crpcount_td's accumulation (Scasa_Rsource.R:528-531, :643-646 and :461-462), fast path: when the
@@ -342,6 +347,7 @@ __global__ void classify_kernel(XDev X, Sample S, Tasks T, int64_t n_tasks, EmOp
                 cls = kClasses - 1;
                 for (int k = kClasses - 2; k >= 0; k--)
                     if (n * p <= C.pairs[k] && (int)need <= C.bytes[k]) cls = k;
+                if (!X.poor[b] && n * p <= C.pair_max && E <= C.pair_max && q * p <= C.pair_max) cls = kPairList;
             }
         }
     }
@@ -357,11 +363,11 @@ __global__ void classify_kernel(XDev X, Sample S, Tasks T, int64_t n_tasks, EmOp
     }
     const unsigned nonempty = __ballot_sync(kFull, cls >= 0);
     if (lane == 0 && nonempty) atomicAdd(&T.counters[4], (unsigned)__popc(nonempty));
-    for (int k = 0; k < kClasses; k++) {
+    for (int k = 0; k < kLists; k++) {
         const unsigned m = __ballot_sync(kFull, cls == k);
         if (!m) continue;
         unsigned base = 0;
-        if (lane == __ffs(m) - 1) base = atomicAdd(&T.counters[k], (unsigned)__popc(m));
+        if (lane == __ffs(m) - 1) base = atomicAdd(&T.counters[k == kPairList ? kPairCounter : k], (unsigned)__popc(m));
         base = __shfl_sync(kFull, base, __ffs(m) - 1);
         if (cls == k) T.list[k][base + __popc(m & ((1u << lane) - 1u))] = (int32_t)t;
     }

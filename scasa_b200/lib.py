@@ -44,7 +44,8 @@ class Timing(C.Structure):
                 ("em_class_tasks", C.c_int64 * 4), ("n_tasks", C.c_int64), ("n_entries", C.c_int64),
                 ("n_active", C.c_int64), ("inner_iters", C.c_int64), ("outer_iters", C.c_int64),
                 ("alg_bytes", C.c_double), ("em_alg_bytes", C.c_double), ("launches", C.c_int32),
-                ("max_slot_bytes", C.c_int32), ("run_parts", C.c_int32)]
+                ("max_slot_bytes", C.c_int32), ("run_parts", C.c_int32), ("em_pair_ms", C.c_float),
+                ("em_pair_tasks", C.c_int64)]
 
     def as_dict(self) -> dict:
         d = {}

@@ -279,6 +279,28 @@ def test_fp32_option_close_to_fp64(xm, oracle, c1):
         g.close()
 
 
+def test_tiny_task_kernel_is_bit_identical_to_the_warp_kernel(xm, c1, monkeypatch):
+    """em_pair_kernel (tiny tasks, two per warp) takes every sum in the same order as em_task_kernel:
+    with the tiny-task list switched off (SCASA_EM_PAIR=0, read at context creation) the same inputs
+    give the same bits, in both modes and both arithmetic types, and the same iteration counts."""
+    from scasa_b200.api import Scasa, chunk_split
+    rowptr, rows, vals = c1
+    chunks = chunk_split(200, 4)
+    for kw in ({}, {"fixed_iter": 1, "maxiter_x": 4, "maxiter_bt": 8}, {"fp32": 1}):
+        res = []
+        for pair in ("16", "0"):
+            monkeypatch.setenv("SCASA_EM_PAIR", pair)
+            g = Scasa(xm, device=0, with_crp=False, **kw)
+            try:
+                iso, iters = g.estimate(chunks, rowptr, rows, vals)
+                res.append((iso, iters, g.timing()["em_pair_tasks"]))
+            finally:
+                g.close()
+        assert res[0][2] > 0 and res[1][2] == 0                  # the tiny-task kernel ran / did not run
+        assert np.array_equal(res[0][0], res[1][0])
+        assert np.array_equal(res[0][1], res[1][1])
+
+
 def test_c2_size_sampled_chunks_match_oracle(xm, oracle):
     """Config C2 (3,955 cells = 40 chunks of 98-99, step2:64-68) in the reference's convergence mode:
     the whole sample goes through scasa_quant (sliced), three of its chunks are re-run by the oracle."""
