@@ -929,8 +929,18 @@ static void run_range(scasa_ctx *w, scasa_ctx *c, int h0, int h1, int part, Rang
         if (st_bytes > 160 * 1024) {           // too many EM blocks for shared memory: cursors in HBM
             w->d_scatter_scratch.ensure((size_t)n_chunks * 3 * w->n_em);
             scratch = w->d_scatter_scratch.p;
-        } else CK(cudaFuncSetAttribute(task_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_bytes));
-        task_scatter_kernel<<<n_chunks, kScatterThreads, scratch ? 0 : st_bytes, s>>>(X, S, T, scratch);
+        }
+        // the per-cell index of the staged path sits behind the cursors (see task_scatter_kernel)
+        const size_t staged_bytes = st_bytes + (size_t)kScatterCap * 6 + (size_t)w->n_em * 2;
+        const int staged = (!scratch && staged_bytes <= 200 * 1024 && !getenv("SCASA_SCATTER_PLAIN")) ? 1 : 0;
+        const size_t sc_smem = scratch ? 0 : (staged ? staged_bytes : st_bytes);
+        if (staged) {
+            CK(cudaFuncSetAttribute(task_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
+            task_scatter_kernel<true><<<n_chunks, kScatterThreads, sc_smem, s>>>(X, S, T, scratch);
+        } else {
+            if (sc_smem) CK(cudaFuncSetAttribute(task_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
+            task_scatter_kernel<false><<<n_chunks, kScatterThreads, sc_smem, s>>>(X, S, T, scratch);
+        }
         CK(cudaGetLastError());
         launches++;
     }

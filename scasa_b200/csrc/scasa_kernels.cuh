@@ -152,6 +152,7 @@ struct Tasks {                // task t = chunk * n_em + em index
 // non-zero rows in ascending order.  Integer adds: the result is independent of their order.
 // Thread i owns the contiguous rows [i*seg, (i+1)*seg), seg odd (no bank conflicts); the histogram
 // is left all-zero for the next cell.
+constexpr int kPackBatch = 8;
 __global__ void __launch_bounds__(512) pack_cells_dense_kernel(int64_t n_cells, const int64_t *__restrict__ cell_ptr,
                                                                const int32_t *__restrict__ eq_id,
                                                                const int32_t *__restrict__ eq_count,
@@ -167,16 +168,46 @@ __global__ void __launch_bounds__(512) pack_cells_dense_kernel(int64_t n_cells, 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     for (int i = tid; i < n_words * 33; i += blockDim.x) pack_sm[i] = 0;
     __syncthreads();
-    for (int64_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
-        const int64_t s = cell_ptr[cell];
-        const int n = (int)(cell_ptr[cell + 1] - s);
-        for (int i = tid; i < n; i += blockDim.x) {
-            const int e = eq_id[s + i];
-            const int r = (e >= 0 && e < n_eq) ? eq_row[e] : -1;
-            const int c = eq_count[s + i];
-            if (r >= 0 && r < n_rows && c > 0) { atomicAdd(&hist[r], c); atomicOr(&bits[r >> 5], 1u << (r & 31)); }   // UMI counts are >= 1
+    // Entries are taken kPackBatch per thread at a time: all their loads are issued before the first
+    // gather through eq_row, all gathers before the first atomic, so a batch costs one memory round
+    // trip per level instead of one per entry.  The next cell's first batch is loaded while this
+    // cell's rows are emitted.
+    const int T = (int)blockDim.x;
+    int e[kPackBatch], c[kPackBatch], r[kPackBatch];
+    auto load_entries = [&](int64_t s, int n, int base) {
+#pragma unroll
+        for (int k = 0; k < kPackBatch; k++) {
+            const int i = base + k * T + tid;
+            e[k] = i < n ? eq_id[s + i] : -1;
+            c[k] = i < n ? eq_count[s + i] : 0;
+        }
+    };
+    auto load_rows = [&]() {
+#pragma unroll
+        for (int k = 0; k < kPackBatch; k++) r[k] = (e[k] >= 0 && e[k] < n_eq) ? eq_row[e[k]] : -1;
+    };
+    int64_t cell = blockIdx.x;
+    int64_t s = 0;
+    int n = 0;
+    if (cell < n_cells) { s = cell_ptr[cell]; n = (int)(cell_ptr[cell + 1] - s); }
+    load_entries(s, n, 0);
+    load_rows();
+    for (; cell < n_cells; cell += gridDim.x) {
+        const int64_t cell2 = cell + gridDim.x;
+        int64_t s2 = 0;
+        int n2 = 0;
+        if (cell2 < n_cells) { s2 = cell_ptr[cell2]; n2 = (int)(cell_ptr[cell2 + 1] - s2); }
+        for (int base = 0; base < n; base += kPackBatch * T) {
+            if (base > 0) { load_entries(s, n, base); load_rows(); }
+#pragma unroll
+            for (int k = 0; k < kPackBatch; k++)
+                if (r[k] >= 0 && r[k] < n_rows && c[k] > 0) {                 // UMI counts are >= 1
+                    atomicAdd(&hist[r[k]], c[k]);
+                    atomicOr(&bits[r[k] >> 5], 1u << (r[k] & 31));
+                }
         }
         __syncthreads();
+        load_entries(s2, n2, 0);                                              // in flight during the emission
         // thread owns words [tid*wpt, (tid+1)*wpt): rows in ascending order across threads
         const int w0 = tid * words_per_thread;
         int cnt = 0;
@@ -193,15 +224,17 @@ __global__ void __launch_bounds__(512) pack_cells_dense_kernel(int64_t n_cells, 
                 unsigned m = bits[w0 + k];
                 bits[w0 + k] = 0;
                 while (m) {
-                    const int r = ((w0 + k) << 5) + __ffs(m) - 1;
+                    const int rr = ((w0 + k) << 5) + __ffs(m) - 1;
                     m &= m - 1;
-                    const int v = hist[r];
-                    hist[r] = 0;
-                    y_row[s + o] = r; y_val[s + o] = (double)v; o++;
+                    const int v = hist[rr];
+                    hist[rr] = 0;
+                    y_row[s + o] = rr; y_val[s + o] = (double)v; o++;
                 }
             }
+        load_rows();
         if (tid == 0) y_len[cell] = total;
         __syncthreads();
+        s = s2; n = n2;
     }
 }
 
@@ -528,6 +561,9 @@ __global__ void __launch_bounds__(kFillThreads) iso_fill_kernel(XDev X, Sample S
 // The chunk's per-task cursors, extents and blob offsets live in shared memory (st[]: 3 words per
 // EM block), or in a global scratch area when the X-matrix has too many EM blocks for that.
 constexpr int kScatterThreads = 512;
+constexpr int kScatterBatch = 8;                               // entries per thread of a staged cell
+constexpr int kScatterCap = kScatterThreads * kScatterBatch;   // cells with more entries take the unstaged path
+template <bool staged>
 __global__ void __launch_bounds__(kScatterThreads) task_scatter_kernel(XDev X, Sample S, Tasks T, uint32_t *scratch)
 {
     extern __shared__ uint32_t scatter_sm[];
@@ -541,73 +577,179 @@ __global__ void __launch_bounds__(kScatterThreads) task_scatter_kernel(XDev X, S
     uint32_t *boff = st + 2 * X.n_em;    // blob offset inside the chunk's blob area, in 16-byte units
     const int64_t chunk_base = T.toff[tbase];
     char *cdata = T.tdata + chunk_base;
+    // staged path (cursors in shared memory and room for it): per cell, the block index and block row of
+    // every entry go to shared memory once, so the run walks below touch no global memory; the
+    // loads are batched (all rows, then all row_info gathers) and the next cell's are in flight
+    // while this cell is placed.  A cell costs two memory round trips instead of ~16 dependent ones.
+    int32_t *se = (int32_t *)(scatter_sm + 3 * (size_t)X.n_em);   // [kScatterCap] EM index of the entry's block, or -1
+    uint16_t *srl = (uint16_t *)(se + kScatterCap);                // [kScatterCap] row inside the block
+    uint16_t *einfo = srl + kScatterCap;                           // [n_em] rows of the block | poor << 15
     for (int e = threadIdx.x; e < X.n_em; e += blockDim.x) {
+        if (staged) {
+            const int b = X.em_blocks[e];
+            einfo[e] = (uint16_t)((X.q_off[b + 1] - X.q_off[b]) | (X.poor[b] ? 0x8000 : 0));
+        }
         cur[e] = 0;
         ext[e] = ((uint32_t)T.runs[tbase + e] << 16) | (uint32_t)T.cnt[tbase + e];
         boff[e] = (uint32_t)((T.toff[tbase + e] - chunk_base) >> 4);
     }
     __syncthreads();
 
+    const int tid = threadIdx.x;
+    int row[kScatterBatch], nrow[kScatterBatch];
+    int2 inf[kScatterBatch];
+    double val[kScatterBatch], nval[kScatterBatch];
+    auto load_rows = [&](int64_t s, int n) {
+#pragma unroll
+        for (int k = 0; k < kScatterBatch; k++) {
+            const int i = k * kScatterThreads + tid;
+            nrow[k] = i < n ? S.y_row[s + i] : -1;
+            nval[k] = i < n ? S.y_val[s + i] : 0.0;
+        }
+    };
+    auto load_info = [&]() {
+#pragma unroll
+        for (int k = 0; k < kScatterBatch; k++) {
+            row[k] = nrow[k]; val[k] = nval[k];
+            inf[k] = row[k] >= 0 ? X.row_info[row[k]] : make_int2(-1, 0);
+        }
+    };
+    int64_t s = 0;
+    int n = 0;
+    if (nc > 0) { s = S.y_start[c0]; n = S.y_len[c0]; }
+    if (staged && n <= kScatterCap) { load_rows(s, n); load_info(); }
     for (int c = 0; c < nc; c++) {
-        const int64_t cell = c0 + c;
-        const int64_t s = S.y_start[cell];
-        const int n = S.y_len[cell];
-        // phase A: place entries; the first entry of a run also writes the record's cell id and start
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const int2 info = X.row_info[S.y_row[s + i]];
-            const int e = info.x;
-            if (e < 0) continue;               // pass-through block: written by iso_fill_kernel
-            const uint32_t x = ext[e];
-            const int nrec = (int)(x >> 16), E = (int)(x & 0xffff);
-            if (nrec == 0) continue;           // task rejected by classify (error flag is set)
-            const double v = S.y_val[s + i];
-            const int rl = info.y;
-            int head = i;
-            while (head > 0 && X.row_info[S.y_row[s + head - 1]].x == e) head--;
-            const BlobLayout L = blob_layout(nrec, E);
-            char *blob = cdata + ((size_t)boff[e] << 4);
-            double *ey = (double *)blob;
-            uint32_t *rcell = (uint32_t *)(blob + L.off_cell);
-            uint16_t *eptr = (uint16_t *)(blob + L.off_ptr);
-            uint16_t *erow = (uint16_t *)(blob + L.off_row);
-            const uint32_t cu = cur[e];
-            const int a = (int)(cu >> 16), k0 = (int)(cu & 0xffff);
-            const bool is_head = (i == head);
-            const int b = X.em_blocks[e];
-            if (X.poor[b]) {                   // dense record: every row of the block
-                const int q = X.q_off[b + 1] - X.q_off[b];
-                ey[k0 + rl] = v;
-                if (is_head) {
-                    int tail = i;
-                    while (tail + 1 < n && X.row_info[S.y_row[s + tail + 1]].x == e) tail++;
-                    int k = head;
-                    for (int r = 0; r < q; r++) {
-                        erow[k0 + r] = (uint16_t)r;
-                        if (k <= tail && X.row_info[S.y_row[s + k]].y == r) k++; else ey[k0 + r] = 0.0;
-                    }
-                    rcell[a] = (uint32_t)c;
-                    eptr[a] = (uint16_t)k0;
-                }
-            } else {
-                ey[k0 + i - head] = v;
-                erow[k0 + i - head] = (uint16_t)rl;
-                if (is_head) { rcell[a] = (uint32_t)c; eptr[a] = (uint16_t)k0; }
+        int64_t s2 = 0;
+        int n2 = 0;
+        if (c + 1 < nc) { s2 = S.y_start[c0 + c + 1]; n2 = S.y_len[c0 + c + 1]; }
+        const bool next_staged = staged && (c + 1 < nc) && n2 <= kScatterCap;
+        if (staged && n <= kScatterCap) {
+#pragma unroll
+            for (int k = 0; k < kScatterBatch; k++) {
+                const int i = k * kScatterThreads + tid;
+                if (i < n) { se[i] = inf[k].x; srl[i] = (uint16_t)inf[k].y; }
             }
+            __syncthreads();
+            if (next_staged) load_rows(s2, n2);
+            // phase A: place entries; the first entry of a run also writes the record's cell id and start
+#pragma unroll
+            for (int k = 0; k < kScatterBatch; k++) {
+                const int i = k * kScatterThreads + tid;
+                const int e = inf[k].x;
+                if (i >= n || e < 0) continue;                // pass-through block: written by iso_fill_kernel
+                const uint32_t x = ext[e];
+                const int nrec = (int)(x >> 16), E = (int)(x & 0xffff);
+                if (nrec == 0) continue;                      // task rejected by classify (error flag is set)
+                const int rl = inf[k].y;
+                int head = i;
+                while (head > 0 && se[head - 1] == e) head--;
+                const BlobLayout L = blob_layout(nrec, E);
+                char *blob = cdata + ((size_t)boff[e] << 4);
+                double *ey = (double *)blob;
+                uint32_t *rcell = (uint32_t *)(blob + L.off_cell);
+                uint16_t *eptr = (uint16_t *)(blob + L.off_ptr);
+                uint16_t *erow = (uint16_t *)(blob + L.off_row);
+                const uint32_t cu = cur[e];
+                const int a = (int)(cu >> 16), k0 = (int)(cu & 0xffff);
+                const bool is_head = (i == head);
+                const unsigned ei = einfo[e];
+                if (ei & 0x8000u) {                           // dense record: every row of the block
+                    const int q = (int)(ei & 0x7fffu);
+                    ey[k0 + rl] = val[k];
+                    if (is_head) {
+                        int tail = i;
+                        while (tail + 1 < n && se[tail + 1] == e) tail++;
+                        int kk = head;
+                        for (int r = 0; r < q; r++) {
+                            erow[k0 + r] = (uint16_t)r;
+                            if (kk <= tail && srl[kk] == r) kk++; else ey[k0 + r] = 0.0;
+                        }
+                        rcell[a] = (uint32_t)c;
+                        eptr[a] = (uint16_t)k0;
+                    }
+                } else {
+                    ey[k0 + i - head] = val[k];
+                    erow[k0 + i - head] = (uint16_t)rl;
+                    if (is_head) { rcell[a] = (uint32_t)c; eptr[a] = (uint16_t)k0; }
+                }
+            }
+            __syncthreads();
+            // phase B: the last entry of each run advances the task's cursors
+#pragma unroll
+            for (int k = 0; k < kScatterBatch; k++) {
+                const int i = k * kScatterThreads + tid;
+                const int e = inf[k].x;
+                if (i >= n || e < 0) continue;
+                if (i != n - 1 && se[i + 1] == e) continue;
+                int head = i;
+                while (head > 0 && se[head - 1] == e) head--;
+                const unsigned ei = einfo[e];
+                const int m = (ei & 0x8000u) ? (int)(ei & 0x7fffu) : (i - head + 1);
+                cur[e] += (1u << 16) + (uint32_t)m;
+            }
+            if (next_staged) load_info();
+            __syncthreads();
+        } else {
+            if (next_staged) load_rows(s2, n2);
+            // phase A: place entries; the first entry of a run also writes the record's cell id and start
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const int2 info = X.row_info[S.y_row[s + i]];
+                const int e = info.x;
+                if (e < 0) continue;               // pass-through block: written by iso_fill_kernel
+                const uint32_t x = ext[e];
+                const int nrec = (int)(x >> 16), E = (int)(x & 0xffff);
+                if (nrec == 0) continue;           // task rejected by classify (error flag is set)
+                const double v = S.y_val[s + i];
+                const int rl = info.y;
+                int head = i;
+                while (head > 0 && X.row_info[S.y_row[s + head - 1]].x == e) head--;
+                const BlobLayout L = blob_layout(nrec, E);
+                char *blob = cdata + ((size_t)boff[e] << 4);
+                double *ey = (double *)blob;
+                uint32_t *rcell = (uint32_t *)(blob + L.off_cell);
+                uint16_t *eptr = (uint16_t *)(blob + L.off_ptr);
+                uint16_t *erow = (uint16_t *)(blob + L.off_row);
+                const uint32_t cu = cur[e];
+                const int a = (int)(cu >> 16), k0 = (int)(cu & 0xffff);
+                const bool is_head = (i == head);
+                const int b = X.em_blocks[e];
+                if (X.poor[b]) {                   // dense record: every row of the block
+                    const int q = X.q_off[b + 1] - X.q_off[b];
+                    ey[k0 + rl] = v;
+                    if (is_head) {
+                        int tail = i;
+                        while (tail + 1 < n && X.row_info[S.y_row[s + tail + 1]].x == e) tail++;
+                        int k = head;
+                        for (int r = 0; r < q; r++) {
+                            erow[k0 + r] = (uint16_t)r;
+                            if (k <= tail && X.row_info[S.y_row[s + k]].y == r) k++; else ey[k0 + r] = 0.0;
+                        }
+                        rcell[a] = (uint32_t)c;
+                        eptr[a] = (uint16_t)k0;
+                    }
+                } else {
+                    ey[k0 + i - head] = v;
+                    erow[k0 + i - head] = (uint16_t)rl;
+                    if (is_head) { rcell[a] = (uint32_t)c; eptr[a] = (uint16_t)k0; }
+                }
+            }
+            __syncthreads();
+            // phase B: the last entry of each run advances the task's cursors
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const int e = X.row_info[S.y_row[s + i]].x;
+                if (e < 0) continue;
+                const bool tail = (i == n - 1) || (X.row_info[S.y_row[s + i + 1]].x != e);
+                if (!tail) continue;
+                int head = i;
+                while (head > 0 && X.row_info[S.y_row[s + head - 1]].x == e) head--;
+                const int b = X.em_blocks[e];
+                const int m = X.poor[b] ? (X.q_off[b + 1] - X.q_off[b]) : (i - head + 1);
+                cur[e] += (1u << 16) + (uint32_t)m;
+            }
+            __syncthreads();
+            if (next_staged) load_info();
         }
-        __syncthreads();
-        // phase B: the last entry of each run advances the task's cursors
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const int e = X.row_info[S.y_row[s + i]].x;
-            if (e < 0) continue;
-            const bool tail = (i == n - 1) || (X.row_info[S.y_row[s + i + 1]].x != e);
-            if (!tail) continue;
-            int head = i;
-            while (head > 0 && X.row_info[S.y_row[s + head - 1]].x == e) head--;
-            const int b = X.em_blocks[e];
-            const int m = X.poor[b] ? (X.q_off[b + 1] - X.q_off[b]) : (i - head + 1);
-            cur[e] += (1u << 16) + (uint32_t)m;
-        }
-        __syncthreads();
+        s = s2; n = n2;
     }
     // close every blob of the chunk (eptr[n] = E); poor tasks get their pseudo cell: all cells of
     // the chunk without counts in the block
