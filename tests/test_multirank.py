@@ -44,7 +44,10 @@ def test_two_ranks_equal_one(tmp_path, oracle):
     assert len(chunks) == 5
     xm.save_npz(str(tmp_path / "xm.npz"))
     np.savez(tmp_path / "problem.npz", chunks=chunks, y=y)
-    port = 29500 + os.getpid() % 2000
+    import socket
+    with socket.socket() as sk:                                   # a port the kernel says is free right now
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     whole, whole_it = oracle.estim_chunks(xm, y, chunks, None)
     parts = [np.load(tmp_path / f"out{r}.npz") for r in range(2)]
