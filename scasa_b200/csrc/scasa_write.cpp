@@ -148,7 +148,7 @@ int scasa_write_table(const char *path, const double *mat, int64_t n_cells, int6
         std::mutex m;
         std::condition_variable cv;
         int64_t written = 0;
-        bool io_error = false;
+        bool io_error = false, draining = false;
         auto work = [&]() {
             std::vector<double> tile((size_t)(kBlock * n_cells));
             char num[64];
@@ -183,14 +183,19 @@ int scasa_write_table(const char *path, const double *mat, int64_t n_cells, int6
                 std::unique_lock<std::mutex> lk(m);
                 ready[(size_t)b].swap(out);
                 done[(size_t)b] = 1;
-                while (written < n_blocks && done[(size_t)written]) {        // whoever completes the next block in line writes
-                    std::string s;
-                    s.swap(ready[(size_t)written]);
-                    lk.unlock();
-                    const bool ok = fwrite(s.data(), 1, s.size(), fp) == s.size();
-                    lk.lock();
-                    if (!ok) io_error = true;
-                    written++;
+                if (!draining) {                 // one writer at a time: the lock is released during fwrite, and a second
+                    draining = true;             // thread entering here would take the same block again (empty) and skip one
+                    while (written < n_blocks && done[(size_t)written]) {    // whoever completes the next block in line writes
+                        std::string s;
+                        s.swap(ready[(size_t)written]);
+                        lk.unlock();
+                        const bool ok = fwrite(s.data(), 1, s.size(), fp) == s.size();
+                        lk.lock();
+                        if (!ok) io_error = true;
+                        written++;
+                        cv.notify_all();
+                    }
+                    draining = false;
                 }
                 cv.notify_all();
             }

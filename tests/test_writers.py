@@ -93,3 +93,21 @@ def test_write_table_layout(tmp_path, threads):
     assert got == "\n".join(want) + "\n"
     write_table(path, mat, rows, cells, n_threads=threads)      # no filter: every column
     assert len(open(path).read().split("\n")) == n_cols + 2
+
+
+def test_write_table_threads_never_reorder_or_drop_blocks(tmp_path):
+    """Many small blocks, more threads than cores, repeated: the block in line is written by exactly one
+    thread (a second writer entering while the first is inside fwrite used to skip a block)."""
+    from scasa_b200.writers import write_table
+    rng = np.random.default_rng(8)
+    n_cells, n_cols = 3, 40 * 32
+    mat = np.round(rng.gamma(0.4, 5.0, (n_cells, n_cols)), 2)
+    rows = [f"T{i}" for i in range(n_cols)]
+    cells = ["A", "C", "G"]
+    path = str(tmp_path / "t.txt")
+    write_table(path, mat, rows, cells, n_threads=1)
+    want = open(path, "rb").read()
+    assert want.count(b"\n") == n_cols + 1
+    for it in range(150):
+        write_table(path, mat, rows, cells, n_threads=2 + it % 7)
+        assert open(path, "rb").read() == want, it
