@@ -135,6 +135,10 @@ class Scasa:
                                               _l.ptr(eq_count, C.c_int32), len(eq_row), _l.ptr(eq_row, C.c_int32)))
 
     def set_gene_map(self, gene_of_col, n_genes: int) -> None:
+        if gene_of_col is None:                                   # no gene sums in the following runs
+            self._ck(self._L.scasa_set_gene_map(self._ctx, None, 0))
+            self.n_genes = 0
+            return
         g = np.ascontiguousarray(gene_of_col, np.int32)
         assert len(g) == self.n_cols
         self._ck(self._L.scasa_set_gene_map(self._ctx, _l.ptr(g, C.c_int32), n_genes))
