@@ -144,6 +144,7 @@ struct scasa_ctx {
 
     // ---- X-matrix (host copies + resident device copies)
     int B = 0, n_em = 0;
+    int max_em_q = 0;                // most rows of an EM block
     int64_t n_rows = 0, n_cols = 0;
     std::vector<int32_t> q_off, p_off, em_blocks, em_index, row_block, poor_em, em_order;
     std::vector<int64_t> x_off;
@@ -555,6 +556,7 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
             }
             c->em_index[k] = (int)c->em_blocks.size();
             c->em_blocks.push_back(k);
+            c->max_em_q = std::max<int>(c->max_em_q, (int)(c->q_off[(size_t)k + 1] - c->q_off[(size_t)k]));
             if (is_poor(c->x.data() + c->x_off[k], q, p)) {
                 c->poor[k] = 1;
                 c->poor_em.push_back(c->em_index[k]);
@@ -932,7 +934,7 @@ static void run_range(scasa_ctx *w, scasa_ctx *c, int h0, int h1, int part, Rang
         }
         // the per-cell index of the staged path sits behind the cursors (see task_scatter_kernel)
         const size_t staged_bytes = st_bytes + (size_t)kScatterCap * 6 + (size_t)w->n_em * 2;
-        const int staged = (!scratch && staged_bytes <= 200 * 1024 && !getenv("SCASA_SCATTER_PLAIN")) ? 1 : 0;
+        const int staged = (!scratch && staged_bytes <= 200 * 1024 && w->max_em_q < 32768 && !getenv("SCASA_SCATTER_PLAIN")) ? 1 : 0;   // rows | poor flag in 16 bits
         const size_t sc_smem = scratch ? 0 : (staged ? staged_bytes : st_bytes);
         if (staged) {
             CK(cudaFuncSetAttribute(task_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
