@@ -93,7 +93,19 @@ struct Part {                                  // what one thread parsed from it
     std::string err;
 };
 
+void parse_range_impl(const scasa_bfh &f, int64_t first_line, int64_t e0, int64_t e1, Part &out);
+
+// thread entry: nothing may escape a std::thread (an allocation failure would otherwise end the process)
 void parse_range(const scasa_bfh &f, int64_t first_line, int64_t e0, int64_t e1, Part &out)
+{
+    try {
+        parse_range_impl(f, first_line, e0, e1, out);
+    } catch (const std::exception &ex) {
+        out.err = std::string("bfh: ") + ex.what();
+    }
+}
+
+void parse_range_impl(const scasa_bfh &f, int64_t first_line, int64_t e0, int64_t e1, Part &out)
 {
     std::vector<Span> rest;
     for (int64_t e = e0; e < e1; e++) {
@@ -181,9 +193,14 @@ int scasa_bfh_open(const char *path, int32_t n_threads, scasa_bfh **out)
         std::vector<Part> parts((size_t)nthr);
         {
             std::vector<std::thread> th;
-            for (int t = 0; t < nthr; t++)
-                th.emplace_back(parse_range, std::cref(*f), first_eq, f->n_eq * t / nthr, f->n_eq * (t + 1) / nthr,
-                                std::ref(parts[(size_t)t]));
+            int started = 0;
+            try {
+                for (; started < nthr - 1; started++)
+                    th.emplace_back(parse_range, std::cref(*f), first_eq, f->n_eq * started / nthr, f->n_eq * (started + 1) / nthr,
+                                    std::ref(parts[(size_t)started]));
+            } catch (const std::exception &) {}      // fewer threads than asked for: this one parses the rest
+            for (int t = started; t < nthr; t++)
+                parse_range(*f, first_eq, f->n_eq * t / nthr, f->n_eq * (t + 1) / nthr, parts[(size_t)t]);
             for (auto &x : th) x.join();
         }
         for (auto &p : parts) if (!p.err.empty()) return bfh_fail(SCASA_ERR_ARG, p.err);

@@ -1107,14 +1107,15 @@ static int run_staged(scasa_ctx *c, bool allow_split)
             if (rc) { rcs[which] = rc; return; }
         }
     };
-    if (parts > 1) {
+    if (parts > 1) {                                 // drive() catches everything itself (guarded)
+        std::thread other;
         try {
-            std::thread other(drive, 1);
-            drive(0);
-            other.join();
+            other = std::thread(drive, 1);
         } catch (const std::exception &e) {
-            return fail(c, SCASA_ERR_NOMEM, e.what());
+            return fail(c, SCASA_ERR_NOMEM, std::string("cannot start the second host thread: ") + e.what());
         }
+        drive(0);
+        other.join();
     } else drive(0);
     if (rcs[0]) return rcs[0];
     if (rcs[1]) return fail(c, rcs[1], std::string("twin context: ") + scasa_last_error(c->twin));
@@ -1217,16 +1218,18 @@ int scasa_expand_pairs(double *out, int64_t n_rows, int64_t n_cols, const int64_
     }
     int nthr = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
     nthr = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(nthr, 256), n_rows));
-    try {
-        std::vector<std::thread> workers;
-        for (int t = 0; t < nthr; t++) {
-            const int64_t a = n_rows * t / nthr, e = n_rows * (t + 1) / nthr;
-            if (a < e) workers.emplace_back(scasa::expand_rows, out, n_cols, a, e, row_start, row_nnz, cols, vals);
-        }
-        for (auto &w : workers) w.join();
-    } catch (const std::exception &e) {
-        return fail(nullptr, SCASA_ERR_NOMEM, e.what());
+    std::vector<std::thread> workers;                 // expand_rows does not allocate or throw
+    for (int t = 0; t < nthr; t++) {
+        const int64_t a = n_rows * t / nthr, e = n_rows * (t + 1) / nthr;
+        if (a >= e) continue;
+        bool started = false;
+        try {
+            workers.emplace_back(scasa::expand_rows, out, n_cols, a, e, row_start, row_nnz, cols, vals);
+            started = true;
+        } catch (const std::exception &) {}
+        if (!started) scasa::expand_rows(out, n_cols, a, e, row_start, row_nnz, cols, vals);   // no more threads: do the range here
     }
+    for (auto &w : workers) w.join();
     return SCASA_OK;
 }
 
@@ -1312,8 +1315,9 @@ int scasa_quant(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const int64_t *
     std::vector<double> colsum_parts;
     if (colsum_out) colsum_parts.assign((size_t)n_slices * c->n_cols, 0.0);
     int rcs[2] = {SCASA_OK, SCASA_OK};
-    auto drive = [&](int which) {
+    auto drive = [&](int which) {                    // runs on its own thread for which == 1: nothing may escape
         scasa_ctx *x = ctxs[which];
+        try {
         std::vector<int64_t> ptr, coff;
         for (int sl = which; sl < n_slices; sl += 2) {
             const int h0 = (int)((int64_t)n_chunks * sl / n_slices), h1 = (int)((int64_t)n_chunks * (sl + 1) / n_slices);
@@ -1332,15 +1336,19 @@ int scasa_quant(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const int64_t *
             if (!rc && iters_out) rc = scasa_fetch_iters(x, iters_out + (int64_t)h0 * c->n_em * 2);
             if (rc) { rcs[which] = rc; return; }
         }
+        } catch (const std::exception &e) {
+            rcs[which] = fail(x, SCASA_ERR_NOMEM, e.what());
+        }
     };
     if (n_slices > 1) {
+        std::thread other;
         try {
-            std::thread other(drive, 1);
-            drive(0);
-            other.join();
+            other = std::thread(drive, 1);
         } catch (const std::exception &e) {
-            return fail(c, SCASA_ERR_NOMEM, e.what());
+            return fail(c, SCASA_ERR_NOMEM, std::string("cannot start the second host thread: ") + e.what());
         }
+        drive(0);
+        other.join();
     } else drive(0);
     if (rcs[0]) return rcs[0];
     if (rcs[1]) return fail(c, rcs[1], std::string("twin context: ") + scasa_last_error(c->twin));

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <atomic>
 #include <thread>
 #include <immintrin.h>
 #include <cstdint>
@@ -252,13 +253,21 @@ void CrpIndex::map(int64_t n_eq, const int64_t *eq_off, const int32_t *eq_tx, in
             eq_row[e] = map_one(eq_tx + eq_off[e], (int)(eq_off[e + 1] - eq_off[e]), scratch);
     };
     if (n_threads == 1) { work(0, n_eq); return; }
+    std::atomic<bool> failed{false};
+    auto entry = [&](int64_t lo, int64_t hi) {       // thread entry: nothing may escape a std::thread
+        try { work(lo, hi); } catch (const std::exception &) { failed = true; }
+    };
     std::vector<std::thread> th;
     int64_t per = (n_eq + n_threads - 1) / n_threads;
     for (int t = 0; t < n_threads; t++) {
         int64_t lo = t * per, hi = std::min<int64_t>(n_eq, lo + per);
-        if (lo < hi) th.emplace_back(work, lo, hi);
+        if (lo >= hi) continue;
+        bool started = false;
+        try { th.emplace_back(entry, lo, hi); started = true; } catch (const std::exception &) {}
+        if (!started) entry(lo, hi);                 // no more threads: do the range here
     }
     for (auto &t : th) t.join();
+    if (failed) throw std::bad_alloc();
 }
 
 // ------------------------------------------------------------------------------------------

@@ -149,7 +149,7 @@ int scasa_write_table(const char *path, const double *mat, int64_t n_cells, int6
         std::condition_variable cv;
         int64_t written = 0;
         bool io_error = false, draining = false;
-        auto work = [&]() {
+        auto work_impl = [&]() {
             std::vector<double> tile((size_t)(kBlock * n_cells));
             char num[64];
             for (;;) {
@@ -200,11 +200,22 @@ int scasa_write_table(const char *path, const double *mat, int64_t n_cells, int6
                 cv.notify_all();
             }
         };
+        auto work = [&]() {                           // thread entry: nothing may escape a std::thread
+            try {
+                work_impl();
+            } catch (const std::exception &) {        // allocation failure: stop everyone, report below
+                std::lock_guard<std::mutex> lk(m);
+                io_error = true;
+                cv.notify_all();
+            }
+        };
         std::vector<std::thread> th;
-        for (int t = 1; t < nthr; t++) th.emplace_back(work);
+        try {
+            for (int t = 1; t < nthr; t++) th.emplace_back(work);
+        } catch (const std::exception &) {}          // fewer threads than asked for: the ones that started and this one do the work
         work();
         for (auto &t : th) t.join();
-        const bool bad = io_error || fclose(fp) != 0;
+        const bool bad = (fclose(fp) != 0) | io_error;
         if (bad) return wfail(SCASA_ERR_ARG, std::string("write to ") + path + " failed");
         return SCASA_OK;
     } catch (const std::bad_alloc &) {
