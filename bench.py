@@ -308,7 +308,7 @@ def main():
     em_ms = float(np.mean([x["em_ms"] for x in tms]))          # average launch duration over the timed steps
     fin_ms = float(np.mean([x["finish_ms"] for x in tms]))
     fin_bytes = n * (xm.n_cols * 8 * 2 + n_genes * 8)           # colsum reads iso; gene_gather reads iso and writes genes
-    roofline = {"bound": "hbm", "kernel": "em_task_kernel<W> (4 persistent launches per step, W = 1/2/4/8 warps per task, side by side on 4 streams; em_ms = fork to join)",
+    roofline = {"bound": "hbm", "kernel": "em_task_kernel<W> + em_pair_kernel (5 persistent launches per step: W = 1/2/4/8 warps per task and the tiny tasks two per warp, side by side on 5 streams; em_ms = fork to join)",
                 "achieved": em_bytes / (em_ms * 1e-3) / 1e9, "peak": peak,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
                 "unit": "GB/s",
