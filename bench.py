@@ -139,9 +139,14 @@ def cpu_reference(xm, args, nthreads: int, steps: int = 1, warmup: int = 0):
     t = float(np.mean(times))
     sample = f"{n} cells of the same generator ({len(chunks) - 1} chunks), " + \
         ("crpcount_td + estim_chunk + gene sums" if have_counts else "estim_chunk + gene sums (Y given)")
+    import shutil
+    rscript = shutil.which("Rscript")                 # probe at run time
     return {"value": n / t, "unit": "cells/s", "cores": nthreads, "kind": "port", "sample": sample,
-            "seconds": t, "note": "C restatement of the R functions (R is not installed); README-derived R "
-            "figures for the whole quant stage: 0.045-0.6 cells/s"}
+            "seconds": t, "rscript": rscript,
+            "note": ("C restatement of the R functions (Rscript probe: not installed on this box)" if not rscript else
+                     "C restatement of the R functions (Rscript is on this box, but the reference's scripts are not: "
+                     "nothing under /root/reference travels)") +
+                    "; README-derived R figures for the whole quant stage: 0.045-0.6 cells/s"}
 
 
 def main():
