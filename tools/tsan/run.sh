@@ -17,3 +17,7 @@ g++ -std=c++17 -O1 -g -fsanitize=thread -I$root/include -I$src $here/host_driver
 g++ -std=c++17 -O1 -g -fsanitize=thread -march=native -I$root/include -I$src -I$out $here/pool_driver.cpp $src/scasa_host.cpp -lpthread -o $out/pool_driver
 $out/host_driver
 $out/pool_driver
+# AddressSanitizer + UBSan: the bfh / bustools readers and the writers through their Python tests,
+# against a host-only build of those sources
+g++ -std=c++17 -O1 -g -fPIC -shared -fsanitize=address,undefined -I$root/include -I$src $here/host_stubs.cpp $src/scasa_write.cpp $src/scasa_bfh.cpp $src/scasa_bus.cpp $src/scasa_host.cpp -lpthread -o $out/libhost_asan.so
+LD_PRELOAD=$(gcc -print-file-name=libasan.so):$(gcc -print-file-name=libubsan.so) ASAN_OPTIONS=detect_leaks=0 python3 $here/run_asan_tests.py 2>&1 | grep -v "Warning\|sparse_coo"
