@@ -307,3 +307,95 @@ def test_error_behaviour_through_the_abi(xm):
         assert e.value.code == -4
     finally:
         g.close()
+
+
+def test_c4_full_size_properties(xm, oracle):
+    """BASELINE.json's metric configuration (C4: 100,000 cells = 1,000 chunks on the shipped X-matrix, eqclass
+    counts in, reference convergence options), checked through properties that hold at any size:
+      * mass: DM0's columns sum to 1, so every estim.BETA iteration keeps sum_j beta_cj = sum_r y_rc per block
+        (Rsource:745), the poor-block de-adjustment removes exactly what was added (:1027-1037) and pass-through
+        blocks are copies (:979-983): a cell's isoform total equals its count total over the rows it was packed into;
+      * the column sums (step2:167) and the gene sums (step3) are sums of the matrix that was returned;
+      * chunks are independent: three chunks staged on their own give the same bits as inside the full run,
+        and the oracle agrees with them (iteration counts, 1e-6).
+    SCASA_TEST_C4_CELLS shrinks the sample (the properties do not depend on it)."""
+    import torch
+    from scasa_b200 import synth
+    from scasa_b200.api import Scasa, chunk_split
+    n = int(os.environ.get("SCASA_TEST_C4_CELLS", "100000"))
+    dev = torch.device("cuda", 0)
+    gen = synth.CellGenerator(xm, seed=4, device=dev)
+    rowptr, rows, vals = gen.counts_csr(0, n)
+    ed = synth.eqclass_dictionary(xm, 4)
+    cell_ptr, eq_id, eq_cnt = synth.counts_to_eqcounts(rowptr, rows, vals, 4, device=dev)
+    del gen, rowptr, rows, vals
+    torch.cuda.empty_cache()
+    cell_ptr, eq_id, eq_cnt = (np.asarray(a) for a in (cell_ptr, eq_id, eq_cnt))
+    chunks = np.asarray(chunk_split(n, 4))
+    n_chunks = len(chunks) - 1
+    n_genes = len(xm.gene_names)
+    goc = np.asarray(xm.gene_of_col, np.int32)
+    g = Scasa(xm, device=0)
+    try:
+        g.set_gene_map(goc, n_genes)
+        eq_row = g.eqclass_map(ed.eq_off, ed.eq_tx, os.cpu_count() or 8)
+        g.stage_eqcounts(chunks, cell_ptr, eq_id, eq_cnt, eq_row)
+        t = g.run()
+        assert t["n_tasks"] > 0 and t["em_pair_tasks"] > 0
+        iso, gene, colsum, iters = g.fetch_iso(), g.fetch_gene(), g.fetch_colsum(), g.fetch_iters()
+
+        # ---- mass
+        cell_of = np.repeat(np.arange(n), np.diff(cell_ptr))
+        packed = (eq_row[eq_id] >= 0) & (eq_cnt > 0)
+        tot_y = np.bincount(cell_of, weights=eq_cnt * packed, minlength=n)
+        tot_iso = iso.sum(axis=1)
+        assert np.isfinite(tot_iso).all()
+        assert iso.min() > -1e-9          # the de-adjustment x - d*x/sum(x) (Rsource:1033) can leave -1e-14 where the estimate is 0
+        assert np.max(np.abs(tot_iso - tot_y) / np.maximum(tot_y, 1.0)) < 1e-9
+        # ---- column sums and the row filter
+        cs = iso.sum(axis=0)
+        assert np.max(np.abs(colsum - cs) / np.maximum(cs, 1e-300)) < 1e-9
+        assert np.array_equal(colsum > 1e-9, iso.max(axis=0) > 1e-9)
+        # ---- gene sums
+        unmapped = np.flatnonzero(goc < 0)
+        tot_mapped = tot_iso - (iso[:, unmapped].sum(axis=1) if len(unmapped) else 0.0)
+        assert np.max(np.abs(gene.sum(axis=1) - tot_mapped) / np.maximum(tot_mapped, 1.0)) < 1e-9
+        nmem = np.bincount(goc[goc >= 0], minlength=n_genes)
+        first_col = np.full(n_genes, -1)
+        first_col[goc[goc >= 0]] = np.flatnonzero(goc >= 0)                  # the member, for single-member genes
+        singles = np.flatnonzero(nmem == 1)
+        for gi in singles[:: max(1, len(singles) // 64)]:                   # copies are bit-exact (step3:39)
+            assert np.array_equal(gene[:, gi], iso[:, first_col[gi]]), gi
+
+        # ---- chunk independence and the oracle on three chunks
+        pick = sorted({0, n_chunks // 2, n_chunks - 1})
+        cells = np.concatenate([np.arange(chunks[h], chunks[h + 1]) for h in pick])
+        lens = np.diff(cell_ptr)[cells]
+        sub_ptr = np.concatenate([[0], np.cumsum(lens)])
+        take = np.concatenate([np.arange(cell_ptr[c], cell_ptr[c + 1]) for c in cells])
+        sub_chunks = np.concatenate([[0], np.cumsum([chunks[h + 1] - chunks[h] for h in pick])])
+        g.stage_eqcounts(sub_chunks, sub_ptr, eq_id[take], eq_cnt[take], eq_row)
+        g.run()
+        iso_s, gene_s, iters_s = g.fetch_iso(), g.fetch_gene(), g.fetch_iters()
+        assert np.array_equal(iso_s.view(np.int64), iso[cells].view(np.int64))
+        assert np.array_equal(gene_s.view(np.int64), gene[cells].view(np.int64))
+        assert np.array_equal(iters_s, iters[pick])
+        yptr, yidx, yval = g.fetch_counts()
+        poor_b, em = g.poor_blocks(), g.em_blocks
+    finally:
+        g.close()
+    del iso, gene
+    y = synth.csr_to_dense(yptr, yidx, yval, xm.n_rows)
+    assert np.array_equal(y.sum(axis=1), tot_y[cells])                          # the packed counts themselves
+    ref, ref_it = oracle.estim_chunks(xm, y, sub_chunks, None, nthreads=os.cpu_count() or 8)
+    p_off = xm.dm0_p_off
+    for i in range(len(pick)):
+        c0, c1 = int(sub_chunks[i]), int(sub_chunks[i + 1])
+        same = np.all(iters_s[i] == ref_it[i][em], axis=1)
+        assert same.mean() >= 0.995, (pick[i], same.mean())
+        worst = 0.0
+        for e, k in enumerate(em):
+            if same[e] and not poor_b[k]:
+                a, b = iso_s[c0:c1, p_off[k]:p_off[k + 1]], ref[c0:c1, p_off[k]:p_off[k + 1]]
+                worst = max(worst, float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-9))))
+        assert worst < 1e-6, (pick[i], worst)
