@@ -42,7 +42,8 @@ extern "C" {
 typedef struct scasa_ctx scasa_ctx;
 
 /* The "same convergence options": estim_chunk's defaults (Rsource:944) and the constants
- * hard-wired next to it.  scasa_opts_default() fills exactly these. */
+ * hard-wired next to it.  scasa_opts_default() fills exactly these.  maxerr / lim govern the outer
+ * (X) test of Rsource:1019-1020 only. */
 typedef struct {
     int32_t maxiter_x;    /* 1000  maxiter.X                              Rsource:944  */
     int32_t maxiter_bt;   /* 1000  maxiter.bt as passed at step2:132                   */
@@ -53,6 +54,12 @@ typedef struct {
     int32_t hamming_dist; /* 1                                            Rsource:534  */
     int32_t fixed_iter;   /* 0     1 = never break: exactly maxiter_x x maxiter_bt iterations (parity mode) */
     int32_t fp32;         /* 0     1 = the EM iterates in fp32 (counts and results stay fp64): ~1e-4 relative to the fp64 path */
+    /* estim_chunk does not forward maxerr / lim to estim.BETA (the call at Rsource:1016 passes maxiter and
+     * modify only), so the inner loop runs with estim.BETA's own defaults (Rsource:726-727) whatever
+     * maxerr / lim above are.  These two are those defaults; a caller who wants the inner loop tightened
+     * as well (BASELINE config C5) sets them explicitly. */
+    double maxerr_bt;     /* 0.01                                         Rsource:726  */
+    double lim_bt;        /* 0.01                                         Rsource:727  */
 } scasa_opts_t;
 
 /* A block list (R list of small dense matrices) flattened; blocks column-major like R. */
@@ -158,6 +165,11 @@ int scasa_gene_sum(scasa_ctx *ctx, const int32_t *gene_of_col, int32_t n_genes, 
  * eqclass' counts are added to, or -1 (dropped). */
 int scasa_eqclass_map(scasa_ctx *ctx, int64_t n_eq, const int64_t *eq_off, const int32_t *eq_tx,
                       int32_t *eq_row, int32_t n_threads);
+
+/* The same without a context or a GPU (host only): builds the index from crp and maps.  For callers that
+ * prepare eq_row ahead of the GPU call, and for tests of the host logic on machines without a device. */
+int scasa_eqclass_map_host(const scasa_crp_t *crp, int32_t hamming_dist, int64_t n_eq, const int64_t *eq_off,
+                           const int32_t *eq_tx, int32_t *eq_row, int32_t n_threads);
 
 /* ---- alevin bfh.txt -> quant inputs (host only; replaces scasa_quant_step1_1_v1.0.0.R:16-68 and
  * the ordering of scasa_quant_step2_v1.0.0.R:59-60) --------------------------------------------

@@ -116,7 +116,7 @@ def estim_chunk(Y, DM0, maxiter_X=1000, maxerr=0.01, lim=0.01, maxiter_bt=1000, 
         n_out = n_in = 0
         for _ in range(maxiter_X):                                # :1015
             n_out += 1
-            BT, k = estim_BETA(X_est0, Ymat, beta0, maxiter_bt, maxerr, lim, modify, fixed_iter)
+            BT, k = estim_BETA(X_est0, Ymat, beta0, maxiter=maxiter_bt, modify=modify, fixed_iter=fixed_iter)   # :1016: maxerr / lim are NOT forwarded
             n_in += k
             X_est = estim_X_em(X_est0, BT, Ymat)
             err = np.abs(X_est - X_est0) / np.where(np.abs(X_est0) > lim, X_est0, lim)

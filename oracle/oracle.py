@@ -29,12 +29,14 @@ class Opts(C.Structure):
     """estim_chunk's defaults, Scasa_Rsource.R:944 (+ adjust_esp :973)."""
     _fields_ = [("maxiter_x", C.c_int), ("maxiter_bt", C.c_int), ("maxerr", C.c_double),
                 ("lim", C.c_double), ("modify", C.c_int), ("adjust_esp", C.c_double),
-                ("fixed_iter", C.c_int)]
+                ("fixed_iter", C.c_int), ("maxerr_bt", C.c_double), ("lim_bt", C.c_double)]
 
     @classmethod
     def make(cls, maxiter_x=1000, maxiter_bt=1000, maxerr=0.01, lim=0.01, modify=1,
-             adjust_esp=2.0, fixed_iter=0):
-        return cls(maxiter_x, maxiter_bt, maxerr, lim, modify, adjust_esp, fixed_iter)
+             adjust_esp=2.0, fixed_iter=0, maxerr_bt=0.01, lim_bt=0.01):
+        """maxerr / lim reach the outer test only (Rsource:1019-1020); estim.BETA keeps its own defaults
+        (Rsource:726-727, not forwarded at :1016) unless maxerr_bt / lim_bt say otherwise."""
+        return cls(maxiter_x, maxiter_bt, maxerr, lim, modify, adjust_esp, fixed_iter, maxerr_bt, lim_bt)
 
 
 def lib():

@@ -249,6 +249,9 @@ typedef struct {
     int modify;
     double adjust_esp;
     int fixed_iter;
+    /* estim_chunk does NOT forward maxerr / lim to estim.BETA (Rsource:1016): the inner loop always runs with
+     * estim.BETA's own defaults (Rsource:726-727), 0.01 / 0.01.  Kept as fields so a test can tighten both. */
+    double maxerr_bt, lim_bt;
 } oracle_opts;
 
 /* One chunk.  y: n × nrow_total cell-major.  out: n × ncol_total cell-major.
@@ -321,8 +324,8 @@ int oracle_estim_chunk(int n_blocks, const int32_t *q_off, const int32_t *p_off,
         }
         int i, inner = 0;
         for (i = 1; i <= o->maxiter_x; i++) {                  /* :1015 */
-            inner += oracle_estim_beta(Xest0, q, p, Ymat, n, beta0, BT, o->maxiter_bt, o->maxerr,
-                                       o->lim, o->modify, o->fixed_iter, work);
+            inner += oracle_estim_beta(Xest0, q, p, Ymat, n, beta0, BT, o->maxiter_bt, o->maxerr_bt,
+                                       o->lim_bt, o->modify, o->fixed_iter, work);
             oracle_estim_x_em(Xest0, q, p, BT, n, Ymat, Xest, work);
             double mx = -INFINITY;                             /* :1019 */
             for (size_t k = 0; k < (size_t)q * p; k++) {

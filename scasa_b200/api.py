@@ -34,6 +34,27 @@ def chunk_split(n_cells: int, core: int = 4) -> np.ndarray:
     return br[: k.value + 1].copy()
 
 
+def eqclass_map_host(xm: XMatrix, eq_off, eq_tx, n_threads: int = 8, hamming_dist: int = 1) -> np.ndarray:
+    """crpcount_td's decision per distinct eqclass (global row or -1) without a GPU: scasa_eqclass_map_host."""
+    L = _l.load()
+    keep = [np.ascontiguousarray(a, t) for a, t in ((xm.q_off, np.int32), (xm.crp_p_off, np.int32), (xm.crp_x_off, np.int64),
+                                                    (xm.crp_x, np.float64), (xm.crp_tx, np.int32), (xm.crp_pat, np.uint8),
+                                                    (xm.name_rank, np.int32))]
+    crp = _l.Crp()
+    crp.m.n_blocks = len(keep[0]) - 1
+    crp.m.q_off, crp.m.p_off = _l.ptr(keep[0], C.c_int32), _l.ptr(keep[1], C.c_int32)
+    crp.m.x_off, crp.m.x = _l.ptr(keep[2], C.c_int64), _l.ptr(keep[3], C.c_double)
+    crp.col_tx, crp.row_pat, crp.name_rank = _l.ptr(keep[4], C.c_int32), _l.ptr(keep[5], C.c_uint8), _l.ptr(keep[6], C.c_int32)
+    eq_off = np.ascontiguousarray(eq_off, np.int64)
+    eq_tx = np.ascontiguousarray(eq_tx, np.int32)
+    out = np.empty(len(eq_off) - 1, np.int32)
+    rc = L.scasa_eqclass_map_host(C.byref(crp), hamming_dist, len(out), _l.ptr(eq_off, C.c_int64), _l.ptr(eq_tx, C.c_int32),
+                                  _l.ptr(out, C.c_int32), n_threads)
+    if rc:
+        raise _l.ScasaError(rc, L.scasa_last_error(None).decode())
+    return out
+
+
 @dataclass
 class QuantResult:
     iso: np.ndarray            # (n_cells, Σp) — estim_chunk's result for all chunks, cell order

@@ -500,6 +500,7 @@ int scasa_opts_default(scasa_opts_t *o)
     if (!o) return SCASA_ERR_ARG;
     o->maxiter_x = 1000; o->maxiter_bt = 1000; o->maxerr = 0.01; o->lim = 0.01; o->modify = 1;
     o->adjust_esp = 2.0; o->hamming_dist = 1; o->fixed_iter = 0; o->fp32 = 0;
+    o->maxerr_bt = 0.01; o->lim_bt = 0.01;
     return SCASA_OK;
 }
 
@@ -510,6 +511,9 @@ int scasa_set_opts(scasa_ctx *c, const scasa_opts_t *o)
     if (!c || !o) return fail(c, SCASA_ERR_ARG, "null argument");
     if (o->maxiter_x < 1 || o->maxiter_bt < 1) return fail(c, SCASA_ERR_ARG, "iteration caps must be >= 1");
     if (o->fp32 != 0 && o->fp32 != 1) return fail(c, SCASA_ERR_ARG, "fp32 must be 0 or 1");
+    if (!(o->maxerr_bt >= 0) || !(o->lim_bt >= 0)) return fail(c, SCASA_ERR_ARG, "maxerr_bt / lim_bt must be >= 0");
+    if (c->crp.ready() && o->hamming_dist != c->opts.hamming_dist)     // the eqclass index was built with the old value
+        return fail(c, SCASA_ERR_STATE, "hamming_dist is fixed when the context is created (it is part of the eqclass index)");
     c->opts = *o;
     return SCASA_OK;
 }
@@ -904,6 +908,7 @@ static void run_range(scasa_ctx *w, scasa_ctx *c, int h0, int h1, int part, Rang
     O.maxiter_x = c->opts.maxiter_x; O.maxiter_bt = c->opts.maxiter_bt; O.modify = c->opts.modify;
     O.fixed_iter = c->opts.fixed_iter;
     O.maxerr = c->opts.maxerr; O.lim = c->opts.lim; O.adjust_esp = c->opts.adjust_esp;
+    O.maxerr_bt = c->opts.maxerr_bt; O.lim_bt = c->opts.lim_bt;
     ClassCfg CC;
     for (int k = 0; k < kClasses; k++) { CC.pairs[k] = c->cls_pairs[k]; CC.bytes[k] = c->cls_bytes[k]; }
     CC.real_bytes = c->opts.fp32 ? 4 : 8;
@@ -1386,6 +1391,20 @@ int scasa_eqclass_map(scasa_ctx *c, int64_t n_eq, const int64_t *eq_off, const i
     if (!c || !eq_off || !eq_row || n_eq < 0) return fail(c, SCASA_ERR_ARG, "bad argument");
     if (!c->crp.ready()) return fail(c, SCASA_ERR_STATE, "context was created without CRP");
     return guarded(c, [&] { c->crp.map(n_eq, eq_off, eq_tx, eq_row, n_threads); });
+}
+
+int scasa_eqclass_map_host(const scasa_crp_t *crp, int32_t hamming_dist, int64_t n_eq, const int64_t *eq_off,
+                           const int32_t *eq_tx, int32_t *eq_row, int32_t n_threads)
+{
+    if (!crp || !eq_off || !eq_row || n_eq < 0 || hamming_dist < 0) return fail(nullptr, SCASA_ERR_ARG, "bad argument");
+    return guarded(nullptr, [&] {
+        check_xmat(&crp->m, "crp");
+        if (!crp->col_tx || !crp->row_pat || !crp->name_rank) throw ArgErr{SCASA_ERR_ARG, "crp: null dimnames arrays"};
+        scasa::CrpIndex idx;
+        idx.build(crp->m.n_blocks, crp->m.q_off, crp->m.p_off, crp->m.x_off, crp->m.x, crp->col_tx, crp->row_pat,
+                  crp->name_rank, hamming_dist);
+        idx.map(n_eq, eq_off, eq_tx, eq_row, n_threads);
+    });
 }
 
 void *scasa_host_alloc(int64_t bytes)

@@ -74,10 +74,11 @@ template <int W> struct Group {
         if (W == 1) __syncwarp();
         else asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(kThreads) : "memory");
     }
-    // group-wide OR (also a barrier)
+    // group-wide OR, and a barrier with memory ordering: the callers read other lanes' shared-memory
+    // writes right after it (a vote alone orders nothing, hence the __syncwarp for W == 1)
     __device__ __forceinline__ bool any(bool v) const
     {
-        if (W == 1) return __any_sync(kFull, v);
+        if (W == 1) { const bool r = __any_sync(kFull, v); __syncwarp(); return r; }
         int out;
         asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(out) : "r"((int)v), "r"(bar), "n"(kThreads) : "memory");
@@ -240,7 +241,7 @@ template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_k
             for (int r = 0; r < q; r++) s += Xc[j * q + r];
             rcs[j] = R(1) / s;
         }
-        const R lim = (R)O.lim, maxerr = (R)O.maxerr;
+        const R lim = (R)O.lim, maxerr = (R)O.maxerr, lim_bt = (R)O.lim_bt, maxerr_bt = (R)O.maxerr_bt;
         for (int a = gl; a < n; a += GT) {
             double ys = 0;
             const int k1 = eptr[a + 1];
@@ -290,8 +291,8 @@ template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_k
                     const R gs = gam[idx] * s;
                     R nb = gs == R(0) ? R(0) : gs * rcs[j];                      // :745 (division by csum as a reciprocal)
                     if (nb != nb) nb = R(0);                                     // :754
-                    const R den = old > lim ? old : lim;                         // :755
-                    if (!(rabs(nb - old) < maxerr * den)) fail = true;
+                    const R den = old > lim_bt ? old : lim_bt;                   // :755
+                    if (!(rabs(nb - old) < maxerr_bt * den)) fail = true;
                     beta[idx] = nb;
                     a += da; j += dj;
                     if (a >= n) { a -= n; j++; }
@@ -418,7 +419,7 @@ template <typename R> __global__ void __launch_bounds__(128, 8) em_pair_kernel(E
     const XDev &X = A.X;
     const EmOpts &O = A.O;
     const unsigned n_list = *A.list_n;
-    const R lim = (R)O.lim, maxerr = (R)O.maxerr;
+    const R lim = (R)O.lim, maxerr = (R)O.maxerr, lim_bt = (R)O.lim_bt, maxerr_bt = (R)O.maxerr_bt;
 
     int phase = LOAD;
     int64_t t = 0;
@@ -524,13 +525,14 @@ template <typename R> __global__ void __launch_bounds__(128, 8) em_pair_kernel(E
                 const R gs = gam[hl] * s0;
                 R nb = gs == R(0) ? R(0) : gs * rcs[pj];
                 if (nb != nb) nb = R(0);
-                const R den = old > lim ? old : lim;
-                if (!(rabs(nb - old) < maxerr * den)) fail = true;
+                const R den = old > lim_bt ? old : lim_bt;
+                if (!(rabs(nb - old) < maxerr_bt * den)) fail = true;
                 beta[hl] = nb;
             }
             it++;
             inner_total++;
             const bool any_fail = __any_sync(hmask, fail);
+            __syncwarp(hmask);                                               // beta[] is read across lanes next
             if ((!O.fixed_iter && !any_fail) || it >= O.maxiter_bt) phase = XUPD;
         }
 
@@ -583,6 +585,7 @@ template <typename R> __global__ void __launch_bounds__(128, 8) em_pair_kernel(E
             }
             outer++;
             const bool any_x = __any_sync(hmask, xfail);
+            __syncwarp(hmask);
             if ((!O.fixed_iter && !any_x) || outer >= O.maxiter_x) phase = OUT;
             else { it = 0; phase = INNER; }
         }

@@ -336,7 +336,8 @@ __global__ void task_count_kernel(XDev X, Sample S, Tasks T)
 
 struct EmOpts {
     int maxiter_x, maxiter_bt, modify, fixed_iter;
-    double maxerr, lim, adjust_esp;
+    double maxerr, lim, adjust_esp;     // maxerr / lim: the outer test (Rsource:1019-1020)
+    double maxerr_bt, lim_bt;           // estim.BETA's own (Rsource:726-727; not forwarded by estim_chunk)
 };
 
 // Per task: records, stored entries, blob size, work class.  Threads enumerate tasks block-major

@@ -25,7 +25,8 @@ class ScasaError(RuntimeError):
 class Opts(C.Structure):
     _fields_ = [("maxiter_x", C.c_int32), ("maxiter_bt", C.c_int32), ("maxerr", C.c_double),
                 ("lim", C.c_double), ("modify", C.c_int32), ("adjust_esp", C.c_double),
-                ("hamming_dist", C.c_int32), ("fixed_iter", C.c_int32), ("fp32", C.c_int32)]
+                ("hamming_dist", C.c_int32), ("fixed_iter", C.c_int32), ("fp32", C.c_int32),
+                ("maxerr_bt", C.c_double), ("lim_bt", C.c_double)]
 
 
 class XMat(C.Structure):
@@ -62,7 +63,7 @@ SYMBOLS = (
     "scasa_chunk_split", "scasa_estimate", "scasa_stage_counts", "scasa_stage_eqcounts", "scasa_run",
     "scasa_fetch_iso", "scasa_fetch_iters", "scasa_fetch_colsum", "scasa_fetch_counts", "scasa_set_gene_map",
     "scasa_fetch_gene", "scasa_gene_sum", "scasa_eqclass_map", "scasa_last_timing", "scasa_host_alloc",
-    "scasa_host_free", "scasa_device_count", "scasa_version", "scasa_set_host_threads", "scasa_expand_pairs", "scasa_quant", "scasa_transfer_bytes", "scasa_bfh_open", "scasa_bfh_close", "scasa_bfh_sizes", "scasa_bfh_read", "scasa_bus_open", "scasa_write_table", "scasa_format_real15", "scasa_set_run_parts",
+    "scasa_host_free", "scasa_device_count", "scasa_version", "scasa_set_host_threads", "scasa_expand_pairs", "scasa_quant", "scasa_transfer_bytes", "scasa_bfh_open", "scasa_bfh_close", "scasa_bfh_sizes", "scasa_bfh_read", "scasa_bus_open", "scasa_write_table", "scasa_format_real15", "scasa_set_run_parts", "scasa_eqclass_map_host",
 )
 
 
@@ -123,6 +124,7 @@ def load():
     L.scasa_fetch_gene.argtypes = [vp, f64p]
     L.scasa_gene_sum.argtypes = [vp, i32p, C.c_int32, f64p, C.c_int64, f64p]
     L.scasa_eqclass_map.argtypes = [vp, C.c_int64, i64p, i32p, i32p, C.c_int32]
+    L.scasa_eqclass_map_host.argtypes = [C.POINTER(Crp), C.c_int32, C.c_int64, i64p, i32p, i32p, C.c_int32]
     L.scasa_last_timing.argtypes = [vp, C.POINTER(Timing)]
     L.scasa_set_host_threads.argtypes = [vp, C.c_int32]
     L.scasa_expand_pairs.argtypes = [f64p, C.c_int64, C.c_int64, i64p, i32p, i32p, f64p, C.c_int32]

@@ -14,6 +14,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests are skipped (not failed) on a machine without a CUDA device; on a GPU box nothing is skipped,
+    and a missing library is an error there, never a skip."""
+    try:
+        from scasa_b200 import lib
+        have = lib.load().scasa_device_count() > 0
+    except Exception:
+        have = os.path.exists("/dev/nvidia0")          # the library must load on a GPU box: let the tests fail loudly
+    if have:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device (run on the B200 box with -m gpu)")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def xm():
     from scasa_b200.xmatrix import XMatrix

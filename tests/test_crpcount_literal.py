@@ -88,3 +88,15 @@ def test_whole_cells_literal_equals_golden(xm):
         for k, v in res.items():
             got[xm.q_off[k]:xm.q_off[k + 1]] = v
         assert np.array_equal(got, y[cell]), cell
+
+
+def test_sweep_library_host_map_equals_literal(xm):
+    """The PRODUCT's eqclass -> row decision (CrpIndex in scasa_host.cpp, through the host-only C-ABI entry
+    scasa_eqclass_map_host: no GPU involved) on EVERY class of the sweep (~400k, ~85 % decided by the median tie-break) against the literal."""
+    from scasa_b200.api import eqclass_map_host
+    eq_off, eq_tx, blocks = sweep_classes(xm, stride=1)
+    want, ties = literal_rows(NPZ, eq_off, eq_tx)
+    assert len(blocks) > 350000 and ties > 250000
+    got = eqclass_map_host(xm, eq_off, eq_tx, 8)
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, (len(bad), bad[:5], got[bad[:5]], want[bad[:5]], blocks[bad[:5]])

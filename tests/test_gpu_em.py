@@ -59,8 +59,9 @@ def test_c1_fixed_iteration_parity(gpu, xm, oracle, c1):
 
 def test_c1_convergence_mode(gpu, xm, oracle, c1):
     """Reference defaults (maxerr=.01, 1000/1000).  A 1-ulp difference may flip a break
-    (SURVEY.md §7 iii), so: iteration counts agree on >= 99.5 % of (chunk, block) tasks and,
-    where they agree, estimates agree to 1e-6."""
+    (SURVEY.md §7 iii), so: iteration counts agree on >= 99.5 % of (chunk, block) tasks; where they
+    agree estimates agree to 1e-6 (poor blocks included, on their absolute scale), where they do not
+    the results are within 2 * maxerr in the reference's own error measure (tests/parity.py)."""
     from scasa_b200.api import chunk_split
     from scasa_b200.synth import csr_to_dense
     rowptr, rows, vals = c1
@@ -68,20 +69,11 @@ def test_c1_convergence_mode(gpu, xm, oracle, c1):
     gpu.set_opts()
     iso, iters = gpu.estimate(chunks, rowptr, rows, vals)
     ref, ref_it = oracle.estim_chunks(xm, csr_to_dense(rowptr, rows, vals, xm.n_rows), chunks, None, nthreads=4)
-    ref_it = ref_it[:, gpu.em_blocks, :]
-    same = np.all(iters == ref_it, axis=2)
-    assert same.mean() >= 0.995, same.mean()
-    p_off = xm.dm0_p_off
-    poor = gpu.poor_blocks()
-    worst = 0.0
-    for h in range(2):
-        cs = slice(chunks[h], chunks[h + 1])
-        for e, k in enumerate(gpu.em_blocks):
-            if same[h, e] and not poor[k]:
-                a, b = iso[cs, p_off[k]:p_off[k + 1]], ref[cs, p_off[k]:p_off[k + 1]]
-                worst = max(worst, rel_err(a, b))
-    assert worst < RTOL, worst
-    assert np.all(np.isfinite(iso))
+    from .parity import compare_tasks
+    rep = compare_tasks(iso, ref, iters, ref_it[:, gpu.em_blocks, :], chunks, gpu.em_blocks, xm.dm0_p_off, xm.q_off,
+                        gpu.poor_blocks())
+    assert rep["n_poor"] > 200                                    # the +2 adjust / de-adjust path in convergence mode
+    print("C1 convergence mode vs oracle:", rep)
 
 
 def test_random_blocks_and_edge_cases(oracle):
@@ -127,16 +119,10 @@ def test_random_blocks_and_edge_cases(oracle):
             ref, ref_it = oracle.estim_chunks(xm, Y, chunk_off,
                                               oracle.Opts.make(fixed_iter=fixed, maxiter_x=mx, maxiter_bt=mb))
             ref_it = ref_it[:, g.em_blocks, :]
-            same = np.all(iters == ref_it, axis=2)
-            if fixed:
-                assert same.all()
-            assert same.mean() > 0.9
-            for h in range(len(chunk_off) - 1):
-                cs = slice(chunk_off[h], chunk_off[h + 1])
-                for e, k in enumerate(g.em_blocks):
-                    if same[h, e]:
-                        a, b = iso[cs, p_off[k]:p_off[k + 1]], ref[cs, p_off[k]:p_off[k + 1]]
-                        assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-6)) < RTOL, (fixed, h, k)
+            from .parity import compare_tasks
+            rep = compare_tasks(iso, ref, iters, ref_it, chunk_off, g.em_blocks, p_off, q_off, g.poor_blocks(),
+                                min_same=1.0 if fixed else 0.9)
+            assert rep["n_poor"] >= 3
             assert np.array_equal(iso[183:190], np.zeros((7, p_off[-1]))) or g.poor_blocks().any()
     finally:
         g.close()
@@ -219,25 +205,17 @@ def test_heavy_multimapping_tight_tolerance(xm, oracle):
     vals = np.minimum(vals, 200.0)
     chunks = chunk_split(n, 4)
     y = synth.csr_to_dense(rowptr, rows, vals, wide.n_rows)
-    g = Scasa(wide, device=0, with_crp=False, maxerr=1e-6, maxiter_x=60, maxiter_bt=60)
+    g = Scasa(wide, device=0, with_crp=False, maxerr=1e-6, maxerr_bt=1e-6, maxiter_x=60, maxiter_bt=60)
     try:
         iso, iters = g.estimate(chunks, rowptr, rows, vals)
     finally:
         g.close()
-    ref, ref_it = oracle.estim_chunks(wide, y, chunks, oracle.Opts.make(maxerr=1e-6, maxiter_x=60, maxiter_bt=60), nthreads=4)
-    ref_it = ref_it[:, wide.em_blocks(), :]
-    same = np.all(iters == ref_it, axis=2)
-    assert same.mean() >= 0.9, same.mean()
+    ref, ref_it = oracle.estim_chunks(wide, y, chunks, oracle.Opts.make(maxerr=1e-6, maxerr_bt=1e-6, maxiter_x=60, maxiter_bt=60), nthreads=4)
+    from .parity import compare_tasks
+    rep = compare_tasks(iso, ref, iters, ref_it[:, wide.em_blocks(), :], chunks, wide.em_blocks(), wide.dm0_p_off, wide.q_off,
+                        np.zeros(wide.n_blocks, bool), maxerr=1e-6, min_same=0.9)
     assert iters[..., 0].max() == 60                             # some tasks hit the outer cap
-    p_off = wide.dm0_p_off
-    worst = 0.0
-    for hh in range(len(chunks) - 1):
-        cs = slice(chunks[hh], chunks[hh + 1])
-        for e, k in enumerate(wide.em_blocks()):
-            if same[hh, e]:
-                worst = max(worst, rel_err(iso[cs, p_off[k]:p_off[k + 1]], ref[cs, p_off[k]:p_off[k + 1]], floor=1e-6))
-    assert worst < RTOL, worst
-    assert np.all(np.isfinite(iso))
+    print("heavy multimapping vs oracle:", rep)
 
 
 def test_fp32_option_close_to_fp64(xm, oracle, c1):
@@ -325,12 +303,6 @@ def test_c2_size_sampled_chunks_match_oracle(xm, oracle):
         sl = slice(rowptr[c0], rowptr[c1])
         y = synth.csr_to_dense(sub_ptr, rows[sl], vals[sl], xm.n_rows)
         ref, ref_it = oracle.estim_chunks(xm, y, np.array([0, c1 - c0]), None, nthreads=4)
-        same = np.all(iters[h] == ref_it[0][em], axis=1)
-        assert same.mean() >= 0.995, (h, same.mean())
-        worst = 0.0
-        for e, k in enumerate(em):
-            if same[e] and not poor_b[k]:
-                worst = max(worst, rel_err(iso[c0:c1, p_off[k]:p_off[k + 1]], ref[:, p_off[k]:p_off[k + 1]]))
-        assert worst < RTOL, (h, worst)
-        pt = np.repeat(np.diff(xm.q_off) == 1, np.diff(p_off))
-        assert np.array_equal(iso[c0:c1][:, pt], ref[:, pt])
+        from .parity import compare_tasks
+        rep = compare_tasks(iso[c0:c1], ref, iters[h:h + 1], ref_it[:, em, :], np.array([0, c1 - c0]), em, p_off, xm.q_off, poor_b)
+        assert rep["n_poor"] > 50
