@@ -133,20 +133,26 @@ int scasa_stage_eqcounts(scasa_ctx *ctx, int64_t n_cells, int32_t n_chunks, cons
                          const int64_t *cell_ptr, const int32_t *eq_id, const int32_t *eq_count,
                          int64_t n_eq, const int32_t *eq_row);
 int scasa_run(scasa_ctx *ctx);   /* pack -> EM -> (gene sums); everything on the device */
-/* Experimental: scasa_run can cut the staged chunks into n_parts ranges that alternate between two
- * sets of streams (EM kernels of one range next to the bandwidth-bound kernels of another).
- * 0 / 1 = one range (default: on B200 the split measured slower).  No result depends on it. */
+/* Retired (kept for ABI stability, does nothing): cutting one run into ranges of chunks on two stream
+ * sets measured slower on B200. */
 int scasa_set_run_parts(scasa_ctx *ctx, int32_t n_parts);
-/* The two dense results travel zero-suppressed ((column, value) pairs, > 90 % of the matrices are
- * zeros) and are re-expanded into the caller's buffer by host threads; the buffer ends up
- * bit-identical to a plain copy.  scasa_set_host_threads: threads of that expansion, 0 = all cores,
- * -1 = plain dense copy instead. */
+/* The device keeps both results sparse (see scasa_fetch_iso_csr); scasa_fetch_iso / scasa_fetch_gene send
+ * the sparse rows over PCIe and host threads expand them into the caller's dense buffer, which ends up
+ * bit-identical to a dense copy.  scasa_set_host_threads: threads of that expansion, 0 = all cores,
+ * -1 = expand on the device and copy densely instead (testing aid). */
 int scasa_set_host_threads(scasa_ctx *ctx, int32_t n_threads);
 /* The host half of that, usable on its own (no GPU, no context): rows of (column, value) pairs,
  * columns strictly ascending inside a row, -> dense n_rows x n_cols matrix; every element written. */
 int scasa_expand_pairs(double *out, int64_t n_rows, int64_t n_cols, const int64_t *row_start, const int32_t *row_nnz,
                        const int32_t *cols, const double *vals, int32_t n_threads);
 int scasa_fetch_iso(scasa_ctx *ctx, double *iso_out);            /* n_cells x n_cols           */
+/* The results as the device holds them: CSR by cell over the entries that CAN be non-zero (a cell's
+ * pass-through counts, the columns of every EM block it has counts in, the two columns of every poor
+ * block), columns ascending; stored zeros are possible.  rowptr [n_cells+1]; cols / vals sized by
+ * scasa_result_nnz (either may be NULL).  The gene matrix likewise, genes ascending. */
+int scasa_result_nnz(scasa_ctx *ctx, int64_t *iso_nnz, int64_t *gene_nnz);
+int scasa_fetch_iso_csr(scasa_ctx *ctx, int64_t *rowptr, int32_t *cols, double *vals);
+int scasa_fetch_gene_csr(scasa_ctx *ctx, int64_t *rowptr, int32_t *genes, double *vals);
 int scasa_fetch_iters(scasa_ctx *ctx, int32_t *iters_out);       /* [n_chunks][n_em_blocks][2] */
 int scasa_fetch_colsum(scasa_ctx *ctx, double *colsum /* [n_cols] */); /* rowSums of step2:167 */
 int scasa_fetch_counts(scasa_ctx *ctx, int64_t *y_rowptr /* [n_cells+1] */, int32_t *y_rowidx,
@@ -227,6 +233,7 @@ typedef struct {
                                sums over ranges that ran side by side (they exceed total_ms) */
     float em_pair_ms;       /* EM kernel time of the tiny-task kernel (two tasks per warp); overlaps the classes above */
     int64_t em_pair_tasks;  /* tasks it ran (not counted in em_class_tasks) */
+    int64_t result_nnz;     /* entries of the sparse isoform result (structure incl. stored zeros) */
 } scasa_timing_t;
 int scasa_last_timing(scasa_ctx *ctx, scasa_timing_t *out);
 

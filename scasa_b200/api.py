@@ -200,6 +200,29 @@ class Scasa:
         self._ck(self._L.scasa_fetch_gene(self._ctx, _l.ptr(out, C.c_double)))
         return out
 
+    def result_nnz(self):
+        """(entries of the sparse isoform result, entries of the sparse gene result)."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._ck(self._L.scasa_result_nnz(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def fetch_iso_csr(self):
+        """The isoform result as the device holds it: CSR by cell (rowptr, cols, vals), columns ascending,
+        over the entries that can be non-zero (stored zeros possible)."""
+        nnz, _ = self.result_nnz()
+        rowptr = np.empty(self.n_cells + 1, np.int64)
+        cols, vals = np.empty(max(nnz, 1), np.int32), np.empty(max(nnz, 1), np.float64)
+        self._ck(self._L.scasa_fetch_iso_csr(self._ctx, _l.ptr(rowptr, C.c_int64), _l.ptr(cols, C.c_int32), _l.ptr(vals, C.c_double)))
+        return rowptr, cols[:nnz], vals[:nnz]
+
+    def fetch_gene_csr(self):
+        """The gene result (scasa_genemat) as CSR by cell: (rowptr, genes, vals), genes ascending."""
+        _, nnz = self.result_nnz()
+        rowptr = np.empty(self.n_cells + 1, np.int64)
+        genes, vals = np.empty(max(nnz, 1), np.int32), np.empty(max(nnz, 1), np.float64)
+        self._ck(self._L.scasa_fetch_gene_csr(self._ctx, _l.ptr(rowptr, C.c_int64), _l.ptr(genes, C.c_int32), _l.ptr(vals, C.c_double)))
+        return rowptr, genes[:nnz], vals[:nnz]
+
     def fetch_iters(self) -> np.ndarray:
         out = np.empty((self.n_chunks, self.n_em, 2), np.int32)
         self._ck(self._L.scasa_fetch_iters(self._ctx, _l.ptr(out, C.c_int32)))

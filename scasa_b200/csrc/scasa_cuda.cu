@@ -146,13 +146,14 @@ struct scasa_ctx {
     int B = 0, n_em = 0;
     int max_em_q = 0;                // most rows of an EM block
     int64_t n_rows = 0, n_cols = 0;
-    std::vector<int32_t> q_off, p_off, em_blocks, em_index, row_block, poor_em, em_order;
+    std::vector<int32_t> q_off, p_off, em_blocks, em_index, row_block, poor_em, em_order, poor_blocks_list;
+    int n_poor = 0, n_emcols = 0;    // poor blocks; columns of all EM blocks
     std::vector<int64_t> x_off;
     std::vector<double> x;
     std::vector<uint8_t> poor;
     int64_t poor_rows = 0;           // sum of q over poor blocks
-    DBuf<int32_t> d_q_off, d_p_off, d_em_blocks, d_em_order, d_row_col;
-    DBuf<int2> d_row_info;
+    DBuf<int32_t> d_q_off, d_p_off, d_em_blocks, d_em_order, d_em_col0, d_poor_rank, d_poor_col0, d_emcol_col;
+    DBuf<int2> d_row_info, d_row_aux, d_em_info;
     DBuf<uint32_t> d_scatter_scratch;
     DBuf<int64_t> d_x_off;
     DBuf<double> d_x;
@@ -187,19 +188,20 @@ struct scasa_ctx {
     DBuf<unsigned long long> d_stats;
     DBuf<int> d_flag;
 
-    // ---- results
-    DBuf<double> d_iso, d_partial, d_colsum, d_colsum_parts, d_gene;
-    int run_parts = 0;           // ranges scasa_run cuts the sample into (0 = automatic)
-    // zero-suppressed fetch: two batches in flight (device pairs -> pinned staging -> threaded expansion)
+    // ---- results: CSR by cell over the structure (scasa_kernels.cuh: struct Result); no dense matrix on the device
+    DBuf<int32_t> d_rs_len, d_rs_col, d_poor_pos, d_g_col, d_g_len, d_gene_of_col;
+    DBuf<int64_t> d_rs_ptr;
+    DBuf<double> d_rs_val, d_g_val, d_colsum, d_colpart, d_gene_park, d_dense_tmp, d_iso_in, d_gene_out;
+    DBuf<uint32_t> d_ypos;
+    int64_t rs_nnz = 0;                  // entries of the result structure of the last run
+    std::vector<int64_t> rs_ptr_host;    // fetched on demand after a run
+    std::vector<int32_t> g_len_host;
+    bool have_rs_host = false, have_glen_host = false, ran_genes = false;
+    // the trip to the host: two batches in flight (device CSR slice -> pinned staging -> threaded expansion)
     struct FetchBuf {
-        DBuf<int32_t> d_cols, d_nnz;
-        DBuf<double> d_vals;
-        DBuf<int64_t> d_start;
-        DBuf<unsigned long long> d_cursor;
         int32_t *h_cols = nullptr, *h_nnz = nullptr;
         double *h_vals = nullptr;
         int64_t *h_start = nullptr;
-        unsigned long long *h_cursor = nullptr;
         size_t cap = 0, rows = 0;
         cudaEvent_t done = nullptr;
     } fb[2];
@@ -212,6 +214,7 @@ struct scasa_ctx {
     int host_threads = 0;        // 0 = hardware concurrency
     int fetch_dense_copy = 0;    // 1 = plain dense D2H (SCASA_FETCH_DENSE)
     int n_genes = 0;
+    int gene_tile = 0, gene_ctas_per_sm = 1;   // gene_rows_kernel: genes per pass (shared-memory slots), resident CTAs
     DBuf<int32_t> d_gene_ptr, d_gene_cols;
     scasa_timing_t timing{};
 };
@@ -269,7 +272,9 @@ XDev xdev(scasa_ctx *c)
     X.q_off = c->d_q_off.p; X.p_off = c->d_p_off.p; X.x_off = c->d_x_off.p; X.x = c->d_x.p;
     X.em_blocks = c->d_em_blocks.p;
     X.poor = c->d_poor.p;
-    X.em_order = c->d_em_order.p; X.row_info = c->d_row_info.p; X.row_col = c->d_row_col.p;
+    X.em_order = c->d_em_order.p; X.row_info = c->d_row_info.p; X.row_aux = c->d_row_aux.p;
+    X.em_info = c->d_em_info.p; X.em_col0 = c->d_em_col0.p; X.poor_rank = c->d_poor_rank.p; X.poor_col0 = c->d_poor_col0.p;
+    X.n_poor = c->n_poor; X.n_emcols = c->n_emcols;
     return X;
 }
 // chunks [h0, h1) of the sample staged in c
@@ -282,6 +287,14 @@ Sample sdev(scasa_ctx *c, int h0, int h1)
     S.cell_chunk = c->d_cell_chunk.p + c0; S.y_start = c->d_y_start.p + c0; S.y_len = c->d_y_len.p + c0;
     S.y_row = c->d_y_row.p; S.y_val = c->d_y_val.p;
     return S;
+}
+Result rdev(scasa_ctx *c)
+{
+    Result R;
+    R.rs_ptr = c->d_rs_ptr.p; R.rs_col = c->d_rs_col.p; R.rs_val = c->d_rs_val.p; R.ypos = c->d_ypos.p;
+    R.poor_pos = c->d_poor_pos.p; R.colsum = c->d_colsum.p; R.colpart = c->d_colpart.p;
+    R.g_col = c->d_g_col.p; R.g_val = c->d_g_val.p; R.g_len = c->d_g_len.p;
+    return R;
 }
 Tasks tdev(scasa_ctx *c)
 {
@@ -305,25 +318,13 @@ void exclusive_scan(scasa_ctx *c, const int32_t *in, int64_t n, int64_t *out, in
     launches += 3;
 }
 
-// column sums (+ gene sums) of a resident isoform matrix
-// column sums (+ gene sums) of n_cells rows of an isoform matrix resident at iso; w supplies the
-// stream, the scratch for the tile sums and the gene map
-void launch_finish(scasa_ctx *w, const double *iso, int64_t n_cells, double *gene, double *colsum, int &launches)
+// scasa_genemat on a dense isoform matrix resident at iso (scasa_gene_sum: a matrix the caller already holds)
+void launch_gene_gather(scasa_ctx *w, const double *iso, int64_t n_cells, double *gene)
 {
-    cudaStream_t s = w->stream;
-    const int n_tiles = (int)((n_cells + kTileCells - 1) / kTileCells);
-    w->d_partial.ensure((size_t)n_tiles * w->n_cols);
-    colsum_kernel<<<dim3(n_tiles, (unsigned)((w->n_cols + kFinCols - 1) / kFinCols)), kFinThreads, 0, s>>>(
-        iso, n_cells, w->n_cols, w->d_partial.p);
-    colsum_reduce<<<(unsigned)((w->n_cols + 255) / 256), 256, 0, s>>>(w->d_partial.p, n_tiles, w->n_cols, colsum);
-    launches += 2;
-    if (gene) {
-        const int tiles = (w->n_genes + kGeneThreads * kGeneIlp - 1) / (kGeneThreads * kGeneIlp);
-        if (n_cells * tiles >= ((int64_t)1 << 31)) throw ArgErr{SCASA_ERR_UNSUPPORTED, "too many cells x genes for one launch"};
-        gene_gather_kernel<<<(unsigned)(n_cells * tiles), kGeneThreads, 0, s>>>(iso, n_cells, w->n_cols, w->d_gene_ptr.p,
-                                                                               w->d_gene_cols.p, w->n_genes, tiles, gene);
-        launches++;
-    }
+    const int tiles = (w->n_genes + kGeneThreads * kGeneIlp - 1) / (kGeneThreads * kGeneIlp);
+    if (n_cells * tiles >= ((int64_t)1 << 31)) throw ArgErr{SCASA_ERR_UNSUPPORTED, "too many cells x genes for one launch"};
+    gene_gather_kernel<<<(unsigned)(n_cells * tiles), kGeneThreads, 0, w->stream>>>(iso, n_cells, w->n_cols, w->d_gene_ptr.p,
+                                                                                   w->d_gene_cols.p, w->n_genes, tiles, gene);
     CK(cudaGetLastError());
 }
 
@@ -358,7 +359,7 @@ void stage_common(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const int64_t
     c->chunk_off.assign(chunk_off, chunk_off + n_chunks + 1);
     c->d_chunk_off.upload(c->chunk_off, c->stream);
     c->d_cell_chunk.upload(cell_chunk, c->stream);
-    c->staged = true; c->ran = false;
+    c->staged = true; c->ran = false; c->have_rs_host = false; c->have_glen_host = false; c->ran_genes = false;
 }
 
 template <int W, typename R> void launch_em_t(const EmArgs &A, unsigned grid, int threads, size_t smem, cudaStream_t s)
@@ -384,101 +385,120 @@ ExpandPool &expand_pool(scasa_ctx *c, int nthr)
 void fetch_buf_ensure(scasa_ctx *c, scasa_ctx::FetchBuf &b, size_t rows, size_t cap)
 {
     if (b.rows >= rows && b.cap >= cap) return;
-    if (b.h_cols) { cudaFreeHost(b.h_cols); cudaFreeHost(b.h_vals); cudaFreeHost(b.h_start); cudaFreeHost(b.h_nnz); cudaFreeHost(b.h_cursor); }
+    if (b.h_cols) { cudaFreeHost(b.h_cols); cudaFreeHost(b.h_vals); cudaFreeHost(b.h_start); cudaFreeHost(b.h_nnz); }
     b.h_cols = nullptr; b.rows = 0; b.cap = 0;
-    b.d_cols.ensure(cap); b.d_vals.ensure(cap); b.d_start.ensure(rows); b.d_nnz.ensure(rows); b.d_cursor.ensure(1);
     CK(cudaHostAlloc((void **)&b.h_cols, cap * sizeof(int32_t), cudaHostAllocDefault));
     CK(cudaHostAlloc((void **)&b.h_vals, cap * sizeof(double), cudaHostAllocDefault));
     CK(cudaHostAlloc((void **)&b.h_start, rows * sizeof(int64_t), cudaHostAllocDefault));
     CK(cudaHostAlloc((void **)&b.h_nnz, rows * sizeof(int32_t), cudaHostAllocDefault));
-    CK(cudaHostAlloc((void **)&b.h_cursor, sizeof(unsigned long long), cudaHostAllocDefault));
     if (!b.done) CK(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
     b.rows = rows; b.cap = cap;
 }
 
-// Dense (n_rows x n_cols) device matrix -> dense host matrix, sent as (column, value) pairs in
-// batches of rows: while the host threads expand batch k, the GPU compacts and copies batch k+1.
-void fetch_dense(scasa_ctx *c, const double *d_mat, int64_t n_rows, int64_t n_cols, double *out)
+// host copies of the row pointers (and gene row lengths) of the last run, fetched once per run
+void need_rs_host(scasa_ctx *c, bool genes)
+{
+    if (!c->have_rs_host) {
+        c->rs_ptr_host.resize((size_t)c->n_cells + 1);
+        CK(cudaMemcpyAsync(c->rs_ptr_host.data(), c->d_rs_ptr.p, ((size_t)c->n_cells + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->wire_d2h += (long long)(c->n_cells + 1) * 8;
+        c->have_rs_host = true;
+    }
+    if (genes && !c->have_glen_host) {
+        c->g_len_host.resize((size_t)c->n_cells);
+        CK(cudaMemcpyAsync(c->g_len_host.data(), c->d_g_len.p, (size_t)c->n_cells * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->wire_d2h += (long long)c->n_cells * 4;
+        c->have_glen_host = true;
+    }
+}
+
+// A CSR result (rows of the isoform matrix, or of the gene matrix when `genes`) -> the caller's dense
+// host matrix.  The sparse rows cross PCIe as they are, in batches of whole rows; while the host threads
+// expand batch k into the caller's matrix (every element written exactly once, streaming stores), batch
+// k+1 is on the wire.  The matrix ends up bit-identical to what a dense copy would give.
+void fetch_dense(scasa_ctx *c, bool genes, double *out)
 {
     cudaStream_t s = c->stream;
-    if (c->fetch_dense_copy || c->host_threads < 0 || n_rows * n_cols < (1 << 20)) {
-        CK(cudaMemcpyAsync(out, d_mat, (size_t)(n_rows * n_cols) * sizeof(double), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        c->wire_d2h += (long long)(n_rows * n_cols) * 8;
+    need_rs_host(c, genes);
+    const int64_t n_rows = c->n_cells, n_cols = genes ? c->n_genes : c->n_cols;
+    const int64_t *ptr = c->rs_ptr_host.data();
+    const int32_t *d_col = genes ? c->d_g_col.p : c->d_rs_col.p;
+    const double *d_val = genes ? c->d_g_val.p : c->d_rs_val.p;
+    if (c->fetch_dense_copy || c->host_threads < 0) {           // expansion on the device, plain dense copy (testing aid)
+        const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(n_rows, ((int64_t)32 << 20) / n_cols));
+        c->d_dense_tmp.ensure((size_t)(batch * n_cols));
+        for (int64_t r0 = 0; r0 < n_rows; r0 += batch) {
+            const int64_t nr = std::min(batch, n_rows - r0);
+            expand_rows_kernel<<<(unsigned)std::min<int64_t>(nr, 4096), 256, 0, s>>>(c->d_rs_ptr.p, genes ? c->d_g_len.p : nullptr, d_col, d_val,
+                                                                                   r0, nr, n_cols, c->d_dense_tmp.p);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(out + r0 * n_cols, c->d_dense_tmp.p, (size_t)(nr * n_cols) * sizeof(double), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            c->wire_d2h += (long long)(nr * n_cols) * 8;
+        }
         return;
     }
     int nthr = c->host_threads > 0 ? c->host_threads : (int)std::thread::hardware_concurrency();
     nthr = std::max(1, std::min(nthr, 256));
-    const int64_t batch = std::max<int64_t>(64, std::min<int64_t>(n_rows, ((int64_t)48 << 20) / n_cols));   // ~48 M cells of the matrix per batch
-    const size_t cap = (size_t)(batch * n_cols / 8 + 1024);     // pairs per batch: 12 % density fits (the results are ~6 % dense); denser batches are copied plainly
-    for (auto &b : c->fb) fetch_buf_ensure(c, b, (size_t)batch, cap);
-    const int64_t n_batches = (n_rows + batch - 1) / batch;
+    // batches of whole rows holding at most `cap` entries (the largest row always fits)
+    int64_t max_row = 1;
+    for (int64_t r = 0; r < n_rows; r++) max_row = std::max(max_row, ptr[r + 1] - ptr[r]);
+    const size_t cap = (size_t)std::max<int64_t>(max_row, (int64_t)6 << 20);
+    std::vector<int64_t> cut{0};
+    for (int64_t r = 0; r < n_rows;) {
+        int64_t e = r + 1;
+        while (e < n_rows && ptr[e + 1] - ptr[r] <= (int64_t)cap && e - r < 65536) e++;
+        cut.push_back(e);
+        r = e;
+    }
+    const int64_t n_batches = (int64_t)cut.size() - 1;
+    size_t max_rows = 1;
+    for (int64_t k = 0; k < n_batches; k++) max_rows = std::max(max_rows, (size_t)(cut[(size_t)k + 1] - cut[(size_t)k]));
+    for (auto &b : c->fb) fetch_buf_ensure(c, b, max_rows, cap);
     auto launch = [&](int64_t k) {
         scasa_ctx::FetchBuf &b = c->fb[k & 1];
-        const int64_t r0 = k * batch, nr = std::min(batch, n_rows - r0);
-        CK(cudaMemsetAsync(b.d_cursor.p, 0, sizeof(unsigned long long), s));
-        const int grid = (int)std::min<int64_t>(nr, (int64_t)c->n_sm * 3);
-        compact_rows_kernel<<<grid, kCompThreads, 0, s>>>(d_mat + r0 * n_cols, nr, n_cols, b.d_cursor.p, (unsigned long long)b.cap,
-                                                         b.d_start.p, b.d_nnz.p, b.d_cols.p, b.d_vals.p);
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(b.h_cursor, b.d_cursor.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(b.h_start, b.d_start.p, nr * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(b.h_nnz, b.d_nnz.p, nr * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));       // the pair count sizes the copy (the other batch is being expanded meanwhile)
-        const size_t used = (size_t)std::min<unsigned long long>(*b.h_cursor, b.cap);
-        if (used) {
-            CK(cudaMemcpyAsync(b.h_cols, b.d_cols.p, used * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(b.h_vals, b.d_vals.p, used * sizeof(double), cudaMemcpyDeviceToHost, s));
+        const int64_t r0 = cut[(size_t)k], r1 = cut[(size_t)k + 1];
+        const int64_t e0 = ptr[r0], ne = ptr[r1] - e0;
+        if (ne) {
+            CK(cudaMemcpyAsync(b.h_cols, d_col + e0, (size_t)ne * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(b.h_vals, d_val + e0, (size_t)ne * sizeof(double), cudaMemcpyDeviceToHost, s));
         }
-        c->wire_d2h += (long long)(used * 12 + (size_t)nr * 12 + 8);
+        for (int64_t r = r0; r < r1; r++) {
+            b.h_start[r - r0] = ptr[r] - e0;
+            b.h_nnz[r - r0] = genes ? c->g_len_host[(size_t)r] : (int32_t)(ptr[r + 1] - ptr[r]);
+        }
+        c->wire_d2h += (long long)ne * 12;
         CK(cudaEventRecord(b.done, s));
     };
-    // the expansion of batch k runs on the pool of worker threads (rows claimed in small chunks) while
-    // this thread drives the GPU for batch k+1
     ExpandPool &pool = expand_pool(c, nthr);
     std::shared_ptr<ExpandPool::Job> pending;           // the batch being expanded (it reads the other staging buffer)
-    auto expand_async = [&](int64_t k) {
-        scasa_ctx::FetchBuf &b = c->fb[k & 1];
-        const int64_t r0 = k * batch, nr = std::min(batch, n_rows - r0);
-        pending = pool.post(out + r0 * n_cols, n_cols, nr, b.h_start, b.h_nnz, b.h_cols, b.h_vals);
-    };
     auto join_all = [&]() { pool.wait(pending); pending.reset(); };
     struct Joiner { decltype(join_all) &j; ~Joiner() { j(); } } joiner{join_all};   // an exception must not leave a job reading freed buffers
     const bool trace = getenv("SCASA_FETCH_TRACE") != nullptr;
-    double t_wait_gpu = 0, t_join = 0, t_launch = 0;
-    unsigned long long pairs = 0;
+    double t_wait_gpu = 0, t_join = 0;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    double t0 = now();
     launch(0);
-    t_launch += now() - t0;
     for (int64_t k = 0; k < n_batches; k++) {
         scasa_ctx::FetchBuf &b = c->fb[k & 1];
-        t0 = now();
+        double t0 = now();
         CK(cudaEventSynchronize(b.done));
         t_wait_gpu += now() - t0;
-        pairs += *b.h_cursor;
-        const int64_t r0 = k * batch, nr = std::min(batch, n_rows - r0);
-        bool overflow = false;
-        for (int64_t r = 0; r < nr; r++) if (b.h_nnz[r] < 0) { overflow = true; break; }
         t0 = now();
         join_all();                                   // batch k-1 (it reads the other buffer, which launch(k+1) reuses)
         t_join += now() - t0;
-        if (overflow) {                               // denser than the staging buffer: plain copy of this batch
-            CK(cudaMemcpyAsync(out + r0 * n_cols, d_mat + r0 * n_cols, (size_t)(nr * n_cols) * sizeof(double), cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
-            c->wire_d2h += (long long)(nr * n_cols) * 8;
-        } else expand_async(k);
-        t0 = now();
+        const int64_t r0 = cut[(size_t)k], nr = cut[(size_t)k + 1] - r0;
+        pending = pool.post(out + r0 * n_cols, n_cols, nr, b.h_start, b.h_nnz, b.h_cols, b.h_vals);
         if (k + 1 < n_batches) launch(k + 1);
-        t_launch += now() - t0;
     }
-    t0 = now();
+    double t0 = now();
     join_all();
     t_join += now() - t0;
     if (trace)
-        fprintf(stderr, "[scasa fetch] %lld x %lld, %lld batches of %lld rows, %llu pairs (%.1f per row): launch+compact %.3f s, "
-                        "wait copy %.3f s, wait expansion %.3f s, %d threads\n", (long long)n_rows, (long long)n_cols,
-                (long long)n_batches, (long long)batch, pairs, (double)pairs / (double)n_rows, t_launch, t_wait_gpu, t_join, nthr);
+        fprintf(stderr, "[scasa fetch] %lld x %lld, %lld batches, %lld entries (%.1f per row): wait copy %.3f s, wait expansion %.3f s, %d threads\n",
+                (long long)n_rows, (long long)n_cols, (long long)n_batches, (long long)ptr[n_rows], (double)ptr[n_rows] / (double)n_rows,
+                t_wait_gpu, t_join, nthr);
 }
 
 }  // namespace
@@ -584,7 +604,12 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
                              [&](int32_t x, int32_t y) { return cost[(size_t)x] > cost[(size_t)y]; });
         }
         if (getenv("SCASA_FETCH_DENSE")) c->fetch_dense_copy = 1;
-        if (const char *env = getenv("SCASA_RUN_PARTS")) c->run_parts = std::max(0, atoi(env));
+        if (const char *env = getenv("SCASA_GENE_TILE")) {      // "genes per pass[:ctas_per_sm]" of gene_rows_kernel
+            int t = 0, cps = 1;
+            const int got = sscanf(env, "%d:%d", &t, &cps);
+            if (got >= 1 && t > 0) c->gene_tile = t;
+            if (got >= 2 && cps >= 1) c->gene_ctas_per_sm = cps;
+        }
         // EM work classes; SCASA_EM_CFG="warps:pairs:bytes:cta_threads:ctas_per_sm,..." overrides (tuning)
         if (const char *env = getenv("SCASA_EM_CFG")) {
             int k = 0;
@@ -632,15 +657,33 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
         c->d_em_order.ensure(c->em_order.size() + 1);
         c->d_em_order.upload(c->em_order, c->stream);
         {
-            std::vector<int2> info((size_t)c->n_rows);
-            std::vector<int32_t> rcol((size_t)c->n_rows);
-            for (int k = 0; k < B; k++)
+            std::vector<int2> info((size_t)c->n_rows), aux((size_t)c->n_rows), em_info((size_t)c->n_em);
+            std::vector<int32_t> poor_rank((size_t)B), poor_col0, em_col0((size_t)c->n_em + 1, 0), emcol_col;
+            int np = 0;
+            for (int k = 0; k < B; k++) {
+                poor_rank[(size_t)k] = np;
                 for (int r = c->q_off[k]; r < c->q_off[k + 1]; r++) {
                     info[(size_t)r] = make_int2(c->em_index[k], r - c->q_off[k]);
-                    rcol[(size_t)r] = c->p_off[k];
+                    aux[(size_t)r] = make_int2(c->p_off[k], np);
                 }
+                if (c->poor[k]) { np++; poor_col0.push_back(c->p_off[k]); c->poor_blocks_list.push_back(k); }
+            }
+            c->n_poor = np;
+            for (int e = 0; e < c->n_em; e++) {
+                const int k = c->em_blocks[(size_t)e], p = c->p_off[k + 1] - c->p_off[k];
+                if (p > 0xffff) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a block may have at most 65535 columns"};
+                em_info[(size_t)e] = make_int2(p | (c->poor[k] ? 1 << 16 : 0), c->p_off[k]);
+                em_col0[(size_t)e + 1] = em_col0[(size_t)e] + p;
+                for (int j = 0; j < p; j++) emcol_col.push_back(c->p_off[k] + j);
+            }
+            c->n_emcols = em_col0[(size_t)c->n_em];
             c->d_row_info.upload(info, c->stream);
-            c->d_row_col.upload(rcol, c->stream);
+            c->d_row_aux.upload(aux, c->stream);
+            c->d_em_info.ensure(em_info.size() + 1); c->d_em_info.upload(em_info, c->stream);
+            c->d_em_col0.upload(em_col0, c->stream);
+            c->d_poor_rank.upload(poor_rank, c->stream);
+            c->d_poor_col0.ensure(poor_col0.size() + 1); c->d_poor_col0.upload(poor_col0, c->stream);
+            c->d_emcol_col.ensure(emcol_col.size() + 1); c->d_emcol_col.upload(emcol_col, c->stream);
         }
         c->d_next.ensure(16); c->d_counters.ensure(8); c->d_stats.ensure(8); c->d_totals.ensure(4); c->d_flag.ensure(1);
         CK(cudaStreamSynchronize(c->stream));
@@ -666,22 +709,24 @@ void scasa_ctx_destroy(scasa_ctx *c)
     if (c->twin) { scasa_ctx_destroy(c->twin); c->twin = nullptr; }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    DBuf<int32_t> *i32[] = {&c->d_q_off, &c->d_p_off, &c->d_em_blocks, &c->d_em_order,
-                            &c->d_cell_chunk, &c->d_y_len, &c->d_y_row, &c->d_eq_id, &c->d_eq_count, &c->d_eq_row,
-                            &c->d_cnt, &c->d_runs, &c->d_tbytes, &c->d_iters, &c->d_row_col,
+    DBuf<int32_t> *i32[] = {&c->d_q_off, &c->d_p_off, &c->d_em_blocks, &c->d_em_order, &c->d_em_col0, &c->d_poor_rank, &c->d_poor_col0,
+                            &c->d_emcol_col, &c->d_cell_chunk, &c->d_y_len, &c->d_y_row, &c->d_eq_id, &c->d_eq_count, &c->d_eq_row,
+                            &c->d_cnt, &c->d_runs, &c->d_tbytes, &c->d_iters,
                             &c->d_list[0], &c->d_list[1], &c->d_list[2], &c->d_list[3], &c->d_list[4],
-                            &c->d_gene_ptr, &c->d_gene_cols};
+                            &c->d_gene_ptr, &c->d_gene_cols, &c->d_rs_len, &c->d_rs_col, &c->d_poor_pos, &c->d_g_col, &c->d_g_len,
+                            &c->d_gene_of_col};
     for (auto b : i32) b->release();
-    DBuf<int64_t> *i64[] = {&c->d_x_off, &c->d_chunk_off, &c->d_y_start, &c->d_cell_ptr, &c->d_toff, &c->d_scan_sums, &c->d_totals};
+    DBuf<int64_t> *i64[] = {&c->d_x_off, &c->d_chunk_off, &c->d_y_start, &c->d_cell_ptr, &c->d_toff, &c->d_scan_sums, &c->d_totals,
+                            &c->d_rs_ptr};
     for (auto b : i64) b->release();
-    DBuf<double> *f64[] = {&c->d_x, &c->d_y_val, &c->d_iso, &c->d_partial,
-                           &c->d_colsum, &c->d_colsum_parts, &c->d_gene};
+    DBuf<double> *f64[] = {&c->d_x, &c->d_y_val, &c->d_rs_val, &c->d_g_val, &c->d_colsum, &c->d_colpart, &c->d_gene_park,
+                           &c->d_dense_tmp, &c->d_iso_in, &c->d_gene_out};
     for (auto b : f64) b->release();
     c->d_poor.release(); c->d_next.release(); c->d_stats.release(); c->d_flag.release();
-    c->d_tdata.release(); c->d_counters.release(); c->d_row_info.release(); c->d_scatter_scratch.release();
+    c->d_tdata.release(); c->d_counters.release(); c->d_row_info.release(); c->d_row_aux.release(); c->d_em_info.release();
+    c->d_scatter_scratch.release(); c->d_ypos.release();
     for (auto &b : c->fb) {
-        b.d_cols.release(); b.d_nnz.release(); b.d_vals.release(); b.d_start.release(); b.d_cursor.release();
-        if (b.h_cols) { cudaFreeHost(b.h_cols); cudaFreeHost(b.h_vals); cudaFreeHost(b.h_start); cudaFreeHost(b.h_nnz); cudaFreeHost(b.h_cursor); }
+        if (b.h_cols) { cudaFreeHost(b.h_cols); cudaFreeHost(b.h_vals); cudaFreeHost(b.h_start); cudaFreeHost(b.h_nnz); }
         if (b.done) cudaEventDestroy(b.done);
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -825,32 +870,37 @@ int scasa_set_gene_map(scasa_ctx *c, const int32_t *gene_of_col, int32_t n_genes
         c->d_gene_ptr.upload(ptr, c->stream);
         c->d_gene_cols.ensure(cols.size() + 1);
         c->d_gene_cols.upload(cols, c->stream);
+        c->d_gene_of_col.upload(goc, c->stream);
         CK(cudaStreamSynchronize(c->stream));
     });
 }
 
 // What one range of chunks contributed to the run statistics.
 struct RangeStats {
-    float pack_ms = 0, tasks_ms = 0, em_ms = 0, finish_ms = 0, cls_ms[kLists] = {0, 0, 0, 0, 0};
+    float pack_ms = 0, tasks_ms = 0, em_ms = 0, finish_ms = 0, gene_ms = 0, cls_ms[kLists] = {0, 0, 0, 0, 0};
     unsigned long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     unsigned int cnts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int64_t blob_bytes = 0;
     int launches = 0;
 };
 
-// Chunks [h0, h1) of the sample staged in c: pack -> tasks -> EM -> column / gene sums, with w's
-// work buffers, streams and X-matrix tables (w is c itself or its twin).  Results go into c's matrices.
-static void run_range(scasa_ctx *w, scasa_ctx *c, int h0, int h1, int part, RangeStats &rs)
+// The sample staged in c: pack -> result structure + tasks -> EM -> column sums -> gene sums.
+static void run_all(scasa_ctx *c, RangeStats &rs)
 {
-    cudaStream_t s = w->stream;
+    scasa_ctx *w = c;
+    cudaStream_t s = c->stream;
     int launches = 0;
-    const int n_chunks = h1 - h0;
-    const int64_t c0 = c->chunk_off[(size_t)h0], n_cells = c->chunk_off[(size_t)h1] - c0;
+    const int n_chunks = c->n_chunks;
+    const int64_t n_cells = c->n_cells;
     const int64_t n_tasks = (int64_t)n_chunks * w->n_em;
-    double *iso = c->d_iso.p + c0 * c->n_cols;
     w->d_cnt.ensure((size_t)n_tasks + 1); w->d_runs.ensure((size_t)n_tasks + 1);
     w->d_tbytes.ensure((size_t)n_tasks + 1); w->d_toff.ensure((size_t)n_tasks + 1);
     for (int k = 0; k < kLists; k++) w->d_list[k].ensure((size_t)n_tasks + 1);
+    c->d_rs_len.ensure((size_t)n_cells + 1); c->d_rs_ptr.ensure((size_t)n_cells + 1);
+    c->d_poor_pos.ensure((size_t)n_cells * std::max(1, c->n_poor));
+    c->d_ypos.ensure((size_t)c->nnz + 1);
+    c->d_colpart.ensure((size_t)n_chunks * std::max(1, c->n_emcols));
+    if (c->n_genes > 0) c->d_g_len.ensure((size_t)n_cells);
 
     CK(cudaEventRecord(w->ev[0], s));
     CK(cudaMemsetAsync(w->d_cnt.p, 0, (n_tasks + 1) * sizeof(int32_t), s));
@@ -859,6 +909,8 @@ static void run_range(scasa_ctx *w, scasa_ctx *c, int h0, int h1, int part, Rang
     CK(cudaMemsetAsync(w->d_next.p, 0, 16 * sizeof(unsigned int), s));
     CK(cudaMemsetAsync(w->d_counters.p, 0, 8 * sizeof(unsigned int), s));
     CK(cudaMemsetAsync(w->d_flag.p, 0, sizeof(int), s));
+    CK(cudaMemsetAsync(c->d_colsum.p, 0, (size_t)c->n_cols * sizeof(double), s));
+    CK(cudaMemsetAsync(c->d_colpart.p, 0, (size_t)n_chunks * std::max(1, c->n_emcols) * sizeof(double), s));
 
     // ---- pack: eqclass counts -> Y
     if (c->have_eq) {
@@ -867,18 +919,18 @@ static void run_range(scasa_ctx *w, scasa_ctx *c, int h0, int h1, int part, Rang
         if (dense_smem <= 200 * 1024 && !getenv("SCASA_PACK_SORT")) {
             CK(cudaFuncSetAttribute(pack_cells_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_smem));
             int grid = (int)std::min<int64_t>(n_cells, (int64_t)w->n_sm);
-            pack_cells_dense_kernel<<<grid, 512, dense_smem, s>>>(n_cells, c->d_cell_ptr.p + c0, c->d_eq_id.p, c->d_eq_count.p,
+            pack_cells_dense_kernel<<<grid, 512, dense_smem, s>>>(n_cells, c->d_cell_ptr.p, c->d_eq_id.p, c->d_eq_count.p,
                                                                   c->d_eq_row.p, c->n_eq, (int)c->n_rows, wpt, c->d_y_row.p,
-                                                                  c->d_y_val.p, c->d_y_len.p + c0);
+                                                                  c->d_y_val.p, c->d_y_len.p);
         } else {
             int cap = 32;
             while (cap < c->max_cell_entries) cap <<= 1;
             size_t smem = (size_t)cap * sizeof(unsigned long long);
             CK(cudaFuncSetAttribute(pack_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int grid = (int)std::min<int64_t>(n_cells, (int64_t)w->n_sm * 8);
-            pack_cells_kernel<<<grid, 256, smem, s>>>(n_cells, c->d_cell_ptr.p + c0, c->d_eq_id.p, c->d_eq_count.p,
+            pack_cells_kernel<<<grid, 256, smem, s>>>(n_cells, c->d_cell_ptr.p, c->d_eq_id.p, c->d_eq_count.p,
                                                       c->d_eq_row.p, c->n_eq, cap, c->d_y_row.p, c->d_y_val.p,
-                                                      c->d_y_len.p + c0, w->d_flag.p);
+                                                      c->d_y_len.p, w->d_flag.p);
         }
         CK(cudaGetLastError());
         launches++;
@@ -886,23 +938,8 @@ static void run_range(scasa_ctx *w, scasa_ctx *c, int h0, int h1, int part, Rang
     CK(cudaEventRecord(w->ev[1], s));
 
     XDev X = xdev(w);
-    Sample S = sdev(c, h0, h1);
-    // ---- result rows: zeros + pass-through blocks, on a side stream next to the task build
-    {
-        cudaStream_t fs = w->cls_stream[0];
-        CK(cudaStreamWaitEvent(fs, w->ev[1], 0));
-        const size_t smem = (size_t)2 * kFillTile * sizeof(double);
-        CK(cudaFuncSetAttribute(iso_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int fill_ctas = getenv("SCASA_FILL_CTAS") ? std::max(1, atoi(getenv("SCASA_FILL_CTAS"))) : 2;
-        const int grid = (int)std::min<int64_t>(n_cells, (int64_t)w->n_sm * fill_ctas);
-        const int use_bulk = (c->n_cols % 2 == 0) && ((uintptr_t)iso % 16 == 0) && !getenv("SCASA_FILL_PLAIN");
-        iso_fill_kernel<<<grid, kFillThreads, smem, fs>>>(X, S, iso, use_bulk);
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(w->ev_fill, fs));
-        launches++;
-    }
-
-    // ---- task extents, work classes, blobs
+    Sample S = sdev(c, 0, n_chunks);
+    // ---- task extents and work classes; size of every result row; the two scans
     Tasks T = tdev(w);
     EmOpts O;
     O.maxiter_x = c->opts.maxiter_x; O.maxiter_bt = c->opts.maxiter_bt; O.modify = c->opts.modify;
@@ -913,21 +950,37 @@ static void run_range(scasa_ctx *w, scasa_ctx *c, int h0, int h1, int part, Rang
     for (int k = 0; k < kClasses; k++) { CC.pairs[k] = c->cls_pairs[k]; CC.bytes[k] = c->cls_bytes[k]; }
     CC.real_bytes = c->opts.fp32 ? 4 : 8;
     CC.pair_max = c->pair_max;
-    int32_t *iters = c->d_iters.p + (int64_t)h0 * w->n_em * 2;
+    int32_t *iters = c->d_iters.p;
     int64_t tot[2] = {0, 0};
     unsigned int *cnts = rs.cnts;
-    if (w->n_em > 0) {
+    {
         const int wpb = 8;
-        task_count_kernel<<<(unsigned)((n_cells + wpb - 1) / wpb), wpb * 32, 0, s>>>(X, S, T);
-        classify_kernel<<<(unsigned)((n_tasks + 255) / 256), 256, 0, s>>>(X, S, T, n_tasks, O, CC, iters, w->d_stats.p);
-        launches += 2;
-        exclusive_scan(w, w->d_tbytes.p, n_tasks, w->d_toff.p, w->d_totals.p + 0, launches);
+        task_count_kernel<<<(unsigned)((n_cells + wpb - 1) / wpb), wpb * 32, 0, s>>>(X, S, T, c->d_rs_len.p);
+        launches++;
+        if (w->n_em > 0) {
+            classify_kernel<<<(unsigned)((n_tasks + 255) / 256), 256, 0, s>>>(X, S, T, n_tasks, O, CC, iters, w->d_stats.p);
+            launches++;
+            exclusive_scan(w, w->d_tbytes.p, n_tasks, w->d_toff.p, w->d_totals.p + 0, launches);
+        } else CK(cudaMemsetAsync(w->d_totals.p, 0, sizeof(int64_t), s));
+        exclusive_scan(w, c->d_rs_len.p, n_cells, c->d_rs_ptr.p, w->d_totals.p + 1, launches);
         CK(cudaMemcpyAsync(tot, w->d_totals.p, sizeof tot, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(cnts, w->d_counters.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         if (cnts[7] == 1) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a poor-condition (2-column) block may have at most 64 rows"};
         if (cnts[7] == 2) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a (chunk, block) task may hold at most 65535 cells-with-counts and 65535 count entries"};
         if (cnts[5] > 200 * 1024) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a (chunk, block) task needs more than 200 KB of shared memory (chunk too large for this block)"};
+    }
+    c->rs_nnz = tot[1];
+    c->d_rs_col.ensure((size_t)tot[1] + 2); c->d_rs_val.ensure((size_t)tot[1] + 2);
+    if (c->n_genes > 0) { c->d_g_col.ensure((size_t)tot[1] + 2); c->d_g_val.ensure((size_t)tot[1] + 2); }
+    Result R = rdev(c);
+    {
+        const int wpb = 8;
+        struct_fill_kernel<<<(unsigned)((n_cells + wpb - 1) / wpb), wpb * 32, 0, s>>>(X, S, R);
+        CK(cudaGetLastError());
+        launches++;
+    }
+    if (w->n_em > 0) {
         w->d_tdata.ensure((size_t)tot[0] + 64);
         T = tdev(w);
         rs.blob_bytes = tot[0];
@@ -943,15 +996,14 @@ static void run_range(scasa_ctx *w, scasa_ctx *c, int h0, int h1, int part, Rang
         const size_t sc_smem = scratch ? 0 : (staged ? staged_bytes : st_bytes);
         if (staged) {
             CK(cudaFuncSetAttribute(task_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
-            task_scatter_kernel<true><<<n_chunks, kScatterThreads, sc_smem, s>>>(X, S, T, scratch);
+            task_scatter_kernel<true><<<n_chunks, kScatterThreads, sc_smem, s>>>(X, S, T, R, scratch);
         } else {
             if (sc_smem) CK(cudaFuncSetAttribute(task_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
-            task_scatter_kernel<false><<<n_chunks, kScatterThreads, sc_smem, s>>>(X, S, T, scratch);
+            task_scatter_kernel<false><<<n_chunks, kScatterThreads, sc_smem, s>>>(X, S, T, R, scratch);
         }
         CK(cudaGetLastError());
         launches++;
     }
-    CK(cudaStreamWaitEvent(s, w->ev_fill, 0));
     CK(cudaEventRecord(w->ev[2], s));
 
     // ---- EM: one persistent kernel per work class, side by side on their own streams
@@ -969,7 +1021,7 @@ static void run_range(scasa_ctx *w, scasa_ctx *c, int h0, int h1, int part, Rang
             const size_t smem = (size_t)slot * groups;
             if (smem > 220 * 1024) throw ArgErr{SCASA_ERR_UNSUPPORTED, "EM work class needs more shared memory than an SM has"};
             EmArgs A;
-            A.X = X; A.S = S; A.T = T; A.O = O; A.out = iso; A.iters = iters; A.stats = w->d_stats.p;
+            A.X = X; A.S = S; A.T = T; A.O = O; A.R = R; A.iters = iters; A.stats = w->d_stats.p;
             A.list = w->d_list[k].p; A.list_n = w->d_counters.p + k; A.next = w->d_next.p + k; A.slot_bytes = slot;
             const unsigned grid = (unsigned)std::min<int64_t>((int64_t)w->n_sm * c->cls_ctas_per_sm[k], ((int64_t)n + groups - 1) / groups);
             cudaStream_t cs = w->cls_stream[k];
@@ -998,7 +1050,7 @@ static void run_range(scasa_ctx *w, scasa_ctx *c, int h0, int h1, int part, Rang
             const size_t smem = (size_t)slot * halves;
             const unsigned n = cnts[kPairCounter];
             EmArgs A;
-            A.X = X; A.S = S; A.T = T; A.O = O; A.out = iso; A.iters = iters; A.stats = w->d_stats.p;
+            A.X = X; A.S = S; A.T = T; A.O = O; A.R = R; A.iters = iters; A.stats = w->d_stats.p;
             A.list = w->d_list[k].p; A.list_n = w->d_counters.p + kPairCounter; A.next = w->d_next.p + k; A.slot_bytes = slot;
             const unsigned grid = (unsigned)std::min<int64_t>((int64_t)w->n_sm * c->pair_ctas_per_sm, ((int64_t)n + halves - 1) / halves);
             cudaStream_t cs = w->cls_stream[k];
@@ -1021,10 +1073,30 @@ static void run_range(scasa_ctx *w, scasa_ctx *c, int h0, int h1, int part, Rang
     }
     CK(cudaEventRecord(w->ev[3], s));
 
-    // ---- column sums (+ gene sums)
-    double *gene = c->n_genes > 0 ? c->d_gene.p + c0 * (int64_t)c->n_genes : nullptr;
-    launch_finish(w, iso, n_cells, gene, c->d_colsum_parts.p + (size_t)part * c->n_cols, launches);
+    // ---- column sums of the EM columns (chunks in order), gene sums
+    if (c->n_emcols > 0) {
+        colsum_em_reduce<<<(unsigned)((c->n_emcols + 255) / 256), 256, 0, s>>>(c->d_colpart.p, n_chunks, c->n_emcols, c->d_emcol_col.p,
+                                                                              c->d_colsum.p);
+        launches++;
+    }
     CK(cudaEventRecord(w->ev[4], s));
+    if (c->n_genes > 0) {
+        // genes per pass: everything when the slots fit in shared memory
+        int tile = c->gene_tile > 0 ? std::min(c->gene_tile, c->n_genes) : c->n_genes;
+        const int max_tile = (int)((200 * 1024 / std::max(1, c->gene_ctas_per_sm) - 4096) / 4.2);
+        tile = std::min(tile, max_tile);
+        const int wpt = ((tile + 31) / 32 + kGeneRowThreads - 1) / kGeneRowThreads;
+        const size_t smem = (size_t)tile * 4 + (size_t)wpt * kGeneRowThreads * 4;
+        const int grid = (int)std::min<int64_t>(n_cells, (int64_t)w->n_sm * c->gene_ctas_per_sm);
+        c->d_gene_park.ensure((size_t)grid * c->n_cols);
+        CK(cudaFuncSetAttribute(gene_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gene_rows_kernel<<<grid, kGeneRowThreads, smem, s>>>(R, n_cells, c->n_cols, c->d_gene_of_col.p, c->d_gene_ptr.p, c->d_gene_cols.p,
+                                                            c->n_genes, tile, wpt, c->d_gene_park.p);
+        CK(cudaGetLastError());
+        launches++;
+        c->ran_genes = true;
+    }
+    CK(cudaEventRecord(w->ev[5], s));
 
     int flag = 0;
     CK(cudaMemcpyAsync(rs.st, w->d_stats.p, sizeof rs.st, cudaMemcpyDeviceToHost, s));
@@ -1035,6 +1107,7 @@ static void run_range(scasa_ctx *w, scasa_ctx *c, int h0, int h1, int part, Rang
     CK(cudaEventElapsedTime(&rs.tasks_ms, w->ev[1], w->ev[2]));
     CK(cudaEventElapsedTime(&rs.em_ms, w->ev[2], w->ev[3]));
     CK(cudaEventElapsedTime(&rs.finish_ms, w->ev[3], w->ev[4]));
+    CK(cudaEventElapsedTime(&rs.gene_ms, w->ev[4], w->ev[5]));
     for (int k = 0; k < kLists; k++)
         if (ran_cls[k]) CK(cudaEventElapsedTime(&rs.cls_ms[k], w->ev_cls[k][0], w->ev_cls[k][1]));
     rs.launches = launches;
@@ -1064,93 +1137,36 @@ static int sync_twin(scasa_ctx *c)
     return SCASA_OK;
 }
 
-// The staged sample is cut into ranges of chunks that alternate between this context and its twin,
-// each driven by its own host thread: the instruction-bound EM kernels of one range run next to
-// the bandwidth-bound pack / row-fill / gene kernels of another.  Chunks are independent, so the
-// cut changes no result.  `allow_split = false` (scasa_quant's slices, which already alternate on
-// the two contexts) runs everything as one range on c.
-static int run_staged(scasa_ctx *c, bool allow_split)
+static int run_staged(scasa_ctx *c)
 {
     if (!c->staged) return fail(c, SCASA_ERR_STATE, "nothing staged: call scasa_stage_counts / scasa_stage_eqcounts first");
-    int parts = 1;
-    if (allow_split) {
-        parts = c->run_parts > 0 ? c->run_parts : 1;   // measured: no gain (the persistent EM kernels fill the SMs' registers
-                                                        // and shared memory, the other range's kernels queue behind them)
-        parts = std::max(1, std::min(parts, c->n_chunks));
-    }
-    if (parts > 1) { int rc = sync_twin(c); if (rc) return rc; }
-    // range boundaries: the first and last ranges are half-size so that the two workers fall out of phase
-    std::vector<int> cut((size_t)parts + 1, 0);
-    {
-        std::vector<double> wgt((size_t)parts, 1.0);
-        if (parts >= 4) { wgt[0] = 0.5; wgt[(size_t)parts - 1] = 0.5; }
-        double tot = 0, acc = 0;
-        for (double x : wgt) tot += x;
-        for (int k = 0; k < parts; k++) {
-            acc += wgt[(size_t)k];
-            cut[(size_t)k + 1] = std::max(cut[(size_t)k] + 1, (int)std::llround(c->n_chunks * acc / tot));
-        }
-        cut[(size_t)parts] = c->n_chunks;
-        for (int k = parts - 1; k > 0; k--) cut[(size_t)k] = std::min(cut[(size_t)k], cut[(size_t)k + 1] - 1);
-    }
-    std::vector<RangeStats> rs((size_t)parts);
-    int rcs[2] = {SCASA_OK, SCASA_OK};
-    int rc0 = guarded(c, [&] {
+    return guarded(c, [&] {
         const int64_t n_tasks = (int64_t)c->n_chunks * c->n_em;
-        c->d_iso.ensure((size_t)(c->n_cells * c->n_cols));
         c->d_iters.ensure((size_t)n_tasks * 2 + 2);
         c->d_colsum.ensure((size_t)c->n_cols);
-        c->d_colsum_parts.ensure((size_t)parts * c->n_cols);
-        if (c->n_genes > 0) c->d_gene.ensure((size_t)c->n_cells * c->n_genes);
+        c->ran = false; c->have_rs_host = false; c->have_glen_host = false; c->ran_genes = false;
         CK(cudaEventRecord(c->ev[6], c->stream));
-    });
-    if (rc0) return rc0;
-    auto drive = [&](int which) {
-        scasa_ctx *w = which ? c->twin : c;
-        for (int k = which; k < parts; k += 2) {
-            int rc = guarded(w, [&] { run_range(w, c, cut[(size_t)k], cut[(size_t)k + 1], k, rs[(size_t)k]); });
-            if (rc) { rcs[which] = rc; return; }
-        }
-    };
-    if (parts > 1) {                                 // drive() catches everything itself (guarded)
-        std::thread other;
-        try {
-            other = std::thread(drive, 1);
-        } catch (const std::exception &e) {
-            return fail(c, SCASA_ERR_NOMEM, std::string("cannot start the second host thread: ") + e.what());
-        }
-        drive(0);
-        other.join();
-    } else drive(0);
-    if (rcs[0]) return rcs[0];
-    if (rcs[1]) return fail(c, rcs[1], std::string("twin context: ") + scasa_last_error(c->twin));
-    return guarded(c, [&] {
+        RangeStats r;
+        run_all(c, r);
         cudaStream_t s = c->stream;
-        colsum_combine<<<(unsigned)((c->n_cols + 255) / 256), 256, 0, s>>>(c->d_colsum_parts.p, parts, c->n_cols, c->d_colsum.p);
-        CK(cudaGetLastError());
         CK(cudaEventRecord(c->ev[7], s));
         CK(cudaStreamSynchronize(s));
         scasa_timing_t &tm = c->timing;
         memset(&tm, 0, sizeof tm);
         CK(cudaEventElapsedTime(&tm.total_ms, c->ev[6], c->ev[7]));
-        unsigned long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (const RangeStats &r : rs) {
-            tm.pack_ms += r.pack_ms; tm.tasks_ms += r.tasks_ms; tm.em_ms += r.em_ms; tm.finish_ms += r.finish_ms;
-            for (int k = 0; k < kClasses; k++) { tm.em_class_ms[k] += r.cls_ms[k]; tm.em_class_tasks[k] += r.cnts[k]; }
-            tm.em_pair_ms += r.cls_ms[kPairList]; tm.em_pair_tasks += r.cnts[kPairCounter];
-            for (int k = 0; k < 8; k++) st[k] += r.st[k];
-            tm.n_entries += r.blob_bytes;
-            tm.launches += r.launches;
-            tm.max_slot_bytes = std::max<int32_t>(tm.max_slot_bytes, (int32_t)r.cnts[5]);
-        }
-        tm.launches += 1;
-        tm.run_parts = parts;
-        tm.gene_ms = c->n_genes > 0 ? tm.finish_ms : 0.f;
-        tm.inner_iters = (int64_t)st[0]; tm.outer_iters = (int64_t)st[1];
-        tm.n_tasks = (int64_t)st[4]; tm.n_active = (int64_t)st[5];
+        tm.pack_ms = r.pack_ms; tm.tasks_ms = r.tasks_ms; tm.em_ms = r.em_ms; tm.finish_ms = r.finish_ms + r.gene_ms; tm.gene_ms = r.gene_ms;
+        for (int k = 0; k < kClasses; k++) { tm.em_class_ms[k] = r.cls_ms[k]; tm.em_class_tasks[k] = r.cnts[k]; }
+        tm.em_pair_ms = r.cls_ms[kPairList]; tm.em_pair_tasks = r.cnts[kPairCounter];
+        tm.n_entries = r.blob_bytes;
+        tm.launches = r.launches;
+        tm.max_slot_bytes = (int32_t)r.cnts[5];
+        tm.run_parts = 1;
+        tm.inner_iters = (int64_t)r.st[0]; tm.outer_iters = (int64_t)r.st[1];
+        tm.n_tasks = (int64_t)r.st[4]; tm.n_active = (int64_t)r.st[5];
         // sum_tasks [in*8*(q+2p)*n_c + out*8*(q+p)*n_c] + n_cells*8*(sum q + sum p)
-        tm.em_alg_bytes = 8.0 * ((double)st[2] + (double)st[3]);
+        tm.em_alg_bytes = 8.0 * ((double)r.st[2] + (double)r.st[3]);
         tm.alg_bytes = tm.em_alg_bytes + (double)c->n_cells * 8.0 * (double)(c->n_rows + c->n_cols);
+        tm.result_nnz = c->rs_nnz;
         c->ran = true;
     });
 }
@@ -1158,13 +1174,13 @@ static int run_staged(scasa_ctx *c, bool allow_split)
 int scasa_run(scasa_ctx *c)
 {
     if (!c) return fail(c, SCASA_ERR_ARG, "null context");
-    return run_staged(c, true);
+    return run_staged(c);
 }
 
 int scasa_set_run_parts(scasa_ctx *c, int32_t n_parts)
 {
+    // kept for ABI stability: cutting one run into ranges measured slower on B200 and was removed
     if (!c || n_parts < 0) return fail(c, SCASA_ERR_ARG, "bad argument");
-    c->run_parts = n_parts;
     return SCASA_OK;
 }
 
@@ -1191,7 +1207,7 @@ int scasa_fetch_iso(scasa_ctx *c, double *out)
 {
     if (!c || !out) return fail(c, SCASA_ERR_ARG, "null argument");
     if (!c->ran) return fail(c, SCASA_ERR_STATE, "scasa_run has not completed");
-    return guarded(c, [&] { fetch_dense(c, c->d_iso.p, c->n_cells, c->n_cols, out); });
+    return guarded(c, [&] { fetch_dense(c, false, out); });
 }
 int scasa_fetch_iters(scasa_ctx *c, int32_t *out)
 {
@@ -1205,8 +1221,76 @@ int scasa_fetch_gene(scasa_ctx *c, double *out)
 {
     if (!c || !out) return fail(c, SCASA_ERR_ARG, "null argument");
     if (!c->ran) return fail(c, SCASA_ERR_STATE, "scasa_run has not completed");
-    if (c->n_genes <= 0) return fail(c, SCASA_ERR_STATE, "no gene map set");
-    return guarded(c, [&] { fetch_dense(c, c->d_gene.p, c->n_cells, c->n_genes, out); });
+    if (c->n_genes <= 0 || !c->ran_genes) return fail(c, SCASA_ERR_STATE, "no gene map was set before the run");
+    return guarded(c, [&] { fetch_dense(c, true, out); });
+}
+
+int scasa_result_nnz(scasa_ctx *c, int64_t *iso_nnz, int64_t *gene_nnz)
+{
+    if (!c) return fail(c, SCASA_ERR_ARG, "null context");
+    if (!c->ran) return fail(c, SCASA_ERR_STATE, "scasa_run has not completed");
+    return guarded(c, [&] {
+        if (iso_nnz) *iso_nnz = c->rs_nnz;
+        if (gene_nnz) {
+            *gene_nnz = 0;
+            if (c->ran_genes) {
+                need_rs_host(c, true);
+                int64_t t = 0;
+                for (int32_t v : c->g_len_host) t += v;
+                *gene_nnz = t;
+            }
+        }
+    });
+}
+
+int scasa_fetch_iso_csr(scasa_ctx *c, int64_t *rowptr, int32_t *cols, double *vals)
+{
+    if (!c || !rowptr) return fail(c, SCASA_ERR_ARG, "null argument");
+    if (!c->ran) return fail(c, SCASA_ERR_STATE, "scasa_run has not completed");
+    return guarded(c, [&] {
+        need_rs_host(c, false);
+        std::copy(c->rs_ptr_host.begin(), c->rs_ptr_host.end(), rowptr);
+        if (cols && c->rs_nnz) CK(cudaMemcpyAsync(cols, c->d_rs_col.p, (size_t)c->rs_nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        if (vals && c->rs_nnz) CK(cudaMemcpyAsync(vals, c->d_rs_val.p, (size_t)c->rs_nnz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->wire_d2h += (long long)c->rs_nnz * ((cols ? 4 : 0) + (vals ? 8 : 0));
+    });
+}
+
+int scasa_fetch_gene_csr(scasa_ctx *c, int64_t *rowptr, int32_t *genes, double *vals)
+{
+    if (!c || !rowptr) return fail(c, SCASA_ERR_ARG, "null argument");
+    if (!c->ran) return fail(c, SCASA_ERR_STATE, "scasa_run has not completed");
+    if (c->n_genes <= 0 || !c->ran_genes) return fail(c, SCASA_ERR_STATE, "no gene map was set before the run");
+    return guarded(c, [&] {
+        need_rs_host(c, true);
+        rowptr[0] = 0;
+        for (int64_t r = 0; r < c->n_cells; r++) rowptr[r + 1] = rowptr[r] + c->g_len_host[(size_t)r];
+        if (!genes && !vals) return;
+        // the device rows have the capacity of the isoform rows: copy in slabs and close the gaps on the way
+        const int64_t slab = (int64_t)4 << 20;
+        std::vector<int32_t> hc((size_t)slab + 1);
+        std::vector<double> hv((size_t)slab + 1);
+        const int64_t *ptr = c->rs_ptr_host.data();
+        for (int64_t r0 = 0; r0 < c->n_cells;) {
+            int64_t r1 = r0 + 1;
+            while (r1 < c->n_cells && ptr[r1 + 1] - ptr[r0] <= slab) r1++;
+            const int64_t e0 = ptr[r0], ne = ptr[r1] - e0;
+            if (ne > slab) { hc.resize((size_t)ne + 1); hv.resize((size_t)ne + 1); }
+            if (ne) {
+                CK(cudaMemcpyAsync(hc.data(), c->d_g_col.p + e0, (size_t)ne * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaMemcpyAsync(hv.data(), c->d_g_val.p + e0, (size_t)ne * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            }
+            CK(cudaStreamSynchronize(c->stream));
+            c->wire_d2h += (long long)ne * 12;
+            for (int64_t r = r0; r < r1; r++) {
+                const int64_t src = ptr[r] - e0, dst = rowptr[r], m = c->g_len_host[(size_t)r];
+                if (genes) std::copy(hc.begin() + src, hc.begin() + src + m, genes + dst);
+                if (vals) std::copy(hv.begin() + src, hv.begin() + src + m, vals + dst);
+            }
+            r0 = r1;
+        }
+    });
 }
 
 int scasa_expand_pairs(double *out, int64_t n_rows, int64_t n_cols, const int64_t *row_start, const int32_t *row_nnz,
@@ -1334,7 +1418,7 @@ int scasa_quant(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const int64_t *
             const int64_t e0 = cell_ptr[c0];
             for (int64_t i = c0; i <= c1; i++) ptr[(size_t)(i - c0)] = cell_ptr[i] - e0;
             int rc = scasa_stage_eqcounts(x, c1 - c0, h1 - h0, coff.data(), ptr.data(), eq_id + e0, eq_count + e0, n_eq, eq_row);
-            if (!rc) rc = run_staged(x, false);
+            if (!rc) rc = run_staged(x);
             if (!rc) rc = scasa_fetch_iso(x, iso_out + c0 * c->n_cols);
             if (!rc && gene_out) rc = scasa_fetch_gene(x, gene_out + c0 * (int64_t)c->n_genes);
             if (!rc && colsum_out) rc = scasa_fetch_colsum(x, colsum_parts.data() + (size_t)sl * c->n_cols);
@@ -1374,13 +1458,11 @@ int scasa_gene_sum(scasa_ctx *c, const int32_t *gene_of_col, int32_t n_genes, co
     if (rc) return rc;
     return guarded(c, [&] {
         cudaStream_t s = c->stream;
-        c->d_iso.ensure((size_t)(n_cells * c->n_cols));
-        c->d_gene.ensure((size_t)n_cells * n_genes);
-        CK(cudaMemcpyAsync(c->d_iso.p, iso, n_cells * c->n_cols * sizeof(double), cudaMemcpyHostToDevice, s));
-        int launches = 0;
-        c->d_colsum.ensure((size_t)c->n_cols);
-        launch_finish(c, c->d_iso.p, n_cells, c->d_gene.p, c->d_colsum.p, launches);
-        CK(cudaMemcpyAsync(gene_out, c->d_gene.p, (size_t)n_cells * n_genes * sizeof(double), cudaMemcpyDeviceToHost, s));
+        c->d_iso_in.ensure((size_t)(n_cells * c->n_cols));
+        c->d_gene_out.ensure((size_t)n_cells * n_genes);
+        CK(cudaMemcpyAsync(c->d_iso_in.p, iso, n_cells * c->n_cols * sizeof(double), cudaMemcpyHostToDevice, s));
+        launch_gene_gather(c, c->d_iso_in.p, n_cells, c->d_gene_out.p);
+        CK(cudaMemcpyAsync(gene_out, c->d_gene_out.p, (size_t)n_cells * n_genes * sizeof(double), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
     });
 }

@@ -56,7 +56,7 @@ struct EmArgs {
     Sample S;
     Tasks T;
     EmOpts O;
-    double *out;
+    Result R;                     // estimates go into R.rs_val, per-chunk column sums into R.colpart
     int32_t *iters;
     unsigned long long *stats;
     const int32_t *list;          // task ids of this work class
@@ -131,6 +131,7 @@ template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_k
         // ---- carve the slot
         double *ey = (double *)slot;
         const uint32_t *rcell = (const uint32_t *)(slot + BL.off_cell);
+        const uint32_t *rpos = (const uint32_t *)(slot + BL.off_pos);
         const uint16_t *eptr = (const uint16_t *)(slot + BL.off_ptr);
         const uint16_t *erow = (const uint16_t *)(slot + BL.off_row);
         R *ew = (R *)(slot + BL.bytes);
@@ -367,33 +368,50 @@ template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_k
             if ((!O.fixed_iter && !any_x) || outer >= O.maxiter_x) break;        // :1020
         }
 
-        // ---- de-adjust (:1027-1037) and scatter BT into the result (:1042)
+        // ---- de-adjust (:1027-1037) and write BT into the result rows (:1042)
         const double deduct = nadj * O.adjust_esp;
         const int64_t cbase = A.S.chunk_off[h] - A.S.cell_base;
-        const int64_t col0 = X.p_off[b];
+        double *vals = A.R.rs_val + A.R.rs_ptr[cbase];                           // the chunk's first value; rpos is relative to it
         for (int a = gl; a < n; a += GT) {
             const uint32_t cw = rcell[a];
             double s = 0;
             if (nadj > 0) for (int j = 0; j < p; j++) s += (double)beta[j * n + a];
             if (!(cw & kPseudo)) {
-                double *o = A.out + (cbase + (int64_t)cw) * X.n_cols + col0;
+                double *o = vals + rpos[a];
                 for (int j = 0; j < p; j++) { double v = (double)beta[j * n + a]; if (nadj > 0) v = v - deduct * (v / s); o[j] = v; }
             }
         }
         if (n > 0 && (rcell[n - 1] & kPseudo) && (rcell[n - 1] & 0xffff) != 0) {
             // cells of the chunk without a record of their own take the pseudo cell's values; the real
-            // cells are listed in ascending order, so walk the gaps
+            // cells are listed in ascending order, so walk the gaps.  Every cell's row holds the two
+            // columns of every poor block (struct_fill_kernel): poor_pos says where.
             const int ap = n - 1;
+            const int kp = X.poor_rank[b];
             double s = 0;
             if (nadj > 0) for (int j = 0; j < p; j++) s += (double)beta[j * n + ap];
             for (int a = gl; a < n; a += GT) {
                 const int lo = a == 0 ? 0 : (int)rcell[a - 1] + 1;
                 const int hi = a == n - 1 ? nc : (int)rcell[a];
                 for (int cc = lo; cc < hi; cc++) {
-                    double *o = A.out + (cbase + cc) * X.n_cols + col0;
+                    double *o = A.R.rs_val + A.R.rs_ptr[cbase + cc] + A.R.poor_pos[(cbase + cc) * X.n_poor + kp];
                     for (int j = 0; j < p; j++) { double v = (double)beta[j * n + ap]; if (nadj > 0) v = v - deduct * (v / s); o[j] = v; }
                 }
             }
+        }
+        // ---- this chunk's share of the column sums (step2:167), records in cell order; the pseudo cell counts pmult times
+        for (int j = gl; j < p; j += GT) {
+            double cs = 0;
+#pragma unroll 1
+            for (int a = 0; a < n; a++) {
+                double v = (double)beta[j * n + a];
+                if (nadj > 0) {
+                    double s = 0;
+                    for (int jj = 0; jj < p; jj++) s += (double)beta[jj * n + a];
+                    v = v - deduct * (v / s);
+                }
+                cs += a == ap ? (double)pmult * v : v;
+            }
+            A.R.colpart[(int64_t)(A.S.chunk_base + h) * X.n_emcols + X.em_col0[e] + j] = cs;
         }
         if (gl == 0) task_done_stats(A.iters, A.stats, t, outer, inner_total, q, p, nc, n);
         G.sync();
@@ -423,11 +441,11 @@ template <typename R> __global__ void __launch_bounds__(128, 8) em_pair_kernel(E
 
     int phase = LOAD;
     int64_t t = 0;
-    int b = 0, q = 1, p = 1, n = 1, E = 1, np = 1, qp = 1, nc = 0, h = 0;
+    int b = 0, q = 1, p = 1, n = 1, E = 1, np = 1, qp = 1, nc = 0, h = 0, em = 0;
     int outer = 0, inner_total = 0, it = 0;
     // slot arrays (set in LOAD)
     double *ey = nullptr;
-    const uint32_t *rcell = nullptr;
+    const uint32_t *rpos = nullptr;
     const uint16_t *eptr = nullptr, *erow = nullptr;
     R *ew = nullptr, *Xc = nullptr, *Xn = nullptr, *rcs = nullptr, *bts = nullptr, *nrm = nullptr, *lnorm = nullptr, *beta = nullptr,
       *gam = nullptr;
@@ -442,9 +460,9 @@ template <typename R> __global__ void __launch_bounds__(128, 8) em_pair_kernel(E
             if (ti >= n_list) phase = DONE;
             else {
                 t = A.list[ti];
-                const int e = (int)(t % X.n_em);
+                em = (int)(t % X.n_em);
                 h = (int)(t / X.n_em);
-                b = X.em_blocks[e];
+                b = X.em_blocks[em];
                 q = X.q_off[b + 1] - X.q_off[b]; p = X.p_off[b + 1] - X.p_off[b];
                 qp = q * p;
                 n = A.T.runs[t]; E = A.T.cnt[t];
@@ -452,7 +470,7 @@ template <typename R> __global__ void __launch_bounds__(128, 8) em_pair_kernel(E
                 nc = (int)(A.S.chunk_off[h + 1] - A.S.chunk_off[h]);
                 const BlobLayout BL = blob_layout(n, E);
                 ey = (double *)slot;
-                rcell = (const uint32_t *)(slot + BL.off_cell);
+                rpos = (const uint32_t *)(slot + BL.off_pos);
                 eptr = (const uint16_t *)(slot + BL.off_ptr);
                 erow = (const uint16_t *)(slot + BL.off_row);
                 ew = (R *)(slot + BL.bytes);
@@ -590,13 +608,17 @@ template <typename R> __global__ void __launch_bounds__(128, 8) em_pair_kernel(E
             else { it = 0; phase = INNER; }
         }
 
-        // ================= BT into the result  :1042
+        // ================= BT into the result rows  :1042, and the chunk's share of the column sums
         if (phase == OUT) {
             const int64_t cbase = A.S.chunk_off[h] - A.S.cell_base;
-            const int64_t col0 = X.p_off[b];
             if (hl < n) {
-                double *o = A.out + (cbase + (int64_t)rcell[hl]) * X.n_cols + col0;
+                double *o = A.R.rs_val + A.R.rs_ptr[cbase] + rpos[hl];
                 for (int j = 0; j < p; j++) o[j] = (double)beta[j * n + hl];
+            }
+            if (hl < p) {
+                double cs = 0;
+                for (int a = 0; a < n; a++) cs += (double)beta[hl * n + a];
+                A.R.colpart[(int64_t)(A.S.chunk_base + h) * X.n_emcols + X.em_col0[em] + hl] = cs;
             }
             if (hl == 0) task_done_stats(A.iters, A.stats, t, outer, inner_total, q, p, nc, n);
             __syncwarp(hmask);

@@ -6,13 +6,15 @@
 //   Y --task_count_kernel--> entries / cells-with-counts per (chunk, EM block) "task"
 //     --classify_kernel--> blob size, shared-memory need and work class per task; a scan gives
 //                          the blob offsets
-//   Y --task_scatter_kernel--> one compact blob per task (counts by cell, rows, cell ids)
-//   Y --iso_fill_kernel--> the dense result rows: zeros, and for pass-through blocks (nrow == 1,
-//        Scasa_Rsource.R:979-983) the count itself; tiles built in shared memory, TMA bulk stores
+//   Y --struct_fill_kernel--> the result rows as CSR by cell (struct Result): the columns that can be
+//        non-zero, the pass-through estimates (nrow == 1, Scasa_Rsource.R:979-983: the count itself) and
+//        their column sums; the dense cells x transcripts matrix never exists on the device
+//   Y --task_scatter_kernel--> one compact blob per task (counts by cell, rows, cell ids, result offsets)
 //   blobs --em_task_kernel<W, R>--> the alternating EM (estim_chunk's loop, Rsource:1010-1042): W warps
-//        stage one task in shared memory and run it to the end; persistent, atomic work queue
-//   result --colsum / gene kernels--> per-column sums (step2:167) and gene sums (step3:32-46)
-//   result --compact_rows_kernel--> (column, value) pairs for the zero-suppressed trip to the host
+//        stage one task in shared memory and run it to the end; persistent, atomic work queue; estimates
+//        go straight into the CSR values, their per-chunk column sums into Result::colpart
+//   result --colsum_em_reduce--> per-column sums (step2:167);  --gene_rows_kernel--> gene sums (step3:32-46)
+//        as CSR by cell
 //
 // Why sparse: a cell with no counts in a block keeps beta = 0 through every iteration of
 // estim.BETA and contributes 0 to every sum of estim.X.em, so only (cell, block) pairs with
@@ -83,7 +85,33 @@ struct XDev {                 // resident X-matrix (DM0) and its derived index m
     const uint8_t *poor;      // [n_blocks] poorCondX (Rsource:957-971)
     const int32_t *em_order;  // [n_em]    EM indices, most expensive block shape first (work-queue order)
     const int2 *row_info;     // [n_rows]  {EM index of the row's block or -1, row index inside the block}
-    const int32_t *row_col;   // [n_rows]  first DM0 column of the row's block
+    const int2 *row_aux;      // [n_rows]  {first DM0 column of the row's block, poor blocks before the row's block}
+    const int2 *em_info;      // [n_em]    {columns p | poor << 16, first DM0 column}
+    const int32_t *em_col0;   // [n_em+1]  columns of the EM blocks before this one (index into the per-chunk column sums)
+    const int32_t *poor_rank; // [n_blocks] poor blocks with a smaller block id
+    const int32_t *poor_col0; // [n_poor]  first DM0 column of the k-th poor block
+    int n_poor, n_emcols;
+};
+
+// ---- results -------------------------------------------------------------------------------
+// The reference's result is a dense cells x transcripts matrix that is ~94 % zeros.  Which entries can
+// be non-zero is known as soon as Y is: a cell's pass-through counts, the p columns of every EM block
+// the cell has counts in, and the two columns of every poor block (the +2 pseudo count of Rsource:1004
+// reaches every cell of the chunk).  The result is therefore kept as CSR by cell over exactly this
+// STRUCTURE, columns ascending; the dense matrix only ever exists on the host, when a caller asks for
+// it.  The gene matrix (step3) is CSR by cell too, genes ascending, in rows of the same capacity.
+struct Result {
+    const int64_t *rs_ptr;    // [n_cells+1] first entry of each cell's row
+    int32_t *rs_col;          // [nnz] DM0 column, ascending inside a row
+    double *rs_val;           // [nnz]
+    uint32_t *ypos;           // [nnz of Y] per Y entry: offset inside the cell's row of the entry's column (pass-through)
+                              //            or of the first column of its block (head entry of a run; EM blocks)
+    int32_t *poor_pos;        // [n_cells * n_poor] offset inside the cell's row of the k-th poor block's two columns
+    double *colsum;           // [n_cols] pass-through columns: sum over cells (exact: the counts are integers)
+    double *colpart;          // [n_chunks * n_emcols] EM columns: sum over the chunk's cells, in cell order
+    int32_t *g_col;           // gene CSR: row c occupies [rs_ptr[c], rs_ptr[c] + g_len[c])
+    double *g_val;
+    int32_t *g_len;           // [n_cells]
 };
 
 struct Sample {               // the cells [cell_base, cell_base + n_cells) = chunks [chunk_base, chunk_base + n_chunks)
@@ -104,16 +132,19 @@ struct Sample {               // the cells [cell_base, cell_base + n_cells) = ch
 // the last record is the pseudo cell) and E entries (record-major, rows ascending inside a record;
 // poor blocks store every row of every record).  The blob is what the EM kernel copies verbatim
 // into the head of its shared-memory slot:
-//     ey[E] f64 | rcell[n] u32 | eptr[n+1] u16 | erow[E] u16 | pad to 16
+//     ey[E] f64 | rcell[n] u32 | rpos[n] u32 | eptr[n+1] u16 | erow[E] u16 | pad to 16
 // rcell: cell index inside the chunk, or kPseudo | multiplicity.
+// rpos:  where the record's p estimates go: offset of its first column in the result values, relative to
+//        the first value of the chunk's first cell.
 constexpr uint32_t kPseudo = 0x80000000u;
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
-struct BlobLayout { int off_cell, off_ptr, off_row, bytes; };
+struct BlobLayout { int off_cell, off_pos, off_ptr, off_row, bytes; };
 __host__ __device__ inline BlobLayout blob_layout(int n, int E)
 {
     BlobLayout L;
     L.off_cell = 8 * E;
-    L.off_ptr = L.off_cell + 4 * n;
+    L.off_pos = L.off_cell + 4 * n;
+    L.off_ptr = L.off_pos + 4 * n;
     L.off_row = L.off_ptr + 2 * (n + 1);
     L.bytes = align16(L.off_row + 2 * E);
     return L;
@@ -316,8 +347,9 @@ __global__ void pack_cells_kernel(int64_t n_cells, const int64_t *__restrict__ c
 }
 
 // ------------------------------------------------------------------------------------------
-// Task extents.  One warp per cell: count this cell's entries and runs per (chunk, EM block).
-__global__ void task_count_kernel(XDev X, Sample S, Tasks T)
+// Task extents.  One warp per cell: count this cell's entries and runs per (chunk, EM block), and the size of
+// the cell's result row (pass-through entries + p per non-poor EM block with counts + 2 per poor block).
+__global__ void task_count_kernel(XDev X, Sample S, Tasks T, int32_t *__restrict__ rs_len)
 {
     int64_t cell = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (cell >= S.n_cells) return;
@@ -325,13 +357,83 @@ __global__ void task_count_kernel(XDev X, Sample S, Tasks T)
     const int64_t s = S.y_start[cell];
     const int n = S.y_len[cell];
     const int64_t tbase = (int64_t)(S.cell_chunk[cell] - S.chunk_base) * X.n_em;
+    int w = 0;
     for (int i = lane; i < n; i += kWarp) {
         const int e = X.row_info[S.y_row[s + i]].x;
-        if (e < 0) continue;
+        if (e < 0) { w++; continue; }
         atomicAdd(&T.cnt[tbase + e], 1);
         const bool head = (i == 0) || (X.row_info[S.y_row[s + i - 1]].x != e);
-        if (head) atomicAdd(&T.runs[tbase + e], 1);
+        if (head) {
+            atomicAdd(&T.runs[tbase + e], 1);
+            const int pi = X.em_info[e].x;
+            if (!(pi >> 16)) w += pi & 0xffff;
+        }
     }
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(kFull, w, o);
+    if (lane == 0) rs_len[cell] = w + 2 * X.n_poor;
+}
+
+// The structure of the result rows (see struct Result): columns of every entry a cell's row can hold, the
+// pass-through estimates themselves (nrow(X0) == 1: the count is the estimate, Scasa_Rsource.R:979-983) and
+// their column sums, zeros everywhere else (the EM kernels overwrite their columns).  One warp per cell
+// walks the cell's Y entries in row order = block order = column order; the poor blocks' columns, which
+// every cell carries, are merged in by the lane whose entry is the first behind them.
+__global__ void struct_fill_kernel(XDev X, Sample S, Result R)
+{
+    int64_t cell = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (cell >= S.n_cells) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t s = S.y_start[cell];
+    const int n = S.y_len[cell];
+    const int64_t base = R.rs_ptr[cell];
+    int32_t *ppos = R.poor_pos + cell * X.n_poor;
+    auto put_poor = [&](int k, int pos) {
+        const int c0 = X.poor_col0[k];
+        ppos[k] = pos;
+        R.rs_col[base + pos] = c0; R.rs_col[base + pos + 1] = c0 + 1;
+        R.rs_val[base + pos] = 0.0; R.rs_val[base + pos + 1] = 0.0;
+    };
+    int running = 0;           // entries of non-poor blocks placed so far
+    int carry_e = -2, carry_pb = 0;
+    for (int i0 = 0; i0 < n; i0 += kWarp) {
+        const int i = i0 + lane;
+        const bool valid = i < n;
+        int e = -2, r_col0 = 0, pb = 0;
+        double y = 0.0;
+        if (valid) {
+            const int r = S.y_row[s + i];
+            e = X.row_info[r].x;
+            const int2 aux = X.row_aux[r];
+            r_col0 = aux.x; pb = aux.y;
+            y = S.y_val[s + i];
+        }
+        int prev_e = __shfl_up_sync(kFull, e, 1), lo = __shfl_up_sync(kFull, pb, 1);
+        if (lane == 0) { prev_e = carry_e; lo = carry_pb; }
+        const bool head = valid && (e < 0 || e != prev_e);
+        int p = 0;
+        bool poorb = false;
+        if (head && e >= 0) { const int pi = X.em_info[e].x; p = pi & 0xffff; poorb = (pi >> 16) != 0; }
+        const int w = !valid ? 0 : (e < 0 ? 1 : (head && !poorb ? p : 0));
+        int inc = w;
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += v; }
+        const int pos_np = running + inc - w;
+        if (valid) {
+            for (int k = lo; k < pb; k++) put_poor(k, pos_np + 2 * k);        // poor blocks between the previous entry's block and this one
+            const int pos = pos_np + 2 * pb;
+            R.ypos[s + i] = (uint32_t)pos;
+            if (e < 0) {
+                R.rs_col[base + pos] = r_col0; R.rs_val[base + pos] = y;
+                atomicAdd(&R.colsum[r_col0], y);                              // integer-valued counts: exact in any order
+            } else if (head && !poorb) {
+                for (int j = 0; j < p; j++) { R.rs_col[base + pos + j] = r_col0 + j; R.rs_val[base + pos + j] = 0.0; }
+            }
+        }
+        const int last = min(31, n - 1 - i0);
+        running += __shfl_sync(kFull, inc, 31);
+        carry_e = __shfl_sync(kFull, e, last);
+        carry_pb = __shfl_sync(kFull, pb, last);
+    }
+    for (int k = carry_pb + lane; k < X.n_poor; k += kWarp) put_poor(k, running + 2 * k);   // poor blocks behind the last entry
 }
 
 struct EmOpts {
@@ -482,80 +584,6 @@ __global__ void scan_add_back(const int32_t *__restrict__ in, int64_t n, const i
 }
 
 // ------------------------------------------------------------------------------------------
-// The dense result rows, first pass: zeros everywhere and, for the blocks with a single row
-// (nrow(X0) == 1, Scasa_Rsource.R:979-983), the count itself as the estimate.  One CTA per cell
-// assembles the row tile by tile in shared memory and writes it out coalesced, so the 26.7 GB
-// matrix (100k cells) is written exactly once here; the EM kernel later fills in its columns.
-constexpr int kFillThreads = 512;
-constexpr int kFillTile = 4096;     // doubles per tile (32 KB); two tiles in flight
-constexpr int kFillKeep = 8;        // Y entries a thread keeps in registers across the tiles of a row
-
-// TMA bulk store of a shared-memory tile (cp.async.bulk, UBLKCP in SASS): one thread hands the whole
-// tile to the copy engine; the CTA goes on to build the next tile in the other buffer.
-__device__ __forceinline__ void bulk_store_tile(double *dst, const double *tile, int n_doubles)
-{
-    const uint32_t s = (uint32_t)__cvta_generic_to_shared(tile);
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(s), "r"(n_doubles * 8) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-
-// use_bulk: rows are 16-byte aligned (n_cols even), which the bulk copy needs; otherwise plain stores.
-__global__ void __launch_bounds__(kFillThreads) iso_fill_kernel(XDev X, Sample S, double *__restrict__ out, int use_bulk)
-{
-    extern __shared__ __align__(128) double fill_tile[];      // 2 x kFillTile
-    const int tid = threadIdx.x;
-    int buf = 0;
-    for (int64_t cell = blockIdx.x; cell < S.n_cells; cell += gridDim.x) {
-        const int64_t s = S.y_start[cell];
-        const int n = S.y_len[cell];
-        double *row = out + cell * X.n_cols;
-        int col[kFillKeep];
-        double val[kFillKeep];
-#pragma unroll
-        for (int u = 0; u < kFillKeep; u++) {
-            const int i = tid + u * kFillThreads;
-            col[u] = -1; val[u] = 0.0;
-            if (i < n) {
-                const int r = S.y_row[s + i];
-                if (X.row_info[r].x < 0) { col[u] = X.row_col[r]; val[u] = S.y_val[s + i]; }
-            }
-        }
-        for (int64_t t0 = 0; t0 < X.n_cols; t0 += kFillTile) {
-            const int tn = (int)min((int64_t)kFillTile, X.n_cols - t0);
-            double *tile = fill_tile + buf * kFillTile;
-            // the store that last read this buffer (two tiles ago) must have finished reading it
-            if (use_bulk) {
-                if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                __syncthreads();
-            }
-            for (int i = tid; i < tn; i += kFillThreads) tile[i] = 0.0;
-            __syncthreads();
-#pragma unroll
-            for (int u = 0; u < kFillKeep; u++)
-                if (col[u] >= t0 && col[u] < t0 + tn) tile[col[u] - t0] = val[u];
-            for (int i = tid + kFillKeep * kFillThreads; i < n; i += kFillThreads) {     // cells with very many entries
-                const int r = S.y_row[s + i];
-                if (X.row_info[r].x < 0) {
-                    const int c = X.row_col[r];
-                    if (c >= t0 && c < t0 + tn) tile[c - t0] = S.y_val[s + i];
-                }
-            }
-            if (use_bulk) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the copy engine
-                __syncthreads();
-                if (tid == 0) bulk_store_tile(row + t0, tile, tn);
-                buf ^= 1;
-            } else {
-                __syncthreads();
-                for (int i = tid; i < tn; i += kFillThreads) __stcs(row + t0 + i, tile[i]);
-                __syncthreads();
-            }
-        }
-    }
-    if (use_bulk && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-
-// ------------------------------------------------------------------------------------------
 // Scatter Y into the task blobs.  One CTA per chunk; cells are visited in order so the records
 // of a task are sorted by cell (and their entries by row) without atomics — the order of every
 // later floating-point sum is therefore fixed (same chunk => same bits on any GPU count).
@@ -565,7 +593,7 @@ constexpr int kScatterThreads = 512;
 constexpr int kScatterBatch = 8;                               // entries per thread of a staged cell
 constexpr int kScatterCap = kScatterThreads * kScatterBatch;   // cells with more entries take the unstaged path
 template <bool staged>
-__global__ void __launch_bounds__(kScatterThreads) task_scatter_kernel(XDev X, Sample S, Tasks T, uint32_t *scratch)
+__global__ void __launch_bounds__(kScatterThreads) task_scatter_kernel(XDev X, Sample S, Tasks T, Result R, uint32_t *scratch)
 {
     extern __shared__ uint32_t scatter_sm[];
     const int h = blockIdx.x;
@@ -598,6 +626,7 @@ __global__ void __launch_bounds__(kScatterThreads) task_scatter_kernel(XDev X, S
 
     const int tid = threadIdx.x;
     int row[kScatterBatch], nrow[kScatterBatch];
+    uint32_t pos[kScatterBatch], npos[kScatterBatch];
     int2 inf[kScatterBatch];
     double val[kScatterBatch], nval[kScatterBatch];
     auto load_rows = [&](int64_t s, int n) {
@@ -606,23 +635,26 @@ __global__ void __launch_bounds__(kScatterThreads) task_scatter_kernel(XDev X, S
             const int i = k * kScatterThreads + tid;
             nrow[k] = i < n ? S.y_row[s + i] : -1;
             nval[k] = i < n ? S.y_val[s + i] : 0.0;
+            npos[k] = i < n ? R.ypos[s + i] : 0u;
         }
     };
     auto load_info = [&]() {
 #pragma unroll
         for (int k = 0; k < kScatterBatch; k++) {
-            row[k] = nrow[k]; val[k] = nval[k];
+            row[k] = nrow[k]; val[k] = nval[k]; pos[k] = npos[k];
             inf[k] = row[k] >= 0 ? X.row_info[row[k]] : make_int2(-1, 0);
         }
     };
+    const int64_t vbase = R.rs_ptr[c0];                            // first result value of the chunk
     int64_t s = 0;
     int n = 0;
     if (nc > 0) { s = S.y_start[c0]; n = S.y_len[c0]; }
     if (staged && n <= kScatterCap) { load_rows(s, n); load_info(); }
+    uint32_t crel = 0, crel2 = 0;                                  // the cell's row start relative to vbase
     for (int c = 0; c < nc; c++) {
         int64_t s2 = 0;
         int n2 = 0;
-        if (c + 1 < nc) { s2 = S.y_start[c0 + c + 1]; n2 = S.y_len[c0 + c + 1]; }
+        if (c + 1 < nc) { s2 = S.y_start[c0 + c + 1]; n2 = S.y_len[c0 + c + 1]; crel2 = (uint32_t)(R.rs_ptr[c0 + c + 1] - vbase); }
         const bool next_staged = staged && (c + 1 < nc) && n2 <= kScatterCap;
         if (staged && n <= kScatterCap) {
 #pragma unroll
@@ -637,7 +669,7 @@ __global__ void __launch_bounds__(kScatterThreads) task_scatter_kernel(XDev X, S
             for (int k = 0; k < kScatterBatch; k++) {
                 const int i = k * kScatterThreads + tid;
                 const int e = inf[k].x;
-                if (i >= n || e < 0) continue;                // pass-through block: written by iso_fill_kernel
+                if (i >= n || e < 0) continue;                // pass-through block: written by struct_fill_kernel
                 const uint32_t x = ext[e];
                 const int nrec = (int)(x >> 16), E = (int)(x & 0xffff);
                 if (nrec == 0) continue;                      // task rejected by classify (error flag is set)
@@ -648,6 +680,7 @@ __global__ void __launch_bounds__(kScatterThreads) task_scatter_kernel(XDev X, S
                 char *blob = cdata + ((size_t)boff[e] << 4);
                 double *ey = (double *)blob;
                 uint32_t *rcell = (uint32_t *)(blob + L.off_cell);
+                uint32_t *rpos = (uint32_t *)(blob + L.off_pos);
                 uint16_t *eptr = (uint16_t *)(blob + L.off_ptr);
                 uint16_t *erow = (uint16_t *)(blob + L.off_row);
                 const uint32_t cu = cur[e];
@@ -666,12 +699,13 @@ __global__ void __launch_bounds__(kScatterThreads) task_scatter_kernel(XDev X, S
                             if (kk <= tail && srl[kk] == r) kk++; else ey[k0 + r] = 0.0;
                         }
                         rcell[a] = (uint32_t)c;
+                        rpos[a] = crel + pos[k];
                         eptr[a] = (uint16_t)k0;
                     }
                 } else {
                     ey[k0 + i - head] = val[k];
                     erow[k0 + i - head] = (uint16_t)rl;
-                    if (is_head) { rcell[a] = (uint32_t)c; eptr[a] = (uint16_t)k0; }
+                    if (is_head) { rcell[a] = (uint32_t)c; rpos[a] = crel + pos[k]; eptr[a] = (uint16_t)k0; }
                 }
             }
             __syncthreads();
@@ -696,7 +730,7 @@ __global__ void __launch_bounds__(kScatterThreads) task_scatter_kernel(XDev X, S
             for (int i = threadIdx.x; i < n; i += blockDim.x) {
                 const int2 info = X.row_info[S.y_row[s + i]];
                 const int e = info.x;
-                if (e < 0) continue;               // pass-through block: written by iso_fill_kernel
+                if (e < 0) continue;               // pass-through block: written by struct_fill_kernel
                 const uint32_t x = ext[e];
                 const int nrec = (int)(x >> 16), E = (int)(x & 0xffff);
                 if (nrec == 0) continue;           // task rejected by classify (error flag is set)
@@ -708,6 +742,7 @@ __global__ void __launch_bounds__(kScatterThreads) task_scatter_kernel(XDev X, S
                 char *blob = cdata + ((size_t)boff[e] << 4);
                 double *ey = (double *)blob;
                 uint32_t *rcell = (uint32_t *)(blob + L.off_cell);
+                uint32_t *rpos = (uint32_t *)(blob + L.off_pos);
                 uint16_t *eptr = (uint16_t *)(blob + L.off_ptr);
                 uint16_t *erow = (uint16_t *)(blob + L.off_row);
                 const uint32_t cu = cur[e];
@@ -726,12 +761,13 @@ __global__ void __launch_bounds__(kScatterThreads) task_scatter_kernel(XDev X, S
                             if (k <= tail && X.row_info[S.y_row[s + k]].y == r) k++; else ey[k0 + r] = 0.0;
                         }
                         rcell[a] = (uint32_t)c;
+                        rpos[a] = crel + R.ypos[s + i];
                         eptr[a] = (uint16_t)k0;
                     }
                 } else {
                     ey[k0 + i - head] = v;
                     erow[k0 + i - head] = (uint16_t)rl;
-                    if (is_head) { rcell[a] = (uint32_t)c; eptr[a] = (uint16_t)k0; }
+                    if (is_head) { rcell[a] = (uint32_t)c; rpos[a] = crel + R.ypos[s + i]; eptr[a] = (uint16_t)k0; }
                 }
             }
             __syncthreads();
@@ -750,7 +786,7 @@ __global__ void __launch_bounds__(kScatterThreads) task_scatter_kernel(XDev X, S
             __syncthreads();
             if (next_staged) load_info();
         }
-        s = s2; n = n2;
+        s = s2; n = n2; crel = crel2;
     }
     // close every blob of the chunk (eptr[n] = E); poor tasks get their pseudo cell: all cells of
     // the chunk without counts in the block
@@ -771,6 +807,7 @@ __global__ void __launch_bounds__(kScatterThreads) task_scatter_kernel(XDev X, S
         const int a = nrec - 1, k0 = a * q;
         for (int r = 0; r < q; r++) { ey[k0 + r] = 0.0; erow[k0 + r] = (uint16_t)r; }
         rcell[a] = kPseudo | (uint32_t)(nc - a);
+        ((uint32_t *)(blob + L.off_pos))[a] = 0u;                  // the pseudo cell's values go wherever poor_pos says
         eptr[a] = (uint16_t)k0;
     }
 }
@@ -788,55 +825,118 @@ __device__ __forceinline__ void task_done_stats(int32_t *iters, unsigned long lo
 }
 
 // ------------------------------------------------------------------------------------------
-// Column sums over cells: the rowSums of step2:167 (rows with sum > 0 survive).  Grid = (tiles of
-// kTileCells cells) x (column slices).  A thread owns kFinPerThread fixed columns and adds them for
-// the cells of its tile in order; tiles are then added in order by colsum_reduce, so the sum is a
-// fixed sequence whatever the GPU count.
-constexpr int kTileCells = 128;
-constexpr int kFinThreads = 512;
-constexpr int kFinPerThread = 8;
-constexpr int kFinCols = kFinThreads * kFinPerThread;
-__global__ void __launch_bounds__(kFinThreads) colsum_kernel(const double *__restrict__ iso, int64_t n_cells,
-                                                             int64_t n_cols, double *__restrict__ partial)
+// Column sums over cells: the rowSums of step2:167 (rows with sum > 0 survive).  Pass-through columns
+// are summed by struct_fill_kernel (integer counts: exact).  An EM column's sum over one chunk is taken by
+// the task that produced it, in cell order (Result::colpart); here the chunks are added in chunk order,
+// so the sum is a fixed sequence whatever the GPU count or the queue order.
+__global__ void colsum_em_reduce(const double *__restrict__ colpart, int n_chunks, int n_emcols,
+                                 const int32_t *__restrict__ emcol_col, double *__restrict__ colsum)
 {
-    const int64_t c0 = (int64_t)blockIdx.x * kTileCells;
-    const int64_t c1 = min(c0 + (int64_t)kTileCells, n_cells);
-    const int64_t j0 = (int64_t)blockIdx.y * kFinCols + threadIdx.x;
-    double cs[kFinPerThread];
-#pragma unroll
-    for (int k = 0; k < kFinPerThread; k++) cs[k] = 0.0;
-    for (int64_t c = c0; c < c1; c++) {
-        const double *row = iso + c * n_cols;
-#pragma unroll
-        for (int k = 0; k < kFinPerThread; k++) {
-            const int64_t j = j0 + (int64_t)k * kFinThreads;
-            if (j < n_cols) cs[k] += row[j];
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < kFinPerThread; k++) {
-        const int64_t j = j0 + (int64_t)k * kFinThreads;
-        if (j < n_cols) partial[(int64_t)blockIdx.x * n_cols + j] = cs[k];
-    }
-}
-__global__ void colsum_reduce(const double *__restrict__ partial, int n_tiles, int64_t n_cols,
-                              double *__restrict__ colsum)
-{
-    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_cols) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_emcols) return;
     double s = 0;
-    for (int t = 0; t < n_tiles; t++) s += partial[(int64_t)t * n_cols + j];
-    colsum[j] = s;
+    for (int h = 0; h < n_chunks; h++) s += colpart[(int64_t)h * n_emcols + j];
+    colsum[emcol_col[j]] = s;
 }
 
-// column sums of a run that was cut into ranges: the ranges' sums added in range order
-__global__ void colsum_combine(const double *__restrict__ parts, int n_parts, int64_t n_cols, double *__restrict__ colsum)
+// ------------------------------------------------------------------------------------------
+// scasa_genemat on the sparse rows (scasa_quant_step3_v1.0.0.R:32-46): gene row = column sum over the
+// gene's isoform rows, members added in row order (parasum's colSums, step3:27); single-member genes are
+// copies (step3:38-40).  One CTA per cell: slot[g] = first entry of the cell's row that belongs to gene g
+// (atomicMin on the entry index); that entry's thread adds the gene's later members, which it finds by
+// binary search in the row (columns ascending), so every sum is taken by one thread in column order.
+// The present genes are then emitted in ascending gene order from a bitmap, like the pack kernel does
+// for rows.  Genes are processed in tiles of `tile` genes so that any number of genes fits.
+constexpr int kGeneRowThreads = 512;
+__global__ void __launch_bounds__(kGeneRowThreads) gene_rows_kernel(Result R, int64_t n_cells, int64_t n_cols,
+                                                                    const int32_t *__restrict__ gene_of_col,
+                                                                    const int32_t *__restrict__ gene_ptr,
+                                                                    const int32_t *__restrict__ gene_cols, int n_genes, int tile,
+                                                                    int words_per_thread, double *__restrict__ park_all)
 {
-    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_cols) return;
-    double s = 0;
-    for (int k = 0; k < n_parts; k++) s += parts[(int64_t)k * n_cols + j];
-    colsum[j] = s;
+    extern __shared__ int gene_sm[];
+    int *slot = gene_sm;                                         // [tile] entry index of the gene's first present member
+    unsigned *bits = (unsigned *)(gene_sm + tile);               // [words_per_thread * blockDim.x] genes present
+    __shared__ int wsum[kGeneRowThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int n_words = words_per_thread * (int)blockDim.x;
+    double *park = park_all + (size_t)blockIdx.x * n_cols;       // gene sums by entry index, until their rank is known
+    for (int i = tid; i < tile; i += blockDim.x) slot[i] = 0x7fffffff;
+    for (int i = tid; i < n_words; i += blockDim.x) bits[i] = 0u;
+    __syncthreads();
+    for (int64_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
+        const int64_t base = R.rs_ptr[cell];
+        const int n = (int)(R.rs_ptr[cell + 1] - base);
+        const int32_t *col = R.rs_col + base;
+        const double *val = R.rs_val + base;
+        int emitted = 0;
+        for (int g0 = 0; g0 < n_genes; g0 += tile) {
+            for (int i = tid; i < n; i += blockDim.x) {
+                const int g = gene_of_col[col[i]] - g0;
+                if (g >= 0 && g < tile) { atomicMin(&slot[g], i); atomicOr(&bits[g >> 5], 1u << (g & 31)); }
+            }
+            __syncthreads();
+            // the thread of a gene's first present member adds the later ones, in column order
+            for (int i = tid; i < n; i += blockDim.x) {
+                const int ci = col[i];
+                const int g = gene_of_col[ci];
+                const int gl = g - g0;
+                if (gl < 0 || gl >= tile || slot[gl] != i) continue;
+                double sum = val[i];
+                const int m1 = gene_ptr[g + 1];
+                for (int m = gene_ptr[g]; m < m1; m++) {
+                    const int cm = gene_cols[m];
+                    if (cm <= ci) continue;
+                    int lo = i + 1, hi = n;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (col[mid] < cm) lo = mid + 1; else hi = mid; }
+                    if (lo < n && col[lo] == cm) sum += val[lo];
+                }
+                park[i] = sum;
+            }
+            __syncthreads();
+            // emission in gene order; thread owns words [tid*wpt, (tid+1)*wpt)
+            const int w0 = tid * words_per_thread;
+            int cnt = 0;
+            for (int k = 0; k < words_per_thread; k++) cnt += __popc(bits[w0 + k]);
+            int inc = cnt;
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += v; }
+            if (lane == 31) wsum[w] = inc;
+            __syncthreads();
+            int before = 0, total = 0;
+            for (int k = 0; k < (int)(blockDim.x >> 5); k++) { const int v = wsum[k]; if (k < w) before += v; total += v; }
+            int64_t o = base + emitted + before + inc - cnt;
+            if (cnt)
+                for (int k = 0; k < words_per_thread; k++) {
+                    unsigned m = bits[w0 + k];
+                    bits[w0 + k] = 0u;
+                    while (m) {
+                        const int gl = ((w0 + k) << 5) + __ffs(m) - 1;
+                        m &= m - 1;
+                        const int i = slot[gl];
+                        slot[gl] = 0x7fffffff;
+                        R.g_col[o] = gl + g0; R.g_val[o] = park[i]; o++;
+                    }
+                }
+            emitted += total;
+            __syncthreads();
+        }
+        if (tid == 0) R.g_len[cell] = emitted;
+    }
+}
+
+// rows [r0, r0 + n) of a CSR result -> dense rows (testing aid: SCASA_FETCH_DENSE); len == nullptr: full rows
+__global__ void expand_rows_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ len, const int32_t *__restrict__ col,
+                                   const double *__restrict__ val, int64_t r0, int64_t n, int64_t n_cols, double *__restrict__ out)
+{
+    for (int64_t r = blockIdx.x; r < n; r += gridDim.x) {
+        double *o = out + r * n_cols;
+        for (int64_t j = threadIdx.x; j < n_cols; j += blockDim.x) o[j] = 0.0;
+        __syncthreads();
+        const int64_t b = ptr[r0 + r];
+        const int m = len ? len[r0 + r] : (int)(ptr[r0 + r + 1] - b);
+        for (int i = threadIdx.x; i < m; i += blockDim.x) o[col[b + i]] = val[b + i];
+        __syncthreads();
+    }
 }
 
 // scasa_genemat as a gather: one thread per (cell, gene), members read straight from the isoform row in
@@ -872,73 +972,6 @@ __global__ void __launch_bounds__(kGeneThreads) gene_gather_kernel(const double 
     for (int u = 0; u < kGeneIlp; u++) {
         const int g = g0 + u * kGeneThreads;
         if (g < n_genes) out[g] = sum[u];
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// Zero suppression for the trip to the host.  The reference's results are dense matrices that are
-// > 90 % zeros; the fetch entry points send (column, value) pairs instead of the dense rows and the
-// host re-expands them with streaming stores (scasa_cuda.cu: fetch_dense).  One CTA per row:
-// pass A counts the row's non-zeros and reserves its slice with one atomic, pass B (the row is in L2
-// by then) writes the pairs in ascending column order.  "Non-zero" is the bit pattern, so -0.0 and
-// NaN survive the round trip: the expanded matrix is bit-identical to the dense one.
-constexpr int kCompThreads = 512;
-constexpr int kCompPer = 8;
-__global__ void __launch_bounds__(kCompThreads) compact_rows_kernel(const double *__restrict__ dense, int64_t n_rows,
-                                                                    int64_t n_cols, unsigned long long *cursor,
-                                                                    unsigned long long cap, int64_t *__restrict__ row_start,
-                                                                    int32_t *__restrict__ row_nnz, int32_t *__restrict__ cols,
-                                                                    double *__restrict__ vals)
-{
-    __shared__ int wsum[kCompThreads / 32];
-    __shared__ unsigned long long s_base;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    constexpr int kTile = kCompThreads * kCompPer;
-    for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
-        const double *r = dense + row * n_cols;
-        // pass A
-        int cnt = 0;
-        for (int64_t j = tid; j < n_cols; j += kCompThreads) cnt += __double_as_longlong(r[j]) != 0;
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(kFull, cnt, o);
-        if (lane == 0) wsum[w] = cnt;
-        __syncthreads();
-        if (tid == 0) {
-            int total = 0;
-            for (int k = 0; k < kCompThreads / 32; k++) total += wsum[k];
-            unsigned long long base = atomicAdd(cursor, (unsigned long long)total);
-            if (base + (unsigned long long)total > cap) { base = ~0ull; total = -1; }   // does not fit: the host copies this batch densely
-            row_start[row] = (int64_t)base;
-            row_nnz[row] = total;
-            s_base = base;
-        }
-        __syncthreads();
-        const unsigned long long base = s_base;
-        if (base == ~0ull) continue;
-        // pass B: thread owns kCompPer consecutive columns of each tile
-        unsigned long long running = base;
-        for (int64_t j0 = 0; j0 < n_cols; j0 += kTile) {
-            const int64_t jb = j0 + (int64_t)tid * kCompPer;
-            double v[kCompPer];
-            int c = 0;
-#pragma unroll
-            for (int u = 0; u < kCompPer; u++) {
-                v[u] = jb + u < n_cols ? r[jb + u] : 0.0;
-                c += __double_as_longlong(v[u]) != 0;
-            }
-            int inc = c;
-            for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += x; }
-            __syncthreads();                       // wsum of the previous tile / pass A has been read
-            if (lane == 31) wsum[w] = inc;
-            __syncthreads();
-            int before = 0, total = 0;
-            for (int k = 0; k < kCompThreads / 32; k++) { const int x = wsum[k]; if (k < w) before += x; total += x; }
-            unsigned long long pos = running + before + inc - c;
-#pragma unroll
-            for (int u = 0; u < kCompPer; u++)
-                if (__double_as_longlong(v[u]) != 0) { cols[pos] = (int32_t)(jb + u); vals[pos] = v[u]; pos++; }
-            running += total;
-        }
-        __syncthreads();
     }
 }
 

@@ -46,7 +46,7 @@ class Timing(C.Structure):
                 ("n_active", C.c_int64), ("inner_iters", C.c_int64), ("outer_iters", C.c_int64),
                 ("alg_bytes", C.c_double), ("em_alg_bytes", C.c_double), ("launches", C.c_int32),
                 ("max_slot_bytes", C.c_int32), ("run_parts", C.c_int32), ("em_pair_ms", C.c_float),
-                ("em_pair_tasks", C.c_int64)]
+                ("em_pair_tasks", C.c_int64), ("result_nnz", C.c_int64)]
 
     def as_dict(self) -> dict:
         d = {}
@@ -64,6 +64,7 @@ SYMBOLS = (
     "scasa_fetch_iso", "scasa_fetch_iters", "scasa_fetch_colsum", "scasa_fetch_counts", "scasa_set_gene_map",
     "scasa_fetch_gene", "scasa_gene_sum", "scasa_eqclass_map", "scasa_last_timing", "scasa_host_alloc",
     "scasa_host_free", "scasa_device_count", "scasa_version", "scasa_set_host_threads", "scasa_expand_pairs", "scasa_quant", "scasa_transfer_bytes", "scasa_bfh_open", "scasa_bfh_close", "scasa_bfh_sizes", "scasa_bfh_read", "scasa_bus_open", "scasa_write_table", "scasa_format_real15", "scasa_set_run_parts", "scasa_eqclass_map_host",
+    "scasa_result_nnz", "scasa_fetch_iso_csr", "scasa_fetch_gene_csr",
 )
 
 
@@ -117,6 +118,9 @@ def load():
     L.scasa_transfer_bytes.argtypes = [vp, i64p, i64p, C.c_int32]
     L.scasa_quant.argtypes = [vp, C.c_int64, C.c_int32, i64p, i64p, i32p, i32p, C.c_int64, i32p, f64p, f64p, f64p, i32p, C.c_int32]
     L.scasa_fetch_iso.argtypes = [vp, f64p]
+    L.scasa_result_nnz.argtypes = [vp, i64p, i64p]
+    L.scasa_fetch_iso_csr.argtypes = [vp, i64p, i32p, f64p]
+    L.scasa_fetch_gene_csr.argtypes = [vp, i64p, i32p, f64p]
     L.scasa_fetch_iters.argtypes = [vp, i32p]
     L.scasa_fetch_colsum.argtypes = [vp, f64p]
     L.scasa_fetch_counts.argtypes = [vp, i64p, i32p, f64p, C.c_int64, i64p]

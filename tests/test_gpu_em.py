@@ -153,6 +153,56 @@ def test_colsum_and_gene_sums(gpu, xm, oracle, c1):
     assert np.array_equal(gpu.fetch_gene(), got)
 
 
+def test_sparse_results_equal_the_dense_ones(gpu, xm, oracle, c1):
+    """The device keeps the results as CSR by cell over the entries that can be non-zero.  The CSR rows
+    (columns strictly ascending, every poor block's two columns present in every cell) expand to exactly
+    the dense matrices the fetch entry points return; the gene rows are the sums of the isoform rows."""
+    from scasa_b200.api import chunk_split
+    rowptr, rows, vals = c1
+    chunks = chunk_split(200, 4)
+    gpu.set_opts()
+    keep = np.ones(xm.n_cols, bool)
+    goc, nmem, names = oracle.gene_layout([xm.gene_names[g] for g in xm.gene_of_col], keep)
+    gpu.set_gene_map(goc, len(names))
+    gpu.stage_counts(chunks, rowptr, rows, vals)
+    gpu.run()
+    iso, gene, colsum = gpu.fetch_iso(), gpu.fetch_gene(), gpu.fetch_colsum()
+    rp, rc, rv = gpu.fetch_iso_csr()
+    n = 200
+    assert rp[0] == 0 and rp[-1] == len(rc) == gpu.result_nnz()[0]
+    cell = np.repeat(np.arange(n), np.diff(rp))
+    d = np.diff(rc)
+    inner = np.ones(len(rc), bool)
+    inner[rp[1:-1]] = False
+    assert np.all(d[inner[1:]] > 0)                                      # ascending inside every row
+    dense = np.zeros((n, xm.n_cols))
+    dense[cell, rc] = rv
+    assert np.array_equal(dense.view(np.int64), iso.view(np.int64))
+    poor_cols = np.flatnonzero(np.repeat(gpu.poor_blocks(), np.diff(xm.dm0_p_off)))
+    present = np.zeros((n, xm.n_cols), bool)
+    present[cell, rc] = True
+    assert present[:, poor_cols].all()
+    assert (np.diff(rp) < 0.2 * xm.n_cols).all()                         # sparse: a few thousand of 33,428 columns per cell
+    # column sums: sums of the matrix (cell order within a chunk, chunks in order)
+    cs = iso.sum(axis=0)
+    assert np.max(np.abs(colsum - cs) / np.maximum(np.abs(cs), 1e-300)) < 1e-12
+    assert np.array_equal(colsum > 0, oracle.keep_rows(iso))
+    # genes
+    gp, gg, gv = gpu.fetch_gene_csr()
+    gcell = np.repeat(np.arange(n), np.diff(gp))
+    gd = np.diff(gg)
+    ginner = np.ones(len(gg), bool)
+    ginner[gp[1:-1]] = False
+    assert np.all(gd[ginner[1:]] > 0)
+    gdense = np.zeros((n, len(names)))
+    gdense[gcell, gg] = gv
+    assert np.array_equal(gdense.view(np.int64), gene.view(np.int64))
+    want = oracle.gene_sum(iso, goc, nmem)
+    single = nmem == 1
+    assert np.array_equal(gene[:, single], want[:, single])              # copies are bit-exact (step3:38-40)
+    assert np.max(np.abs(gene - want) / np.maximum(np.abs(want), 1e-9)) < 1e-12
+
+
 def test_large_resampled_xmatrix_uses_the_general_paths(xm, oracle):
     """Config C3's shape ("GRCh38.106-like": more blocks than the shipped X-matrix).  With 110k
     blocks the row histogram no longer fits in shared memory (pack_cells_kernel, the sort path) and
