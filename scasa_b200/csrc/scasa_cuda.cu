@@ -214,7 +214,9 @@ struct scasa_ctx {
     int host_threads = 0;        // 0 = hardware concurrency
     int fetch_dense_copy = 0;    // 1 = plain dense D2H (SCASA_FETCH_DENSE)
     int n_genes = 0;
-    int gene_tile = 0, gene_ctas_per_sm = 1;   // gene_rows_kernel: genes per pass (shared-memory slots), resident CTAs
+    int gene_tile = 0, gene_ctas_per_sm = 2;   // gene_rows_kernel: genes per pass (shared-memory slots), resident CTAs
+    int gene_max_members = 1;
+    DBuf<int2> d_col_gene;                     // per column: {gene or -1, position among the gene's members}
     DBuf<int32_t> d_gene_ptr, d_gene_cols;
     scasa_timing_t timing{};
 };
@@ -605,7 +607,7 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
         }
         if (getenv("SCASA_FETCH_DENSE")) c->fetch_dense_copy = 1;
         if (const char *env = getenv("SCASA_GENE_TILE")) {      // "genes per pass[:ctas_per_sm]" of gene_rows_kernel
-            int t = 0, cps = 1;
+            int t = 0, cps = 2;
             const int got = sscanf(env, "%d:%d", &t, &cps);
             if (got >= 1 && t > 0) c->gene_tile = t;
             if (got >= 2 && cps >= 1) c->gene_ctas_per_sm = cps;
@@ -724,7 +726,7 @@ void scasa_ctx_destroy(scasa_ctx *c)
     for (auto b : f64) b->release();
     c->d_poor.release(); c->d_next.release(); c->d_stats.release(); c->d_flag.release();
     c->d_tdata.release(); c->d_counters.release(); c->d_row_info.release(); c->d_row_aux.release(); c->d_em_info.release();
-    c->d_scatter_scratch.release(); c->d_ypos.release();
+    c->d_scatter_scratch.release(); c->d_ypos.release(); c->d_col_gene.release();
     for (auto &b : c->fb) {
         if (b.h_cols) { cudaFreeHost(b.h_cols); cudaFreeHost(b.h_vals); cudaFreeHost(b.h_start); cudaFreeHost(b.h_nnz); }
         if (b.done) cudaEventDestroy(b.done);
@@ -871,6 +873,17 @@ int scasa_set_gene_map(scasa_ctx *c, const int32_t *gene_of_col, int32_t n_genes
         c->d_gene_cols.ensure(cols.size() + 1);
         c->d_gene_cols.upload(cols, c->stream);
         c->d_gene_of_col.upload(goc, c->stream);
+        {
+            std::vector<int2> cg((size_t)c->n_cols, make_int2(-1, 0));
+            int mx = 1;
+            for (int g = 0; g < n_genes; g++)
+                for (int m = ptr[(size_t)g]; m < ptr[(size_t)g + 1]; m++) {
+                    cg[(size_t)cols[(size_t)m]] = make_int2(g, m - ptr[(size_t)g]);
+                    mx = std::max(mx, m - ptr[(size_t)g] + 1);
+                }
+            c->gene_max_members = mx;
+            c->d_col_gene.upload(cg, c->stream);
+        }
         CK(cudaStreamSynchronize(c->stream));
     });
 }
@@ -1081,17 +1094,25 @@ static void run_all(scasa_ctx *c, RangeStats &rs)
     }
     CK(cudaEventRecord(w->ev[4], s));
     if (c->n_genes > 0) {
-        // genes per pass: everything when the slots fit in shared memory
+        // genes per pass: everything when the slots fit in shared memory; 16-bit slots when no row can hold 65535 entries
+        const bool small = c->n_cols < 65535;
+        const int cps = std::max(1, c->gene_ctas_per_sm);
+        const size_t budget = (size_t)(216 * 1024) / cps - 1024 - (size_t)kGeneAcc * 8;
         int tile = c->gene_tile > 0 ? std::min(c->gene_tile, c->n_genes) : c->n_genes;
-        const int max_tile = (int)((200 * 1024 / std::max(1, c->gene_ctas_per_sm) - 4096) / 4.2);
-        tile = std::min(tile, max_tile);
+        tile = (int)std::min<size_t>((size_t)tile, (size_t)(budget / (small ? 2.2 : 4.2)));
         const int wpt = ((tile + 31) / 32 + kGeneRowThreads - 1) / kGeneRowThreads;
-        const size_t smem = (size_t)tile * 4 + (size_t)wpt * kGeneRowThreads * 4;
-        const int grid = (int)std::min<int64_t>(n_cells, (int64_t)w->n_sm * c->gene_ctas_per_sm);
+        const size_t smem = (size_t)kGeneAcc * 8 + (size_t)wpt * kGeneRowThreads * 4 + (size_t)tile * (small ? 2 : 4);
+        const int grid = (int)std::min<int64_t>(n_cells, (int64_t)w->n_sm * cps);
         c->d_gene_park.ensure((size_t)grid * c->n_cols);
-        CK(cudaFuncSetAttribute(gene_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gene_rows_kernel<<<grid, kGeneRowThreads, smem, s>>>(R, n_cells, c->n_cols, c->d_gene_of_col.p, c->d_gene_ptr.p, c->d_gene_cols.p,
-                                                            c->n_genes, tile, wpt, c->d_gene_park.p);
+        if (small) {
+            CK(cudaFuncSetAttribute(gene_rows_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gene_rows_kernel<uint16_t><<<grid, kGeneRowThreads, smem, s>>>(R, n_cells, c->n_cols, c->d_col_gene.p, c->n_genes, tile, wpt,
+                                                                          c->gene_max_members, c->d_gene_park.p);
+        } else {
+            CK(cudaFuncSetAttribute(gene_rows_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gene_rows_kernel<int32_t><<<grid, kGeneRowThreads, smem, s>>>(R, n_cells, c->n_cols, c->d_col_gene.p, c->n_genes, tile, wpt,
+                                                                         c->gene_max_members, c->d_gene_park.p);
+        }
         CK(cudaGetLastError());
         launches++;
         c->ran_genes = true;

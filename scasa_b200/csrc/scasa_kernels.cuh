@@ -842,26 +842,31 @@ __global__ void colsum_em_reduce(const double *__restrict__ colpart, int n_chunk
 // ------------------------------------------------------------------------------------------
 // scasa_genemat on the sparse rows (scasa_quant_step3_v1.0.0.R:32-46): gene row = column sum over the
 // gene's isoform rows, members added in row order (parasum's colSums, step3:27); single-member genes are
-// copies (step3:38-40).  One CTA per cell: slot[g] = first entry of the cell's row that belongs to gene g
-// (atomicMin on the entry index); that entry's thread adds the gene's later members, which it finds by
-// binary search in the row (columns ascending), so every sum is taken by one thread in column order.
-// The present genes are then emitted in ascending gene order from a bitmap, like the pack kernel does
-// for rows.  Genes are processed in tiles of `tile` genes so that any number of genes fits.
+// copies (step3:38-40).  One CTA per cell.  col_gene[j] = {gene of column j or -1, position of j among the
+// gene's members}.  The row is processed in ROUNDS by member position: in round r the entries that are the
+// r-th member of their gene either open the gene (slot[g] = entry, acc = value) or add their value to it.
+// A gene has at most one entry per round, so there is no race and every sum is taken in member = column
+// order, whatever the thread count.  The present genes are then emitted in ascending gene order from a
+// bitmap, like the pack kernel does for rows.  Genes are processed in tiles of `tile` genes so that any
+// number of genes fits; T = uint16_t when a row cannot have 65535 entries (two CTAs per SM fit then).
 constexpr int kGeneRowThreads = 512;
-__global__ void __launch_bounds__(kGeneRowThreads) gene_rows_kernel(Result R, int64_t n_cells, int64_t n_cols,
-                                                                    const int32_t *__restrict__ gene_of_col,
-                                                                    const int32_t *__restrict__ gene_ptr,
-                                                                    const int32_t *__restrict__ gene_cols, int n_genes, int tile,
-                                                                    int words_per_thread, double *__restrict__ park_all)
+constexpr int kGeneKeep = 6;                 // entries a thread keeps in registers across the rounds
+constexpr int kGeneAcc = 4096;               // rows up to this length accumulate in shared memory, longer ones in HBM
+template <typename T>
+__global__ void __launch_bounds__(kGeneRowThreads, 2) gene_rows_kernel(Result R, int64_t n_cells, int64_t n_cols,
+                                                                    const int2 *__restrict__ col_gene, int n_genes, int tile,
+                                                                    int words_per_thread, int max_members,
+                                                                    double *__restrict__ park_all)
 {
-    extern __shared__ int gene_sm[];
-    int *slot = gene_sm;                                         // [tile] entry index of the gene's first present member
-    unsigned *bits = (unsigned *)(gene_sm + tile);               // [words_per_thread * blockDim.x] genes present
+    extern __shared__ __align__(16) unsigned char gene_sm_raw[];
+    constexpr T kEmpty = (T)~(T)0;
+    double *acc_sm = (double *)gene_sm_raw;                                        // [kGeneAcc]
+    unsigned *bits = (unsigned *)(acc_sm + kGeneAcc);                              // [words_per_thread * blockDim.x] genes present
+    const int n_words = words_per_thread * (int)blockDim.x;
+    T *slot = (T *)(bits + n_words);                                               // [tile] entry that opened the gene
     __shared__ int wsum[kGeneRowThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int n_words = words_per_thread * (int)blockDim.x;
-    double *park = park_all + (size_t)blockIdx.x * n_cols;       // gene sums by entry index, until their rank is known
-    for (int i = tid; i < tile; i += blockDim.x) slot[i] = 0x7fffffff;
+    for (int i = tid; i < tile; i += blockDim.x) slot[i] = kEmpty;
     for (int i = tid; i < n_words; i += blockDim.x) bits[i] = 0u;
     __syncthreads();
     for (int64_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
@@ -869,41 +874,43 @@ __global__ void __launch_bounds__(kGeneRowThreads) gene_rows_kernel(Result R, in
         const int n = (int)(R.rs_ptr[cell + 1] - base);
         const int32_t *col = R.rs_col + base;
         const double *val = R.rs_val + base;
+        double *acc = n <= kGeneAcc ? acc_sm : park_all + (size_t)blockIdx.x * n_cols;
+        int2 cg[kGeneKeep];
+        double v[kGeneKeep];
+#pragma unroll
+        for (int k = 0; k < kGeneKeep; k++) {
+            const int i = tid + k * kGeneRowThreads;
+            cg[k] = make_int2(-1, 0); v[k] = 0.0;
+            if (i < n) { cg[k] = col_gene[col[i]]; v[k] = val[i]; }
+        }
         int emitted = 0;
         for (int g0 = 0; g0 < n_genes; g0 += tile) {
-            for (int i = tid; i < n; i += blockDim.x) {
-                const int g = gene_of_col[col[i]] - g0;
-                if (g >= 0 && g < tile) { atomicMin(&slot[g], i); atomicOr(&bits[g >> 5], 1u << (g & 31)); }
+            for (int r = 0; r < max_members; r++) {
+                bool more = false;
+                auto visit = [&](int i, int2 c, double x) {
+                    const int gl = c.x - g0;
+                    if (c.x < 0 || gl < 0 || gl >= tile) return;
+                    if (c.y > r) { more = true; return; }
+                    if (c.y < r) return;
+                    const T sl = slot[gl];
+                    if (sl == kEmpty) { slot[gl] = (T)i; acc[i] = x; atomicOr(&bits[gl >> 5], 1u << (gl & 31)); }
+                    else acc[sl] += x;
+                };
+#pragma unroll
+                for (int k = 0; k < kGeneKeep; k++) visit(tid + k * kGeneRowThreads, cg[k], v[k]);
+                for (int i = tid + kGeneKeep * kGeneRowThreads; i < n; i += kGeneRowThreads) visit(i, col_gene[col[i]], val[i]);
+                if (!__syncthreads_or(more)) break;
             }
-            __syncthreads();
-            // the thread of a gene's first present member adds the later ones, in column order
-            for (int i = tid; i < n; i += blockDim.x) {
-                const int ci = col[i];
-                const int g = gene_of_col[ci];
-                const int gl = g - g0;
-                if (gl < 0 || gl >= tile || slot[gl] != i) continue;
-                double sum = val[i];
-                const int m1 = gene_ptr[g + 1];
-                for (int m = gene_ptr[g]; m < m1; m++) {
-                    const int cm = gene_cols[m];
-                    if (cm <= ci) continue;
-                    int lo = i + 1, hi = n;
-                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (col[mid] < cm) lo = mid + 1; else hi = mid; }
-                    if (lo < n && col[lo] == cm) sum += val[lo];
-                }
-                park[i] = sum;
-            }
-            __syncthreads();
             // emission in gene order; thread owns words [tid*wpt, (tid+1)*wpt)
             const int w0 = tid * words_per_thread;
             int cnt = 0;
             for (int k = 0; k < words_per_thread; k++) cnt += __popc(bits[w0 + k]);
             int inc = cnt;
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += v; }
+            for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += x; }
             if (lane == 31) wsum[w] = inc;
             __syncthreads();
             int before = 0, total = 0;
-            for (int k = 0; k < (int)(blockDim.x >> 5); k++) { const int v = wsum[k]; if (k < w) before += v; total += v; }
+            for (int k = 0; k < (int)(blockDim.x >> 5); k++) { const int x = wsum[k]; if (k < w) before += x; total += x; }
             int64_t o = base + emitted + before + inc - cnt;
             if (cnt)
                 for (int k = 0; k < words_per_thread; k++) {
@@ -912,9 +919,9 @@ __global__ void __launch_bounds__(kGeneRowThreads) gene_rows_kernel(Result R, in
                     while (m) {
                         const int gl = ((w0 + k) << 5) + __ffs(m) - 1;
                         m &= m - 1;
-                        const int i = slot[gl];
-                        slot[gl] = 0x7fffffff;
-                        R.g_col[o] = gl + g0; R.g_val[o] = park[i]; o++;
+                        const int i = (int)slot[gl];
+                        slot[gl] = kEmpty;
+                        R.g_col[o] = gl + g0; R.g_val[o] = acc[i]; o++;
                     }
                 }
             emitted += total;

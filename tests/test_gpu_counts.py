@@ -248,9 +248,10 @@ def test_bfh_file_to_quant_equals_arrays(xm, tmp_path):
     assert np.array_equal(r1.iters, r0.iters)
 
 
-def test_run_parts_do_not_change_results(xm):
-    """scasa_run cuts the staged chunks into ranges that run side by side on two stream sets
-    (EM kernels of one range next to the bandwidth-bound kernels of another): bitwise the same."""
+def test_repeated_runs_are_bitwise_reproducible(xm):
+    """Task order in the work queues, and which warp runs which task, differ from run to run; no result may
+    depend on it: three runs of the same staged sample give the same bits (estimates, gene sums, iteration
+    counts, column sums, counts).  scasa_set_run_parts is retired and must stay a harmless no-op."""
     from scasa_b200 import synth
     from scasa_b200.api import Scasa, chunk_split
     n = 730
@@ -263,17 +264,13 @@ def test_run_parts_do_not_change_results(xm):
         eq_row = g.eqclass_map(ed.eq_off, ed.eq_tx, 4)
         g.stage_eqcounts(chunk_split(n, 4), cell_ptr, eq_id, eq_cnt, eq_row)
         out = {}
-        for parts in (1, 2, 5, 7):
+        for parts in (1, 2, 5):
             g.set_run_parts(parts)
-            t = g.run()
-            assert t["run_parts"] == parts
-            out[parts] = (g.fetch_iso(), g.fetch_gene(), g.fetch_iters(), g.fetch_colsum(), g.fetch_counts())
-        for parts in (2, 5, 7):
-            for a, b in zip(out[parts][:3], out[1][:3]):
+            g.run()
+            out[parts] = (g.fetch_iso(), g.fetch_gene(), g.fetch_iters(), g.fetch_colsum(), *g.fetch_counts())
+        for parts in (2, 5):
+            for a, b in zip(out[parts], out[1]):
                 assert np.array_equal(a.view(np.int64) if a.dtype == np.float64 else a, b.view(np.int64) if b.dtype == np.float64 else b), parts
-            assert np.allclose(out[parts][3], out[1][3], rtol=1e-12, atol=0)
-            for a, b in zip(out[parts][4], out[1][4]):
-                assert np.array_equal(a, b)
     finally:
         g.close()
 
