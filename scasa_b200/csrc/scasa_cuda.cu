@@ -152,7 +152,7 @@ struct scasa_ctx {
     std::vector<double> x;
     std::vector<uint8_t> poor;
     int64_t poor_rows = 0;           // sum of q over poor blocks
-    DBuf<int32_t> d_q_off, d_p_off, d_em_blocks, d_em_order, d_em_col0, d_poor_rank, d_poor_col0, d_emcol_col;
+    DBuf<int32_t> d_q_off, d_p_off, d_em_blocks, d_em_order, d_em_col0, d_poor_rank, d_poor_col0, d_emcol_col, d_col_emcol;
     DBuf<int2> d_row_info, d_row_aux, d_em_info;
     DBuf<uint32_t> d_scatter_scratch;
     DBuf<int64_t> d_x_off;
@@ -172,6 +172,7 @@ struct scasa_ctx {
 
     // ---- task arrays
     DBuf<int32_t> d_cnt, d_runs, d_tbytes, d_iters, d_list[kLists];
+    DBuf<int4> d_desc;
     DBuf<int64_t> d_toff, d_scan_sums, d_totals;
     DBuf<char> d_tdata;
     DBuf<unsigned int> d_next, d_counters;
@@ -185,6 +186,7 @@ struct scasa_ctx {
     int cls_ctas_per_sm[kClasses] = {8, 4, 2, 2};
     int pair_max = 16;                // tiny tasks two per warp (em_pair_kernel); SCASA_EM_PAIR=0 turns it off
     int pair_ctas_per_sm = 8;
+    int em_big_n = 24, em_big_row = 12, em_prefetch = 1;   // SCASA_EM_BIG="n:rowlen", SCASA_EM_PREFETCH=0|1 (tuning; see EmOpts)
     DBuf<unsigned long long> d_stats;
     DBuf<int> d_flag;
 
@@ -305,6 +307,7 @@ Tasks tdev(scasa_ctx *c)
     T.toff = c->d_toff.p;
     T.tdata = c->d_tdata.p;
     for (int k = 0; k < kLists; k++) T.list[k] = c->d_list[k].p;
+    T.desc = c->d_desc.p;
     T.counters = c->d_counters.p;
     return T;
 }
@@ -600,6 +603,7 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
                 int k = c->em_blocks[e];
                 int64_t q = c->q_off[k + 1] - c->q_off[k], p = c->p_off[k + 1] - c->p_off[k];
                 if (p > 1024) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a block may have at most 1024 columns"};
+                if (c->x_off[(size_t)k] > 0x7fffffff) throw ArgErr{SCASA_ERR_UNSUPPORTED, "the X-matrix may hold at most 2^31 values"};
                 cost[(size_t)e] = q * p * p;
             }
             std::stable_sort(c->em_order.begin(), c->em_order.end(),
@@ -635,6 +639,8 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
             if (got >= 1) c->pair_max = std::max(0, std::min(16, m));
             if (got >= 2 && cps >= 1) c->pair_ctas_per_sm = cps;
         }
+        if (const char *env = getenv("SCASA_EM_BIG")) { int a = 24, b = 12; if (sscanf(env, "%d:%d", &a, &b) >= 1) { c->em_big_n = a; c->em_big_row = b; } }
+        if (const char *env = getenv("SCASA_EM_PREFETCH")) c->em_prefetch = atoi(env) != 0;
         for (int k = 0; k < kLists; k++) {
             {   // the classes with few, long tasks get scheduling priority: their CTAs go first when an SM has room,
                 // the many-small-tasks class fills what is left and takes over when they are done
@@ -686,6 +692,9 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
             c->d_poor_rank.upload(poor_rank, c->stream);
             c->d_poor_col0.ensure(poor_col0.size() + 1); c->d_poor_col0.upload(poor_col0, c->stream);
             c->d_emcol_col.ensure(emcol_col.size() + 1); c->d_emcol_col.upload(emcol_col, c->stream);
+            std::vector<int32_t> col_emcol((size_t)c->n_cols, -1);
+            for (size_t j = 0; j < emcol_col.size(); j++) col_emcol[(size_t)emcol_col[j]] = (int32_t)j;
+            c->d_col_emcol.upload(col_emcol, c->stream);
         }
         c->d_next.ensure(16); c->d_counters.ensure(8); c->d_stats.ensure(8); c->d_totals.ensure(4); c->d_flag.ensure(1);
         CK(cudaStreamSynchronize(c->stream));
@@ -712,7 +721,7 @@ void scasa_ctx_destroy(scasa_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DBuf<int32_t> *i32[] = {&c->d_q_off, &c->d_p_off, &c->d_em_blocks, &c->d_em_order, &c->d_em_col0, &c->d_poor_rank, &c->d_poor_col0,
-                            &c->d_emcol_col, &c->d_cell_chunk, &c->d_y_len, &c->d_y_row, &c->d_eq_id, &c->d_eq_count, &c->d_eq_row,
+                            &c->d_emcol_col, &c->d_col_emcol, &c->d_cell_chunk, &c->d_y_len, &c->d_y_row, &c->d_eq_id, &c->d_eq_count, &c->d_eq_row,
                             &c->d_cnt, &c->d_runs, &c->d_tbytes, &c->d_iters,
                             &c->d_list[0], &c->d_list[1], &c->d_list[2], &c->d_list[3], &c->d_list[4],
                             &c->d_gene_ptr, &c->d_gene_cols, &c->d_rs_len, &c->d_rs_col, &c->d_poor_pos, &c->d_g_col, &c->d_g_len,
@@ -726,7 +735,7 @@ void scasa_ctx_destroy(scasa_ctx *c)
     for (auto b : f64) b->release();
     c->d_poor.release(); c->d_next.release(); c->d_stats.release(); c->d_flag.release();
     c->d_tdata.release(); c->d_counters.release(); c->d_row_info.release(); c->d_row_aux.release(); c->d_em_info.release();
-    c->d_scatter_scratch.release(); c->d_ypos.release(); c->d_col_gene.release();
+    c->d_scatter_scratch.release(); c->d_ypos.release(); c->d_col_gene.release(); c->d_desc.release();
     for (auto &b : c->fb) {
         if (b.h_cols) { cudaFreeHost(b.h_cols); cudaFreeHost(b.h_vals); cudaFreeHost(b.h_start); cudaFreeHost(b.h_nnz); }
         if (b.done) cudaEventDestroy(b.done);
@@ -909,6 +918,7 @@ static void run_all(scasa_ctx *c, RangeStats &rs)
     w->d_cnt.ensure((size_t)n_tasks + 1); w->d_runs.ensure((size_t)n_tasks + 1);
     w->d_tbytes.ensure((size_t)n_tasks + 1); w->d_toff.ensure((size_t)n_tasks + 1);
     for (int k = 0; k < kLists; k++) w->d_list[k].ensure((size_t)n_tasks + 1);
+    w->d_desc.ensure((size_t)n_tasks + 1);
     c->d_rs_len.ensure((size_t)n_cells + 1); c->d_rs_ptr.ensure((size_t)n_cells + 1);
     c->d_poor_pos.ensure((size_t)n_cells * std::max(1, c->n_poor));
     c->d_ypos.ensure((size_t)c->nnz + 1);
@@ -923,7 +933,6 @@ static void run_all(scasa_ctx *c, RangeStats &rs)
     CK(cudaMemsetAsync(w->d_counters.p, 0, 8 * sizeof(unsigned int), s));
     CK(cudaMemsetAsync(w->d_flag.p, 0, sizeof(int), s));
     CK(cudaMemsetAsync(c->d_colsum.p, 0, (size_t)c->n_cols * sizeof(double), s));
-    CK(cudaMemsetAsync(c->d_colpart.p, 0, (size_t)n_chunks * std::max(1, c->n_emcols) * sizeof(double), s));
 
     // ---- pack: eqclass counts -> Y
     if (c->have_eq) {
@@ -959,6 +968,7 @@ static void run_all(scasa_ctx *c, RangeStats &rs)
     O.fixed_iter = c->opts.fixed_iter;
     O.maxerr = c->opts.maxerr; O.lim = c->opts.lim; O.adjust_esp = c->opts.adjust_esp;
     O.maxerr_bt = c->opts.maxerr_bt; O.lim_bt = c->opts.lim_bt;
+    O.big_n = std::max(17, c->em_big_n); O.big_row = std::max(1, c->em_big_row); O.prefetch = c->em_prefetch;
     ClassCfg CC;
     for (int k = 0; k < kClasses; k++) { CC.pairs[k] = c->cls_pairs[k]; CC.bytes[k] = c->cls_bytes[k]; }
     CC.real_bytes = c->opts.fp32 ? 4 : 8;
@@ -1088,6 +1098,11 @@ static void run_all(scasa_ctx *c, RangeStats &rs)
 
     // ---- column sums of the EM columns (chunks in order), gene sums
     if (c->n_emcols > 0) {
+        const int cs_tile = std::min(c->n_emcols, 12288);          // 96 KB of column slots: two CTAs per SM
+        const size_t cs_smem = (size_t)cs_tile * sizeof(double);
+        CK(cudaFuncSetAttribute(colsum_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
+        colsum_chunk_kernel<<<n_chunks, kColsumThreads, cs_smem, s>>>(S, R, c->d_col_emcol.p, c->n_emcols, cs_tile);
+        launches++;
         colsum_em_reduce<<<(unsigned)((c->n_emcols + 255) / 256), 256, 0, s>>>(c->d_colpart.p, n_chunks, c->n_emcols, c->d_emcol_col.p,
                                                                               c->d_colsum.p);
         launches++;
@@ -1151,6 +1166,7 @@ static int sync_twin(scasa_ctx *c)
         t->cls_cta_threads[k] = c->cls_cta_threads[k]; t->cls_ctas_per_sm[k] = c->cls_ctas_per_sm[k];
     }
     t->pair_max = c->pair_max; t->pair_ctas_per_sm = c->pair_ctas_per_sm;
+    t->em_big_n = c->em_big_n; t->em_big_row = c->em_big_row; t->em_prefetch = c->em_prefetch;
     if (c->n_genes > 0 && (t->n_genes != c->n_genes || t->gene_of_col_host != c->gene_of_col_host)) {
         int rc = scasa_set_gene_map(t, c->gene_of_col_host.data(), c->n_genes);
         if (rc) return fail(c, rc, std::string("twin context: ") + scasa_last_error(t));

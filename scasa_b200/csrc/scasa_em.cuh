@@ -56,7 +56,7 @@ struct EmArgs {
     Sample S;
     Tasks T;
     EmOpts O;
-    Result R;                     // estimates go into R.rs_val, per-chunk column sums into R.colpart
+    Result R;                     // estimates go into R.rs_val
     int32_t *iters;
     unsigned long long *stats;
     const int32_t *list;          // task ids of this work class
@@ -118,14 +118,17 @@ template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_k
         }
         if (ti >= n_list) break;
         const int64_t t = A.list[ti];
-        const int e = (int)(t % X.n_em), h = (int)(t / X.n_em);
-        const int b = X.em_blocks[e];
-        const int q = X.q_off[b + 1] - X.q_off[b], p = X.p_off[b + 1] - X.p_off[b];
+        const int h = (int)(t / X.n_em);
+        const int4 td = A.T.desc[t];                                  // block, shape and extents in one load
+        const int64_t blob_off = A.T.toff[t];
+        const int64_t cb0 = A.S.chunk_off[h], cb1 = A.S.chunk_off[h + 1];
+        const int b = td.x;
+        const int q = td.y & 0xffff, p = td.y >> 16;
         const int qp = q * p;
-        const int n = A.T.runs[t], E = A.T.cnt[t];
+        const int n = td.z & 0xffff, E = (int)((unsigned)td.z >> 16);
         const int np = n * p;
         const bool poor = X.poor[b] != 0;
-        const int nc = (int)(A.S.chunk_off[h + 1] - A.S.chunk_off[h]);
+        const int nc = (int)(cb1 - cb0);
         const BlobLayout BL = blob_layout(n, E);
 
         // ---- carve the slot
@@ -142,10 +145,10 @@ template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_k
 
         // ---- stage: blob image, X.est0 = X0 (:1011)
         {
-            const uint4 *src = (const uint4 *)(A.T.tdata + A.T.toff[t]);
+            const uint4 *src = (const uint4 *)(A.T.tdata + blob_off);
             uint4 *dst = (uint4 *)slot;
             for (int i = gl; i < (BL.bytes >> 4); i += GT) dst[i] = __ldcs(src + i);
-            const double *X0 = X.x + X.x_off[b];
+            const double *X0 = X.x + td.w;
             for (int k = gl; k < qp; k += GT) Xc[k] = (R)X0[k];
         }
         G.sync();
@@ -154,6 +157,7 @@ template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_k
         const int ap = (last_cw & kPseudo) ? n - 1 : -1;
         const R pmult = (last_cw & kPseudo) ? (R)(last_cw & 0xffff) : R(0);
         const int n_real = ap >= 0 ? n - 1 : n;
+        const bool big = n >= O.big_n && E >= O.big_row * q;   // sums over cells split over eight lanes (big_n > 16: never in em_pair_kernel)
         for (int a = gl; a < n; a += GT) {
             const int k1 = eptr[a + 1];
             for (int k = eptr[a]; k < k1; k++) erec[k] = (uint16_t)a;
@@ -211,7 +215,7 @@ template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_k
                 rs[r] = (R)s;
             }
             G.sync();
-            const double *X0 = X.x + X.x_off[b];
+            const double *X0 = X.x + td.w;
             double tot = 0;
             for (int r = 0; r < q; r++) tot += (double)rs[r];
             int best = -1;
@@ -304,12 +308,32 @@ template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_k
             }
 
             // ================= estim.X.em(X.est0, BT, Ymat)  :898-922
-            for (int j = gl; j < p; j += GT) {                                   // BTsum = colSums(BETA)  :904
-                R s = 0;
+            if (!big) {
+                for (int j = gl; j < p; j += GT) {                               // BTsum = colSums(BETA)  :904
+                    R s = 0;
 #pragma unroll 1
-                for (int a = 0; a < n_real; a++) s += beta[j * n + a];
-                if (ap >= 0) s += pmult * beta[j * n + ap];                      // the pseudo cell stands for pmult cells
-                bts[j] = s > 0 ? s : R(0.1);                                     // :917 (may be denormal: no reciprocal)
+                    for (int a = 0; a < n_real; a++) s += beta[j * n + a];
+                    if (ap >= 0) s += pmult * beta[j * n + ap];                  // the pseudo cell stands for pmult cells
+                    bts[j] = s > 0 ? s : R(0.1);                                 // :917 (may be denormal: no reciprocal)
+                }
+            } else {
+                // many cells: eight lanes per column, lane s adds the cells a = s, s + 8, ... in order, then the
+                // eight partial sums are added in lane order: a fixed association that only depends on n
+#pragma unroll 1
+                for (int base = 0; base < 8 * p; base += GT) {
+                    const int idx = base + gl, j = idx >> 3, s8 = idx & 7;
+                    R part = 0;
+                    if (j < p)
+#pragma unroll 1
+                        for (int a = s8; a < n_real; a += 8) part += beta[j * n + a];
+                    R s = part;
+#pragma unroll
+                    for (int k = 1; k < 8; k++) { const R v = __shfl_sync(kFull, part, (lane & ~7) + k); s += v; }
+                    if (j < p && s8 == 0) {
+                        if (ap >= 0) s += pmult * beta[j * n + ap];
+                        bts[j] = s > 0 ? s : R(0.1);
+                    }
+                }
             }
 #pragma unroll 1
             for (int k = gl; k < E; k += GT) {
@@ -321,19 +345,45 @@ template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_k
                 ew[k] = mult * (R)ey[k] / (mu > 0 ? mu : R(0.1));                // :908-910
             }
             G.sync();
+            if (!big) {
 #pragma unroll 1
-            for (int idx = gl, j = xj_first, r = xr_first; idx < qp; idx += GT) {   // X.est = colSums(x2 * Y) / BTsum  :911-917
-                const R x = Xc[idx];
-                R acc = 0;
-                const int i1 = rptr[r + 1];
+                for (int idx = gl, j = xj_first, r = xr_first; idx < qp; idx += GT) {   // X.est = colSums(x2 * Y) / BTsum  :911-917
+                    const R x = Xc[idx];
+                    R acc = 0;
+                    const int i1 = rptr[r + 1];
 #pragma unroll 1
-                for (int i = rptr[r]; i < i1; i++) {
-                    const int k = perm[i];
-                    acc += beta[j * n + erec[k]] * x * ew[k];
+                    for (int i = rptr[r]; i < i1; i++) {
+                        const int k = perm[i];
+                        acc += beta[j * n + erec[k]] * x * ew[k];
+                    }
+                    Xn[idx] = acc == R(0) ? R(0) : acc / bts[j];                 // zero numerators would take the slow division path
+                    r += dxr; j += dxj;
+                    if (r >= q) { r -= q; j++; }
                 }
-                Xn[idx] = acc == R(0) ? R(0) : acc / bts[j];                     // zero numerators would take the slow division path
-                r += dxr; j += dxj;
-                if (r >= q) { r -= q; j++; }
+            } else {
+                // eight lanes per X element: lane s takes the row's entries i = s, s + 8, ... (cell order), partial sums
+                // added in lane order
+#pragma unroll 1
+                for (int base = 0; base < 8 * qp; base += GT) {
+                    const int idx8 = base + gl, idx = idx8 >> 3, s8 = idx8 & 7;
+                    R part = 0;
+                    int j = 0;
+                    if (idx < qp) {
+                        j = idx / q;
+                        const int r = idx - j * q;
+                        const R x = Xc[idx];
+                        const int i1 = rptr[r + 1];
+#pragma unroll 1
+                        for (int i = rptr[r] + s8; i < i1; i += 8) {
+                            const int k = perm[i];
+                            part += beta[j * n + erec[k]] * x * ew[k];
+                        }
+                    }
+                    R acc = part;
+#pragma unroll
+                    for (int k = 1; k < 8; k++) { const R v = __shfl_sync(kFull, part, (lane & ~7) + k); acc += v; }
+                    if (idx < qp && s8 == 0) Xn[idx] = acc == R(0) ? R(0) : acc / bts[j];
+                }
             }
             G.sync();
             for (int j = gl; j < p; j += GT) {                                   // csum = colSums(X.est)  :918
@@ -370,7 +420,7 @@ template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_k
 
         // ---- de-adjust (:1027-1037) and write BT into the result rows (:1042)
         const double deduct = nadj * O.adjust_esp;
-        const int64_t cbase = A.S.chunk_off[h] - A.S.cell_base;
+        const int64_t cbase = cb0 - A.S.cell_base;
         double *vals = A.R.rs_val + A.R.rs_ptr[cbase];                           // the chunk's first value; rpos is relative to it
         for (int a = gl; a < n; a += GT) {
             const uint32_t cw = rcell[a];
@@ -397,21 +447,6 @@ template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_k
                     for (int j = 0; j < p; j++) { double v = (double)beta[j * n + ap]; if (nadj > 0) v = v - deduct * (v / s); o[j] = v; }
                 }
             }
-        }
-        // ---- this chunk's share of the column sums (step2:167), records in cell order; the pseudo cell counts pmult times
-        for (int j = gl; j < p; j += GT) {
-            double cs = 0;
-#pragma unroll 1
-            for (int a = 0; a < n; a++) {
-                double v = (double)beta[j * n + a];
-                if (nadj > 0) {
-                    double s = 0;
-                    for (int jj = 0; jj < p; jj++) s += (double)beta[jj * n + a];
-                    v = v - deduct * (v / s);
-                }
-                cs += a == ap ? (double)pmult * v : v;
-            }
-            A.R.colpart[(int64_t)(A.S.chunk_base + h) * X.n_emcols + X.em_col0[e] + j] = cs;
         }
         if (gl == 0) task_done_stats(A.iters, A.stats, t, outer, inner_total, q, p, nc, n);
         G.sync();
@@ -441,8 +476,9 @@ template <typename R> __global__ void __launch_bounds__(128, 8) em_pair_kernel(E
 
     int phase = LOAD;
     int64_t t = 0;
-    int b = 0, q = 1, p = 1, n = 1, E = 1, np = 1, qp = 1, nc = 0, h = 0, em = 0;
+    int q = 1, p = 1, n = 1, E = 1, np = 1, qp = 1, nc = 0;
     int outer = 0, inner_total = 0, it = 0;
+    double *vals = nullptr;                                    // first result value of the task's chunk
     // slot arrays (set in LOAD)
     double *ey = nullptr;
     const uint32_t *rpos = nullptr;
@@ -451,23 +487,45 @@ template <typename R> __global__ void __launch_bounds__(128, 8) em_pair_kernel(E
       *gam = nullptr;
     uint16_t *erec = nullptr, *rptr = nullptr, *perm = nullptr;
 
+    // The next task is fetched one task ahead: ticket, task id, descriptor, blob offset, chunk extent and the
+    // chunk's result offset are four dependent memory round trips, which are in flight while the current task
+    // iterates.  nt < 0: the queue is empty.
+    int64_t nt = -1, n_off = 0, n_vb = 0;
+    int4 nd = make_int4(0, 0, 0, 0);
+    int n_nc = 0;
+    auto fetch_next = [&]() {
+        unsigned ti = 0;
+        if (hl == 0) ti = atomicAdd(A.next, 1u);
+        ti = __shfl_sync(hmask, ti, hlead);
+        nt = -1;
+        if (ti < n_list) {
+            nt = A.list[ti];
+            const int hh = (int)(nt / X.n_em);
+            nd = A.T.desc[nt];
+            n_off = A.T.toff[nt];
+            const int64_t c0 = A.S.chunk_off[hh], c1 = A.S.chunk_off[hh + 1];
+            n_nc = (int)(c1 - c0);
+            n_vb = A.R.rs_ptr[c0 - A.S.cell_base];
+        }
+    };
+    if (O.prefetch) fetch_next();
+
     for (;;) {
         // ================= LOAD: next task of the queue into this half's slot
         if (phase == LOAD) {
-            unsigned ti = 0;
-            if (hl == 0) ti = atomicAdd(A.next, 1u);
-            ti = __shfl_sync(hmask, ti, hlead);
-            if (ti >= n_list) phase = DONE;
+            if (!O.prefetch) fetch_next();
+            if (nt < 0) phase = DONE;
             else {
-                t = A.list[ti];
-                em = (int)(t % X.n_em);
-                h = (int)(t / X.n_em);
-                b = X.em_blocks[em];
-                q = X.q_off[b + 1] - X.q_off[b]; p = X.p_off[b + 1] - X.p_off[b];
+                t = nt;
+                const int4 td = nd;
+                const int64_t blob_off = n_off;
+                nc = n_nc;
+                vals = A.R.rs_val + n_vb;
+                if (O.prefetch) fetch_next();                  // for the task after this one
+                q = td.y & 0xffff; p = td.y >> 16;
                 qp = q * p;
-                n = A.T.runs[t]; E = A.T.cnt[t];
+                n = td.z & 0xffff; E = (int)((unsigned)td.z >> 16);
                 np = n * p;
-                nc = (int)(A.S.chunk_off[h + 1] - A.S.chunk_off[h]);
                 const BlobLayout BL = blob_layout(n, E);
                 ey = (double *)slot;
                 rpos = (const uint32_t *)(slot + BL.off_pos);
@@ -478,10 +536,10 @@ template <typename R> __global__ void __launch_bounds__(128, 8) em_pair_kernel(E
                 beta = lnorm + n; gam = beta + np;
                 erec = (uint16_t *)(gam + np); rptr = erec + E; perm = rptr + q + 1;
                 {
-                    const uint4 *src = (const uint4 *)(A.T.tdata + A.T.toff[t]);
+                    const uint4 *src = (const uint4 *)(A.T.tdata + blob_off);
                     uint4 *dst = (uint4 *)slot;
                     for (int i = hl; i < (BL.bytes >> 4); i += 16) dst[i] = __ldcs(src + i);
-                    const double *X0 = X.x + X.x_off[b];
+                    const double *X0 = X.x + td.w;
                     if (hl < qp) Xc[hl] = (R)X0[hl];
                 }
                 __syncwarp(hmask);
@@ -608,17 +666,11 @@ template <typename R> __global__ void __launch_bounds__(128, 8) em_pair_kernel(E
             else { it = 0; phase = INNER; }
         }
 
-        // ================= BT into the result rows  :1042, and the chunk's share of the column sums
+        // ================= BT into the result rows  :1042
         if (phase == OUT) {
-            const int64_t cbase = A.S.chunk_off[h] - A.S.cell_base;
             if (hl < n) {
-                double *o = A.R.rs_val + A.R.rs_ptr[cbase] + rpos[hl];
+                double *o = vals + rpos[hl];
                 for (int j = 0; j < p; j++) o[j] = (double)beta[j * n + hl];
-            }
-            if (hl < p) {
-                double cs = 0;
-                for (int a = 0; a < n; a++) cs += (double)beta[hl * n + a];
-                A.R.colpart[(int64_t)(A.S.chunk_base + h) * X.n_emcols + X.em_col0[em] + hl] = cs;
             }
             if (hl == 0) task_done_stats(A.iters, A.stats, t, outer, inner_total, q, p, nc, n);
             __syncwarp(hmask);

@@ -108,7 +108,7 @@ struct Result {
                               //            or of the first column of its block (head entry of a run; EM blocks)
     int32_t *poor_pos;        // [n_cells * n_poor] offset inside the cell's row of the k-th poor block's two columns
     double *colsum;           // [n_cols] pass-through columns: sum over cells (exact: the counts are integers)
-    double *colpart;          // [n_chunks * n_emcols] EM columns: sum over the chunk's cells, in cell order
+    double *colpart;          // [n_chunks * n_emcols] EM columns: sum over the chunk's cells, in cell order (colsum_chunk_kernel)
     int32_t *g_col;           // gene CSR: row c occupies [rs_ptr[c], rs_ptr[c] + g_len[c])
     double *g_val;
     int32_t *g_len;           // [n_cells]
@@ -173,6 +173,8 @@ struct Tasks {                // task t = chunk * n_em + em index
     int32_t *tbytes;          // [n_tasks] blob bytes
     int64_t *toff;            // [n_tasks+1] exclusive scan of tbytes
     char *tdata;              // blobs
+    int4 *desc;               // [n_tasks] {block, q | p << 16, records n | entries E << 16, first X value of the block}: what an EM
+                              //           group needs to know about a task, in one 16-byte load (non-empty tasks only)
     int32_t *list[kLists];    // task ids per work class (+ the tiny-task list), expensive block shapes first
     unsigned int *counters;   // [0..3] list lengths [4] non-empty tasks [5] largest slot need [6] tiny-task list length [7] error flag
 };
@@ -440,6 +442,9 @@ struct EmOpts {
     int maxiter_x, maxiter_bt, modify, fixed_iter;
     double maxerr, lim, adjust_esp;     // maxerr / lim: the outer test (Rsource:1019-1020)
     double maxerr_bt, lim_bt;           // estim.BETA's own (Rsource:726-727; not forwarded by estim_chunk)
+    int big_n, big_row;                 // tasks with >= big_n records and >= big_row entries per block row on average split
+                                        // their sums over cells over eight lanes (a fixed association; see em_task_kernel)
+    int prefetch;                       // em_pair_kernel fetches the next task's descriptor one task ahead
 };
 
 // Per task: records, stored entries, blob size, work class.  Threads enumerate tasks block-major
@@ -478,6 +483,7 @@ __global__ void classify_kernel(XDev X, Sample S, Tasks T, int64_t n_tasks, EmOp
             T.runs[t] = n;
             T.cnt[t] = E;
             T.tbytes[t] = blob_layout(n, E).bytes;
+            T.desc[t] = make_int4(b, q | (p << 16), n | (E << 16), (int)X.x_off[b]);
             if (n > 0) {
                 need = (unsigned)slot_bytes_of(q, p, n, E, C.real_bytes);
                 cls = kClasses - 1;
@@ -826,9 +832,56 @@ __device__ __forceinline__ void task_done_stats(int32_t *iters, unsigned long lo
 
 // ------------------------------------------------------------------------------------------
 // Column sums over cells: the rowSums of step2:167 (rows with sum > 0 survive).  Pass-through columns
-// are summed by struct_fill_kernel (integer counts: exact).  An EM column's sum over one chunk is taken by
-// the task that produced it, in cell order (Result::colpart); here the chunks are added in chunk order,
-// so the sum is a fixed sequence whatever the GPU count or the queue order.
+// are summed by struct_fill_kernel (integer counts: exact).  EM columns: colsum_chunk_kernel, one CTA per
+// chunk, walks the chunk's result rows in cell order and adds every EM entry to its column's slot in
+// shared memory (a row holds a column at most once: no conflict inside a cell; a barrier between cells),
+// which gives the chunk's sums in cell order (Result::colpart); colsum_em_reduce then adds the chunks in
+// chunk order.  The sum is a fixed sequence whatever the GPU count or the queue order.
+constexpr int kColsumThreads = 512;
+__global__ void __launch_bounds__(kColsumThreads) colsum_chunk_kernel(Sample S, Result R, const int32_t *__restrict__ col_emcol,
+                                                                      int n_emcols, int tile)
+{
+    extern __shared__ double colsum_sm[];                         // [tile] EM columns j0 .. j0 + tile of this pass
+    const int h = blockIdx.x;
+    const int64_t c0 = S.chunk_off[h] - S.cell_base, c1 = S.chunk_off[h + 1] - S.cell_base;
+    double *out = R.colpart + (int64_t)(S.chunk_base + h) * n_emcols;
+    constexpr int K = 6;
+    int col[K];
+    double val[K];
+    auto load = [&](int64_t b0, int64_t e0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const int64_t i = b0 + threadIdx.x + (int64_t)k * kColsumThreads;
+            col[k] = -1; val[k] = 0.0;
+            if (i < e0) { col[k] = col_emcol[R.rs_col[i]]; val[k] = R.rs_val[i]; }
+        }
+    };
+    for (int j0 = 0; j0 < n_emcols; j0 += tile) {                 // one pass unless the X-matrix has very many EM columns
+        const int jn = min(tile, n_emcols - j0);
+        for (int j = threadIdx.x; j < jn; j += blockDim.x) colsum_sm[j] = 0.0;
+        __syncthreads();
+        // the next cell's entries are loaded while this cell's are added
+        int64_t b = c0 < c1 ? R.rs_ptr[c0] : 0, e = c0 < c1 ? R.rs_ptr[c0 + 1] : 0;
+        load(b, e);
+        for (int64_t c = c0; c < c1; c++) {
+            int jj[K];
+            double vv[K];
+#pragma unroll
+            for (int k = 0; k < K; k++) { jj[k] = col[k] - j0; vv[k] = val[k]; }
+            const int64_t b0 = b, e0 = e;
+            if (c + 1 < c1) { b = e; e = R.rs_ptr[c + 2]; load(b, e); }
+#pragma unroll
+            for (int k = 0; k < K; k++) if (jj[k] >= 0 && jj[k] < jn) colsum_sm[jj[k]] += vv[k];
+            for (int64_t i = b0 + threadIdx.x + (int64_t)K * kColsumThreads; i < e0; i += kColsumThreads) {
+                const int j = col_emcol[R.rs_col[i]] - j0;
+                if (j >= 0 && j < jn) colsum_sm[j] += R.rs_val[i];
+            }
+            __syncthreads();
+        }
+        for (int j = threadIdx.x; j < jn; j += blockDim.x) out[j0 + j] = colsum_sm[j];
+        __syncthreads();
+    }
+}
 __global__ void colsum_em_reduce(const double *__restrict__ colpart, int n_chunks, int n_emcols,
                                  const int32_t *__restrict__ emcol_col, double *__restrict__ colsum)
 {
