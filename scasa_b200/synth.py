@@ -194,6 +194,28 @@ def resample_xmatrix(xm: XMatrix, n_blocks: int, seed: int, min_q: int = 1, min_
     p_all = np.diff(xm.dm0_p_off)
     pool = np.nonzero((q_all >= min_q) & (p_all >= min_p))[0]
     pick = pool[rng.integers(0, len(pool), n_blocks)]
+    return assemble_xmatrix(xm, pick)
+
+
+def heavy_multimapping_xmatrix(xm: XMatrix, seed: int, min_q: int = 8, min_p: int = 4) -> XMatrix:
+    """BASELINE config C5 (SURVEY.md §8 d): the shipped block list with every EM block (nrow > 1) replaced by a
+    draw from the shipped blocks with q >= 8 rows and p >= 4 merged columns (up to 53 x 14 / 50 x 20);
+    pass-through blocks stay where they are."""
+    rng = np.random.default_rng(seed + 49979687)
+    q_all = np.diff(xm.q_off)
+    p_all = np.diff(xm.dm0_p_off)
+    pool = np.nonzero((q_all >= min_q) & (p_all >= min_p))[0]
+    pick = np.arange(xm.n_blocks)
+    em = np.nonzero(q_all > 1)[0]
+    pick[em] = pool[rng.integers(0, len(pool), len(em))]
+    return assemble_xmatrix(xm, pick)
+
+
+def assemble_xmatrix(xm: XMatrix, pick: np.ndarray) -> XMatrix:
+    """The X-matrix whose i-th block is a copy of block pick[i] of xm, with fresh transcript ids."""
+    n_blocks = len(pick)
+    q_all = np.diff(xm.q_off)
+    p_all = np.diff(xm.dm0_p_off)
     q = q_all[pick]
     pd = p_all[pick]
     pc = np.diff(xm.crp_p_off)[pick]
