@@ -123,6 +123,17 @@ int scasa_quant(scasa_ctx *ctx, int64_t n_cells, int32_t n_chunks, const int64_t
                 const int32_t *eq_row, double *iso_out, double *gene_out, double *colsum_out,
                 int32_t *iters_out, int32_t n_slices);
 
+/* The same over several GPUs of one box — what `registerDoParallel(cores = core)` + the two `foreach ... %dopar%`
+ * loops of scasa_quant_step2_v1.0.0.R:82-136 are to the reference: ctxs[r] was created on device r with the same
+ * X-matrix (options and the gene map are taken from ctxs[0]).  Contiguous chunk ranges per GPU balanced by their
+ * number of (cell, eqclass) entries, one host thread per GPU, every GPU writes its own rows of the caller's
+ * matrices; no collective (chunks are independent).  Every output, column sums included, is bitwise what one
+ * GPU gives. */
+int scasa_quant_multi(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off,
+                      const int64_t *cell_ptr, const int32_t *eq_id, const int32_t *eq_count, int64_t n_eq,
+                      const int32_t *eq_row, double *iso_out, double *gene_out, double *colsum_out,
+                      int32_t *iters_out, int32_t n_slices);
+
 /* ---- the same in resident stages (what scasa_estimate is made of) ----------------------- */
 int scasa_stage_counts(scasa_ctx *ctx, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off,
                        const int64_t *y_rowptr, const int32_t *y_rowidx, const double *y_val);

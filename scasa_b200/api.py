@@ -301,9 +301,12 @@ class Scasa:
         return out
 
     def quant(self, cell_ptr, eq_id, eq_count, eq_off, eq_tx, core: int = 4, gene_of_col=None, n_genes: int = 0,
-              n_threads: int = 8, n_slices: int = 0, iso_out=None, gene_out=None, want_iters: bool = True) -> QuantResult:
+              n_threads: int = 8, n_slices: int = 0, iso_out=None, gene_out=None, want_iters: bool = True,
+              peers=()) -> QuantResult:
         """step2's two foreach bodies (+ step3's gene sums) for a whole sample: one scasa_quant call
-        (host buffers in and out; chunks processed in slices that overlap compute and transfer)."""
+        (host buffers in and out; chunks processed in slices that overlap compute and transfer).
+        peers: further Scasa contexts on other GPUs of the box (same X-matrix): one scasa_quant_multi call,
+        contiguous chunk ranges per GPU, results bitwise those of one GPU."""
         cell_ptr = np.ascontiguousarray(cell_ptr, np.int64)
         eq_id = np.ascontiguousarray(eq_id, np.int32)
         eq_count = np.ascontiguousarray(eq_count, np.int32)
@@ -319,13 +322,17 @@ class Scasa:
             gene = gene_out if gene_out is not None else np.empty((n_cells, self.n_genes), np.float64)
         colsum = np.empty(self.n_cols, np.float64)
         iters = np.empty((self.n_chunks, self.n_em, 2), np.int32) if want_iters else None
-        self._ck(self._L.scasa_quant(self._ctx, n_cells, self.n_chunks, _l.ptr(chunks, C.c_int64), _l.ptr(cell_ptr, C.c_int64),
-                                     _l.ptr(eq_id, C.c_int32), _l.ptr(eq_count, C.c_int32), len(eq_row),
-                                     _l.ptr(eq_row, C.c_int32), _l.ptr(iso, C.c_double),
-                                     _l.ptr(gene, C.c_double) if gene is not None else None,
-                                     _l.ptr(colsum, C.c_double), _l.ptr(iters, C.c_int32) if iters is not None else None,
-                                     n_slices))
-        return QuantResult(iso, gene, colsum, iters, {"n_slices": n_slices})
+        tail = (n_cells, self.n_chunks, _l.ptr(chunks, C.c_int64), _l.ptr(cell_ptr, C.c_int64),
+                _l.ptr(eq_id, C.c_int32), _l.ptr(eq_count, C.c_int32), len(eq_row),
+                _l.ptr(eq_row, C.c_int32), _l.ptr(iso, C.c_double),
+                _l.ptr(gene, C.c_double) if gene is not None else None,
+                _l.ptr(colsum, C.c_double), _l.ptr(iters, C.c_int32) if iters is not None else None, n_slices)
+        if peers:
+            arr = (C.c_void_p * (1 + len(peers)))(self._ctx, *[p._ctx for p in peers])
+            self._ck(self._L.scasa_quant_multi(arr, len(arr), *tail))
+        else:
+            self._ck(self._L.scasa_quant(self._ctx, *tail))
+        return QuantResult(iso, gene, colsum, iters, {"n_slices": n_slices, "n_gpus": 1 + len(peers)})
 
 
 def dense_to_csr(y_dense: np.ndarray):

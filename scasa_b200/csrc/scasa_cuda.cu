@@ -1420,33 +1420,45 @@ int scasa_estimate(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const int64_
     return rc;
 }
 
-// One call for a whole sample, host buffers in and out: the chunks are cut into slices and the
-// slices alternate between this context and a twin on the same GPU, each driven by its own host
-// thread: while one slice's results are expanded into the caller's matrices (host-memory bound)
-// the next slice is staged and computed.  Chunks are independent, so slicing changes no result;
-// device memory is sized by the slice, not by the sample.
-int scasa_quant(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off, const int64_t *cell_ptr,
-                const int32_t *eq_id, const int32_t *eq_count, int64_t n_eq, const int32_t *eq_row, double *iso_out,
-                double *gene_out, double *colsum_out, int32_t *iters_out, int32_t n_slices)
+// ---- one call for a whole sample -------------------------------------------------------------------------
+// What a quant call can deliver per slice of chunks.  Dense matrices are expanded into the caller's buffers;
+// the sparse sinks receive the slice's CSR rows as they are on the device (for callers that never want the
+// dense form: the text writers).
+struct SparseSink {                       // CSR by cell of the whole sample, assembled from the slices
+    std::vector<int64_t> rowptr;          // [n_cells+1], filled per slice with slice-local offsets; finish() makes them global
+    std::vector<std::vector<int32_t>> cols;   // per slice
+    std::vector<std::vector<double>> vals;
+    std::vector<int64_t> slice_c0, slice_c1;
+};
+struct QuantOut {
+    double *iso = nullptr, *gene = nullptr, *colsum = nullptr;
+    int32_t *iters = nullptr;
+    SparseSink *iso_csr = nullptr, *gene_csr = nullptr;
+};
+
+// Chunks [H0, H1) of the caller's sample on context c (and its twin): cut into n_slices slices that alternate
+// between the two contexts, each driven by its own host thread, so that while one slice's results cross PCIe
+// and are expanded on the host the next slice is staged and computed.  Chunks are independent, so slicing
+// changes no result.  colparts ([n_chunks x n_emcols], rows H0..H1 written) and ptsum ([n_cols], this range's
+// exact pass-through sums added under the mutex) are what the caller builds the column sums from.
+static int quant_range(scasa_ctx *c, int H0, int H1, const int64_t *chunk_off, const int64_t *cell_ptr, const int32_t *eq_id,
+                       const int32_t *eq_count, int64_t n_eq, const int32_t *eq_row, const QuantOut &out, double *colparts,
+                       double *ptsum, std::mutex *ptsum_mutex, int32_t n_slices, int sink_slice0)
 {
-    if (!c) return fail(c, SCASA_ERR_ARG, "null context");
-    if (n_cells <= 0 || n_chunks <= 0 || !chunk_off || !cell_ptr || !eq_id || !eq_count || !eq_row || !iso_out)
-        return fail(c, SCASA_ERR_ARG, "bad argument");
-    if (chunk_off[0] != 0 || chunk_off[n_chunks] != n_cells) return fail(c, SCASA_ERR_ARG, "chunk_off must cover [0, n_cells]");
-    if (gene_out && c->n_genes <= 0) return fail(c, SCASA_ERR_STATE, "no gene map set");
+    const int n_chunks = H1 - H0;
+    if (n_chunks <= 0) return SCASA_OK;
     if (n_slices <= 0) n_slices = std::max(2, std::min(8, n_chunks / 128));   // measured: 4-8 slices of >= 100 chunks are best
     n_slices = std::max(1, std::min(n_slices, n_chunks));
     if (n_slices > 1) { int rc = sync_twin(c); if (rc) return rc; }
     scasa_ctx *ctxs[2] = {c, n_slices > 1 ? c->twin : c};
-    std::vector<double> colsum_parts;
-    if (colsum_out) colsum_parts.assign((size_t)n_slices * c->n_cols, 0.0);
     int rcs[2] = {SCASA_OK, SCASA_OK};
     auto drive = [&](int which) {                    // runs on its own thread for which == 1: nothing may escape
         scasa_ctx *x = ctxs[which];
         try {
         std::vector<int64_t> ptr, coff;
+        std::vector<double> pt;
         for (int sl = which; sl < n_slices; sl += 2) {
-            const int h0 = (int)((int64_t)n_chunks * sl / n_slices), h1 = (int)((int64_t)n_chunks * (sl + 1) / n_slices);
+            const int h0 = H0 + (int)((int64_t)n_chunks * sl / n_slices), h1 = H0 + (int)((int64_t)n_chunks * (sl + 1) / n_slices);
             if (h1 <= h0) continue;
             const int64_t c0 = chunk_off[h0], c1 = chunk_off[h1];
             coff.resize((size_t)(h1 - h0) + 1);
@@ -1456,10 +1468,47 @@ int scasa_quant(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const int64_t *
             for (int64_t i = c0; i <= c1; i++) ptr[(size_t)(i - c0)] = cell_ptr[i] - e0;
             int rc = scasa_stage_eqcounts(x, c1 - c0, h1 - h0, coff.data(), ptr.data(), eq_id + e0, eq_count + e0, n_eq, eq_row);
             if (!rc) rc = run_staged(x);
-            if (!rc) rc = scasa_fetch_iso(x, iso_out + c0 * c->n_cols);
-            if (!rc && gene_out) rc = scasa_fetch_gene(x, gene_out + c0 * (int64_t)c->n_genes);
-            if (!rc && colsum_out) rc = scasa_fetch_colsum(x, colsum_parts.data() + (size_t)sl * c->n_cols);
-            if (!rc && iters_out) rc = scasa_fetch_iters(x, iters_out + (int64_t)h0 * c->n_em * 2);
+            if (!rc && out.iso) rc = scasa_fetch_iso(x, out.iso + c0 * c->n_cols);
+            if (!rc && out.gene) rc = scasa_fetch_gene(x, out.gene + c0 * (int64_t)c->n_genes);
+            if (!rc && out.iters) rc = scasa_fetch_iters(x, out.iters + (int64_t)h0 * c->n_em * 2);
+            if (!rc && out.iso_csr) {
+                SparseSink &k = *out.iso_csr;
+                const int si = sink_slice0 + sl;
+                k.slice_c0[(size_t)si] = c0; k.slice_c1[(size_t)si] = c1;
+                int64_t nz = 0;
+                rc = scasa_result_nnz(x, &nz, nullptr);
+                if (!rc) {
+                    k.cols[(size_t)si].resize((size_t)nz + 1); k.vals[(size_t)si].resize((size_t)nz + 1);
+                    std::vector<int64_t> rp((size_t)(c1 - c0) + 1);
+                    rc = scasa_fetch_iso_csr(x, rp.data(), k.cols[(size_t)si].data(), k.vals[(size_t)si].data());
+                    for (int64_t i = c0; i < c1; i++) k.rowptr[(size_t)i + 1] = rp[(size_t)(i - c0) + 1] - rp[(size_t)(i - c0)];
+                    k.cols[(size_t)si].resize((size_t)nz); k.vals[(size_t)si].resize((size_t)nz);
+                }
+            }
+            if (!rc && out.gene_csr) {
+                SparseSink &k = *out.gene_csr;
+                const int si = sink_slice0 + sl;
+                k.slice_c0[(size_t)si] = c0; k.slice_c1[(size_t)si] = c1;
+                int64_t nz = 0;
+                rc = scasa_result_nnz(x, nullptr, &nz);
+                if (!rc) {
+                    k.cols[(size_t)si].resize((size_t)nz + 1); k.vals[(size_t)si].resize((size_t)nz + 1);
+                    std::vector<int64_t> rp((size_t)(c1 - c0) + 1);
+                    rc = scasa_fetch_gene_csr(x, rp.data(), k.cols[(size_t)si].data(), k.vals[(size_t)si].data());
+                    for (int64_t i = c0; i < c1; i++) k.rowptr[(size_t)i + 1] = rp[(size_t)(i - c0) + 1] - rp[(size_t)(i - c0)];
+                    k.cols[(size_t)si].resize((size_t)nz); k.vals[(size_t)si].resize((size_t)nz);
+                }
+            }
+            if (!rc && colparts && c->n_emcols > 0)
+                rc = fetch(x, colparts + (size_t)h0 * c->n_emcols, x->d_colpart.p, (size_t)(h1 - h0) * c->n_emcols * sizeof(double));
+            if (!rc && ptsum) {
+                pt.resize((size_t)c->n_cols);
+                rc = scasa_fetch_colsum(x, pt.data());
+                if (!rc) {
+                    std::lock_guard<std::mutex> lk(*ptsum_mutex);
+                    for (int64_t j = 0; j < c->n_cols; j++) ptsum[j] += pt[(size_t)j];   // only the pass-through columns are read: integer sums, exact in any order
+                }
+            }
             if (rc) { rcs[which] = rc; return; }
         }
         } catch (const std::exception &e) {
@@ -1478,13 +1527,125 @@ int scasa_quant(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const int64_t *
     } else drive(0);
     if (rcs[0]) return rcs[0];
     if (rcs[1]) return fail(c, rcs[1], std::string("twin context: ") + scasa_last_error(c->twin));
-    if (colsum_out)                                   // slices added in order: a fixed sequence for a given n_slices
-        for (int64_t j = 0; j < c->n_cols; j++) {
-            double acc = 0;
-            for (int sl = 0; sl < n_slices; sl++) acc += colsum_parts[(size_t)sl * c->n_cols + j];
-            colsum_out[j] = acc;
-        }
     return SCASA_OK;
+}
+
+// The column sums of the whole sample (step2:167) from what the ranges delivered: pass-through columns are exact
+// integer sums; EM columns are added chunk by chunk in chunk order — the same sequence scasa_run's own reduction
+// follows, so the sums do not depend on the slicing or on the number of GPUs.
+static void finish_colsum(const scasa_ctx *c, int n_chunks, const double *colparts, const double *ptsum, double *colsum_out)
+{
+    for (int64_t j = 0; j < c->n_cols; j++) colsum_out[j] = ptsum[j];
+    std::vector<double> acc((size_t)std::max(1, c->n_emcols), 0.0);
+    for (int h = 0; h < n_chunks; h++) {
+        const double *row = colparts + (size_t)h * c->n_emcols;
+        for (int j = 0; j < c->n_emcols; j++) acc[(size_t)j] += row[j];
+    }
+    for (int e = 0, j = 0; e < c->n_em; e++) {
+        const int k = c->em_blocks[(size_t)e];
+        for (int col = c->p_off[(size_t)k]; col < c->p_off[(size_t)k + 1]; col++) colsum_out[col] = acc[(size_t)j++];
+    }
+}
+
+static int quant_multi_impl(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off,
+                            const int64_t *cell_ptr, const int32_t *eq_id, const int32_t *eq_count, int64_t n_eq, const int32_t *eq_row,
+                            const QuantOut &out, int32_t n_slices)
+{
+    scasa_ctx *c = ctxs ? ctxs[0] : nullptr;
+    if (!c || n_ctx < 1) return fail(c, SCASA_ERR_ARG, "null context");
+    if (n_cells <= 0 || n_chunks <= 0 || !chunk_off || !cell_ptr || !eq_id || !eq_count || !eq_row)
+        return fail(c, SCASA_ERR_ARG, "bad argument");
+    if (chunk_off[0] != 0 || chunk_off[n_chunks] != n_cells) return fail(c, SCASA_ERR_ARG, "chunk_off must cover [0, n_cells]");
+    if ((out.gene || out.gene_csr) && c->n_genes <= 0) return fail(c, SCASA_ERR_STATE, "no gene map set");
+    for (int r = 1; r < n_ctx; r++) {
+        if (!ctxs[r] || ctxs[r]->n_cols != c->n_cols || ctxs[r]->n_rows != c->n_rows || ctxs[r]->n_em != c->n_em)
+            return fail(c, SCASA_ERR_ARG, "the contexts of a multi-GPU call must hold the same X-matrix");
+        ctxs[r]->opts = c->opts;
+        if (c->n_genes > 0 && (ctxs[r]->n_genes != c->n_genes || ctxs[r]->gene_of_col_host != c->gene_of_col_host)) {
+            int rc = scasa_set_gene_map(ctxs[r], c->gene_of_col_host.data(), c->n_genes);
+            if (rc) return fail(c, rc, std::string("context ") + std::to_string(r) + ": " + scasa_last_error(ctxs[r]));
+        }
+    }
+    n_ctx = std::min<int32_t>(n_ctx, n_chunks);
+    // contiguous chunk ranges per GPU, balanced by the number of (cell, eqclass) entries
+    std::vector<int> cut((size_t)n_ctx + 1, 0);
+    {
+        const double total = (double)cell_ptr[n_cells];
+        int h = 0;
+        for (int r = 1; r < n_ctx; r++) {
+            const double want = total * r / n_ctx;
+            while (h < n_chunks - (n_ctx - r) && (double)cell_ptr[chunk_off[h + 1]] <= want) h++;
+            h = std::max(h, cut[(size_t)r - 1] + 1);
+            cut[(size_t)r] = h;
+        }
+        cut[(size_t)n_ctx] = n_chunks;
+    }
+    std::vector<double> colparts, ptsum;
+    std::mutex ptm;
+    if (out.colsum) { colparts.assign((size_t)n_chunks * std::max(1, c->n_emcols), 0.0); ptsum.assign((size_t)c->n_cols, 0.0); }
+    // slices per rank are fixed up front so that the sparse sinks can be sized before the threads start
+    std::vector<int> nsl((size_t)n_ctx), sl0((size_t)n_ctx + 1, 0);
+    for (int r = 0; r < n_ctx; r++) {
+        const int nch = cut[(size_t)r + 1] - cut[(size_t)r];
+        int k = n_slices > 0 ? n_slices : std::max(2, std::min(8, nch / 128));
+        nsl[(size_t)r] = std::max(1, std::min(k, nch));
+        sl0[(size_t)r + 1] = sl0[(size_t)r] + nsl[(size_t)r];
+    }
+    for (SparseSink *k : {out.iso_csr, out.gene_csr})
+        if (k) {
+            k->rowptr.assign((size_t)n_cells + 1, 0);
+            k->cols.assign((size_t)sl0[(size_t)n_ctx], {}); k->vals.assign((size_t)sl0[(size_t)n_ctx], {});
+            k->slice_c0.assign((size_t)sl0[(size_t)n_ctx], 0); k->slice_c1.assign((size_t)sl0[(size_t)n_ctx], 0);
+        }
+    std::vector<int> rcs((size_t)n_ctx, SCASA_OK);
+    auto rank = [&](int r) {
+        rcs[(size_t)r] = quant_range(ctxs[r], cut[(size_t)r], cut[(size_t)r + 1], chunk_off, cell_ptr, eq_id, eq_count, n_eq, eq_row, out,
+                                     out.colsum ? colparts.data() : nullptr, out.colsum ? ptsum.data() : nullptr, &ptm,
+                                     nsl[(size_t)r], sl0[(size_t)r]);
+    };
+    {
+        std::vector<std::thread> th;
+        try {
+            for (int r = 1; r < n_ctx; r++) th.emplace_back(rank, r);
+        } catch (const std::exception &e) {
+            for (auto &t : th) t.join();
+            return fail(c, SCASA_ERR_NOMEM, std::string("cannot start a host thread per GPU: ") + e.what());
+        }
+        rank(0);
+        for (auto &t : th) t.join();
+    }
+    for (int r = 0; r < n_ctx; r++)
+        if (rcs[(size_t)r]) return r == 0 ? rcs[0] : fail(c, rcs[(size_t)r], std::string("GPU ") + std::to_string(ctxs[r]->device) + ": " + scasa_last_error(ctxs[r]));
+    if (out.colsum) finish_colsum(c, n_chunks, colparts.data(), ptsum.data(), out.colsum);
+    for (SparseSink *k : {out.iso_csr, out.gene_csr})
+        if (k) for (int64_t i = 0; i < n_cells; i++) k->rowptr[(size_t)i + 1] += k->rowptr[(size_t)i];
+    return SCASA_OK;
+}
+
+int scasa_quant(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off, const int64_t *cell_ptr,
+                const int32_t *eq_id, const int32_t *eq_count, int64_t n_eq, const int32_t *eq_row, double *iso_out,
+                double *gene_out, double *colsum_out, int32_t *iters_out, int32_t n_slices)
+{
+    if (!c) return fail(c, SCASA_ERR_ARG, "null context");
+    if (!iso_out) return fail(c, SCASA_ERR_ARG, "bad argument");
+    QuantOut out;
+    out.iso = iso_out; out.gene = gene_out; out.colsum = colsum_out; out.iters = iters_out;
+    return quant_multi_impl(&c, 1, n_cells, n_chunks, chunk_off, cell_ptr, eq_id, eq_count, n_eq, eq_row, out, n_slices);
+}
+
+// The same over several GPUs of one box: ctxs[r] created on device r with the same X-matrix; contiguous chunk
+// ranges per GPU, one host thread per GPU (each of which slices its range as scasa_quant does), every GPU
+// writes its own rows of the caller's matrices.  No collective: chunks are independent (SURVEY.md §8 e).
+// Results are bitwise those of a single GPU, column sums included.
+int scasa_quant_multi(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off,
+                      const int64_t *cell_ptr, const int32_t *eq_id, const int32_t *eq_count, int64_t n_eq, const int32_t *eq_row,
+                      double *iso_out, double *gene_out, double *colsum_out, int32_t *iters_out, int32_t n_slices)
+{
+    if (!ctxs || n_ctx < 1 || !ctxs[0]) return fail(nullptr, SCASA_ERR_ARG, "null context list");
+    if (!iso_out) return fail(ctxs[0], SCASA_ERR_ARG, "bad argument");
+    QuantOut out;
+    out.iso = iso_out; out.gene = gene_out; out.colsum = colsum_out; out.iters = iters_out;
+    return quant_multi_impl(ctxs, n_ctx, n_cells, n_chunks, chunk_off, cell_ptr, eq_id, eq_count, n_eq, eq_row, out, n_slices);
 }
 
 int scasa_gene_sum(scasa_ctx *c, const int32_t *gene_of_col, int32_t n_genes, const double *iso, int64_t n_cells,

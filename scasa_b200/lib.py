@@ -64,7 +64,7 @@ SYMBOLS = (
     "scasa_fetch_iso", "scasa_fetch_iters", "scasa_fetch_colsum", "scasa_fetch_counts", "scasa_set_gene_map",
     "scasa_fetch_gene", "scasa_gene_sum", "scasa_eqclass_map", "scasa_last_timing", "scasa_host_alloc",
     "scasa_host_free", "scasa_device_count", "scasa_version", "scasa_set_host_threads", "scasa_expand_pairs", "scasa_quant", "scasa_transfer_bytes", "scasa_bfh_open", "scasa_bfh_close", "scasa_bfh_sizes", "scasa_bfh_read", "scasa_bus_open", "scasa_write_table", "scasa_format_real15", "scasa_set_run_parts", "scasa_eqclass_map_host",
-    "scasa_result_nnz", "scasa_fetch_iso_csr", "scasa_fetch_gene_csr",
+    "scasa_result_nnz", "scasa_fetch_iso_csr", "scasa_fetch_gene_csr", "scasa_quant_multi",
 )
 
 
@@ -117,6 +117,8 @@ def load():
     L.scasa_bfh_read.argtypes = [vp, C.c_char_p, C.c_char_p, i64p, i32p, i64p, i32p, i32p]
     L.scasa_transfer_bytes.argtypes = [vp, i64p, i64p, C.c_int32]
     L.scasa_quant.argtypes = [vp, C.c_int64, C.c_int32, i64p, i64p, i32p, i32p, C.c_int64, i32p, f64p, f64p, f64p, i32p, C.c_int32]
+    L.scasa_quant_multi.argtypes = [C.POINTER(vp), C.c_int32, C.c_int64, C.c_int32, i64p, i64p, i32p, i32p, C.c_int64, i32p, f64p, f64p, f64p,
+                                    i32p, C.c_int32]
     L.scasa_fetch_iso.argtypes = [vp, f64p]
     L.scasa_result_nnz.argtypes = [vp, i64p, i64p]
     L.scasa_fetch_iso_csr.argtypes = [vp, i64p, i32p, f64p]

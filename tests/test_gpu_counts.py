@@ -275,6 +275,52 @@ def test_repeated_runs_are_bitwise_reproducible(xm):
         g.close()
 
 
+def _multi_case(xm, devices):
+    from scasa_b200 import synth
+    from scasa_b200.api import Scasa
+    n = 1130                                                      # 11 chunks
+    rowptr, rows, vals = synth.CellGenerator(xm, seed=12).counts_csr(0, n)
+    ed = synth.eqclass_dictionary(xm, 12)
+    cell_ptr, eq_id, eq_cnt = synth.counts_to_eqcounts(rowptr, rows, vals, 12)
+    goc, ng = np.asarray(xm.gene_of_col, np.int32), len(xm.gene_names)
+    ctx = [Scasa(xm, device=d) for d in devices]
+    try:
+        ctx[0].set_gene_map(goc, ng)
+        one = ctx[0].quant(cell_ptr, eq_id, eq_cnt, ed.eq_off, ed.eq_tx, n_slices=1)
+        sliced = ctx[0].quant(cell_ptr, eq_id, eq_cnt, ed.eq_off, ed.eq_tx, n_slices=3)
+        multi = ctx[0].quant(cell_ptr, eq_id, eq_cnt, ed.eq_off, ed.eq_tx, peers=ctx[1:])
+        # and the staged single run, whose column sums are reduced on the device
+        ctx[0].stage_eqcounts(np.asarray(__import__("scasa_b200.api", fromlist=["chunk_split"]).chunk_split(n, 4)), cell_ptr, eq_id, eq_cnt,
+                              ctx[0].eqclass_map(ed.eq_off, ed.eq_tx, 4))
+        ctx[0].run()
+        dev_colsum = ctx[0].fetch_colsum()
+    finally:
+        for c in ctx:
+            c.close()
+    for other in (sliced, multi):
+        assert np.array_equal(other.iso.view(np.int64), one.iso.view(np.int64))
+        assert np.array_equal(other.gene.view(np.int64), one.gene.view(np.int64))
+        assert np.array_equal(other.iters, one.iters)
+        assert np.array_equal(other.colsum.view(np.int64), one.colsum.view(np.int64))      # chunk order: independent of slicing / GPUs
+    assert np.array_equal(dev_colsum.view(np.int64), one.colsum.view(np.int64))
+    assert multi.timing["n_gpus"] == len(devices)
+
+
+def test_quant_multi_two_contexts_equal_one(xm):
+    """scasa_quant_multi — the single call behind the R seam that shards a sample over the GPUs of a box
+    (step2:82-136's fork pool) — with two contexts: chunk ranges, per-rank slices, row offsets and the
+    chunk-ordered column sums give bitwise what one context gives.  (Two contexts on device 0: the host-side
+    logic is the same; the two-device run is the next test.)"""
+    _multi_case(xm, [0, 0])
+
+
+def test_two_gpus_equal_one_gpu_through_the_library(xm):
+    from scasa_b200 import lib
+    if lib.load().scasa_device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    _multi_case(xm, [0, 1])
+
+
 def test_error_behaviour_through_the_abi(xm):
     """Malformed input and wrong call order come back as error codes with a message (the R shim turns
     them into stop()); nothing crashes, and the context stays usable afterwards."""
