@@ -134,6 +134,24 @@ int scasa_quant_multi(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, in
                       const int32_t *eq_row, double *iso_out, double *gene_out, double *colsum_out,
                       int32_t *iters_out, int32_t n_slices);
 
+/* ---- eqclass counts in, the two text files out (step2:88-170 + step3:21-52) --------------------------------
+ * scasa_isoform_counts.txt (README.md:80 calls it scasa_isoform_expression.txt) and scasa_gene_expression.txt,
+ * byte for byte what scasa_write_table writes from the dense matrices, but no dense matrix ever exists: the
+ * sparse rows of every slice are collected on the host, transposed to transcript-major (step2:166) and streamed
+ * through scasa_write_table_sparse.  Rows: isoforms with rowSums > 0 (step2:167) under tx_names (one line per
+ * isoform column); genes with a surviving isoform, single-isoform genes first, then the others, each group in
+ * the order gene_rank gives (the rank of the gene's name under the caller's sort(); NULL = id order), under
+ * gene_names (one line per gene id of scasa_set_gene_map).  gene_path may be NULL. */
+typedef struct {
+    double quant_s, transpose_s, write_iso_s, write_gene_s;    /* wall seconds */
+    int64_t iso_bytes, gene_bytes, iso_rows, gene_rows;
+} scasa_files_timing_t;
+int scasa_quant_files(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off,
+                      const int64_t *cell_ptr, const int32_t *eq_id, const int32_t *eq_count, int64_t n_eq,
+                      const int32_t *eq_row, const char *iso_path, const char *gene_path, const char *tx_names,
+                      const char *gene_names, const int32_t *gene_rank, const char *cell_names, int32_t n_threads,
+                      double *colsum_out, scasa_files_timing_t *timing);
+
 /* ---- the same in resident stages (what scasa_estimate is made of) ----------------------- */
 int scasa_stage_counts(scasa_ctx *ctx, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off,
                        const int64_t *y_rowptr, const int32_t *y_rowidx, const double *y_val);
@@ -222,6 +240,18 @@ int scasa_bus_open(const char *bus_txt, const char *matrix_ec, const char *trans
  * row_names / cell_names: one name per line, '\n'-terminated. */
 int scasa_write_table(const char *path, const double *mat, int64_t n_cells, int64_t n_cols, const uint8_t *keep,
                       const char *row_names, const char *cell_names, int32_t n_threads);
+/* The same bytes from a sparse, column-wise matrix (no dense matrix anywhere): source column j (a transcript, or a
+ * gene) holds the entries [colptr[j], colptr[j+1]) = (cell, value), cells ascending; output line k is source
+ * column out_src[k] under the k-th line of out_names; absent cells and stored zeros print as 0.
+ * bytes_written (nullable) receives the file size. */
+int scasa_write_table_sparse(const char *path, int64_t n_cells, int64_t n_src, const int64_t *colptr, const int32_t *cell_idx,
+                             const double *vals, int64_t n_out, const int32_t *out_src, const char *out_names,
+                             const char *cell_names, int32_t n_threads, int64_t *bytes_written);
+/* CSR by row -> CSC with the entries of a column in row order (host threads, deterministic): turns the cell-major
+ * results of scasa_fetch_iso_csr / scasa_fetch_gene_csr into the transcript-major form the text files need
+ * (the t() of scasa_quant_step2_v1.0.0.R:166). */
+int scasa_csr_transpose(int64_t n_rows, int64_t n_cols, const int64_t *rowptr, const int32_t *cols, const double *vals,
+                        int64_t *colptr /* [n_cols+1] */, int32_t *rows_out, double *vals_out, int32_t n_threads);
 /* the text R's write.table gives one number; returns its length (buf needs 32 bytes) */
 int scasa_format_real15(double x, char *buf, int32_t cap);
 

@@ -335,6 +335,38 @@ class Scasa:
         return QuantResult(iso, gene, colsum, iters, {"n_slices": n_slices, "n_gpus": 1 + len(peers)})
 
 
+def quant_files(contexts, cell_ptr, eq_id, eq_count, eq_off, eq_tx, iso_path: str, gene_path, tx_names, gene_names, barcodes,
+                core: int = 4, n_threads: int = 0, gene_rank=None):
+    """scasa_quant_files: eqclass counts in, scasa_isoform_counts.txt and scasa_gene_expression.txt out, over the
+    given contexts (one per GPU; the first one's gene map and options are used).  Returns (colsum, timing dict)."""
+    g0 = contexts[0]
+    L = g0._L
+    cell_ptr = np.ascontiguousarray(cell_ptr, np.int64)
+    eq_id = np.ascontiguousarray(eq_id, np.int32)
+    eq_count = np.ascontiguousarray(eq_count, np.int32)
+    n_cells = len(cell_ptr) - 1
+    chunks = chunk_split(n_cells, core)
+    eq_row = g0.eqclass_map(eq_off, eq_tx, n_threads or 8)
+    if gene_rank is None and gene_path:
+        order = sorted(range(len(gene_names)), key=lambda g: gene_names[g].encode())
+        gene_rank = np.empty(len(gene_names), np.int32)
+        gene_rank[order] = np.arange(len(gene_names), dtype=np.int32)
+    gr = np.ascontiguousarray(gene_rank, np.int32) if gene_rank is not None else None
+    colsum = np.empty(g0.n_cols, np.float64)
+    tm = _l.FilesTiming()
+    arr = (C.c_void_p * len(contexts))(*[c._ctx for c in contexts])
+    rc = L.scasa_quant_files(arr, len(contexts), n_cells, len(chunks) - 1, _l.ptr(chunks, C.c_int64), _l.ptr(cell_ptr, C.c_int64),
+                             _l.ptr(eq_id, C.c_int32), _l.ptr(eq_count, C.c_int32), len(eq_row), _l.ptr(eq_row, C.c_int32),
+                             iso_path.encode(), gene_path.encode() if gene_path else None,
+                             ("\n".join(tx_names) + "\n").encode(),
+                             ("\n".join(gene_names) + "\n").encode() if gene_path else None,
+                             _l.ptr(gr, C.c_int32) if gr is not None else None, ("\n".join(barcodes) + "\n").encode(), n_threads,
+                             _l.ptr(colsum, C.c_double), C.byref(tm))
+    if rc:
+        raise _l.ScasaError(rc, L.scasa_last_error(g0._ctx).decode())
+    return colsum, {k: getattr(tm, k) for k, _ in tm._fields_}
+
+
 def dense_to_csr(y_dense: np.ndarray):
     """(n_cells, Σq) dense counts -> CSR by cell (rows ascending)."""
     y_dense = np.asarray(y_dense)

@@ -1648,6 +1648,139 @@ int scasa_quant_multi(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, in
     return quant_multi_impl(ctxs, n_ctx, n_cells, n_chunks, chunk_off, cell_ptr, eq_id, eq_count, n_eq, eq_row, out, n_slices);
 }
 
+// ---- eqclass counts in, the two text files out -----------------------------------------------------------
+// step2:88-170 + step3:21-52 without the dense matrices: the sparse rows of every slice are collected on the
+// host, transposed to transcript-major (step2:166) and streamed through the sparse writer.
+namespace {
+struct Flat { std::vector<int64_t> rowptr; std::vector<int32_t> cols; std::vector<double> vals; };
+void flatten(SparseSink &k, Flat &f)
+{
+    f.rowptr.swap(k.rowptr);
+    const int64_t nnz = f.rowptr.empty() ? 0 : f.rowptr.back();
+    f.cols.resize((size_t)nnz); f.vals.resize((size_t)nnz);
+    // slices are in cell order once sorted by their first cell
+    std::vector<size_t> order(k.cols.size());
+    std::iota(order.begin(), order.end(), (size_t)0);
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return k.slice_c0[a] < k.slice_c0[b]; });
+    for (size_t si : order) {
+        if (k.cols[si].empty()) continue;
+        const int64_t e0 = f.rowptr[(size_t)k.slice_c0[si]];
+        std::copy(k.cols[si].begin(), k.cols[si].end(), f.cols.begin() + e0);
+        std::copy(k.vals[si].begin(), k.vals[si].end(), f.vals.begin() + e0);
+        std::vector<int32_t>().swap(k.cols[si]);
+        std::vector<double>().swap(k.vals[si]);
+    }
+}
+double wall_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+}  // namespace
+
+int scasa_quant_files(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off,
+                      const int64_t *cell_ptr, const int32_t *eq_id, const int32_t *eq_count, int64_t n_eq, const int32_t *eq_row,
+                      const char *iso_path, const char *gene_path, const char *tx_names, const char *gene_names,
+                      const int32_t *gene_rank, const char *cell_names, int32_t n_threads, double *colsum_out,
+                      scasa_files_timing_t *timing)
+{
+    if (!ctxs || n_ctx < 1 || !ctxs[0]) return fail(nullptr, SCASA_ERR_ARG, "null context list");
+    scasa_ctx *c = ctxs[0];
+    if (!iso_path || !tx_names || !cell_names) return fail(c, SCASA_ERR_ARG, "bad argument");
+    if (gene_path && (c->n_genes <= 0 || !gene_names)) return fail(c, SCASA_ERR_STATE, "gene file asked for, but no gene map / gene names");
+    scasa_files_timing_t tm;
+    memset(&tm, 0, sizeof tm);
+    try {
+        SparseSink iso_sink, gene_sink;
+        QuantOut out;
+        std::vector<double> colsum((size_t)c->n_cols);
+        out.iso_csr = &iso_sink; out.gene_csr = gene_path ? &gene_sink : nullptr; out.colsum = colsum.data();
+        double t0 = wall_now();
+        int rc = quant_multi_impl(ctxs, n_ctx, n_cells, n_chunks, chunk_off, cell_ptr, eq_id, eq_count, n_eq, eq_row, out, 0);
+        if (rc) return rc;
+        tm.quant_s = wall_now() - t0;
+        if (colsum_out) std::copy(colsum.begin(), colsum.end(), colsum_out);
+
+        // ---- isoforms: transpose, keep rows with rowSums > 0 (step2:167), write
+        t0 = wall_now();
+        Flat f;
+        flatten(iso_sink, f);
+        std::vector<int64_t> colptr((size_t)c->n_cols + 1);
+        std::vector<int32_t> cell_idx(f.cols.size());
+        std::vector<double> tvals(f.vals.size());
+        rc = scasa_csr_transpose(n_cells, c->n_cols, f.rowptr.data(), f.cols.data(), f.vals.data(), colptr.data(), cell_idx.data(),
+                                 tvals.data(), n_threads);
+        if (rc) return fail(c, rc, scasa_last_error(nullptr));
+        Flat().rowptr.swap(f.rowptr); std::vector<int32_t>().swap(f.cols); std::vector<double>().swap(f.vals);
+        tm.transpose_s = wall_now() - t0;
+        t0 = wall_now();
+        std::vector<int32_t> src;
+        std::string names;
+        {
+            const char *p = tx_names;
+            for (int64_t j = 0; j < c->n_cols; j++) {
+                const char *nl = strchr(p, '\n');
+                if (!nl) return fail(c, SCASA_ERR_ARG, "tx_names must hold one '\\n'-terminated name per isoform column");
+                if (colsum[(size_t)j] > 0) { src.push_back((int32_t)j); names.append(p, nl + 1); }
+                p = nl + 1;
+            }
+        }
+        rc = scasa_write_table_sparse(iso_path, n_cells, c->n_cols, colptr.data(), cell_idx.data(), tvals.data(), (int64_t)src.size(),
+                                      src.data(), names.c_str(), cell_names, n_threads, &tm.iso_bytes);
+        if (rc) return fail(c, rc, scasa_last_error(nullptr));
+        tm.iso_rows = (int64_t)src.size();
+        tm.write_iso_s = wall_now() - t0;
+
+        // ---- genes (step3:32-46): rows = genes with a surviving isoform; single-isoform genes first, then the others,
+        // each group in sort() order of the gene names (gene_rank: the caller's collation)
+        if (gene_path) {
+            t0 = wall_now();
+            Flat g;
+            flatten(gene_sink, g);
+            const int64_t ng = c->n_genes;
+            std::vector<int64_t> gptr((size_t)ng + 1);
+            std::vector<int32_t> gcell(g.cols.size());
+            std::vector<double> gvals(g.vals.size());
+            rc = scasa_csr_transpose(n_cells, ng, g.rowptr.data(), g.cols.data(), g.vals.data(), gptr.data(), gcell.data(), gvals.data(), n_threads);
+            if (rc) return fail(c, rc, scasa_last_error(nullptr));
+            tm.transpose_s += wall_now() - t0;
+            t0 = wall_now();
+            std::vector<int32_t> kept_members((size_t)ng, 0);
+            for (int64_t j = 0; j < c->n_cols; j++) {
+                const int32_t gi = c->gene_of_col_host[(size_t)j];
+                if (gi >= 0 && colsum[(size_t)j] > 0) kept_members[(size_t)gi]++;
+            }
+            std::vector<int32_t> order;
+            for (int32_t gi = 0; gi < ng; gi++) if (kept_members[(size_t)gi] > 0) order.push_back(gi);
+            std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+                const bool ma = kept_members[(size_t)a] > 1, mb = kept_members[(size_t)b] > 1;
+                if (ma != mb) return !ma;                                        // singles (mat1) before multis (mat2), step3:43
+                return gene_rank ? gene_rank[a] < gene_rank[b] : a < b;
+            });
+            std::vector<const char *> gn;
+            {
+                const char *p = gene_names;
+                for (int64_t k = 0; k < ng; k++) {
+                    gn.push_back(p);
+                    const char *nl = strchr(p, '\n');
+                    if (!nl) return fail(c, SCASA_ERR_ARG, "gene_names must hold one '\\n'-terminated name per gene");
+                    p = nl + 1;
+                }
+                gn.push_back(p);
+            }
+            std::string gnames;
+            for (int32_t gi : order) gnames.append(gn[(size_t)gi], gn[(size_t)gi + 1]);
+            rc = scasa_write_table_sparse(gene_path, n_cells, ng, gptr.data(), gcell.data(), gvals.data(), (int64_t)order.size(), order.data(),
+                                          gnames.c_str(), cell_names, n_threads, &tm.gene_bytes);
+            if (rc) return fail(c, rc, scasa_last_error(nullptr));
+            tm.gene_rows = (int64_t)order.size();
+            tm.write_gene_s = wall_now() - t0;
+        }
+        if (timing) *timing = tm;
+        return SCASA_OK;
+    } catch (const std::bad_alloc &) {
+        return fail(c, SCASA_ERR_NOMEM, "host allocation failed");
+    } catch (const std::exception &e) {
+        return fail(c, SCASA_ERR_ARG, e.what());
+    }
+}
+
 int scasa_gene_sum(scasa_ctx *c, const int32_t *gene_of_col, int32_t n_genes, const double *iso, int64_t n_cells,
                    double *gene_out)
 {

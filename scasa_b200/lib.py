@@ -39,6 +39,11 @@ class Crp(C.Structure):
                 ("name_rank", C.POINTER(C.c_int32))]
 
 
+class FilesTiming(C.Structure):
+    _fields_ = [("quant_s", C.c_double), ("transpose_s", C.c_double), ("write_iso_s", C.c_double), ("write_gene_s", C.c_double),
+                ("iso_bytes", C.c_int64), ("gene_bytes", C.c_int64), ("iso_rows", C.c_int64), ("gene_rows", C.c_int64)]
+
+
 class Timing(C.Structure):
     _fields_ = [("total_ms", C.c_float), ("pack_ms", C.c_float), ("tasks_ms", C.c_float), ("em_ms", C.c_float),
                 ("finish_ms", C.c_float), ("gene_ms", C.c_float), ("em_class_ms", C.c_float * 4),
@@ -64,7 +69,7 @@ SYMBOLS = (
     "scasa_fetch_iso", "scasa_fetch_iters", "scasa_fetch_colsum", "scasa_fetch_counts", "scasa_set_gene_map",
     "scasa_fetch_gene", "scasa_gene_sum", "scasa_eqclass_map", "scasa_last_timing", "scasa_host_alloc",
     "scasa_host_free", "scasa_device_count", "scasa_version", "scasa_set_host_threads", "scasa_expand_pairs", "scasa_quant", "scasa_transfer_bytes", "scasa_bfh_open", "scasa_bfh_close", "scasa_bfh_sizes", "scasa_bfh_read", "scasa_bus_open", "scasa_write_table", "scasa_format_real15", "scasa_set_run_parts", "scasa_eqclass_map_host",
-    "scasa_result_nnz", "scasa_fetch_iso_csr", "scasa_fetch_gene_csr", "scasa_quant_multi",
+    "scasa_result_nnz", "scasa_fetch_iso_csr", "scasa_fetch_gene_csr", "scasa_quant_multi", "scasa_write_table_sparse", "scasa_csr_transpose", "scasa_quant_files",
 )
 
 
@@ -108,6 +113,9 @@ def load():
     L.scasa_run.argtypes = [vp]
     L.scasa_set_run_parts.argtypes = [vp, C.c_int32]
     L.scasa_write_table.argtypes = [C.c_char_p, f64p, C.c_int64, C.c_int64, u8p, C.c_char_p, C.c_char_p, C.c_int32]
+    L.scasa_write_table_sparse.argtypes = [C.c_char_p, C.c_int64, C.c_int64, i64p, i32p, f64p, C.c_int64, i32p, C.c_char_p, C.c_char_p,
+                                           C.c_int32, i64p]
+    L.scasa_csr_transpose.argtypes = [C.c_int64, C.c_int64, i64p, i32p, f64p, i64p, i32p, f64p, C.c_int32]
     L.scasa_format_real15.argtypes = [C.c_double, C.c_char_p, C.c_int32]
     L.scasa_bfh_open.argtypes = [C.c_char_p, C.c_int32, C.POINTER(vp)]
     L.scasa_bfh_close.argtypes = [vp]
@@ -119,6 +127,8 @@ def load():
     L.scasa_quant.argtypes = [vp, C.c_int64, C.c_int32, i64p, i64p, i32p, i32p, C.c_int64, i32p, f64p, f64p, f64p, i32p, C.c_int32]
     L.scasa_quant_multi.argtypes = [C.POINTER(vp), C.c_int32, C.c_int64, C.c_int32, i64p, i64p, i32p, i32p, C.c_int64, i32p, f64p, f64p, f64p,
                                     i32p, C.c_int32]
+    L.scasa_quant_files.argtypes = [C.POINTER(vp), C.c_int32, C.c_int64, C.c_int32, i64p, i64p, i32p, i32p, C.c_int64, i32p, C.c_char_p,
+                                    C.c_char_p, C.c_char_p, C.c_char_p, i32p, C.c_char_p, C.c_int32, f64p, C.POINTER(FilesTiming)]
     L.scasa_fetch_iso.argtypes = [vp, f64p]
     L.scasa_result_nnz.argtypes = [vp, i64p, i64p]
     L.scasa_fetch_iso_csr.argtypes = [vp, i64p, i32p, f64p]

@@ -290,8 +290,8 @@ def _multi_case(xm, devices):
         sliced = ctx[0].quant(cell_ptr, eq_id, eq_cnt, ed.eq_off, ed.eq_tx, n_slices=3)
         multi = ctx[0].quant(cell_ptr, eq_id, eq_cnt, ed.eq_off, ed.eq_tx, peers=ctx[1:])
         # and the staged single run, whose column sums are reduced on the device
-        ctx[0].stage_eqcounts(np.asarray(__import__("scasa_b200.api", fromlist=["chunk_split"]).chunk_split(n, 4)), cell_ptr, eq_id, eq_cnt,
-                              ctx[0].eqclass_map(ed.eq_off, ed.eq_tx, 4))
+        from scasa_b200.api import chunk_split
+        ctx[0].stage_eqcounts(chunk_split(n, 4), cell_ptr, eq_id, eq_cnt, ctx[0].eqclass_map(ed.eq_off, ed.eq_tx, 4))
         ctx[0].run()
         dev_colsum = ctx[0].fetch_colsum()
     finally:
@@ -319,6 +319,45 @@ def test_two_gpus_equal_one_gpu_through_the_library(xm):
     if lib.load().scasa_device_count() < 2:
         pytest.skip("needs two GPUs (gpurun --gpus 2)")
     _multi_case(xm, [0, 1])
+
+
+@pytest.mark.parametrize("n", [200, 3955])
+def test_quant_files_writes_what_the_dense_path_writes(xm, tmp_path, n):
+    """scasa_quant_files (eqclass counts in, both text files out, no dense matrix anywhere) on configs C1 and C2:
+    byte-identical to writing the dense results of Scasa.quant with the dense writer — rows with rowSums > 0
+    (step2:167), gene rows in scasa_genemat's layout after the filter (step3:34-43)."""
+    from scasa_b200 import synth, writers
+    from scasa_b200.api import Scasa, quant_files
+    seed = 1 if n == 200 else 2
+    rowptr, rows, vals = synth.CellGenerator(xm, seed=seed).counts_csr(0, n)
+    ed = synth.eqclass_dictionary(xm, seed)
+    cell_ptr, eq_id, eq_cnt = synth.counts_to_eqcounts(rowptr, rows, vals, seed)
+    goc, gnames = np.asarray(xm.gene_of_col, np.int32), xm.gene_names
+    bc = synth.barcodes(n, seed)
+    tx = xm.dm0_colnames()
+    g = Scasa(xm, device=0)
+    g2 = Scasa(xm, device=0)
+    try:
+        g.set_gene_map(goc, len(gnames))
+        r = g.quant(cell_ptr, eq_id, eq_cnt, ed.eq_off, ed.eq_tx)
+        a_iso, a_gene = str(tmp_path / "dense_iso.txt"), str(tmp_path / "dense_gene.txt")
+        writers.write_isoform_counts(a_iso, r.iso, r.colsum, xm, bc, n_threads=4)
+        writers.write_gene_expression(a_gene, r.gene, goc, gnames, r.colsum, bc, n_threads=4)
+        b_iso, b_gene = str(tmp_path / "scasa_isoform_counts.txt"), str(tmp_path / "scasa_gene_expression.txt")
+        colsum, tm = quant_files([g, g2], cell_ptr, eq_id, eq_cnt, ed.eq_off, ed.eq_tx, b_iso, b_gene, tx, gnames, bc, n_threads=4)
+    finally:
+        g.close()
+        g2.close()
+    assert np.array_equal(colsum.view(np.int64), r.colsum.view(np.int64))
+    assert open(a_iso, "rb").read() == open(b_iso, "rb").read()
+    assert open(a_gene, "rb").read() == open(b_gene, "rb").read()
+    assert tm["iso_rows"] == int((r.colsum > 0).sum()) and tm["iso_bytes"] == os.path.getsize(b_iso)
+    # the gene file holds exactly the genes with a surviving isoform, singles first
+    order, cnt = writers.gene_layout(goc, gnames, r.colsum > 0)
+    with open(b_gene) as f:
+        f.readline()
+        got = [ln.split("\t", 1)[0] for ln in f]
+    assert got == [gnames[k] for k in order] and tm["gene_rows"] == len(order)
 
 
 def test_error_behaviour_through_the_abi(xm):

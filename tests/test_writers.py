@@ -111,3 +111,70 @@ def test_write_table_threads_never_reorder_or_drop_blocks(tmp_path):
     for it in range(150):
         write_table(path, mat, rows, cells, n_threads=2 + it % 7)
         assert open(path, "rb").read() == want, it
+
+
+# ---------------------------------------------------------------------------------------------- sparse path
+def _random_sparse(rng, n_cells, n_cols, density):
+    dense = rng.gamma(0.3, 40.0, (n_cells, n_cols)) * (rng.random((n_cells, n_cols)) < density)
+    dense[rng.random((n_cells, n_cols)) < 0.01] = 1e-7 * rng.random()          # small values: scientific notation
+    dense[:, 3] = 0.0                                                            # an all-zero column
+    mask = (dense != 0) | (rng.random((n_cells, n_cols)) < 0.02)                 # stored zeros too
+    rowptr = np.concatenate([[0], np.cumsum(mask.sum(axis=1))]).astype(np.int64)
+    cells, cols = np.nonzero(mask)
+    return dense, rowptr, cols.astype(np.int32), dense[cells, cols]
+
+
+def test_csr_transpose_is_the_stable_counting_sort():
+    from scasa_b200.writers import csr_transpose
+    rng = np.random.default_rng(3)
+    for n_cells, n_cols, nthr in ((1, 5, 1), (37, 11, 3), (900, 260, 8), (5000, 40, 16)):
+        dense, rowptr, cols, vals = _random_sparse(rng, n_cells, n_cols, 0.15)
+        colptr, rows, tv = csr_transpose(rowptr, cols, vals, n_cols, nthr)
+        cell = np.repeat(np.arange(n_cells), np.diff(rowptr))
+        order = np.argsort(cols, kind="stable")                                  # column-major, cells ascending inside a column
+        assert np.array_equal(colptr, np.concatenate([[0], np.cumsum(np.bincount(cols, minlength=n_cols))]))
+        assert np.array_equal(rows, cell[order]) and np.array_equal(tv, vals[order])
+    # empty matrix
+    colptr, rows, tv = csr_transpose(np.zeros(4, np.int64), np.zeros(0, np.int32), np.zeros(0), 6, 2)
+    assert np.array_equal(colptr, np.zeros(7)) and len(rows) == 0
+
+
+def test_sparse_writer_writes_the_bytes_of_the_dense_writer(tmp_path):
+    """scasa_write_table_sparse from the transposed sparse rows == scasa_write_table from the dense matrix,
+    byte for byte: kept rows, a row order that is a permutation (the gene layout), stored zeros, empty cells."""
+    from scasa_b200.writers import csr_transpose, write_table, write_table_sparse
+    rng = np.random.default_rng(5)
+    n_cells, n_cols = 333, 190
+    dense, rowptr, cols, vals = _random_sparse(rng, n_cells, n_cols, 0.08)
+    names = [f"NM_{j:06d} NM_{j + 7}" if j % 9 == 0 else f"NR_{j}" for j in range(n_cols)]
+    cells = [f"CELL{c:05d}" for c in range(n_cells)]
+    colptr, rows, tv = csr_transpose(rowptr, cols, vals, n_cols, 4)
+    keep = dense.sum(axis=0) > 0
+    a, b = str(tmp_path / "dense.txt"), str(tmp_path / "sparse.txt")
+    write_table(a, dense, names, cells, keep=keep, n_threads=3)
+    src = np.flatnonzero(keep)
+    size = write_table_sparse(b, n_cells, colptr, rows, tv, src, [names[j] for j in src], cells, n_threads=5)
+    assert open(a, "rb").read() == open(b, "rb").read() and size == os.path.getsize(b)
+    perm = rng.permutation(src)[:77]                                              # any order / subset of source columns
+    write_table(a, np.ascontiguousarray(dense[:, perm]), [names[j] for j in perm], cells, n_threads=2)
+    write_table_sparse(b, n_cells, colptr, rows, tv, perm, [names[j] for j in perm], cells, n_threads=2)
+    assert open(a, "rb").read() == open(b, "rb").read()
+
+
+def test_gene_layout_is_scasa_genemats(oracle, xm):
+    """scasa_b200.writers.gene_layout against the oracle's restatement of step3:34-43 on the shipped gene map, with
+    a filter that removes isoforms (genes disappear, multi-isoform genes become single-isoform ones)."""
+    from scasa_b200.writers import gene_layout
+    rng = np.random.default_rng(8)
+    keep = rng.random(xm.n_cols) < 0.6
+    names_of_col = [xm.gene_names[g] for g in xm.gene_of_col]
+    want_goc, want_nmem, want_names = oracle.gene_layout(names_of_col, keep)
+    order, cnt = gene_layout(xm.gene_of_col, xm.gene_names, keep)
+    assert [xm.gene_names[g] for g in order] == want_names
+    assert np.array_equal(cnt[order], want_nmem)
+    # every kept column lands in the row the oracle assigns
+    pos = np.full(len(xm.gene_names), -1)
+    pos[order] = np.arange(len(order))
+    assert np.array_equal(np.where(keep, pos[xm.gene_of_col], -1), want_goc)
+    moved = (np.bincount(xm.gene_of_col, minlength=len(cnt)) > 1) & (cnt == 1)
+    assert moved.sum() > 100                                                      # multis that became singles are exercised
