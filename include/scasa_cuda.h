@@ -206,6 +206,17 @@ int scasa_eqclass_map(scasa_ctx *ctx, int64_t n_eq, const int64_t *eq_off, const
 int scasa_eqclass_map_host(const scasa_crp_t *crp, int32_t hamming_dist, int64_t n_eq, const int64_t *eq_off,
                            const int32_t *eq_tx, int32_t *eq_row, int32_t n_threads);
 
+/* ---- can `DM0 <- lapply(CRP, ccrpfun, 30)` (scasa_quant_step2_v1.0.0.R:127; serial svd + kmeans(nstart = 100) over
+ * 29,351 blocks in the R master, minutes) be skipped in favour of the shipped CCRP?  (host only)
+ * crp_member[c] = global DM0 column CRP column c was merged into (the DM0 column whose name lists it), -1 = dropped.
+ * *is_fixed_point = 1 when, for every block, DM0 is a point ccrpfun's loop (Scasa_Rsource.R:168-193) stops at:
+ * the dropped columns are exactly the zero-sum ones, every DM0 column is the mean of its members (a k-means centre),
+ * all condition numbers max(sval)/sval of DM0 are < clim, and wherever columns were merged the unmerged block was not
+ * separated.  Which partition k-means picks among those is R's RNG and is not checked.  first_bad_block (nullable)
+ * receives the first block that fails, or -1. */
+int scasa_dm0_is_fixed_point(const scasa_xmat_t *crp, const scasa_xmat_t *dm0, const int32_t *crp_member, double clim,
+                             int32_t n_threads, int32_t *is_fixed_point, int64_t *first_bad_block);
+
 /* ---- alevin bfh.txt -> quant inputs (host only; replaces scasa_quant_step1_1_v1.0.0.R:16-68 and
  * the ordering of scasa_quant_step2_v1.0.0.R:59-60) --------------------------------------------
  * Cells are the barcodes that occur in some eqclass, in byte order of their sequences

@@ -9,12 +9,27 @@
 #include <R.h>
 #include <Rinternals.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "scasa_cuda.h"
 
-static void ctx_fin(SEXP p)
+#define SCASA_R_MAX_GPUS 16
+typedef struct { int n; scasa_ctx *ctx[SCASA_R_MAX_GPUS]; } scasa_r_handle;   /* one context per GPU of the box */
+
+static void handle_fin(SEXP p)
 {
-    scasa_ctx_destroy((scasa_ctx *)R_ExternalPtrAddr(p));
+    scasa_r_handle *h = (scasa_r_handle *)R_ExternalPtrAddr(p);
+    if (h) {
+        for (int i = 0; i < h->n; i++) scasa_ctx_destroy(h->ctx[i]);
+        free(h);
+    }
     R_ClearExternalPtr(p);
+}
+
+static scasa_r_handle *handle_of(SEXP p)
+{
+    scasa_r_handle *h = (scasa_r_handle *)R_ExternalPtrAddr(p);
+    if (!h || h->n < 1) error("scasa context was destroyed");
+    return h;
 }
 
 static int64_t *as_i64(SEXP v)          /* numeric vector -> transient int64 array (freed by R at the end of .Call) */
@@ -26,66 +41,146 @@ static int64_t *as_i64(SEXP v)          /* numeric vector -> transient int64 arr
     return out;
 }
 
-/* dm0 = list(q_off, p_off, x_off, x); crp = list(q_off, p_off, x_off, x, col_tx, row_pat, name_rank):
- * the flattened block lists prepared in R (scasa_quant_step2_patch.R) */
-SEXP scasa_r_create(SEXP dm0, SEXP crp, SEXP device)
+static void xmat_of(SEXP l, scasa_xmat_t *m)   /* list(q_off, p_off, x_off, x) as flat() of the patch builds it */
+{
+    m->n_blocks = (int32_t)(XLENGTH(VECTOR_ELT(l, 0)) - 1);
+    m->q_off = INTEGER(VECTOR_ELT(l, 0));
+    m->p_off = INTEGER(VECTOR_ELT(l, 1));
+    m->x_off = as_i64(VECTOR_ELT(l, 2));
+    m->x = REAL(VECTOR_ELT(l, 3));
+}
+
+/* N3: TRUE when the shipped CCRP is a point `lapply(CRP, ccrpfun, clim)` (step2:127) stops at, so the serial
+ * recompute can be skipped.  crp / dm0 = flat(CRP) / flat(CCRP); member = 0-based global DM0 column of every CRP
+ * column (-1 = dropped), see scasa_quant_step2_patch.R. */
+SEXP scasa_r_dm0_is_fixed_point(SEXP crp, SEXP dm0, SEXP member, SEXP clim)
+{
+    scasa_xmat_t c, d;
+    int32_t ok = 0;
+    xmat_of(crp, &c);
+    xmat_of(dm0, &d);
+    if (scasa_dm0_is_fixed_point(&c, &d, INTEGER(member), asReal(clim), 0, &ok, NULL)) error("%s", scasa_last_error(NULL));
+    return ScalarLogical(ok);
+}
+
+/* dm0 = list(q_off, p_off, x_off, x); crp = list(q_off, p_off, x_off, x, col_tx, row_pat, name_rank): the flattened
+ * block lists prepared in R (scasa_quant_step2_patch.R).  n_gpus: contexts on devices 0 .. n_gpus-1 (capped by the
+ * devices present) — the library shards the chunks over them inside one call, like step2's fork pool does over cores. */
+SEXP scasa_r_create(SEXP dm0, SEXP crp, SEXP n_gpus)
 {
     scasa_xmat_t d;
-    d.n_blocks = (int32_t)(XLENGTH(VECTOR_ELT(dm0, 0)) - 1);
-    d.q_off = INTEGER(VECTOR_ELT(dm0, 0));
-    d.p_off = INTEGER(VECTOR_ELT(dm0, 1));
-    d.x_off = as_i64(VECTOR_ELT(dm0, 2));
-    d.x = REAL(VECTOR_ELT(dm0, 3));
     scasa_crp_t c;
-    c.m.n_blocks = (int32_t)(XLENGTH(VECTOR_ELT(crp, 0)) - 1);
-    c.m.q_off = INTEGER(VECTOR_ELT(crp, 0));
-    c.m.p_off = INTEGER(VECTOR_ELT(crp, 1));
-    c.m.x_off = as_i64(VECTOR_ELT(crp, 2));
-    c.m.x = REAL(VECTOR_ELT(crp, 3));
+    xmat_of(dm0, &d);
+    xmat_of(crp, &c.m);
     c.col_tx = INTEGER(VECTOR_ELT(crp, 4));
     c.row_pat = RAW(VECTOR_ELT(crp, 5));
     c.name_rank = INTEGER(VECTOR_ELT(crp, 6));
-    scasa_ctx *ctx = NULL;
-    if (scasa_ctx_create(&d, &c, NULL, asInteger(device), &ctx)) error("%s", scasa_last_error(NULL));
-    SEXP p = PROTECT(R_MakeExternalPtr(ctx, R_NilValue, R_NilValue));
-    R_RegisterCFinalizerEx(p, ctx_fin, TRUE);
+    int n = asInteger(n_gpus), have = scasa_device_count();
+    if (n < 1) n = 1;
+    if (n > have) n = have;
+    if (n > SCASA_R_MAX_GPUS) n = SCASA_R_MAX_GPUS;
+    if (have < 1) error("no CUDA device: libscasa_cuda has no CPU path");
+    scasa_r_handle *h = (scasa_r_handle *)calloc(1, sizeof *h);
+    if (!h) error("out of memory");
+    for (int i = 0; i < n; i++) {
+        /* only the first context needs CRP (the eqclass -> row map is taken once, on the host) */
+        if (scasa_ctx_create(&d, i == 0 ? &c : NULL, NULL, i, &h->ctx[i])) {
+            for (int k = 0; k < i; k++) scasa_ctx_destroy(h->ctx[k]);
+            free(h);
+            error("%s", scasa_last_error(NULL));
+        }
+        h->n = i + 1;
+    }
+    SEXP p = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(p, handle_fin, TRUE);
     UNPROTECT(1);
     return p;
 }
 
-/* The quant call that replaces step2:88-136 (crpcount_td over all cells + estim_chunk over all chunks).
- * cell_ptr (numeric, n+1), eq_id / eq_count (integer, one per (cell, eqclass)), eq_off (numeric, E+1),
- * eq_tx (integer, transcript ids of the eqclasses), core (step2's chunk rule for n <= 100).
- * Returns the tx x cells matrix: column-major (tx, cell) is the library's cell-major layout. */
-SEXP scasa_r_quant(SEXP p, SEXP cell_ptr, SEXP eq_id, SEXP eq_count, SEXP eq_off, SEXP eq_tx, SEXP core)
+/* common argument conversion of the two quant calls */
+typedef struct {
+    int64_t n, E, *cp, *eo, *ch;
+    int32_t nch, *row;
+} quant_in;
+
+static void quant_prepare(scasa_r_handle *h, SEXP cell_ptr, SEXP eq_off, SEXP eq_tx, SEXP core, quant_in *q)
 {
-    scasa_ctx *ctx = (scasa_ctx *)R_ExternalPtrAddr(p);
-    if (!ctx) error("scasa context was destroyed");
-    const int64_t n = (int64_t)XLENGTH(cell_ptr) - 1, E = (int64_t)XLENGTH(eq_off) - 1;
-    int64_t *cp = as_i64(cell_ptr), *eo = as_i64(eq_off);
-    const int64_t cap = n / 50 + 8;
-    int64_t *ch = (int64_t *)R_alloc((size_t)cap, sizeof(int64_t));
-    int32_t *row = (int32_t *)R_alloc((size_t)E + 1, sizeof(int32_t));
-    int32_t nch = 0;
-    SEXP iso = PROTECT(allocMatrix(REALSXP, (int)scasa_n_cols(ctx), (int)n));
-    if (scasa_chunk_split(n, asInteger(core), ch, cap, &nch) ||
-        scasa_eqclass_map(ctx, E, eo, INTEGER(eq_tx), row, 0 /* all cores */) ||
-        scasa_quant(ctx, n, nch, ch, cp, INTEGER(eq_id), INTEGER(eq_count), E, row, REAL(iso),
-                    NULL /* gene_out: after scasa_r_gene_map */, NULL /* colsum */, NULL /* iters */, 0 /* slices: auto */))
-        error("%s", scasa_last_error(ctx));
+    q->n = (int64_t)XLENGTH(cell_ptr) - 1;
+    q->E = (int64_t)XLENGTH(eq_off) - 1;
+    q->cp = as_i64(cell_ptr);
+    q->eo = as_i64(eq_off);
+    const int nc = asInteger(core);
+    const int64_t cap = (q->n / 50 + 8 > nc + 2) ? q->n / 50 + 8 : nc + 2;   /* n <= 100: `core` chunks (step2:66) */
+    q->ch = (int64_t *)R_alloc((size_t)cap, sizeof(int64_t));
+    q->row = (int32_t *)R_alloc((size_t)q->E + 1, sizeof(int32_t));
+    q->nch = 0;
+    if (scasa_chunk_split(q->n, nc, q->ch, cap, &q->nch)) error("%s", scasa_last_error(NULL));   /* host-only entry: global message */
+    if (scasa_eqclass_map(h->ctx[0], q->E, q->eo, INTEGER(eq_tx), q->row, 0 /* all cores */)) error("%s", scasa_last_error(h->ctx[0]));
+}
+
+/* The quant call that replaces step2:88-136 (crpcount_td over all cells + estim_chunk over all chunks) and, when
+ * gene_of_col is not NULL, step3:48 (scasa_genemat) as well.
+ * cell_ptr (numeric, n+1), eq_id / eq_count (integer, one per (cell, eqclass)), eq_off (numeric, E+1), eq_tx (integer,
+ * transcript ids of the eqclasses), core (step2's chunk rule for n <= 100), gene_of_col (integer, 0-based gene id per
+ * isoform row, NA -> -1) or NULL, n_genes.
+ * Returns list(iso = tx x cells, gene = genes x cells or NULL, colsum = rowSums of iso): column-major (tx, cell) is the
+ * library's cell-major layout, so no transposition happens anywhere. */
+SEXP scasa_r_quant(SEXP p, SEXP cell_ptr, SEXP eq_id, SEXP eq_count, SEXP eq_off, SEXP eq_tx, SEXP core, SEXP gene_of_col,
+                   SEXP n_genes)
+{
+    scasa_r_handle *h = handle_of(p);
+    quant_in q;
+    quant_prepare(h, cell_ptr, eq_off, eq_tx, core, &q);
+    const int want_gene = gene_of_col != R_NilValue, ng = want_gene ? asInteger(n_genes) : 0;
+    if (scasa_set_gene_map(h->ctx[0], want_gene ? INTEGER(gene_of_col) : NULL, ng)) error("%s", scasa_last_error(h->ctx[0]));
+    const int ncol = (int)scasa_n_cols(h->ctx[0]);
+    SEXP out = PROTECT(allocVector(VECSXP, 3));
+    SEXP iso = PROTECT(allocMatrix(REALSXP, ncol, (int)q.n));
+    SEXP gene = PROTECT(want_gene ? allocMatrix(REALSXP, ng, (int)q.n) : R_NilValue);
+    SEXP colsum = PROTECT(allocVector(REALSXP, ncol));
+    if (scasa_quant_multi(h->ctx, h->n, q.n, q.nch, q.ch, q.cp, INTEGER(eq_id), INTEGER(eq_count), q.E, q.row, REAL(iso),
+                          want_gene ? REAL(gene) : NULL, REAL(colsum), NULL /* iters */, 0 /* slices: auto */))
+        error("%s", scasa_last_error(h->ctx[0]));
+    SET_VECTOR_ELT(out, 0, iso);
+    SET_VECTOR_ELT(out, 1, gene);
+    SET_VECTOR_ELT(out, 2, colsum);
+    UNPROTECT(4);
+    return out;
+}
+
+/* The same, but straight to scasa_isoform_counts.txt and scasa_gene_expression.txt (step2:165-170, step3:48-52): R never
+ * holds the dense matrices.  tx_names / gene_names / cell_names: one string each, names joined and terminated by "\n";
+ * gene_rank: 0-based rank of every gene name under R's sort() (the session collation decides the row order, step3:36).
+ * gene_path, gene_of_col may be NULL.  Returns the rowSums of the isoform matrix (rows with 0 are not written). */
+SEXP scasa_r_quant_files(SEXP p, SEXP cell_ptr, SEXP eq_id, SEXP eq_count, SEXP eq_off, SEXP eq_tx, SEXP core, SEXP gene_of_col,
+                         SEXP n_genes, SEXP iso_path, SEXP gene_path, SEXP tx_names, SEXP gene_names, SEXP gene_rank,
+                         SEXP cell_names)
+{
+    scasa_r_handle *h = handle_of(p);
+    quant_in q;
+    quant_prepare(h, cell_ptr, eq_off, eq_tx, core, &q);
+    const int want_gene = gene_of_col != R_NilValue && gene_path != R_NilValue;
+    if (scasa_set_gene_map(h->ctx[0], want_gene ? INTEGER(gene_of_col) : NULL, want_gene ? asInteger(n_genes) : 0))
+        error("%s", scasa_last_error(h->ctx[0]));
+    SEXP colsum = PROTECT(allocVector(REALSXP, (R_xlen_t)scasa_n_cols(h->ctx[0])));
+    if (scasa_quant_files(h->ctx, h->n, q.n, q.nch, q.ch, q.cp, INTEGER(eq_id), INTEGER(eq_count), q.E, q.row,
+                          CHAR(STRING_ELT(iso_path, 0)), want_gene ? CHAR(STRING_ELT(gene_path, 0)) : NULL,
+                          CHAR(STRING_ELT(tx_names, 0)), want_gene ? CHAR(STRING_ELT(gene_names, 0)) : NULL,
+                          want_gene && gene_rank != R_NilValue ? INTEGER(gene_rank) : NULL, CHAR(STRING_ELT(cell_names, 0)),
+                          0 /* all cores */, REAL(colsum), NULL))
+        error("%s", scasa_last_error(h->ctx[0]));
     UNPROTECT(1);
-    return iso;
+    return colsum;
 }
 
 /* scasa_genemat (step3:24-46) for a matrix already in R: gene_of_col = 0-based gene row of each isoform
  * row (NA -> -1), n_genes rows out.  iso is tx x cells as returned above. */
 SEXP scasa_r_genemat(SEXP p, SEXP iso, SEXP gene_of_col, SEXP n_genes)
 {
-    scasa_ctx *ctx = (scasa_ctx *)R_ExternalPtrAddr(p);
-    if (!ctx) error("scasa context was destroyed");
+    scasa_r_handle *h = handle_of(p);
     const int ng = asInteger(n_genes), n = ncols(iso);
     SEXP out = PROTECT(allocMatrix(REALSXP, ng, n));
-    if (scasa_gene_sum(ctx, INTEGER(gene_of_col), ng, REAL(iso), n, REAL(out))) error("%s", scasa_last_error(ctx));
+    if (scasa_gene_sum(h->ctx[0], INTEGER(gene_of_col), ng, REAL(iso), n, REAL(out))) error("%s", scasa_last_error(h->ctx[0]));
     UNPROTECT(1);
     return out;
 }

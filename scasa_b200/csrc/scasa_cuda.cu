@@ -1820,6 +1820,23 @@ int scasa_eqclass_map_host(const scasa_crp_t *crp, int32_t hamming_dist, int64_t
     });
 }
 
+int scasa_dm0_is_fixed_point(const scasa_xmat_t *crp, const scasa_xmat_t *dm0, const int32_t *crp_member, double clim,
+                             int32_t n_threads, int32_t *is_fixed_point, int64_t *first_bad_block)
+{
+    if (!crp || !dm0 || !crp_member || !is_fixed_point || !(clim > 0)) return fail(nullptr, SCASA_ERR_ARG, "bad argument");
+    return guarded(nullptr, [&] {
+        check_xmat(crp, "crp");
+        check_xmat(dm0, "dm0");
+        if (crp->n_blocks != dm0->n_blocks) throw ArgErr{SCASA_ERR_ARG, "crp and dm0 differ in block count"};
+        for (int k = 0; k <= crp->n_blocks; k++)
+            if (crp->q_off[k] != dm0->q_off[k]) throw ArgErr{SCASA_ERR_ARG, "crp and dm0 differ in rows"};
+        const int64_t bad = scasa::dm0_fixed_point_check(crp->n_blocks, crp->q_off, crp->p_off, crp->x_off, crp->x, dm0->p_off, dm0->x_off,
+                                                         dm0->x, crp_member, clim, n_threads);
+        *is_fixed_point = bad < 0;
+        if (first_bad_block) *first_bad_block = bad;
+    });
+}
+
 void *scasa_host_alloc(int64_t bytes)
 {
     void *p = nullptr;

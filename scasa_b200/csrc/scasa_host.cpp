@@ -353,5 +353,112 @@ void expand_rows(double *out, int64_t n_cols, int64_t r0, int64_t r1, const int6
     _mm_sfence();
 }
 
-}  // namespace scasa
+// ---- N3: is DM0 what ccrpfun(CRP[[k]], clim) stops at? (Scasa_Rsource.R:168-193; scasa_quant_step2_v1.0.0.R:127) ----
+// Singular values of a small dense block (q x p, column-major) from the eigenvalues of its Gram matrix by
+// cyclic Jacobi rotations.  Only the ratios max(sv)/sv against clim (30) matter, for which the squared
+// conditioning of the Gram route is harmless.
+static void singular_values(const double *A, int q, int p, std::vector<double> &sv)
+{
+    std::vector<double> G((size_t)p * p);
+    for (int i = 0; i < p; i++)
+        for (int j = i; j < p; j++) {
+            long double s = 0;
+            for (int r = 0; r < q; r++) s += (long double)A[(size_t)i * q + r] * A[(size_t)j * q + r];
+            G[(size_t)i * p + j] = G[(size_t)j * p + i] = (double)s;
+        }
+    for (int sweep = 0; sweep < 60; sweep++) {
+        double off = 0;
+        for (int i = 0; i < p; i++) for (int j = i + 1; j < p; j++) off += G[(size_t)i * p + j] * G[(size_t)i * p + j];
+        if (off < 1e-30) break;
+        for (int i = 0; i < p; i++)
+            for (int j = i + 1; j < p; j++) {
+                const double g = G[(size_t)i * p + j];
+                if (std::fabs(g) < 1e-300) continue;
+                const double theta = (G[(size_t)j * p + j] - G[(size_t)i * p + i]) / (2.0 * g);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < p; k++) {
+                    const double a = G[(size_t)k * p + i], b = G[(size_t)k * p + j];
+                    G[(size_t)k * p + i] = c * a - sn * b; G[(size_t)k * p + j] = sn * a + c * b;
+                }
+                for (int k = 0; k < p; k++) {
+                    const double a = G[(size_t)i * p + k], b = G[(size_t)j * p + k];
+                    G[(size_t)i * p + k] = c * a - sn * b; G[(size_t)j * p + k] = sn * a + c * b;
+                }
+            }
+    }
+    sv.resize((size_t)p);
+    for (int i = 0; i < p; i++) sv[(size_t)i] = std::sqrt(std::max(0.0, G[(size_t)i * p + i]));
+}
 
+static bool all_separated(const double *A, int q, int p, double clim)   // nsc == ncol(newx), Rsource:175-179
+{
+    if (p < 1) return true;
+    std::vector<double> sv;
+    singular_values(A, q, p, sv);
+    const double mx = *std::max_element(sv.begin(), sv.end());
+    for (double v : sv) if (!(std::fabs(mx / v) < clim)) return false;
+    return true;
+}
+
+// For every block: (i) the CRP columns without a member are exactly the zero-sum ones (:171-172); (ii) every DM0
+// column is the mean of its member CRP columns — a k-means centre (:186-187); (iii) all condition numbers of DM0
+// are < clim, so the repeat loop stops at it (:175-179); (iv) where DM0 merged columns, the unmerged block was NOT
+// separated (otherwise ccrpfun would have returned it unmerged).  What cannot be checked without R's RNG is that
+// k-means would pick this very partition among those that satisfy (ii)-(iii).  Returns the first block that
+// fails, or -1.
+int64_t dm0_fixed_point_check(int n_blocks, const int32_t *q_off, const int32_t *crp_p_off, const int64_t *crp_x_off,
+                              const double *crp_x, const int32_t *dm0_p_off, const int64_t *dm0_x_off, const double *dm0_x,
+                              const int32_t *crp_member, double clim, int n_threads)
+{
+    std::atomic<int64_t> bad{INT64_MAX};
+    std::atomic<int> next{0};
+    auto work = [&]() {
+        std::vector<double> mean, sup;
+        for (;;) {
+            const int k0 = next.fetch_add(256);
+            if (k0 >= n_blocks) return;
+            for (int k = k0; k < std::min(n_blocks, k0 + 256); k++) {
+                const int q = q_off[k + 1] - q_off[k], pc = crp_p_off[k + 1] - crp_p_off[k], pd = dm0_p_off[k + 1] - dm0_p_off[k];
+                const double *C = crp_x + crp_x_off[k], *D = dm0_x + dm0_x_off[k];
+                const int32_t *mem = crp_member + crp_p_off[k];
+                bool ok = true;
+                int n_sup = 0;
+                for (int c = 0; c < pc && ok; c++) {
+                    long double s = 0;
+                    for (int r = 0; r < q; r++) s += C[(size_t)c * q + r];
+                    const bool supported = (double)s > 0;
+                    n_sup += supported;
+                    if (supported != (mem[c] >= 0)) ok = false;
+                    if (mem[c] >= 0 && (mem[c] < dm0_p_off[k] || mem[c] >= dm0_p_off[k + 1])) ok = false;
+                }
+                for (int j = 0; j < pd && ok; j++) {
+                    mean.assign((size_t)q, 0.0);
+                    int cnt = 0;
+                    for (int c = 0; c < pc; c++)
+                        if (mem[c] == dm0_p_off[k] + j) { cnt++; for (int r = 0; r < q; r++) mean[(size_t)r] += C[(size_t)c * q + r]; }
+                    if (!cnt) { ok = false; break; }
+                    for (int r = 0; r < q; r++)
+                        if (std::fabs(mean[(size_t)r] / cnt - D[(size_t)j * q + r]) > 1e-12) { ok = false; break; }
+                }
+                if (ok && pd >= 1 && !all_separated(D, q, pd, clim)) ok = false;
+                if (ok && pd < n_sup) {                         // merged: the supported columns themselves must not be separated
+                    sup.clear();
+                    for (int c = 0; c < pc; c++)
+                        if (mem[c] >= 0) sup.insert(sup.end(), C + (size_t)c * q, C + (size_t)(c + 1) * q);
+                    if (all_separated(sup.data(), q, n_sup, clim)) ok = false;
+                }
+                if (!ok) { int64_t cur = bad.load(); while (k < cur && !bad.compare_exchange_weak(cur, k)) {} }
+            }
+        }
+    };
+    int nthr = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nthr = std::max(1, std::min(nthr, 64));
+    std::vector<std::thread> th;
+    try { for (int t = 1; t < nthr; t++) th.emplace_back(work); } catch (const std::exception &) {}
+    work();
+    for (auto &t : th) t.join();
+    return bad.load() == INT64_MAX ? -1 : bad.load();
+}
+
+}  // namespace scasa

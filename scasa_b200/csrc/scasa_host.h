@@ -45,6 +45,11 @@ void r_format_roundtrip(const double *v, int n, double *back, uint8_t *is_zero_t
 void expand_rows(double *out, int64_t n_cols, int64_t r0, int64_t r1, const int64_t *start, const int32_t *nnz,
                  const int32_t *cols, const double *vals);
 
+// N3: first block where DM0 is not what ccrpfun(CRP[[k]], clim) stops at, or -1 (see scasa_host.cpp)
+int64_t dm0_fixed_point_check(int n_blocks, const int32_t *q_off, const int32_t *crp_p_off, const int64_t *crp_x_off,
+                              const double *crp_x, const int32_t *dm0_p_off, const int64_t *dm0_x_off, const double *dm0_x,
+                              const int32_t *crp_member, double clim, int n_threads);
+
 // message returned by scasa_last_error(NULL) on the calling thread (for the host-only entry points)
 void set_global_error(const std::string &m);
 

@@ -69,7 +69,7 @@ SYMBOLS = (
     "scasa_fetch_iso", "scasa_fetch_iters", "scasa_fetch_colsum", "scasa_fetch_counts", "scasa_set_gene_map",
     "scasa_fetch_gene", "scasa_gene_sum", "scasa_eqclass_map", "scasa_last_timing", "scasa_host_alloc",
     "scasa_host_free", "scasa_device_count", "scasa_version", "scasa_set_host_threads", "scasa_expand_pairs", "scasa_quant", "scasa_transfer_bytes", "scasa_bfh_open", "scasa_bfh_close", "scasa_bfh_sizes", "scasa_bfh_read", "scasa_bus_open", "scasa_write_table", "scasa_format_real15", "scasa_set_run_parts", "scasa_eqclass_map_host",
-    "scasa_result_nnz", "scasa_fetch_iso_csr", "scasa_fetch_gene_csr", "scasa_quant_multi", "scasa_write_table_sparse", "scasa_csr_transpose", "scasa_quant_files",
+    "scasa_result_nnz", "scasa_fetch_iso_csr", "scasa_fetch_gene_csr", "scasa_quant_multi", "scasa_write_table_sparse", "scasa_csr_transpose", "scasa_quant_files", "scasa_dm0_is_fixed_point",
 )
 
 
@@ -141,6 +141,7 @@ def load():
     L.scasa_gene_sum.argtypes = [vp, i32p, C.c_int32, f64p, C.c_int64, f64p]
     L.scasa_eqclass_map.argtypes = [vp, C.c_int64, i64p, i32p, i32p, C.c_int32]
     L.scasa_eqclass_map_host.argtypes = [C.POINTER(Crp), C.c_int32, C.c_int64, i64p, i32p, i32p, C.c_int32]
+    L.scasa_dm0_is_fixed_point.argtypes = [C.POINTER(XMat), C.POINTER(XMat), i32p, C.c_double, C.c_int32, i32p, i64p]
     L.scasa_last_timing.argtypes = [vp, C.POINTER(Timing)]
     L.scasa_set_host_threads.argtypes = [vp, C.c_int32]
     L.scasa_expand_pairs.argtypes = [f64p, C.c_int64, C.c_int64, i64p, i32p, i32p, f64p, C.c_int32]

@@ -101,28 +101,29 @@ class XMatrix:
         return [" ".join(self.tx_names[t] for t in self.crp_tx[self.crp_p_off[k]:self.crp_p_off[k + 1]])
                 for k in range(self.n_blocks)]
 
-    def dm0_is_ccrpfun_fixed_point(self, clim: float = 30.0, blocks=None) -> bool:
+    def dm0_is_ccrpfun_fixed_point(self, clim: float = 30.0, n_threads: int = 0):
         """N3 (SURVEY.md §8 f): can ``DM0 <- lapply(CRP, ccrpfun, clim)`` (scasa_quant_step2_v1.0.0.R:127,
         serial minutes of svd + kmeans in the R master) be skipped in favour of the shipped ``CCRP``?
-        True when, for every block (or the given ones), DM0 is what ccrpfun's loop (Scasa_Rsource.R:168-193)
-        stops at: the zero-sum CRP columns are gone (:171-172), every DM0 column is the mean of its member
-        CRP columns (kmeans centres, :186-187) and all condition numbers max(sval)/sval are < clim (:175-179),
-        so ccrpfun applied to it again returns it unchanged."""
-        ks = range(self.n_blocks) if blocks is None else blocks
-        for k in ks:
-            crp, dm0 = self.crp_block(k), self.dm0_block(k)
-            mem = self.crp_member[self.crp_p_off[k]:self.crp_p_off[k + 1]]
-            if not np.array_equal(crp.sum(axis=0) > 0, mem >= 0):
-                return False
-            mem = mem - self.dm0_p_off[k]
-            for j in range(dm0.shape[1]):
-                if not (mem == j).any() or np.max(np.abs(crp[:, mem == j].mean(axis=1) - dm0[:, j])) > 1e-15:
-                    return False
-            if dm0.shape[1] >= 2:
-                sv = np.linalg.svd(dm0, compute_uv=False)
-                if not np.all(np.abs(sv.max() / sv) < clim):
-                    return False
-        return True
+        Calls the library's host-only ``scasa_dm0_is_fixed_point`` (the same entry the R shim uses): True when
+        every block of DM0 is a point ccrpfun's loop (Scasa_Rsource.R:168-193) stops at.  Returns
+        (is_fixed_point, first_bad_block or -1)."""
+        import ctypes as C
+        from . import lib as _l
+        L = _l.load()
+        keep = [np.ascontiguousarray(a, t) for a, t in ((self.q_off, np.int32), (self.crp_p_off, np.int32), (self.crp_x_off, np.int64),
+                                                        (self.crp_x, np.float64), (self.dm0_p_off, np.int32), (self.dm0_x_off, np.int64),
+                                                        (self.dm0_x, np.float64), (self.crp_member, np.int32))]
+        crp, dm0 = _l.XMat(), _l.XMat()
+        crp.n_blocks = dm0.n_blocks = self.n_blocks
+        crp.q_off = dm0.q_off = _l.ptr(keep[0], C.c_int32)
+        crp.p_off, crp.x_off, crp.x = _l.ptr(keep[1], C.c_int32), _l.ptr(keep[2], C.c_int64), _l.ptr(keep[3], C.c_double)
+        dm0.p_off, dm0.x_off, dm0.x = _l.ptr(keep[4], C.c_int32), _l.ptr(keep[5], C.c_int64), _l.ptr(keep[6], C.c_double)
+        ok, bad = C.c_int32(0), C.c_int64(-1)
+        rc = L.scasa_dm0_is_fixed_point(C.byref(crp), C.byref(dm0), _l.ptr(keep[7], C.c_int32), float(clim), n_threads,
+                                        C.byref(ok), C.byref(bad))
+        if rc:
+            raise _l.ScasaError(rc, L.scasa_last_error(None).decode())
+        return bool(ok.value), int(bad.value)
 
     def em_blocks(self) -> np.ndarray:
         """Blocks that go through the AEM loop: nrow(X0) > 1 (Scasa_Rsource.R:979)."""

@@ -25,3 +25,11 @@ SEXP R_MakeExternalPtr(void *, SEXP, SEXP);
 void R_RegisterCFinalizerEx(SEXP, R_CFinalizer_t, Rboolean);
 char *R_alloc(size_t, int);
 void error(const char *, ...) __attribute__((noreturn));
+#define VECSXP 19
+#define STRSXP 16
+double asReal(SEXP);
+SEXP ScalarLogical(int);
+SEXP allocVector(unsigned int, R_xlen_t);
+SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP);
+SEXP STRING_ELT(SEXP, R_xlen_t);
+const char *CHAR(SEXP);

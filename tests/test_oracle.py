@@ -204,9 +204,21 @@ def test_shipped_xmatrix_relations(xm):
             sv = np.linalg.svd(dm0, compute_uv=False)
             worst = max(worst, sv.max() / sv.min())
     assert worst < 30                                                                                 # K6: clim = 30
-    sample = np.random.default_rng(1).choice(xm.n_blocks, 3000, replace=False)
-    assert xm.dm0_is_ccrpfun_fixed_point(30.0, sample)                                                # N3: the recompute can be skipped
-    assert not xm.dm0_is_ccrpfun_fixed_point(1.5, xm.em_blocks()[:400])                               # ... but not for a stricter clim
+    # N3 through the C ABI (scasa_dm0_is_fixed_point, what the R patch calls): all 29,351 blocks of the shipped CCRP are
+    # a point ccrpfun(., 30) stops at, so step2:127's serial recompute can be skipped ...
+    assert xm.dm0_is_ccrpfun_fixed_point(30.0) == (True, -1)
+    ok, bad = xm.dm0_is_ccrpfun_fixed_point(1.5)                                                      # ... not for a stricter clim
+    assert not ok and bad >= 0
+    import copy
+    y = copy.copy(xm)                                                                                 # a DM0 value that is not the members' mean
+    y.dm0_x = xm.dm0_x.copy()
+    k = int(xm.em_blocks()[7])
+    y.dm0_x[xm.dm0_x_off[k]] += 1e-6
+    assert y.dm0_is_ccrpfun_fixed_point(30.0) == (False, k)
+    y = copy.copy(xm)                                                                                 # a supported column reported as dropped
+    y.crp_member = xm.crp_member.copy()
+    y.crp_member[np.flatnonzero(xm.crp_member >= 0)[123]] = -1
+    assert not y.dm0_is_ccrpfun_fixed_point(30.0)[0]
     assert (xm.gene_of_col >= 0).all()                                                                # K7
     assert sum(" " in n for n in xm.dm0_colnames()) == 12140                                          # K8
 
