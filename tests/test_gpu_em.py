@@ -270,9 +270,10 @@ def test_heavy_multimapping_tight_tolerance(xm, oracle):
 
 def test_fp32_option_close_to_fp64(xm, oracle, c1):
     """scasa_opts_t.fp32: the EM iterates in fp32 (counts and results stay fp64).  north_star asks for
-    1e-4 relative in fixed-iteration mode; that holds for all but a handful of ill-conditioned
-    two-transcript splits (nearly collinear columns that are not flagged poor), whose block totals
-    still agree.  Iteration counts in convergence mode agree on >= 99 % of the tasks."""
+    1e-4 relative in fixed-iteration mode; the contract the header states, and this test holds it to: every entry
+    within 1e-4 except in blocks with two nearly collinear columns (cosine >= 0.9, not flagged poor), where the
+    split between the two transcripts may be off by up to 2e-3 while the block total stays within 1e-4.
+    Iteration counts in convergence mode agree on >= 99 % of the tasks."""
     from scasa_b200.api import Scasa, chunk_split
     from scasa_b200.synth import csr_to_dense
     rowptr, rows, vals = c1
@@ -287,8 +288,20 @@ def test_fp32_option_close_to_fp64(xm, oracle, c1):
         err = np.abs(iso - ref) / np.maximum(np.abs(ref), 1e-3)
         err[:, poor] = 0
         assert np.all(np.isfinite(iso))
+        # the stated contract (include/scasa_cuda.h, scasa_opts_t.fp32): 1e-4 relative, except in blocks with two nearly
+        # collinear columns (cosine >= 0.9: the split between them is ill-conditioned, fp32 rounding of X moves it), where
+        # single entries may be off by up to 2e-3 while the block total stays within 1e-4
+        cos_block = np.zeros(xm.n_blocks)
+        for k in xm.em_blocks():
+            X = xm.dm0_block(k)
+            if X.shape[1] >= 2:
+                Xn = X / np.linalg.norm(X, axis=0)
+                cos_block[k] = (Xn.T @ Xn - np.eye(X.shape[1])).max()
+        cos_col = np.repeat(cos_block, np.diff(xm.dm0_p_off))
+        bad_cols = np.flatnonzero((err > 1e-4).any(axis=0))
         assert (err > 1e-4).sum() <= 20, (err > 1e-4).sum()              # of 6.6 M entries
-        assert err.max() < 5e-3, err.max()
+        assert np.all(cos_col[bad_cols] >= 0.9), cos_col[bad_cols]
+        assert err.max() < 2e-3, err.max()
         assert np.max(np.abs(iso[:, poor] - ref[:, poor])) < 1e-3
         # block totals per cell (what the split distributes) agree much more tightly
         col_block = np.repeat(np.arange(xm.n_blocks), np.diff(xm.dm0_p_off))
@@ -356,3 +369,43 @@ def test_c2_size_sampled_chunks_match_oracle(xm, oracle):
         from .parity import compare_tasks
         rep = compare_tasks(iso[c0:c1], ref, iters[h:h + 1], ref_it[:, em, :], np.array([0, c1 - c0]), em, p_off, xm.q_off, poor_b)
         assert rep["n_poor"] > 50
+
+
+def test_bustools_xmatrix_quant_matches_oracle(oracle):
+    """N4: the kallisto/bustools X-matrix (Xmatrix_hg38_bustools.RData as the committed fixture: 29,088 blocks,
+    4,563 EM blocks, the largest 57 x 21) through scasa_quant from eqclass counts, C1-shaped synthetic cells
+    (3 chunks): counts bit-exact against the oracle's crpcount_td, estimates task by task against estim_chunk."""
+    import os
+    from scasa_b200 import synth
+    from scasa_b200.api import Scasa, chunk_split
+    from scasa_b200.xmatrix import XMatrix
+    from .parity import compare_tasks
+    bx = XMatrix.load_npz(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "xmatrix_hg38_bustools.npz"))
+    assert bx.n_blocks == 29088 and len(bx.em_blocks()) == 4563               # SURVEY.md §8
+    q, p = np.diff(bx.q_off), np.diff(bx.dm0_p_off)
+    assert q.max() == 57 and p[q.argmax()] == 21
+    n = 300
+    rowptr, rows, vals = synth.CellGenerator(bx, seed=14).counts_csr(0, n)
+    ed = synth.eqclass_dictionary(bx, 14)
+    cell_ptr, eq_id, eq_cnt = synth.counts_to_eqcounts(rowptr, rows, vals, 14)
+    chunks = chunk_split(n, 4)
+    assert len(chunks) == 4
+    g = Scasa(bx, device=0)
+    try:
+        r = g.quant(cell_ptr, eq_id, eq_cnt, ed.eq_off, ed.eq_tx, n_slices=2)
+        eq_row = g.eqclass_map(ed.eq_off, ed.eq_tx, 4)
+        g.stage_eqcounts(chunks, cell_ptr, eq_id, eq_cnt, eq_row)
+        t = g.run()
+        yp, yi, yv = g.fetch_counts()
+        poor, em = g.poor_blocks(), g.em_blocks
+    finally:
+        g.close()
+    h = oracle.CrpHandle(bx)
+    y = oracle.crpcount_cells(h, ed.eq_off, ed.eq_tx, cell_ptr, eq_id, eq_cnt, nthreads=8)
+    assert np.array_equal(synth.csr_to_dense(yp, yi, yv, bx.n_rows), y)
+    big = int(q.argmax())
+    assert y[:, bx.q_off[big]:bx.q_off[big + 1]].sum() > 0                    # the 57 x 21 block is exercised
+    ref, ref_it = oracle.estim_chunks(bx, y, chunks, None, nthreads=8)
+    rep = compare_tasks(r.iso, ref, r.iters, ref_it[:, em, :], chunks, em, bx.dm0_p_off, bx.q_off, poor)
+    assert t["max_slot_bytes"] > 20000
+    print("bustools X-matrix vs oracle:", rep)
