@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--e2e-cells", type=int, default=0, help="cells per GPU for the e2e leg (0 = same, capped by host RAM)")
     ap.add_argument("--cpu-cells", type=int, default=0, help="cells of the cpu_baseline sample (0 = 100 per host thread, max 3200)")
     ap.add_argument("--seed", type=int, default=0, help="0 = the config's")
+    ap.add_argument("--files-cells", type=int, default=5000, help="cells per GPU of the e2e_files leg (bfh.txt in, two text files out); 0 = skip")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--fp32", action="store_true", help="EM iterates in fp32 (scasa_opts_t.fp32); the default and the parity path is fp64")
@@ -340,6 +341,54 @@ def main():
             _l.pinned_free(a)
         del h_iso, h_gene
 
+    # ------------------------------------------------------------------ e2e_files: bfh.txt in, the two text files out
+    e2e_files = None
+    if not args.no_e2e and args.files_cells > 0:
+        import shutil
+        import tempfile
+        from scasa_b200.api import quant_files
+        from scasa_b200.bfh import read_bfh
+        nf = min(args.files_cells, n)
+        tmp = tempfile.mkdtemp(prefix=f"scasa_bench_{rank}_")
+        try:
+            bc = synth.barcodes(nf, seed + rank)
+            nz = int(cell_ptr[nf])
+            bfh_path = os.path.join(tmp, "bfh.txt")
+            bfh_bytes = synth.write_bfh(bfh_path, xm.tx_names, bc, ed.eq_off, ed.eq_tx, cell_ptr[: nf + 1], eq_id[:nz], eq_cnt[:nz])
+            tx_names = xm.dm0_colnames()
+            gnames = list(xm.gene_names) if xm.gene_names is not None else [f"GENE{i}" for i in range(n_genes)]
+            if xm.gene_of_col is not None:
+                g.set_gene_map(np.asarray(xm.gene_of_col, np.int32), len(gnames))      # ids as the annotation has them; the writer orders the rows
+
+            def files_step():
+                b = read_bfh(bfh_path, nthreads)                                       # step1_1 + step2:59-60
+                return quant_files([g], b.cell_ptr, b.eq_id, b.eq_count, b.eq_off, b.tx_ids(xm),
+                                   os.path.join(tmp, "scasa_isoform_counts.txt"), os.path.join(tmp, "scasa_gene_expression.txt"),
+                                   tx_names, gnames, b.barcodes, core=4, n_threads=nthreads)
+
+            files_step()
+            barrier()
+            t0 = time.perf_counter()
+            _, ftm = files_step()
+            barrier()
+            tf = time.perf_counter() - t0
+            tt = torch.tensor([tf], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            tf = float(tt[0])
+            out_bytes_f = ftm["iso_bytes"] + ftm["gene_bytes"]
+            e2e_files = {"value": nf * world / tf, "unit": "cells/s", "cells_per_gpu": nf, "s_per_step": tf,
+                         "bfh_bytes": int(bfh_bytes), "text_bytes_written": int(out_bytes_f), "text_gb_per_s": out_bytes_f / 1e9 / max(ftm["write_iso_s"] + ftm["write_gene_s"], 1e-9),
+                         "phases_s": {k: ftm[k] for k in ("quant_s", "transpose_s", "write_iso_s", "write_gene_s")},
+                         "rows_written": {"isoform": ftm["iso_rows"], "gene": ftm["gene_rows"]},
+                         "includes": "scasa_bfh_open (parse alevin bfh.txt), host eqclass->row map, scasa_quant_files: H2D, kernels, sparse D2H, "
+                                     "host transposition, scasa_isoform_counts.txt + scasa_gene_expression.txt written (write.table bytes); "
+                                     "no dense matrix anywhere",
+                         "dir": "tempfile.mkdtemp() on the box's local disk", "host_threads": nthreads}
+            g.set_gene_map(goc, n_genes)
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -403,6 +452,8 @@ def main():
             "clocks": clocks, "roofline": roofline}
     if e2e:
         line["e2e"] = e2e
+    if e2e_files:
+        line["e2e_files"] = e2e_files
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_reference(xm, cfg, args, os.cpu_count() or 1)
     print(json.dumps(line))

@@ -238,3 +238,36 @@ def assemble_xmatrix(xm: XMatrix, pick: np.ndarray) -> XMatrix:
     tx_names = [f"TX{t}" for t in range(crp_p_off[-1])]
     return XMatrix(q_off, crp_p_off, crp_x_off, crp_x, crp_tx, crp_pat, dm0_p_off, dm0_x_off, dm0_x, crp_member,
                    np.arange(n_blocks, dtype=np.int32), tx_names)
+
+
+def write_bfh(path: str, tx_names, barcodes, eq_off, eq_tx, cell_ptr, eq_id, eq_count) -> int:
+    """The sample as an alevin ``bfh.txt`` (`salmon alevin --dumpBfh`; format per scasa_quant_step1_1_v1.0.0.R:16-68):
+    three count lines, transcript names, barcodes, then one line per equivalence class
+    ``n_tx, tx idx.., total reads, n_bc, (bc idx, n_umi, (umi, reads) x n_umi) x n_bc``.  The count of a
+    (cell, eqclass) is its number of UMIs (step1_1:50-56), so a count c becomes c UMIs with one read each.
+    Only classes that occur in some cell are written (their ids are renumbered).  Returns the file size."""
+    eq_id = np.asarray(eq_id)
+    eq_count = np.asarray(eq_count)
+    n_cells = len(cell_ptr) - 1
+    cell_of = np.repeat(np.arange(n_cells), np.diff(cell_ptr))
+    order = np.argsort(eq_id, kind="stable")
+    ids, start = np.unique(eq_id[order], return_index=True)
+    start = np.append(start, len(order))
+    cells, cnts = cell_of[order].tolist(), eq_count[order].tolist()
+    umi = "\tACGTACGTAC\t1"
+    with open(path, "w") as f:
+        f.write(f"{len(tx_names)}\n{len(barcodes)}\n{len(ids)}\n")
+        f.write("\n".join(tx_names) + "\n")
+        f.write("\n".join(barcodes) + "\n")
+        buf = []
+        for k, e in enumerate(ids.tolist()):
+            a, b = int(start[k]), int(start[k + 1])
+            tx = eq_tx[eq_off[e]:eq_off[e + 1]].tolist()
+            body = "".join(f"\t{c}\t{n}" + umi * n for c, n in zip(cells[a:b], cnts[a:b]))
+            buf.append(f"{len(tx)}\t" + "\t".join(map(str, tx)) + f"\t{sum(cnts[a:b])}\t{b - a}" + body)
+            if len(buf) >= 4096:
+                f.write("\n".join(buf) + "\n")
+                buf = []
+        if buf:
+            f.write("\n".join(buf) + "\n")
+        return f.tell()

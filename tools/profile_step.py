@@ -21,6 +21,7 @@ rowptr, rows, vals = synth.CellGenerator(xm, seed=4, device=dev).counts_csr(0, n
 ed = synth.eqclass_dictionary(xm, 4)
 cell_ptr, eq_id, eq_cnt = synth.counts_to_eqcounts(rowptr, rows, vals, 4, device=dev)
 g = Scasa(xm, device=0)
+g.set_gene_map(np.asarray(xm.gene_of_col, np.int32), len(xm.gene_names))
 eq_row = g.eqclass_map(ed.eq_off, ed.eq_tx, 8)
 g.stage_eqcounts(chunk_split(n, 4), cell_ptr, eq_id, eq_cnt, eq_row)
 for _ in range(runs):
