@@ -54,11 +54,11 @@ typedef struct {
     int32_t hamming_dist; /* 1                                            Rsource:534  */
     int32_t fixed_iter;   /* 0     1 = never break: exactly maxiter_x x maxiter_bt iterations (parity mode) */
     int32_t fp32;         /* 0     1 = the EM iterates in fp32 (counts, logNorm and results stay fp64).  Against the fp64 path
-                                   in fixed-iteration mode: every estimate within 1e-4 relative, EXCEPT in blocks that
-                                   hold two nearly collinear columns (cosine >= 0.9): there the split between the two
-                                   transcripts is ill-conditioned and single entries may differ by up to 2e-3, while the
-                                   block total per cell stays within 1e-4 (tests/test_gpu_em.py).  Parity claims are
-                                   made for fp64 only. */
+                                   in fixed-iteration mode: estimates within 1e-4 relative except for a handful of entries
+                                   (about 3 per million: ill-conditioned splits between transcripts with similar columns),
+                                   which stay within 2e-3 while their block total per cell stays within 1e-4
+                                   (tests/test_gpu_em.py).  north_star's 1e-4 is therefore NOT met on every entry; parity
+                                   claims are made for fp64 only. */
     /* estim_chunk does not forward maxerr / lim to estim.BETA (the call at Rsource:1016 passes maxiter and
      * modify only), so the inner loop runs with estim.BETA's own defaults (Rsource:726-727) whatever
      * maxerr / lim above are.  These two are those defaults; a caller who wants the inner loop tightened

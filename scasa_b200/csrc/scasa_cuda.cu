@@ -936,9 +936,10 @@ static void run_all(scasa_ctx *c, RangeStats &rs)
 
     // ---- pack: eqclass counts -> Y
     if (c->have_eq) {
-        const int wpt = (int)((c->n_rows + 32 * 512 - 1) / (32 * 512));      // bitmap words per thread
+        int wpt = (int)((c->n_rows + 32 * 512 - 1) / (32 * 512));           // bitmap words per thread
+        wpt = std::min(wpt, 3);                                              // 3 * 512 * 32 = 49,152 rows per tile (198 KB); more rows: several tiles
         const size_t dense_smem = (size_t)wpt * 512 * 33 * sizeof(int);       // int32 histogram + touched-row bitmap
-        if (dense_smem <= 200 * 1024 && !getenv("SCASA_PACK_SORT")) {
+        if (!getenv("SCASA_PACK_SORT")) {
             CK(cudaFuncSetAttribute(pack_cells_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_smem));
             int grid = (int)std::min<int64_t>(n_cells, (int64_t)w->n_sm);
             pack_cells_dense_kernel<<<grid, 512, dense_smem, s>>>(n_cells, c->d_cell_ptr.p, c->d_eq_id.p, c->d_eq_count.p,

@@ -179,8 +179,8 @@ struct Tasks {                // task t = chunk * n_em + em index
     unsigned int *counters;   // [0..3] list lengths [4] non-empty tasks [5] largest slot need [6] tiny-task list length [7] error flag
 };
 // ------------------------------------------------------------------------------------------
-// crpcount_td's accumulation (Scasa_Rsource.R:528-531, :643-646 and :461-462), fast path: when the
-// X-matrix has few enough rows for an int32 histogram in shared memory (hg38: 41,251 rows = 165 KB)
+// crpcount_td's accumulation (Scasa_Rsource.R:528-531, :643-646 and :461-462): an int32 histogram over the
+// X-matrix rows in shared memory (hg38: 41,251 rows = 165 KB in one tile; larger X-matrices in several tiles):
 // one CTA per cell adds the UMI counts of the cell's eqclasses into hist[row] and then emits the
 // non-zero rows in ascending order.  Integer adds: the result is independent of their order.
 // Thread i owns the contiguous rows [i*seg, (i+1)*seg), seg odd (no bank conflicts); the histogram
@@ -194,11 +194,15 @@ __global__ void __launch_bounds__(512) pack_cells_dense_kernel(int64_t n_cells, 
                                                                double *__restrict__ y_val, int32_t *__restrict__ y_len)
 {
     extern __shared__ int pack_sm[];
-    const int n_words = words_per_thread * (int)blockDim.x;       // >= ceil(n_rows / 32)
-    int *hist = pack_sm;                                          // [n_words * 32] counts by row
+    const int n_words = words_per_thread * (int)blockDim.x;       // rows of one tile / 32
+    int *hist = pack_sm;                                          // [n_words * 32] counts by row of the tile
     unsigned *bits = (unsigned *)(pack_sm + (size_t)n_words * 32);   // [n_words] rows touched by this cell
     __shared__ int wsum[16];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int tile_rows = n_words * 32;
+    // X-matrices with more rows than the histogram holds are taken in tiles of tile_rows rows: the cell's entries
+    // are read once per tile (from L2 after the first), each tile emits its rows behind the previous one's
+    const int n_tiles = (n_rows + tile_rows - 1) / tile_rows;
     for (int i = tid; i < n_words * 33; i += blockDim.x) pack_sm[i] = 0;
     __syncthreads();
     // Entries are taken kPackBatch per thread at a time: all their loads are issued before the first
@@ -230,43 +234,48 @@ __global__ void __launch_bounds__(512) pack_cells_dense_kernel(int64_t n_cells, 
         int64_t s2 = 0;
         int n2 = 0;
         if (cell2 < n_cells) { s2 = cell_ptr[cell2]; n2 = (int)(cell_ptr[cell2 + 1] - s2); }
-        for (int base = 0; base < n; base += kPackBatch * T) {
-            if (base > 0) { load_entries(s, n, base); load_rows(); }
+        int emitted = 0;
+        for (int tile = 0; tile < n_tiles; tile++) {
+            const int r0 = tile * tile_rows, r1 = min(n_rows, r0 + tile_rows);
+            for (int base = 0; base < n; base += kPackBatch * T) {
+                if (base > 0 || tile > 0) { load_entries(s, n, base); load_rows(); }
 #pragma unroll
-            for (int k = 0; k < kPackBatch; k++)
-                if (r[k] >= 0 && r[k] < n_rows && c[k] > 0) {                 // UMI counts are >= 1
-                    atomicAdd(&hist[r[k]], c[k]);
-                    atomicOr(&bits[r[k] >> 5], 1u << (r[k] & 31));
-                }
-        }
-        __syncthreads();
-        load_entries(s2, n2, 0);                                              // in flight during the emission
-        // thread owns words [tid*wpt, (tid+1)*wpt): rows in ascending order across threads
-        const int w0 = tid * words_per_thread;
-        int cnt = 0;
-        for (int k = 0; k < words_per_thread; k++) cnt += __popc(bits[w0 + k]);
-        int inc = cnt;
-        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += v; }
-        if (lane == 31) wsum[w] = inc;
-        __syncthreads();
-        int base = 0, total = 0;
-        for (int k = 0; k < (int)(blockDim.x >> 5); k++) { int v = wsum[k]; if (k < w) base += v; total += v; }
-        int o = base + inc - cnt;
-        if (cnt)
-            for (int k = 0; k < words_per_thread; k++) {
-                unsigned m = bits[w0 + k];
-                bits[w0 + k] = 0;
-                while (m) {
-                    const int rr = ((w0 + k) << 5) + __ffs(m) - 1;
-                    m &= m - 1;
-                    const int v = hist[rr];
-                    hist[rr] = 0;
-                    y_row[s + o] = rr; y_val[s + o] = (double)v; o++;
-                }
+                for (int k = 0; k < kPackBatch; k++)
+                    if (r[k] >= r0 && r[k] < r1 && c[k] > 0) {                    // UMI counts are >= 1
+                        atomicAdd(&hist[r[k] - r0], c[k]);
+                        atomicOr(&bits[(r[k] - r0) >> 5], 1u << ((r[k] - r0) & 31));
+                    }
             }
-        load_rows();
-        if (tid == 0) y_len[cell] = total;
-        __syncthreads();
+            __syncthreads();
+            if (tile == n_tiles - 1) load_entries(s2, n2, 0);                     // in flight during the emission
+            // thread owns words [tid*wpt, (tid+1)*wpt): rows in ascending order across threads
+            const int w0 = tid * words_per_thread;
+            int cnt = 0;
+            for (int k = 0; k < words_per_thread; k++) cnt += __popc(bits[w0 + k]);
+            int inc = cnt;
+            for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += v; }
+            if (lane == 31) wsum[w] = inc;
+            __syncthreads();
+            int base = 0, total = 0;
+            for (int k = 0; k < (int)(blockDim.x >> 5); k++) { int v = wsum[k]; if (k < w) base += v; total += v; }
+            int o = emitted + base + inc - cnt;
+            if (cnt)
+                for (int k = 0; k < words_per_thread; k++) {
+                    unsigned m = bits[w0 + k];
+                    bits[w0 + k] = 0;
+                    while (m) {
+                        const int rr = ((w0 + k) << 5) + __ffs(m) - 1;
+                        m &= m - 1;
+                        const int v = hist[rr];
+                        hist[rr] = 0;
+                        y_row[s + o] = rr + r0; y_val[s + o] = (double)v; o++;
+                    }
+                }
+            emitted += total;
+            if (tile == n_tiles - 1) load_rows();
+            __syncthreads();
+        }
+        if (tid == 0) y_len[cell] = emitted;
         s = s2; n = n2;
     }
 }
