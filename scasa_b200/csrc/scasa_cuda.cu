@@ -186,7 +186,6 @@ struct scasa_ctx {
     int cls_ctas_per_sm[kClasses] = {8, 4, 2, 2};
     int pair_max = 16;                // tiny tasks two per warp (em_pair_kernel); SCASA_EM_PAIR=0 turns it off
     int pair_ctas_per_sm = 8;
-    int em_big_n = 24, em_big_row = 12, em_prefetch = 1;   // SCASA_EM_BIG="n:rowlen", SCASA_EM_PREFETCH=0|1 (tuning; see EmOpts)
     DBuf<unsigned long long> d_stats;
     DBuf<int> d_flag;
 
@@ -639,8 +638,6 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
             if (got >= 1) c->pair_max = std::max(0, std::min(16, m));
             if (got >= 2 && cps >= 1) c->pair_ctas_per_sm = cps;
         }
-        if (const char *env = getenv("SCASA_EM_BIG")) { int a = 24, b = 12; if (sscanf(env, "%d:%d", &a, &b) >= 1) { c->em_big_n = a; c->em_big_row = b; } }
-        if (const char *env = getenv("SCASA_EM_PREFETCH")) c->em_prefetch = atoi(env) != 0;
         for (int k = 0; k < kLists; k++) {
             {   // the classes with few, long tasks get scheduling priority: their CTAs go first when an SM has room,
                 // the many-small-tasks class fills what is left and takes over when they are done
@@ -969,7 +966,6 @@ static void run_all(scasa_ctx *c, RangeStats &rs)
     O.fixed_iter = c->opts.fixed_iter;
     O.maxerr = c->opts.maxerr; O.lim = c->opts.lim; O.adjust_esp = c->opts.adjust_esp;
     O.maxerr_bt = c->opts.maxerr_bt; O.lim_bt = c->opts.lim_bt;
-    O.big_n = std::max(17, c->em_big_n); O.big_row = std::max(1, c->em_big_row); O.prefetch = c->em_prefetch;
     ClassCfg CC;
     for (int k = 0; k < kClasses; k++) { CC.pairs[k] = c->cls_pairs[k]; CC.bytes[k] = c->cls_bytes[k]; }
     CC.real_bytes = c->opts.fp32 ? 4 : 8;
@@ -1167,7 +1163,6 @@ static int sync_twin(scasa_ctx *c)
         t->cls_cta_threads[k] = c->cls_cta_threads[k]; t->cls_ctas_per_sm[k] = c->cls_ctas_per_sm[k];
     }
     t->pair_max = c->pair_max; t->pair_ctas_per_sm = c->pair_ctas_per_sm;
-    t->em_big_n = c->em_big_n; t->em_big_row = c->em_big_row; t->em_prefetch = c->em_prefetch;
     if (c->n_genes > 0 && (t->n_genes != c->n_genes || t->gene_of_col_host != c->gene_of_col_host)) {
         int rc = scasa_set_gene_map(t, c->gene_of_col_host.data(), c->n_genes);
         if (rc) return fail(c, rc, std::string("twin context: ") + scasa_last_error(t));

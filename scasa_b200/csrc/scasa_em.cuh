@@ -25,6 +25,36 @@ namespace scasa {
 //   digamma(x) = log(xs) - 1/(2 xs) - series(1/xs^2) - sum_{i<9} 1/(x+i),   xs = x + 9 for x < 9
 //   => exp(digamma(x) - L) = xs * exp(-(1/(2 xs) + series + rec + L)),
 // one division serving both 1/xs and the folded reciprocal sum (see digamma_pos).
+// exp(y) for the argument range of em_gamma_fast (y <= ~0.6; very negative for dying transcripts): Cody-Waite
+// reduction by ln 2, degree-13 Taylor polynomial on |r| <= 0.347 (truncation 4e-18), scaling through the exponent
+// field.  Below -700 (results under 1e-304) the library exp takes over, so underflow to denormals and to an exact 0
+// is what R's exp gives (Rsource:738: gamma = 0 is how a transcript dies).  ~25 instructions instead of ~60 executed
+// of the library's 135; differs from it by at most 1-2 ulp.
+__device__ __forceinline__ double em_exp(double y)
+{
+    if (y < -700.0) return y < -746.0 ? 0.0 : exp(y);
+    const double kd = rint(y * 1.4426950408889634074);
+    double r = fma(kd, -6.93147180369123816490e-01, y);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = 1.0 / 6227020800.0;
+    p = fma(p, r, 1.0 / 479001600.0);
+    p = fma(p, r, 1.0 / 39916800.0);
+    p = fma(p, r, 1.0 / 3628800.0);
+    p = fma(p, r, 1.0 / 362880.0);
+    p = fma(p, r, 1.0 / 40320.0);
+    p = fma(p, r, 1.0 / 5040.0);
+    p = fma(p, r, 1.0 / 720.0);
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int k = (int)kd;                                    // >= -1010 here: the result is a normal number
+    return __hiloint2double(__double2hiint(p) + k * 1048576, __double2loint(p));
+}
+__device__ __forceinline__ float em_exp(float y) { return expf(y); }
+
 template <typename R> __device__ __forceinline__ R em_gamma_fast(R beta, R lnorm)
 {
     const R x = beta + R(0.00000001);
@@ -46,7 +76,7 @@ template <typename R> __device__ __forceinline__ R em_gamma_fast(R beta, R lnorm
     const R r2 = r * r;
     const R s = r2 * (R(1.0 / 12.0) - r2 * (R(1.0 / 120.0) - r2 * (R(1.0 / 252.0) - r2 * (R(1.0 / 240.0) -
                 r2 * (R(1.0 / 132.0) - r2 * (R(691.0 / 32760.0) - r2 * R(1.0 / 12.0)))))));
-    return xs * exp(-(R(0.5) * r + s + rec + lnorm));
+    return xs * em_exp(-(R(0.5) * r + s + rec + lnorm));
 }
 __device__ __forceinline__ double rabs(double x) { return fabs(x); }
 __device__ __forceinline__ float rabs(float x) { return fabsf(x); }
@@ -157,7 +187,6 @@ template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_k
         const int ap = (last_cw & kPseudo) ? n - 1 : -1;
         const R pmult = (last_cw & kPseudo) ? (R)(last_cw & 0xffff) : R(0);
         const int n_real = ap >= 0 ? n - 1 : n;
-        const bool big = n >= O.big_n && E >= O.big_row * q;   // sums over cells split over eight lanes (big_n > 16: never in em_pair_kernel)
         for (int a = gl; a < n; a += GT) {
             const int k1 = eptr[a + 1];
             for (int k = eptr[a]; k < k1; k++) erec[k] = (uint16_t)a;
@@ -308,32 +337,12 @@ template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_k
             }
 
             // ================= estim.X.em(X.est0, BT, Ymat)  :898-922
-            if (!big) {
-                for (int j = gl; j < p; j += GT) {                               // BTsum = colSums(BETA)  :904
-                    R s = 0;
+            for (int j = gl; j < p; j += GT) {                                   // BTsum = colSums(BETA)  :904
+                R s = 0;
 #pragma unroll 1
-                    for (int a = 0; a < n_real; a++) s += beta[j * n + a];
-                    if (ap >= 0) s += pmult * beta[j * n + ap];                  // the pseudo cell stands for pmult cells
-                    bts[j] = s > 0 ? s : R(0.1);                                 // :917 (may be denormal: no reciprocal)
-                }
-            } else {
-                // many cells: eight lanes per column, lane s adds the cells a = s, s + 8, ... in order, then the
-                // eight partial sums are added in lane order: a fixed association that only depends on n
-#pragma unroll 1
-                for (int base = 0; base < 8 * p; base += GT) {
-                    const int idx = base + gl, j = idx >> 3, s8 = idx & 7;
-                    R part = 0;
-                    if (j < p)
-#pragma unroll 1
-                        for (int a = s8; a < n_real; a += 8) part += beta[j * n + a];
-                    R s = part;
-#pragma unroll
-                    for (int k = 1; k < 8; k++) { const R v = __shfl_sync(kFull, part, (lane & ~7) + k); s += v; }
-                    if (j < p && s8 == 0) {
-                        if (ap >= 0) s += pmult * beta[j * n + ap];
-                        bts[j] = s > 0 ? s : R(0.1);
-                    }
-                }
+                for (int a = 0; a < n_real; a++) s += beta[j * n + a];
+                if (ap >= 0) s += pmult * beta[j * n + ap];                      // the pseudo cell stands for pmult cells
+                bts[j] = s > 0 ? s : R(0.1);                                     // :917 (may be denormal: no reciprocal)
             }
 #pragma unroll 1
             for (int k = gl; k < E; k += GT) {
@@ -345,45 +354,19 @@ template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_k
                 ew[k] = mult * (R)ey[k] / (mu > 0 ? mu : R(0.1));                // :908-910
             }
             G.sync();
-            if (!big) {
 #pragma unroll 1
-                for (int idx = gl, j = xj_first, r = xr_first; idx < qp; idx += GT) {   // X.est = colSums(x2 * Y) / BTsum  :911-917
-                    const R x = Xc[idx];
-                    R acc = 0;
-                    const int i1 = rptr[r + 1];
+            for (int idx = gl, j = xj_first, r = xr_first; idx < qp; idx += GT) {   // X.est = colSums(x2 * Y) / BTsum  :911-917
+                const R x = Xc[idx];
+                R acc = 0;
+                const int i1 = rptr[r + 1];
 #pragma unroll 1
-                    for (int i = rptr[r]; i < i1; i++) {
-                        const int k = perm[i];
-                        acc += beta[j * n + erec[k]] * x * ew[k];
-                    }
-                    Xn[idx] = acc == R(0) ? R(0) : acc / bts[j];                 // zero numerators would take the slow division path
-                    r += dxr; j += dxj;
-                    if (r >= q) { r -= q; j++; }
+                for (int i = rptr[r]; i < i1; i++) {
+                    const int k = perm[i];
+                    acc += beta[j * n + erec[k]] * x * ew[k];
                 }
-            } else {
-                // eight lanes per X element: lane s takes the row's entries i = s, s + 8, ... (cell order), partial sums
-                // added in lane order
-#pragma unroll 1
-                for (int base = 0; base < 8 * qp; base += GT) {
-                    const int idx8 = base + gl, idx = idx8 >> 3, s8 = idx8 & 7;
-                    R part = 0;
-                    int j = 0;
-                    if (idx < qp) {
-                        j = idx / q;
-                        const int r = idx - j * q;
-                        const R x = Xc[idx];
-                        const int i1 = rptr[r + 1];
-#pragma unroll 1
-                        for (int i = rptr[r] + s8; i < i1; i += 8) {
-                            const int k = perm[i];
-                            part += beta[j * n + erec[k]] * x * ew[k];
-                        }
-                    }
-                    R acc = part;
-#pragma unroll
-                    for (int k = 1; k < 8; k++) { const R v = __shfl_sync(kFull, part, (lane & ~7) + k); acc += v; }
-                    if (idx < qp && s8 == 0) Xn[idx] = acc == R(0) ? R(0) : acc / bts[j];
-                }
+                Xn[idx] = acc == R(0) ? R(0) : acc / bts[j];                     // zero numerators would take the slow division path
+                r += dxr; j += dxj;
+                if (r >= q) { r -= q; j++; }
             }
             G.sync();
             for (int j = gl; j < p; j += GT) {                                   // csum = colSums(X.est)  :918
@@ -437,15 +420,14 @@ template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_k
             // columns of every poor block (struct_fill_kernel): poor_pos says where.
             const int ap = n - 1;
             const int kp = X.poor_rank[b];
-            double s = 0;
-            if (nadj > 0) for (int j = 0; j < p; j++) s += (double)beta[j * n + ap];
-            for (int a = gl; a < n; a += GT) {
-                const int lo = a == 0 ? 0 : (int)rcell[a - 1] + 1;
-                const int hi = a == n - 1 ? nc : (int)rcell[a];
-                for (int cc = lo; cc < hi; cc++) {
-                    double *o = A.R.rs_val + A.R.rs_ptr[cbase + cc] + A.R.poor_pos[(cbase + cc) * X.n_poor + kp];
-                    for (int j = 0; j < p; j++) { double v = (double)beta[j * n + ap]; if (nadj > 0) v = v - deduct * (v / s); o[j] = v; }
-                }
+            double s = 0, v0 = (double)beta[ap], v1 = (double)beta[n + ap];      // a poor block has two columns
+            if (nadj > 0) { s = v0 + v1; v0 = v0 - deduct * (v0 / s); v1 = v1 - deduct * (v1 / s); }
+            for (int cc = gl; cc < nc; cc += GT) {                               // a lane per cell of the chunk: is it a real record?
+                int lo = 0, hi = ap;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)rcell[mid] < cc) lo = mid + 1; else hi = mid; }
+                if (lo < ap && (int)rcell[lo] == cc) continue;
+                double *o = A.R.rs_val + A.R.rs_ptr[cbase + cc] + A.R.poor_pos[(cbase + cc) * X.n_poor + kp];
+                o[0] = v0; o[1] = v1;
             }
         }
         if (gl == 0) task_done_stats(A.iters, A.stats, t, outer, inner_total, q, p, nc, n);
@@ -487,41 +469,21 @@ template <typename R> __global__ void __launch_bounds__(128, 8) em_pair_kernel(E
       *gam = nullptr;
     uint16_t *erec = nullptr, *rptr = nullptr, *perm = nullptr;
 
-    // The next task is fetched one task ahead: ticket, task id, descriptor, blob offset, chunk extent and the
-    // chunk's result offset are four dependent memory round trips, which are in flight while the current task
-    // iterates.  nt < 0: the queue is empty.
-    int64_t nt = -1, n_off = 0, n_vb = 0;
-    int4 nd = make_int4(0, 0, 0, 0);
-    int n_nc = 0;
-    auto fetch_next = [&]() {
-        unsigned ti = 0;
-        if (hl == 0) ti = atomicAdd(A.next, 1u);
-        ti = __shfl_sync(hmask, ti, hlead);
-        nt = -1;
-        if (ti < n_list) {
-            nt = A.list[ti];
-            const int hh = (int)(nt / X.n_em);
-            nd = A.T.desc[nt];
-            n_off = A.T.toff[nt];
-            const int64_t c0 = A.S.chunk_off[hh], c1 = A.S.chunk_off[hh + 1];
-            n_nc = (int)(c1 - c0);
-            n_vb = A.R.rs_ptr[c0 - A.S.cell_base];
-        }
-    };
-    if (O.prefetch) fetch_next();
-
     for (;;) {
         // ================= LOAD: next task of the queue into this half's slot
         if (phase == LOAD) {
-            if (!O.prefetch) fetch_next();
-            if (nt < 0) phase = DONE;
+            unsigned ti = 0;
+            if (hl == 0) ti = atomicAdd(A.next, 1u);
+            ti = __shfl_sync(hmask, ti, hlead);
+            if (ti >= n_list) phase = DONE;
             else {
-                t = nt;
-                const int4 td = nd;
-                const int64_t blob_off = n_off;
-                nc = n_nc;
-                vals = A.R.rs_val + n_vb;
-                if (O.prefetch) fetch_next();                  // for the task after this one
+                t = A.list[ti];
+                const int hh = (int)(t / X.n_em);
+                const int4 td = A.T.desc[t];                   // block, shape and extents in one load
+                const int64_t blob_off = A.T.toff[t];
+                const int64_t c0 = A.S.chunk_off[hh], c1 = A.S.chunk_off[hh + 1];
+                nc = (int)(c1 - c0);
+                vals = A.R.rs_val + A.R.rs_ptr[c0 - A.S.cell_base];
                 q = td.y & 0xffff; p = td.y >> 16;
                 qp = q * p;
                 n = td.z & 0xffff; E = (int)((unsigned)td.z >> 16);

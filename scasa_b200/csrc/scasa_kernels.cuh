@@ -451,9 +451,6 @@ struct EmOpts {
     int maxiter_x, maxiter_bt, modify, fixed_iter;
     double maxerr, lim, adjust_esp;     // maxerr / lim: the outer test (Rsource:1019-1020)
     double maxerr_bt, lim_bt;           // estim.BETA's own (Rsource:726-727; not forwarded by estim_chunk)
-    int big_n, big_row;                 // tasks with >= big_n records and >= big_row entries per block row on average split
-                                        // their sums over cells over eight lanes (a fixed association; see em_task_kernel)
-    int prefetch;                       // em_pair_kernel fetches the next task's descriptor one task ahead
 };
 
 // Per task: records, stored entries, blob size, work class.  Threads enumerate tasks block-major
