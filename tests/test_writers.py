@@ -63,6 +63,8 @@ def test_format_real15_random_values_agree_with_independent_restatement():
         rng.gamma(0.5, 3.0, 3000),
         np.round(rng.gamma(2.0, 40.0, 2000), 3),
         10.0 ** rng.integers(-30, 30, 200),
+        rng.integers(1, 1000, 3000).astype(float) * 10.0 ** rng.integers(0, 13, 3000),      # whole numbers with trailing zeros
+        np.arange(1.0, 1200.0),                                                            # the counts themselves
     ])
     for x in xs:
         a = format_real15(float(x))
