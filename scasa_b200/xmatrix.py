@@ -156,12 +156,18 @@ class XMatrix:
 
     # --------------------------------------------------------------- from R
     @classmethod
-    def from_rdata(cls, xmatrix_path: str, groups_path: str | None = None) -> "XMatrix":
+    def from_rdata(cls, xmatrix_path: str, groups_path: str | None = None, collate=None) -> "XMatrix":
         """Flatten ``CRP`` and ``CCRP`` of an ``Xmatrix_*.RData``; optionally attach the
         tx→gene map ``genes.tx.map.all.final`` of an ``isoform_groups_*.RData``
-        (scasa_quant_step3_v1.0.0.R:22,35)."""
+        (scasa_quant_step3_v1.0.0.R:22,35).
+
+        ``name_rank`` (the order ``sort()`` puts the block names in, which breaks Jaccard ties at Rsource:484-505)
+        is taken over ``names(CRP)`` with ``collate`` as the sort key; the default, bytes, is ``LC_COLLATE=C``.
+        R sorts in the session's collation (en_US ignores spaces and punctuation at the first level), so a
+        caller that must match such a session passes its own key; the R shim passes R's own ranks."""
         ws = load_rdata(xmatrix_path)
         crp_l, ccrp_l = ws["CRP"].value, ws["CCRP"].value
+        crp_names = list(ws["CRP"].names) if getattr(ws["CRP"], "names", None) is not None else None
         B = len(crp_l)
         q_off = np.zeros(B + 1, np.int32)
         cp_off = np.zeros(B + 1, np.int32)
@@ -197,7 +203,10 @@ class XMatrix:
                     where[t] = int(dp_off[k]) + j
             member.extend(where.get(t, -1) for t in cn)
         names = [" ".join(c.dimnames[1]) for c in crp_l]
-        order = sorted(range(B), key=lambda i: names[i].encode())
+        if crp_names is not None and crp_names != names:          # K1: t2c / c2t are built from names(CRP) (Rsource:423-427)
+            raise ValueError("names(CRP) are not the blocks' column names joined by ' ' (SURVEY.md K1)")
+        key = collate or (lambda s: s.encode())
+        order = sorted(range(B), key=lambda i: key(names[i]))
         rank = np.empty(B, np.int32)
         rank[order] = np.arange(B, dtype=np.int32)
         xm = cls(q_off, cp_off, cx_off, np.concatenate(crp_x), np.asarray(crp_tx, np.int32),
