@@ -192,7 +192,7 @@ struct scasa_ctx {
     // ---- results: CSR by cell over the structure (scasa_kernels.cuh: struct Result); no dense matrix on the device
     DBuf<int32_t> d_rs_len, d_rs_col, d_poor_pos, d_g_col, d_g_len, d_gene_of_col;
     DBuf<int64_t> d_rs_ptr;
-    DBuf<double> d_rs_val, d_g_val, d_colsum, d_colpart, d_gene_park, d_dense_tmp, d_iso_in, d_gene_out;
+    DBuf<double> d_rs_val, d_g_val, d_colsum, d_colpart, d_dense_tmp, d_iso_in, d_gene_out;
     DBuf<uint32_t> d_ypos;
     int64_t rs_nnz = 0;                  // entries of the result structure of the last run
     std::vector<int64_t> rs_ptr_host;    // fetched on demand after a run
@@ -215,8 +215,8 @@ struct scasa_ctx {
     int host_threads = 0;        // 0 = hardware concurrency
     int fetch_dense_copy = 0;    // 1 = plain dense D2H (SCASA_FETCH_DENSE)
     int n_genes = 0;
-    int gene_tile = 0, gene_ctas_per_sm = 2;   // gene_rows_kernel: genes per pass (shared-memory slots), resident CTAs
-    int gene_max_members = 1;
+    int gene_ctas_per_sm = 4;                  // gene_rows_kernel: resident CTAs per SM (SCASA_GENE_CTAS)
+    int gene_max_members = 1, gene_n_multi = 0;   // most isoforms of a gene; genes with more than one
     DBuf<int2> d_col_gene;                     // per column: {gene or -1, position among the gene's members}
     DBuf<int32_t> d_gene_ptr, d_gene_cols;
     scasa_timing_t timing{};
@@ -609,12 +609,7 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
                              [&](int32_t x, int32_t y) { return cost[(size_t)x] > cost[(size_t)y]; });
         }
         if (getenv("SCASA_FETCH_DENSE")) c->fetch_dense_copy = 1;
-        if (const char *env = getenv("SCASA_GENE_TILE")) {      // "genes per pass[:ctas_per_sm]" of gene_rows_kernel
-            int t = 0, cps = 2;
-            const int got = sscanf(env, "%d:%d", &t, &cps);
-            if (got >= 1 && t > 0) c->gene_tile = t;
-            if (got >= 2 && cps >= 1) c->gene_ctas_per_sm = cps;
-        }
+        if (const char *env = getenv("SCASA_GENE_CTAS")) c->gene_ctas_per_sm = std::max(1, atoi(env));
         // EM work classes; SCASA_EM_CFG="warps:pairs:bytes:cta_threads:ctas_per_sm,..." overrides (tuning)
         if (const char *env = getenv("SCASA_EM_CFG")) {
             int k = 0;
@@ -727,7 +722,7 @@ void scasa_ctx_destroy(scasa_ctx *c)
     DBuf<int64_t> *i64[] = {&c->d_x_off, &c->d_chunk_off, &c->d_y_start, &c->d_cell_ptr, &c->d_toff, &c->d_scan_sums, &c->d_totals,
                             &c->d_rs_ptr};
     for (auto b : i64) b->release();
-    DBuf<double> *f64[] = {&c->d_x, &c->d_y_val, &c->d_rs_val, &c->d_g_val, &c->d_colsum, &c->d_colpart, &c->d_gene_park,
+    DBuf<double> *f64[] = {&c->d_x, &c->d_y_val, &c->d_rs_val, &c->d_g_val, &c->d_colsum, &c->d_colpart,
                            &c->d_dense_tmp, &c->d_iso_in, &c->d_gene_out};
     for (auto b : f64) b->release();
     c->d_poor.release(); c->d_next.release(); c->d_stats.release(); c->d_flag.release();
@@ -881,13 +876,16 @@ int scasa_set_gene_map(scasa_ctx *c, const int32_t *gene_of_col, int32_t n_genes
         c->d_gene_of_col.upload(goc, c->stream);
         {
             std::vector<int2> cg((size_t)c->n_cols, make_int2(-1, 0));
-            int mx = 1;
-            for (int g = 0; g < n_genes; g++)
-                for (int m = ptr[(size_t)g]; m < ptr[(size_t)g + 1]; m++) {
-                    cg[(size_t)cols[(size_t)m]] = make_int2(g, m - ptr[(size_t)g]);
-                    mx = std::max(mx, m - ptr[(size_t)g] + 1);
-                }
-            c->gene_max_members = mx;
+            int mx = 1, n_multi = 0;
+            for (int g = 0; g < n_genes; g++) {
+                const int nm = ptr[(size_t)g + 1] - ptr[(size_t)g];
+                if (nm > 255) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a gene may have at most 255 isoform columns"};
+                const int slot = nm > 1 ? ++n_multi : 0;             // 1 + index among the multi-isoform genes
+                for (int m = ptr[(size_t)g]; m < ptr[(size_t)g + 1]; m++)
+                    cg[(size_t)cols[(size_t)m]] = make_int2(g, (m - ptr[(size_t)g]) | (slot << 8));
+                mx = std::max(mx, nm);
+            }
+            c->gene_max_members = mx; c->gene_n_multi = n_multi;
             c->d_col_gene.upload(cg, c->stream);
         }
         CK(cudaStreamSynchronize(c->stream));
@@ -1106,24 +1104,18 @@ static void run_all(scasa_ctx *c, RangeStats &rs)
     }
     CK(cudaEventRecord(w->ev[4], s));
     if (c->n_genes > 0) {
-        // genes per pass: everything when the slots fit in shared memory; 16-bit slots when no row can hold 65535 entries
-        const bool small = c->n_cols < 65535;
-        const int cps = std::max(1, c->gene_ctas_per_sm);
-        const size_t budget = (size_t)(216 * 1024) / cps - 1024 - (size_t)kGeneAcc * 8;
-        int tile = c->gene_tile > 0 ? std::min(c->gene_tile, c->n_genes) : c->n_genes;
-        tile = (int)std::min<size_t>((size_t)tile, (size_t)(budget / (small ? 2.2 : 4.2)));
-        const int wpt = ((tile + 31) / 32 + kGeneRowThreads - 1) / kGeneRowThreads;
-        const size_t smem = (size_t)kGeneAcc * 8 + (size_t)wpt * kGeneRowThreads * 4 + (size_t)tile * (small ? 2 : 4);
+        const bool small = c->n_cols < 65535;                        // 16-bit entry indices when no row can hold 65535 entries
+        const int wpt = ((c->n_genes + 31) / 32 + kGeneRowThreads - 1) / kGeneRowThreads;
+        const size_t smem = (size_t)c->gene_n_multi * (8 + (small ? 2 : 4)) + (size_t)wpt * kGeneRowThreads * 8 + 16;
+        if (smem > 200 * 1024) throw ArgErr{SCASA_ERR_UNSUPPORTED, "gene map: too many multi-isoform genes for the gene kernel's shared memory"};
+        const int cps = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->gene_ctas_per_sm, (size_t)(220 * 1024) / (smem + 1024)));
         const int grid = (int)std::min<int64_t>(n_cells, (int64_t)w->n_sm * cps);
-        c->d_gene_park.ensure((size_t)grid * c->n_cols);
         if (small) {
             CK(cudaFuncSetAttribute(gene_rows_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            gene_rows_kernel<uint16_t><<<grid, kGeneRowThreads, smem, s>>>(R, n_cells, c->n_cols, c->d_col_gene.p, c->n_genes, tile, wpt,
-                                                                          c->gene_max_members, c->d_gene_park.p);
+            gene_rows_kernel<uint16_t><<<grid, kGeneRowThreads, smem, s>>>(R, n_cells, c->d_col_gene.p, c->n_genes, c->gene_n_multi, wpt, c->gene_max_members);
         } else {
             CK(cudaFuncSetAttribute(gene_rows_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            gene_rows_kernel<int32_t><<<grid, kGeneRowThreads, smem, s>>>(R, n_cells, c->n_cols, c->d_col_gene.p, c->n_genes, tile, wpt,
-                                                                         c->gene_max_members, c->d_gene_park.p);
+            gene_rows_kernel<int32_t><<<grid, kGeneRowThreads, smem, s>>>(R, n_cells, c->d_col_gene.p, c->n_genes, c->gene_n_multi, wpt, c->gene_max_members);
         }
         CK(cudaGetLastError());
         launches++;

@@ -901,39 +901,40 @@ __global__ void colsum_em_reduce(const double *__restrict__ colpart, int n_chunk
 // ------------------------------------------------------------------------------------------
 // scasa_genemat on the sparse rows (scasa_quant_step3_v1.0.0.R:32-46): gene row = column sum over the
 // gene's isoform rows, members added in row order (parasum's colSums, step3:27); single-member genes are
-// copies (step3:38-40).  One CTA per cell.  col_gene[j] = {gene of column j or -1, position of j among the
-// gene's members}.  The row is processed in ROUNDS by member position: in round r the entries that are the
-// r-th member of their gene either open the gene (slot[g] = entry, acc = value) or add their value to it.
-// A gene has at most one entry per round, so there is no race and every sum is taken in member = column
-// order, whatever the thread count.  The present genes are then emitted in ascending gene order from a
-// bitmap, like the pack kernel does for rows.  Genes are processed in tiles of `tile` genes so that any
-// number of genes fits; T = uint16_t when a row cannot have 65535 entries (two CTAs per SM fit then).
-constexpr int kGeneRowThreads = 512;
-constexpr int kGeneKeep = 6;                 // entries a thread keeps in registers across the rounds
-constexpr int kGeneAcc = 4096;               // rows up to this length accumulate in shared memory, longer ones in HBM
-template <typename T>
-__global__ void __launch_bounds__(kGeneRowThreads, 2) gene_rows_kernel(Result R, int64_t n_cells, int64_t n_cols,
-                                                                    const int2 *__restrict__ col_gene, int n_genes, int tile,
-                                                                    int words_per_thread, int max_members,
-                                                                    double *__restrict__ park_all)
+// copies (step3:38-40).  One CTA per cell (four per SM).
+//   col_gene[j] = {gene of column j or -1, position of j among the gene's members | (1 + slot of the gene among the
+//                  multi-member genes) << 8; slot part 0 for single-member genes}
+//   A  every entry sets its gene's bit in a bitmap over the genes
+//   B  a block scan of the bitmap's word counts: an entry's output position is the number of present genes before
+//      its own = word prefix + popcount below its bit; no sort
+//   C  multi-member genes are summed in ROUNDS by member position: in round r the entries that are the r-th member
+//      of their gene either open the gene's accumulator or add to it.  A gene has at most one entry per round, so
+//      there is no race and every sum is taken in member = column order, whatever the thread count.
+//   D  single-member entries write (gene, value) to their position; the entry that opened a multi-member gene
+//      writes the gene's sum.  Output rows are ascending in gene id by construction.
+constexpr int kGeneRowThreads = 256;
+constexpr int kGeneKeep = 10;                // entries a thread keeps in registers (rows up to 2,560 entries; the rest is re-read)
+template <typename T>                        // T = uint16_t when a row cannot have 65535 entries (smaller shared-memory footprint)
+__global__ void __launch_bounds__(kGeneRowThreads, 4) gene_rows_kernel(Result R, int64_t n_cells, const int2 *__restrict__ col_gene,
+                                                                       int n_genes, int n_multi, int words_per_thread, int max_members)
 {
     extern __shared__ __align__(16) unsigned char gene_sm_raw[];
     constexpr T kEmpty = (T)~(T)0;
-    double *acc_sm = (double *)gene_sm_raw;                                        // [kGeneAcc]
-    unsigned *bits = (unsigned *)(acc_sm + kGeneAcc);                              // [words_per_thread * blockDim.x] genes present
-    const int n_words = words_per_thread * (int)blockDim.x;
-    T *slot = (T *)(bits + n_words);                                               // [tile] entry that opened the gene
+    const int n_words = words_per_thread * kGeneRowThreads;                         // >= ceil(n_genes / 32)
+    double *macc = (double *)gene_sm_raw;                                           // [n_multi] sums of the multi-member genes
+    unsigned *bits = (unsigned *)(macc + n_multi);                                  // [n_words] genes present
+    int *wpre = (int *)(bits + n_words);                                            // [n_words] present genes before the word
+    T *mhead = (T *)(wpre + n_words);                                               // [n_multi] entry that opened the gene's accumulator
     __shared__ int wsum[kGeneRowThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    for (int i = tid; i < tile; i += blockDim.x) slot[i] = kEmpty;
-    for (int i = tid; i < n_words; i += blockDim.x) bits[i] = 0u;
+    for (int i = tid; i < n_words; i += kGeneRowThreads) bits[i] = 0u;
+    for (int i = tid; i < n_multi; i += kGeneRowThreads) mhead[i] = kEmpty;
     __syncthreads();
     for (int64_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
         const int64_t base = R.rs_ptr[cell];
         const int n = (int)(R.rs_ptr[cell + 1] - base);
         const int32_t *col = R.rs_col + base;
         const double *val = R.rs_val + base;
-        double *acc = n <= kGeneAcc ? acc_sm : park_all + (size_t)blockIdx.x * n_cols;
         int2 cg[kGeneKeep];
         double v[kGeneKeep];
 #pragma unroll
@@ -942,51 +943,85 @@ __global__ void __launch_bounds__(kGeneRowThreads, 2) gene_rows_kernel(Result R,
             cg[k] = make_int2(-1, 0); v[k] = 0.0;
             if (i < n) { cg[k] = col_gene[col[i]]; v[k] = val[i]; }
         }
-        int emitted = 0;
-        for (int g0 = 0; g0 < n_genes; g0 += tile) {
-            for (int r = 0; r < max_members; r++) {
-                bool more = false;
-                auto visit = [&](int i, int2 c, double x) {
-                    const int gl = c.x - g0;
-                    if (c.x < 0 || gl < 0 || gl >= tile) return;
-                    if (c.y > r) { more = true; return; }
-                    if (c.y < r) return;
-                    const T sl = slot[gl];
-                    if (sl == kEmpty) { slot[gl] = (T)i; acc[i] = x; atomicOr(&bits[gl >> 5], 1u << (gl & 31)); }
-                    else acc[sl] += x;
-                };
+        // f(entry index, {gene, pos | slot << 8}, value) for every entry of the row this thread owns
+        auto for_entries = [&](auto &&f) {
 #pragma unroll
-                for (int k = 0; k < kGeneKeep; k++) visit(tid + k * kGeneRowThreads, cg[k], v[k]);
-                for (int i = tid + kGeneKeep * kGeneRowThreads; i < n; i += kGeneRowThreads) visit(i, col_gene[col[i]], val[i]);
-                if (!__syncthreads_or(more)) break;
+            for (int k = 0; k < kGeneKeep; k++) f(tid + k * kGeneRowThreads, cg[k], v[k]);
+            for (int i = tid + kGeneKeep * kGeneRowThreads; i < n; i += kGeneRowThreads) f(i, col_gene[col[i]], val[i]);
+        };
+        // ---- A
+        unsigned pend = 0;                                            // register entries that belong to multi-member genes
+#pragma unroll
+        for (int k = 0; k < kGeneKeep; k++)
+            if (cg[k].x >= 0) {
+                atomicOr(&bits[cg[k].x >> 5], 1u << (cg[k].x & 31));
+                if ((cg[k].y >> 8) > 0) pend |= 1u << k;
             }
-            // emission in gene order; thread owns words [tid*wpt, (tid+1)*wpt)
-            const int w0 = tid * words_per_thread;
-            int cnt = 0;
-            for (int k = 0; k < words_per_thread; k++) cnt += __popc(bits[w0 + k]);
-            int inc = cnt;
-            for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += x; }
-            if (lane == 31) wsum[w] = inc;
-            __syncthreads();
-            int before = 0, total = 0;
-            for (int k = 0; k < (int)(blockDim.x >> 5); k++) { const int x = wsum[k]; if (k < w) before += x; total += x; }
-            int64_t o = base + emitted + before + inc - cnt;
-            if (cnt)
-                for (int k = 0; k < words_per_thread; k++) {
-                    unsigned m = bits[w0 + k];
-                    bits[w0 + k] = 0u;
-                    while (m) {
-                        const int gl = ((w0 + k) << 5) + __ffs(m) - 1;
-                        m &= m - 1;
-                        const int i = (int)slot[gl];
-                        slot[gl] = kEmpty;
-                        R.g_col[o] = gl + g0; R.g_val[o] = acc[i]; o++;
-                    }
-                }
-            emitted += total;
-            __syncthreads();
+        const bool long_row = n > kGeneKeep * kGeneRowThreads;
+        if (long_row)
+            for (int i = tid + kGeneKeep * kGeneRowThreads; i < n; i += kGeneRowThreads) {
+                const int g = col_gene[col[i]].x;
+                if (g >= 0) atomicOr(&bits[g >> 5], 1u << (g & 31));
+            }
+        __syncthreads();
+        // ---- B: thread owns words [tid*wpt, (tid+1)*wpt)
+        const int w0 = tid * words_per_thread;
+        int cnt = 0;
+        for (int k = 0; k < words_per_thread; k++) cnt += __popc(bits[w0 + k]);
+        int inc = cnt;
+        for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += x; }
+        if (lane == 31) wsum[w] = inc;
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int k = 0; k < kGeneRowThreads / 32; k++) { const int x = wsum[k]; if (k < w) before += x; total += x; }
+        {
+            int run = before + inc - cnt;
+            for (int k = 0; k < words_per_thread; k++) { wpre[w0 + k] = run; run += __popc(bits[w0 + k]); }
         }
-        if (tid == 0) R.g_len[cell] = emitted;
+        // ---- C (its first barrier also publishes wpre): only the entries still pending are looked at in a round
+        for (int r = 0; r < max_members; r++) {
+            auto visit = [&](int i, int2 c, double x) -> bool {     // true: this entry is done
+                const int ms = (c.y >> 8) - 1, pos = c.y & 0xff;
+                if (pos != r) return false;
+                const T h = mhead[ms];
+                if (h == kEmpty) { mhead[ms] = (T)i; macc[ms] = x; }
+                else macc[ms] += x;
+                return true;
+            };
+            if (pend) {
+#pragma unroll
+                for (int k = 0; k < kGeneKeep; k++)
+                    if ((pend >> k) & 1u)
+                        if (visit(tid + k * kGeneRowThreads, cg[k], v[k])) pend &= ~(1u << k);
+            }
+            bool more = pend != 0;
+            if (long_row)
+                for (int i = tid + kGeneKeep * kGeneRowThreads; i < n; i += kGeneRowThreads) {
+                    const int2 c = col_gene[col[i]];
+                    if (c.x < 0 || (c.y >> 8) == 0) continue;
+                    if ((c.y & 0xff) > r) more = true;
+                    else if ((c.y & 0xff) == r) visit(i, c, val[i]);
+                }
+            if (!__syncthreads_or(more)) break;
+        }
+        // ---- D
+        for_entries([&](int i, int2 c, double x) {
+            if (c.x < 0) return;
+            const int ms = (c.y >> 8) - 1;
+            if (ms >= 0) {
+                if (mhead[ms] != (T)i) return;                        // a later member: already in the opener's sum
+                x = macc[ms];
+            }
+            const int g = c.x;
+            const int64_t o = base + wpre[g >> 5] + __popc(bits[g >> 5] & ((1u << (g & 31)) - 1u));
+            R.g_col[o] = g; R.g_val[o] = x;
+        });
+        if (tid == 0) R.g_len[cell] = total;
+        __syncthreads();
+        // ---- reset for the next cell
+        for (int k = 0; k < words_per_thread; k++) bits[w0 + k] = 0u;
+        for_entries([&](int, int2 c, double) { if (c.x >= 0 && (c.y >> 8) > 0) mhead[(c.y >> 8) - 1] = kEmpty; });
+        __syncthreads();
     }
 }
 
