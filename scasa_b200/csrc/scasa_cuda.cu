@@ -215,7 +215,7 @@ struct scasa_ctx {
     int host_threads = 0;        // 0 = hardware concurrency
     int fetch_dense_copy = 0;    // 1 = plain dense D2H (SCASA_FETCH_DENSE)
     int n_genes = 0;
-    int gene_ctas_per_sm = 4;                  // gene_rows_kernel: resident CTAs per SM (SCASA_GENE_CTAS)
+    int gene_ctas_per_sm = 2;                  // gene_rows_kernel: resident CTAs per SM (SCASA_GENE_CTAS)
     int gene_max_members = 1, gene_n_multi = 0;   // most isoforms of a gene; genes with more than one
     DBuf<int2> d_col_gene;                     // per column: {gene or -1, position among the gene's members}
     DBuf<int32_t> d_gene_ptr, d_gene_cols;

@@ -901,7 +901,7 @@ __global__ void colsum_em_reduce(const double *__restrict__ colpart, int n_chunk
 // ------------------------------------------------------------------------------------------
 // scasa_genemat on the sparse rows (scasa_quant_step3_v1.0.0.R:32-46): gene row = column sum over the
 // gene's isoform rows, members added in row order (parasum's colSums, step3:27); single-member genes are
-// copies (step3:38-40).  One CTA per cell (four per SM).
+// copies (step3:38-40).  One CTA per cell (two per SM, 512 threads).
 //   col_gene[j] = {gene of column j or -1, position of j among the gene's members | (1 + slot of the gene among the
 //                  multi-member genes) << 8; slot part 0 for single-member genes}
 //   A  every entry sets its gene's bit in a bitmap over the genes
@@ -912,10 +912,10 @@ __global__ void colsum_em_reduce(const double *__restrict__ colpart, int n_chunk
 //      there is no race and every sum is taken in member = column order, whatever the thread count.
 //   D  single-member entries write (gene, value) to their position; the entry that opened a multi-member gene
 //      writes the gene's sum.  Output rows are ascending in gene id by construction.
-constexpr int kGeneRowThreads = 256;
-constexpr int kGeneKeep = 10;                // entries a thread keeps in registers (rows up to 2,560 entries; the rest is re-read)
+constexpr int kGeneRowThreads = 512;
+constexpr int kGeneKeep = 7;                 // entries a thread keeps in registers (rows up to 3,584 entries; the rest is re-read)
 template <typename T>                        // T = uint16_t when a row cannot have 65535 entries (smaller shared-memory footprint)
-__global__ void __launch_bounds__(kGeneRowThreads, 4) gene_rows_kernel(Result R, int64_t n_cells, const int2 *__restrict__ col_gene,
+__global__ void __launch_bounds__(kGeneRowThreads, 2) gene_rows_kernel(Result R, int64_t n_cells, const int2 *__restrict__ col_gene,
                                                                        int n_genes, int n_multi, int words_per_thread, int max_members)
 {
     extern __shared__ __align__(16) unsigned char gene_sm_raw[];
