@@ -933,10 +933,12 @@ static void run_all(scasa_ctx *c, RangeStats &rs)
     if (c->have_eq) {
         int wpt = (int)((c->n_rows + 32 * 512 - 1) / (32 * 512));           // bitmap words per thread
         wpt = std::min(wpt, 3);                                              // 3 * 512 * 32 = 49,152 rows per tile (198 KB); more rows: several tiles
+        if (const char *env = getenv("SCASA_PACK_WPT")) wpt = std::max(1, std::min(3, atoi(env)));   // smaller tiles: more CTAs per SM, more passes
         const size_t dense_smem = (size_t)wpt * 512 * 33 * sizeof(int);       // int32 histogram + touched-row bitmap
         if (!getenv("SCASA_PACK_SORT")) {
             CK(cudaFuncSetAttribute(pack_cells_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_smem));
-            int grid = (int)std::min<int64_t>(n_cells, (int64_t)w->n_sm);
+            const int pack_ctas = (int)std::max<size_t>(1, (size_t)(220 * 1024) / (dense_smem + 1024));
+            int grid = (int)std::min<int64_t>(n_cells, (int64_t)w->n_sm * pack_ctas);
             pack_cells_dense_kernel<<<grid, 512, dense_smem, s>>>(n_cells, c->d_cell_ptr.p, c->d_eq_id.p, c->d_eq_count.p,
                                                                   c->d_eq_row.p, c->n_eq, (int)c->n_rows, wpt, c->d_y_row.p,
                                                                   c->d_y_val.p, c->d_y_len.p);
