@@ -185,7 +185,7 @@ struct scasa_ctx {
     int cls_cta_threads[kClasses] = {128, 256, 256, 256};
     int cls_ctas_per_sm[kClasses] = {8, 4, 2, 2};
     int pair_max = 16;                // tiny tasks two per warp (em_pair_kernel); SCASA_EM_PAIR=0 turns it off
-    int pair_ctas_per_sm = 8;
+    int pair_ctas_per_sm = 12;
     DBuf<unsigned long long> d_stats;
     DBuf<int> d_flag;
 
@@ -628,7 +628,7 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
         }
         c->cls_pairs[kClasses - 1] = 1 << 30; c->cls_bytes[kClasses - 1] = 1 << 30;
         if (const char *env = getenv("SCASA_EM_PAIR")) {      // "max[:ctas_per_sm]"
-            int m = 16, cps = 8;
+            int m = 16, cps = 12;
             const int got = sscanf(env, "%d:%d", &m, &cps);
             if (got >= 1) c->pair_max = std::max(0, std::min(16, m));
             if (got >= 2 && cps >= 1) c->pair_ctas_per_sm = cps;

@@ -500,6 +500,7 @@ template <typename R> __global__ void __launch_bounds__(128, 8) em_pair_kernel(E
                 {
                     const uint4 *src = (const uint4 *)(A.T.tdata + blob_off);
                     uint4 *dst = (uint4 *)slot;
+#pragma unroll 1
                     for (int i = hl; i < (BL.bytes >> 4); i += 16) dst[i] = __ldcs(src + i);
                     const double *X0 = X.x + td.w;
                     if (hl < qp) Xc[hl] = (R)X0[hl];
@@ -507,12 +508,14 @@ template <typename R> __global__ void __launch_bounds__(128, 8) em_pair_kernel(E
                 __syncwarp(hmask);
                 if (hl < n) {
                     const int k1 = eptr[hl + 1];
+#pragma unroll 1
                     for (int k = eptr[hl]; k < k1; k++) erec[k] = (uint16_t)hl;
                 }
                 // entries by row, stable in cell order: rank of an entry = entries with a smaller (row, index)
                 {
                     const int myrow = hl < E ? erow[hl] : 0x7fffffff;
                     int rank = 0, below = 0;
+#pragma unroll 1
                     for (int k = 0; k < E; k++) {
                         const int rk = __shfl_sync(hmask, myrow, hlead + k);
                         rank += (rk < myrow) || (rk == myrow && k < hl);
@@ -524,15 +527,18 @@ template <typename R> __global__ void __launch_bounds__(128, 8) em_pair_kernel(E
                 }
                 if (hl < p) {                                               // 1/colSums(X)  :731, :745
                     R s0 = 0;
+#pragma unroll 1
                     for (int r = 0; r < q; r++) s0 += Xc[hl * q + r];
                     rcs[hl] = R(1) / s0;
                 }
                 if (hl < n) {                                               // logNorm :732-733, beta0 :1012-1013
                     double ys = 0;
                     const int k1 = eptr[hl + 1];
+#pragma unroll 1
                     for (int k = eptr[hl]; k < k1; k++) ys += ey[k];
                     lnorm[hl] = (R)digamma_pos(ys + 0.00000001);
                     const R b0 = (R)(ys / p);
+#pragma unroll 1
                     for (int j = 0; j < p; j++) beta[j * n + hl] = b0;
                 }
                 __syncwarp(hmask);
@@ -550,6 +556,7 @@ template <typename R> __global__ void __launch_bounds__(128, 8) em_pair_kernel(E
             if (hl < E) {                                                    // S2
                 const int r = erow[hl], a = erec[hl];
                 R mu = 0;
+#pragma unroll 1
                 for (int j = 0; j < p; j++) mu += Xc[j * q + r] * gam[j * n + a];
                 ew[hl] = (R)ey[hl] / (mu > 0 ? mu : R(1));
             }
@@ -558,6 +565,7 @@ template <typename R> __global__ void __launch_bounds__(128, 8) em_pair_kernel(E
             if (hl < np) {                                                   // S3
                 R s0 = 0;
                 const int k1 = eptr[pa + 1];
+#pragma unroll 1
                 for (int k = eptr[pa]; k < k1; k++) s0 += Xc[pj * q + erow[k]] * ew[k];
                 const R old = beta[hl];
                 const R gs = gam[hl] * s0;
@@ -578,12 +586,14 @@ template <typename R> __global__ void __launch_bounds__(128, 8) em_pair_kernel(E
         if (phase == XUPD) {
             if (hl < p) {                                                    // BTsum  :904, :917
                 R s0 = 0;
+#pragma unroll 1
                 for (int a = 0; a < n; a++) s0 += beta[hl * n + a];
                 bts[hl] = s0 > 0 ? s0 : R(0.1);
             }
             if (hl < E) {
                 const int r = erow[hl], a = erec[hl];
                 R mu = 0;
+#pragma unroll 1
                 for (int j = 0; j < p; j++) mu += beta[j * n + a] * Xc[j * q + r];
                 ew[hl] = (R)ey[hl] / (mu > 0 ? mu : R(0.1));                 // mult = 1: no pseudo cell here
             }
@@ -593,6 +603,7 @@ template <typename R> __global__ void __launch_bounds__(128, 8) em_pair_kernel(E
                 const R x = Xc[hl];
                 R acc = 0;
                 const int i1 = rptr[xr + 1];
+#pragma unroll 1
                 for (int i = rptr[xr]; i < i1; i++) {
                     const int k = perm[i];
                     acc += beta[xj * n + erec[k]] * x * ew[k];
@@ -602,11 +613,13 @@ template <typename R> __global__ void __launch_bounds__(128, 8) em_pair_kernel(E
             __syncwarp(hmask);
             if (hl < p) {
                 R csum = 0;
+#pragma unroll 1
                 for (int r = 0; r < q; r++) csum += Xn[hl * q + r];
                 const R sc = csum < R(0.00001) ? R(-1) : R(1) / (csum > 0 ? csum : R(0.1));
                 nrm[hl] = sc;
                 if (sc >= 0) {
                     R s2 = 0;
+#pragma unroll 1
                     for (int r = 0; r < q; r++) s2 += Xn[hl * q + r] * sc;
                     rcs[hl] = R(1) / s2;
                 }
@@ -632,6 +645,7 @@ template <typename R> __global__ void __launch_bounds__(128, 8) em_pair_kernel(E
         if (phase == OUT) {
             if (hl < n) {
                 double *o = vals + rpos[hl];
+#pragma unroll 1
                 for (int j = 0; j < p; j++) o[j] = (double)beta[j * n + hl];
             }
             if (hl == 0) task_done_stats(A.iters, A.stats, t, outer, inner_total, q, p, nc, n);

@@ -414,7 +414,7 @@ def test_c4_full_size_properties(xm, oracle):
         (Rsource:745), the poor-block de-adjustment removes exactly what was added (:1027-1037) and pass-through
         blocks are copies (:979-983): a cell's isoform total equals its count total over the rows it was packed into;
       * the column sums (step2:167) and the gene sums (step3) are sums of the matrix that was returned;
-      * chunks are independent: three chunks staged on their own give the same bits as inside the full run,
+      * chunks are independent: twelve chunks staged on their own give the same bits as inside the full run,
         and the oracle agrees with them (iteration counts, 1e-6).
     SCASA_TEST_C4_CELLS shrinks the sample (the properties do not depend on it)."""
     import torch
@@ -466,7 +466,7 @@ def test_c4_full_size_properties(xm, oracle):
             assert np.array_equal(gene[:, gi], iso[:, first_col[gi]]), gi
 
         # ---- chunk independence and the oracle on three chunks
-        pick = sorted({0, n_chunks // 2, n_chunks - 1})
+        pick = sorted(set(np.linspace(0, n_chunks - 1, 12).astype(int).tolist()))     # 12 chunks spread over the sample (47,520 tasks)
         cells = np.concatenate([np.arange(chunks[h], chunks[h + 1]) for h in pick])
         lens = np.diff(cell_ptr)[cells]
         sub_ptr = np.concatenate([[0], np.cumsum(lens)])
@@ -489,4 +489,5 @@ def test_c4_full_size_properties(xm, oracle):
     from .parity import compare_tasks
     rep = compare_tasks(iso_s, ref, iters_s, ref_it[:, em, :], sub_chunks, em, xm.dm0_p_off, xm.q_off, poor_b)
     assert rep["n_poor"] > 100                                    # poor blocks are compared, not skipped
-    print("C4 sampled chunks vs oracle:", rep)
+    # how often does a break flip (the kernels compare |d| < maxerr * den where R divides; sums associate differently)?
+    print("C4 sampled chunks vs oracle:", rep, "tasks compared:", len(pick) * len(em), "with other iteration counts:", rep["n_diff"])
