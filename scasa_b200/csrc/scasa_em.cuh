@@ -234,9 +234,11 @@ template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_k
         int nadj = 0;
         if (poor) {
             R *rs = Xn;
+#pragma unroll 1
             for (int r = gl; r < q; r += GT) {
                 double s = 0;
                 const int i1 = rptr[r + 1];
+#pragma unroll 1
                 for (int i = rptr[r]; i < i1; i++) {
                     const int k = perm[i];
                     s += (erec[k] == ap ? (double)pmult : 1.0) * ey[k];
@@ -246,11 +248,14 @@ template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_k
             G.sync();
             const double *X0 = X.x + td.w;
             double tot = 0;
+#pragma unroll 1
             for (int r = 0; r < q; r++) tot += (double)rs[r];
             int best = -1;
             double bestv = -INFINITY;
+#pragma unroll 1
             for (int j = 0; j < p; j++) {                               // which.max(cos_sim(X0[,j], rs/sum(rs)))  :991-995
                 double ab = 0, aa = 0, bb = 0;
+#pragma unroll 1
                 for (int r = 0; r < q; r++) {
                     const double xv = X0[j * q + r], rv = (double)rs[r] / tot;
                     ab += xv * rv; aa += xv * xv; bb += rv * rv;
@@ -260,9 +265,11 @@ template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_k
             }
             unsigned long long adjmask = 0;
             if (best >= 0)
+#pragma unroll 1
                 for (int r = 0; r < q; r++)
                     if (X0[best * q + r] > 0) { adjmask |= 1ull << r; nadj++; }   // adjID  :997
             G.sync();
+#pragma unroll 1
             for (int k = gl; k < E; k += GT)
                 if ((adjmask >> erow[k]) & 1ull) ey[k] += O.adjust_esp;
             G.sync();
@@ -405,12 +412,14 @@ template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_k
         const double deduct = nadj * O.adjust_esp;
         const int64_t cbase = cb0 - A.S.cell_base;
         double *vals = A.R.rs_val + A.R.rs_ptr[cbase];                           // the chunk's first value; rpos is relative to it
+#pragma unroll 1
         for (int a = gl; a < n; a += GT) {
             const uint32_t cw = rcell[a];
             double s = 0;
             if (nadj > 0) for (int j = 0; j < p; j++) s += (double)beta[j * n + a];
             if (!(cw & kPseudo)) {
                 double *o = vals + rpos[a];
+#pragma unroll 1
                 for (int j = 0; j < p; j++) { double v = (double)beta[j * n + a]; if (nadj > 0) v = v - deduct * (v / s); o[j] = v; }
             }
         }
@@ -422,6 +431,7 @@ template <int W, typename R> __global__ void __launch_bounds__(256, 4) em_task_k
             const int kp = X.poor_rank[b];
             double s = 0, v0 = (double)beta[ap], v1 = (double)beta[n + ap];      // a poor block has two columns
             if (nadj > 0) { s = v0 + v1; v0 = v0 - deduct * (v0 / s); v1 = v1 - deduct * (v1 / s); }
+#pragma unroll 1
             for (int cc = gl; cc < nc; cc += GT) {                               // a lane per cell of the chunk: is it a real record?
                 int lo = 0, hi = ap;
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)rcell[mid] < cc) lo = mid + 1; else hi = mid; }

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Device time of the C4 step under different tuning switches (read when a context is created).
-    python tools/em_sweep.py [cells] KEY=VAL[,KEY=VAL] ...    (each argument = one configuration; "-" = defaults)"""
+    python tools/em_sweep.py [cells] "KEY=VAL[;KEY=VAL]" ...    (each argument = one configuration; "-" = defaults)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -22,7 +22,7 @@ eq_row = None
 for cfg in args or ["-"]:
     keys = []
     if cfg != "-":
-        for kv in cfg.split(","):
+        for kv in cfg.split(";"):
             k, v = kv.split("=", 1); os.environ[k] = v; keys.append(k)
     g = Scasa(xm, device=0)
     g.set_gene_map(goc, len(xm.gene_names))
