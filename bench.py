@@ -142,8 +142,11 @@ def cpu_reference(xm, cfg, args, nthreads: int, steps: int = 1, warmup: int = 0)
     O.build()
     seed = args.seed or cfg["seed"]
     n = args.cpu_cells or min(3200, 100 * nthreads, cfg["cells"] if cfg["cells"] < 1000 else 1 << 30)
-    if cfg["x"] != "shipped" and not args.cpu_cells:
-        n = min(n, 64 if cfg["x"] == "heavy" else 800)        # the wide / many-block X-matrices are much slower per cell
+    if cfg["x"] == "grch38_106_like" and not args.cpu_cells:
+        n = min(n, 800)                                       # three times the blocks: slower per cell
+    # C5 keeps 100 cells per thread: a chunk of ~100 cells is the unit of work (cells of a chunk are coupled through the X
+    # update), and one such chunk of wide blocks at maxerr 1e-6 takes a core about a minute — fewer cells would mean
+    # smaller chunks, which converge much faster and are not the workload
     gen = synth.CellGenerator(xm, seed=seed, device="cpu", lib_scale=cfg.get("lib_scale", 1.0))
     rowptr, rows, vals = gen.counts_csr(0, n)
     chunks = O.chunk_split(n, nthreads if n <= 100 else 4)
