@@ -401,3 +401,36 @@ def test_bustools_xmatrix_quant_matches_oracle(oracle):
     rep = compare_tasks(r.iso, ref, r.iters, ref_it[:, em, :], chunks, em, bx.dm0_p_off, bx.q_off, poor)
     assert t["max_slot_bytes"] > 10000                                        # a large task went through the 8-warp class
     print("bustools X-matrix vs oracle:", rep)
+
+
+@pytest.mark.parametrize("config", ["C3", "C5"])
+def test_full_shape_configs_sampled_chunks_match_oracle(xm, oracle, config):
+    """BASELINE configs C3 and C5 at their full X-matrix shape (bench.py's generators): C3 = 93,400 blocks / ~250k
+    transcripts resampled from the shipped blocks; C5 = every EM block wide (q >= 8, p >= 4), library x4, maxerr 1e-6 on
+    the outer and the inner test, caps 1000/1000.  Three chunks of ~100 cells go through scasa_quant from eqclass counts
+    and are compared with the oracle task by task (tests/parity.py: nothing skipped)."""
+    import os
+    from scasa_b200 import synth
+    from scasa_b200.api import Scasa, chunk_split
+    from .parity import compare_tasks
+    if config == "C3":
+        big, seed, lib, opts = synth.resample_xmatrix(xm, 93400, seed=106), 3, 1.0, {}
+    else:
+        big, seed, lib, opts = synth.heavy_multimapping_xmatrix(xm, seed=5), 5, 4.0, dict(maxerr=1e-6, maxerr_bt=1e-6)
+    n = 300
+    rowptr, rows, vals = synth.CellGenerator(big, seed=seed, lib_scale=lib).counts_csr(0, n)
+    ed = synth.eqclass_dictionary(big, seed)
+    cell_ptr, eq_id, eq_cnt = synth.counts_to_eqcounts(rowptr, rows, vals, seed)
+    chunks = chunk_split(n, 4)
+    g = Scasa(big, device=0, **opts)
+    try:
+        r = g.quant(cell_ptr, eq_id, eq_cnt, ed.eq_off, ed.eq_tx, n_slices=2)
+        poor, em = g.poor_blocks(), g.em_blocks
+    finally:
+        g.close()
+    h = oracle.CrpHandle(big)
+    y = oracle.crpcount_cells(h, ed.eq_off, ed.eq_tx, cell_ptr, eq_id, eq_cnt, nthreads=os.cpu_count() or 8)
+    ref, ref_it = oracle.estim_chunks(big, y, chunks, oracle.Opts.make(**opts), nthreads=os.cpu_count() or 8)
+    rep = compare_tasks(r.iso, ref, r.iters, ref_it[:, em, :], chunks, em, big.dm0_p_off, big.q_off, poor,
+                        maxerr=opts.get("maxerr", 0.01), min_same=0.98)
+    print(config, "full-shape chunks vs oracle:", rep, "max inner iterations", int(r.iters[..., 1].max()))
