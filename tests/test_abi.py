@@ -47,6 +47,7 @@ def test_opts_default_are_the_reference_defaults(L):
     # estim_chunk(Y, DM0, maxiter.X=1000, maxerr=0.01, lim=0.01, maxiter.bt=1000, modify=TRUE)  Rsource:944
     assert (o.maxiter_x, o.maxiter_bt, o.maxerr, o.lim, o.modify) == (1000, 1000, 0.01, 0.01, 1)
     assert (o.adjust_esp, o.hamming_dist, o.fixed_iter, o.fp32) == (2.0, 1, 0, 0)   # Rsource:973, :534
+    assert (o.maxerr_bt, o.lim_bt) == (0.01, 0.01)      # estim.BETA's own defaults (Rsource:726-727): estim_chunk does not forward its maxerr / lim (:1016)
 
 
 def test_chunk_split_equals_oracle(L, oracle):
