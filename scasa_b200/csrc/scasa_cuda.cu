@@ -1642,24 +1642,37 @@ int scasa_quant_multi(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, in
 // step2:88-170 + step3:21-52 without the dense matrices: the sparse rows of every slice are collected on the
 // host, transposed to transcript-major (step2:166) and streamed through the sparse writer.
 namespace {
-struct Flat { std::vector<int64_t> rowptr; std::vector<int32_t> cols; std::vector<double> vals; };
+// big host arrays without the zero fill of std::vector (the first touch happens in the threads that write them)
+extern "C++" {
+template <class T> struct RawBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    void alloc(size_t m) { release(); n = m; p = (T *)malloc(std::max<size_t>(m, 1) * sizeof(T)); if (!p) throw std::bad_alloc(); }
+    void release() { free(p); p = nullptr; n = 0; }
+    ~RawBuf() { free(p); }
+};
+}
+struct Flat { std::vector<int64_t> rowptr; RawBuf<int32_t> cols; RawBuf<double> vals; };
 void flatten(SparseSink &k, Flat &f)
 {
     f.rowptr.swap(k.rowptr);
     const int64_t nnz = f.rowptr.empty() ? 0 : f.rowptr.back();
-    f.cols.resize((size_t)nnz); f.vals.resize((size_t)nnz);
-    // slices are in cell order once sorted by their first cell
-    std::vector<size_t> order(k.cols.size());
-    std::iota(order.begin(), order.end(), (size_t)0);
-    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return k.slice_c0[a] < k.slice_c0[b]; });
-    for (size_t si : order) {
-        if (k.cols[si].empty()) continue;
+    f.cols.alloc((size_t)nnz); f.vals.alloc((size_t)nnz);
+    std::vector<std::thread> th;                      // a thread per slice: the copies are memory-bound and independent
+    auto copy_slice = [&](size_t si) {
+        if (k.cols[si].empty()) return;
         const int64_t e0 = f.rowptr[(size_t)k.slice_c0[si]];
-        std::copy(k.cols[si].begin(), k.cols[si].end(), f.cols.begin() + e0);
-        std::copy(k.vals[si].begin(), k.vals[si].end(), f.vals.begin() + e0);
+        std::copy(k.cols[si].begin(), k.cols[si].end(), f.cols.p + e0);
+        std::copy(k.vals[si].begin(), k.vals[si].end(), f.vals.p + e0);
         std::vector<int32_t>().swap(k.cols[si]);
         std::vector<double>().swap(k.vals[si]);
+    };
+    for (size_t si = 0; si < k.cols.size(); si++) {
+        bool started = false;
+        try { th.emplace_back(copy_slice, si); started = true; } catch (const std::exception &) {}
+        if (!started) copy_slice(si);
     }
+    for (auto &t : th) t.join();
 }
 double wall_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 }  // namespace
@@ -1692,12 +1705,12 @@ int scasa_quant_files(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, in
         Flat f;
         flatten(iso_sink, f);
         std::vector<int64_t> colptr((size_t)c->n_cols + 1);
-        std::vector<int32_t> cell_idx(f.cols.size());
-        std::vector<double> tvals(f.vals.size());
-        rc = scasa_csr_transpose(n_cells, c->n_cols, f.rowptr.data(), f.cols.data(), f.vals.data(), colptr.data(), cell_idx.data(),
-                                 tvals.data(), n_threads);
+        RawBuf<int32_t> cell_idx;
+        RawBuf<double> tvals;
+        cell_idx.alloc(f.cols.n); tvals.alloc(f.vals.n);
+        rc = scasa_csr_transpose(n_cells, c->n_cols, f.rowptr.data(), f.cols.p, f.vals.p, colptr.data(), cell_idx.p, tvals.p, n_threads);
         if (rc) return fail(c, rc, scasa_last_error(nullptr));
-        Flat().rowptr.swap(f.rowptr); std::vector<int32_t>().swap(f.cols); std::vector<double>().swap(f.vals);
+        Flat().rowptr.swap(f.rowptr); f.cols.release(); f.vals.release();
         tm.transpose_s = wall_now() - t0;
         t0 = wall_now();
         std::vector<int32_t> src;
@@ -1711,7 +1724,7 @@ int scasa_quant_files(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, in
                 p = nl + 1;
             }
         }
-        rc = scasa_write_table_sparse(iso_path, n_cells, c->n_cols, colptr.data(), cell_idx.data(), tvals.data(), (int64_t)src.size(),
+        rc = scasa_write_table_sparse(iso_path, n_cells, c->n_cols, colptr.data(), cell_idx.p, tvals.p, (int64_t)src.size(),
                                       src.data(), names.c_str(), cell_names, n_threads, &tm.iso_bytes);
         if (rc) return fail(c, rc, scasa_last_error(nullptr));
         tm.iso_rows = (int64_t)src.size();
@@ -1725,9 +1738,10 @@ int scasa_quant_files(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, in
             flatten(gene_sink, g);
             const int64_t ng = c->n_genes;
             std::vector<int64_t> gptr((size_t)ng + 1);
-            std::vector<int32_t> gcell(g.cols.size());
-            std::vector<double> gvals(g.vals.size());
-            rc = scasa_csr_transpose(n_cells, ng, g.rowptr.data(), g.cols.data(), g.vals.data(), gptr.data(), gcell.data(), gvals.data(), n_threads);
+            RawBuf<int32_t> gcell;
+            RawBuf<double> gvals;
+            gcell.alloc(g.cols.n); gvals.alloc(g.vals.n);
+            rc = scasa_csr_transpose(n_cells, ng, g.rowptr.data(), g.cols.p, g.vals.p, gptr.data(), gcell.p, gvals.p, n_threads);
             if (rc) return fail(c, rc, scasa_last_error(nullptr));
             tm.transpose_s += wall_now() - t0;
             t0 = wall_now();
@@ -1756,7 +1770,7 @@ int scasa_quant_files(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, in
             }
             std::string gnames;
             for (int32_t gi : order) gnames.append(gn[(size_t)gi], gn[(size_t)gi + 1]);
-            rc = scasa_write_table_sparse(gene_path, n_cells, ng, gptr.data(), gcell.data(), gvals.data(), (int64_t)order.size(), order.data(),
+            rc = scasa_write_table_sparse(gene_path, n_cells, ng, gptr.data(), gcell.p, gvals.p, (int64_t)order.size(), order.data(),
                                           gnames.c_str(), cell_names, n_threads, &tm.gene_bytes);
             if (rc) return fail(c, rc, scasa_last_error(nullptr));
             tm.gene_rows = (int64_t)order.size();
