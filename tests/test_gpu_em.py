@@ -434,3 +434,59 @@ def test_full_shape_configs_sampled_chunks_match_oracle(xm, oracle, config):
     rep = compare_tasks(r.iso, ref, r.iters, ref_it[:, em, :], chunks, em, big.dm0_p_off, big.q_off, poor,
                         maxerr=opts.get("maxerr", 0.01), min_same=0.98)
     print(config, "full-shape chunks vs oracle:", rep, "max inner iterations", int(r.iters[..., 1].max()))
+
+
+def test_gene_rows_with_scattered_members_and_unmapped_columns(xm, c1):
+    """gene_rows_kernel on a hostile gene map: random members all over the column range (nothing contiguous), genes of
+    1 to 40 isoforms, a third of the columns unmapped, and a cell whose row is longer than the kernel keeps in
+    registers.  Every gene value must be the sequential sum of its members in column order (step3:27), bit for bit."""
+    from scasa_b200.api import Scasa, chunk_split
+    rowptr, rows, vals = c1
+    rng = np.random.default_rng(17)
+    n_cols = xm.n_cols
+    sizes = []
+    while sum(sizes) < int(0.67 * n_cols):
+        sizes.append(int(rng.choice([1, 1, 1, 2, 3, 5, 9, 40])))
+    perm = rng.permutation(n_cols)
+    goc = np.full(n_cols, -1, np.int32)
+    at = 0
+    for gi, sz in enumerate(sizes):
+        goc[perm[at:at + sz]] = gi
+        at += sz
+    n_genes = len(sizes)
+    # one cell with counts in (almost) every row: a result row of ~20k entries
+    dense_cell = np.arange(xm.n_rows, dtype=np.int32)[:: 2]
+    rp = np.concatenate([rowptr, [rowptr[-1] + len(dense_cell)]])
+    rr = np.concatenate([rows, dense_cell])
+    vv = np.concatenate([vals, np.ones(len(dense_cell))])
+    n = len(rp) - 1
+    g = Scasa(xm, device=0, with_crp=False, fixed_iter=1, maxiter_x=2, maxiter_bt=3)
+    try:
+        g.set_gene_map(goc, n_genes)
+        g.stage_counts(np.array([0, 100, n], np.int64), rp, rr, vv)
+        g.run()
+        iso, gene = g.fetch_iso(), g.fetch_gene()
+        gp, gg, gv = g.fetch_gene_csr()
+    finally:
+        g.close()
+    assert (iso[-1] != 0).sum() > 8000                               # the long row really is long
+    want = np.zeros((n, n_genes))
+    started = np.zeros(n_genes, bool)
+    for j in range(n_cols):                                           # members in column order, one sequential sum per gene
+        gi = goc[j]
+        if gi < 0:
+            continue
+        if not started[gi]:
+            want[:, gi] = iso[:, j]
+            started[gi] = True
+        else:
+            want[:, gi] += iso[:, j]
+    assert np.array_equal(gene.view(np.int64), want.view(np.int64))
+    # rows of the sparse form: ascending genes, only genes with a structural member
+    cell = np.repeat(np.arange(n), np.diff(gp))
+    d = np.zeros((n, n_genes))
+    d[cell, gg] = gv
+    assert np.array_equal(d.view(np.int64), gene.view(np.int64))
+    inner = np.ones(len(gg), bool)
+    inner[gp[1:-1]] = False
+    assert np.all(np.diff(gg)[inner[1:]] > 0)
