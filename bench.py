@@ -100,7 +100,7 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def load_x(kind: str):
+def load_x(kind: str = "shipped"):
     from scasa_b200 import synth
     from scasa_b200.xmatrix import XMatrix
     xm = XMatrix.load_npz(os.path.join(ROOT, "tests", "golden", "xmatrix_hg38_alevin.npz"))

@@ -7,8 +7,6 @@ import torch
 from scasa_b200 import lib as _l, synth
 from scasa_b200.api import Scasa
 from bench import load_x, gene_map
-load_x_ = load_x
-load_x = lambda: load_x_("shipped")
 n = 100000
 xm = load_x()
 dev = torch.device("cuda", 0)

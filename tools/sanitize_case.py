@@ -1,4 +1,4 @@
-"""A small run of every kernel of the library (eqclass counts -> Y -> EM -> genes -> zero-suppressed fetch),
+"""A small run of every kernel of the library (eqclass counts -> Y -> EM -> genes -> sparse fetch),
 for compute-sanitizer.  ~150 cells on a 600-block resampled X-matrix (all block shapes, poor blocks included)."""
 import os, sys
 import numpy as np
@@ -19,7 +19,6 @@ for name, m, n in (("mixed", small, 150), ("wide", wide, 130)):
     for fp32 in (0, 1):
         g = Scasa(m, device=0, fp32=fp32, maxiter_x=30, maxiter_bt=30)
         r = g.quant(cell_ptr, eq_id, eq_cnt, ed.eq_off, ed.eq_tx, gene_of_col=goc, n_genes=int(goc.max()) + 1, n_slices=2)
-        g.set_run_parts(3)
         eq_row = g.eqclass_map(ed.eq_off, ed.eq_tx, 2)
         from scasa_b200.api import chunk_split
         g.stage_eqcounts(chunk_split(n, 4), cell_ptr, eq_id, eq_cnt, eq_row)
