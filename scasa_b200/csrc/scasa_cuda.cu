@@ -186,6 +186,7 @@ struct scasa_ctx {
     int cls_ctas_per_sm[kClasses] = {8, 4, 2, 2};
     int pair_max = 16;                // tiny tasks two per warp (em_pair_kernel); SCASA_EM_PAIR=0 turns it off
     int pair_ctas_per_sm = 12;
+    int poison = 0;                  // SCASA_POISON=1 (testing): result and blob buffers start as 0xFF bytes in every run
     DBuf<unsigned long long> d_stats;
     DBuf<int> d_flag;
 
@@ -609,6 +610,7 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
                              [&](int32_t x, int32_t y) { return cost[(size_t)x] > cost[(size_t)y]; });
         }
         if (getenv("SCASA_FETCH_DENSE")) c->fetch_dense_copy = 1;
+        if (getenv("SCASA_POISON")) c->poison = 1;
         if (const char *env = getenv("SCASA_GENE_CTAS")) c->gene_ctas_per_sm = std::max(1, atoi(env));
         // EM work classes; SCASA_EM_CFG="warps:pairs:bytes:cta_threads:ctas_per_sm,..." overrides (tuning)
         if (const char *env = getenv("SCASA_EM_CFG")) {
@@ -993,6 +995,18 @@ static void run_all(scasa_ctx *c, RangeStats &rs)
     c->rs_nnz = tot[1];
     c->d_rs_col.ensure((size_t)tot[1] + 2); c->d_rs_val.ensure((size_t)tot[1] + 2);
     if (c->n_genes > 0) { c->d_g_col.ensure((size_t)tot[1] + 2); c->d_g_val.ensure((size_t)tot[1] + 2); }
+    if (c->poison) {       // SCASA_POISON: every byte the kernels are supposed to write starts as 0xFF (NaN / -1): a test finds what was left
+        CK(cudaMemsetAsync(c->d_rs_col.p, 0xFF, ((size_t)tot[1] + 2) * sizeof(int32_t), s));
+        CK(cudaMemsetAsync(c->d_rs_val.p, 0xFF, ((size_t)tot[1] + 2) * sizeof(double), s));
+        CK(cudaMemsetAsync(c->d_ypos.p, 0xFF, ((size_t)c->nnz + 1) * sizeof(uint32_t), s));
+        CK(cudaMemsetAsync(c->d_poor_pos.p, 0xFF, (size_t)n_cells * std::max(1, c->n_poor) * sizeof(int32_t), s));
+        CK(cudaMemsetAsync(c->d_colpart.p, 0xFF, (size_t)n_chunks * std::max(1, c->n_emcols) * sizeof(double), s));
+        if (c->n_genes > 0) {
+            CK(cudaMemsetAsync(c->d_g_col.p, 0xFF, ((size_t)tot[1] + 2) * sizeof(int32_t), s));
+            CK(cudaMemsetAsync(c->d_g_val.p, 0xFF, ((size_t)tot[1] + 2) * sizeof(double), s));
+            CK(cudaMemsetAsync(c->d_g_len.p, 0xFF, (size_t)n_cells * sizeof(int32_t), s));
+        }
+    }
     Result R = rdev(c);
     {
         const int wpb = 8;
@@ -1002,6 +1016,7 @@ static void run_all(scasa_ctx *c, RangeStats &rs)
     }
     if (w->n_em > 0) {
         w->d_tdata.ensure((size_t)tot[0] + 64);
+        if (c->poison) CK(cudaMemsetAsync(w->d_tdata.p, 0xFF, (size_t)tot[0] + 64, s));
         T = tdev(w);
         rs.blob_bytes = tot[0];
         const size_t st_bytes = (size_t)3 * w->n_em * sizeof(uint32_t);
@@ -1156,7 +1171,7 @@ static int sync_twin(scasa_ctx *c)
         t->cls_warps[k] = c->cls_warps[k]; t->cls_pairs[k] = c->cls_pairs[k]; t->cls_bytes[k] = c->cls_bytes[k];
         t->cls_cta_threads[k] = c->cls_cta_threads[k]; t->cls_ctas_per_sm[k] = c->cls_ctas_per_sm[k];
     }
-    t->pair_max = c->pair_max; t->pair_ctas_per_sm = c->pair_ctas_per_sm;
+    t->pair_max = c->pair_max; t->pair_ctas_per_sm = c->pair_ctas_per_sm; t->poison = c->poison;
     if (c->n_genes > 0 && (t->n_genes != c->n_genes || t->gene_of_col_host != c->gene_of_col_host)) {
         int rc = scasa_set_gene_map(t, c->gene_of_col_host.data(), c->n_genes);
         if (rc) return fail(c, rc, std::string("twin context: ") + scasa_last_error(t));

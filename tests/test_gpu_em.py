@@ -490,3 +490,34 @@ def test_gene_rows_with_scattered_members_and_unmapped_columns(xm, c1):
     inner = np.ones(len(gg), bool)
     inner[gp[1:-1]] = False
     assert np.all(np.diff(gg)[inner[1:]] > 0)
+
+
+def test_every_result_and_blob_byte_is_written(xm, c1, monkeypatch):
+    """compute-sanitizer is not available on the GPU pool, so: with SCASA_POISON=1 every result, index and task-blob
+    buffer starts as 0xFF bytes (NaN / -1) in each run.  Nothing of that may survive into what the library returns,
+    and the run must give the bits of an unpoisoned one — an entry the kernels forget to write, or a blob field the
+    scatter kernel leaves out, shows up here."""
+    from scasa_b200.api import Scasa, chunk_split
+    rowptr, rows, vals = c1
+    chunks = chunk_split(200, 4)
+    goc, ng = np.asarray(xm.gene_of_col, np.int32), len(xm.gene_names)
+    res = []
+    for poison in (False, True):
+        if poison:
+            monkeypatch.setenv("SCASA_POISON", "1")
+        g = Scasa(xm, device=0, with_crp=False)
+        try:
+            g.set_gene_map(goc, ng)
+            g.stage_counts(chunks, rowptr, rows, vals)
+            g.run()
+            g.run()                                                     # buffers are reused: the second run starts poisoned too
+            res.append((g.fetch_iso_csr(), g.fetch_gene_csr(), g.fetch_colsum(), g.fetch_iters(), g.fetch_iso(), g.fetch_gene()))
+        finally:
+            g.close()
+    monkeypatch.delenv("SCASA_POISON")
+    (rp, rc, rv), (gp, gg, gv), colsum, iters, iso, gene = res[1]
+    assert np.isfinite(rv).all() and np.isfinite(gv).all() and np.isfinite(colsum).all()
+    assert rc.min() >= 0 and rc.max() < xm.n_cols and gg.min() >= 0 and gg.max() < ng and iters.min() >= 1
+    for a, b in zip(res[0], res[1]):
+        for x, y in zip(a if isinstance(a, tuple) else (a,), b if isinstance(b, tuple) else (b,)):
+            assert np.array_equal(x.view(np.int64) if x.dtype == np.float64 else x, y.view(np.int64) if y.dtype == np.float64 else y)
