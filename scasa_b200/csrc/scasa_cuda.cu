@@ -153,7 +153,8 @@ struct scasa_ctx {
     std::vector<uint8_t> poor;
     int64_t poor_rows = 0;           // sum of q over poor blocks
     DBuf<int32_t> d_q_off, d_p_off, d_em_blocks, d_em_order, d_em_col0, d_poor_rank, d_poor_col0, d_emcol_col, d_col_emcol;
-    DBuf<int2> d_row_info, d_row_aux, d_em_info;
+    DBuf<int2> d_row_info, d_em_info;
+    DBuf<int4> d_row_aux;
     DBuf<uint32_t> d_scatter_scratch;
     DBuf<int64_t> d_x_off;
     DBuf<double> d_x;
@@ -659,14 +660,16 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
         c->d_em_order.ensure(c->em_order.size() + 1);
         c->d_em_order.upload(c->em_order, c->stream);
         {
-            std::vector<int2> info((size_t)c->n_rows), aux((size_t)c->n_rows), em_info((size_t)c->n_em);
+            std::vector<int2> info((size_t)c->n_rows), em_info((size_t)c->n_em);
+            std::vector<int4> aux((size_t)c->n_rows);
             std::vector<int32_t> poor_rank((size_t)B), poor_col0, em_col0((size_t)c->n_em + 1, 0), emcol_col;
             int np = 0;
             for (int k = 0; k < B; k++) {
                 poor_rank[(size_t)k] = np;
                 for (int r = c->q_off[k]; r < c->q_off[k + 1]; r++) {
                     info[(size_t)r] = make_int2(c->em_index[k], r - c->q_off[k]);
-                    aux[(size_t)r] = make_int2(c->p_off[k], np);
+                    const int e = c->em_index[k], p = c->p_off[k + 1] - c->p_off[k];
+                    aux[(size_t)r] = make_int4(c->p_off[k], np, e < 0 ? 0 : (p | (c->poor[k] ? 1 << 16 : 0)), e);
                 }
                 if (c->poor[k]) { np++; poor_col0.push_back(c->p_off[k]); c->poor_blocks_list.push_back(k); }
             }

@@ -85,7 +85,8 @@ struct XDev {                 // resident X-matrix (DM0) and its derived index m
     const uint8_t *poor;      // [n_blocks] poorCondX (Rsource:957-971)
     const int32_t *em_order;  // [n_em]    EM indices, most expensive block shape first (work-queue order)
     const int2 *row_info;     // [n_rows]  {EM index of the row's block or -1, row index inside the block}
-    const int2 *row_aux;      // [n_rows]  {first DM0 column of the row's block, poor blocks before the row's block}
+    const int4 *row_aux;      // [n_rows]  {first DM0 column of the row's block, poor blocks before it, p | poor << 16 of an EM block
+                              //            (0: pass-through), EM index or -1}: all that the per-entry passes need in one load
     const int2 *em_info;      // [n_em]    {columns p | poor << 16, first DM0 column}
     const int32_t *em_col0;   // [n_em+1]  columns of the EM blocks before this one (index into the per-chunk column sums)
     const int32_t *poor_rank; // [n_blocks] poor blocks with a smaller block id
@@ -368,15 +369,21 @@ __global__ void task_count_kernel(XDev X, Sample S, Tasks T, int32_t *__restrict
     const int64_t s = S.y_start[cell];
     const int n = S.y_len[cell];
     const int64_t tbase = (int64_t)(S.cell_chunk[cell] - S.chunk_base) * X.n_em;
-    int w = 0;
-    for (int i = lane; i < n; i += kWarp) {
-        const int e = X.row_info[S.y_row[s + i]].x;
+    int w = 0, carry_e = -2;
+    int r_nx = lane < n ? S.y_row[s + lane] : -1;
+    for (int i0 = 0; i0 < n; i0 += kWarp) {
+        const int i = i0 + lane, r = r_nx;
+        if (i + kWarp < n) r_nx = S.y_row[s + i + kWarp];      // the next pass' rows are in flight during this one
+        int e = -2, pi = 0;
+        if (i < n) { const int4 a = X.row_aux[r]; e = a.w; pi = a.z; }
+        int prev_e = __shfl_up_sync(kFull, e, 1);
+        if (lane == 0) prev_e = carry_e;
+        carry_e = __shfl_sync(kFull, e, min(31, n - 1 - i0));
+        if (i >= n) continue;
         if (e < 0) { w++; continue; }
         atomicAdd(&T.cnt[tbase + e], 1);
-        const bool head = (i == 0) || (X.row_info[S.y_row[s + i - 1]].x != e);
-        if (head) {
+        if (e != prev_e) {
             atomicAdd(&T.runs[tbase + e], 1);
-            const int pi = X.em_info[e].x;
             if (!(pi >> 16)) w += pi & 0xffff;
         }
     }
@@ -406,24 +413,28 @@ __global__ void struct_fill_kernel(XDev X, Sample S, Result R)
     };
     int running = 0;           // entries of non-poor blocks placed so far
     int carry_e = -2, carry_pb = 0;
+    // two-deep software pipeline: this pass' row records and the rows of the pass after it are in flight
+    // while the previous pass is placed (a pass = 32 entries; the chain row -> record -> position would
+    // otherwise be paid once per pass)
+    int r_nx = -1;
+    double y_cur = 0.0, y_nx = 0.0;
+    int4 a_cur = make_int4(0, 0, 0, -2);
+    if (lane < n) { a_cur = X.row_aux[S.y_row[s + lane]]; y_cur = S.y_val[s + lane]; }
+    if (lane + kWarp < n) { r_nx = S.y_row[s + lane + kWarp]; y_nx = S.y_val[s + lane + kWarp]; }
     for (int i0 = 0; i0 < n; i0 += kWarp) {
         const int i = i0 + lane;
         const bool valid = i < n;
-        int e = -2, r_col0 = 0, pb = 0;
-        double y = 0.0;
-        if (valid) {
-            const int r = S.y_row[s + i];
-            e = X.row_info[r].x;
-            const int2 aux = X.row_aux[r];
-            r_col0 = aux.x; pb = aux.y;
-            y = S.y_val[s + i];
-        }
+        const int4 a = a_cur;
+        const double y = y_cur;
+        if (i + kWarp < n) { a_cur = X.row_aux[r_nx]; y_cur = y_nx; }
+        if (i + 2 * kWarp < n) { r_nx = S.y_row[s + i + 2 * kWarp]; y_nx = S.y_val[s + i + 2 * kWarp]; }
+        int e = -2, r_col0 = 0, pb = 0, pi = 0;
+        if (valid) { r_col0 = a.x; pb = a.y; pi = a.z; e = a.w; }
         int prev_e = __shfl_up_sync(kFull, e, 1), lo = __shfl_up_sync(kFull, pb, 1);
         if (lane == 0) { prev_e = carry_e; lo = carry_pb; }
         const bool head = valid && (e < 0 || e != prev_e);
-        int p = 0;
-        bool poorb = false;
-        if (head && e >= 0) { const int pi = X.em_info[e].x; p = pi & 0xffff; poorb = (pi >> 16) != 0; }
+        const int p = pi & 0xffff;
+        const bool poorb = (pi >> 16) != 0;
         const int w = !valid ? 0 : (e < 0 ? 1 : (head && !poorb ? p : 0));
         int inc = w;
         for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += v; }

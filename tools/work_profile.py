@@ -46,3 +46,35 @@ m = nonempty
 cs = (ncell * p[None, :] * inner)
 for thr in (2, 4, 8, 16, 32, 64, 128):
     print(f"  digammas in tasks with inner > {thr:3d}: {cs[m & (inner > thr)].sum() / cs[m].sum():.3f}   tasks {((inner > thr) & m).sum() / m.sum():.4f}")
+
+# ---- lane use by task shape: a warp instruction of the pair stages (S1, S3) covers 32 (cell, transcript) pairs, of
+# the entry stage (S2) 32 entries; "issue slots" = inner iterations x passes, "lanes" = the useful share of them
+np_ = ncell * p[None, :]
+E = np.where(poor[None, :], ncell * q[None, :], ents)
+qp = np.broadcast_to((q * p)[None, :], nact.shape)
+tiny = nonempty & ~poor[None, :] & (np_ <= 16) & (E <= 16) & (qp <= 16)
+def slots(width, mask):
+    s1 = np.ceil(np_[mask] / width) * inner[mask]
+    s2 = np.ceil(E[mask] / width) * inner[mask]
+    used = ((np_[mask] * 2 + E[mask]) * inner[mask]).sum()
+    return (2 * s1 + s2).sum(), used
+print("\nshape class                          tasks   share of issue slots   lanes used of the width")
+rows_ = []
+for name, mask, width in (
+        ("tiny (pair kernel, 16 lanes)", tiny, 16),
+        ("np<=16, E<=32, qp<=32 not tiny", nonempty & ~tiny & ~poor[None, :] & (np_ <= 16) & (E <= 32) & (qp <= 32), 32),
+        ("np<=16 other (incl. poor)", nonempty & ~tiny & (np_ <= 16) & ~(~poor[None, :] & (E <= 32) & (qp <= 32)), 32),
+        ("np 17..32", nonempty & (np_ > 16) & (np_ <= 32), 32),
+        ("np 33..64", nonempty & (np_ > 32) & (np_ <= 64), 32),
+        ("np 65..96", nonempty & (np_ > 64) & (np_ <= 96), 32),
+        ("np 97..256 (2 warps)", nonempty & (np_ > 96) & (np_ <= 256), 64),
+        ("np 257..512 (4 warps)", nonempty & (np_ > 256) & (np_ <= 512), 128),
+        ("np > 512 (8 warps)", nonempty & (np_ > 512), 256)):
+    if not mask.any():
+        continue
+    s, used = slots(width, mask)
+    # warp instructions: every one of the W warps issues each pass; a 16-lane task shares its warp with the other half
+    rows_.append((name, int(mask.sum()), s * (width / 32.0), used / (s * width)))
+tot = sum(r[2] for r in rows_)
+for name, cnt, w, frac in rows_:
+    print(f"{name:34s} {cnt:8d}   {w / tot:6.3f}                 {frac:5.2f}")
