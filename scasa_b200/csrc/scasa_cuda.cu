@@ -219,7 +219,9 @@ struct scasa_ctx {
     int n_genes = 0;
     int gene_ctas_per_sm = 2;                  // gene_rows_kernel: resident CTAs per SM (SCASA_GENE_CTAS)
     int gene_max_members = 1, gene_n_multi = 0;   // most isoforms of a gene; genes with more than one
-    DBuf<int2> d_col_gene;                     // per column: {gene or -1, position among the gene's members}
+    DBuf<int2> d_col_gene;                     // per column: {gene or -1, slot in the gene kernel's member table or -1}
+    DBuf<int32_t> d_gene_stops;                // the member table's stop marks
+    int gene_slots = 1;
     DBuf<int32_t> d_gene_ptr, d_gene_cols;
     scasa_timing_t timing{};
 };
@@ -732,7 +734,7 @@ void scasa_ctx_destroy(scasa_ctx *c)
     for (auto b : f64) b->release();
     c->d_poor.release(); c->d_next.release(); c->d_stats.release(); c->d_flag.release();
     c->d_tdata.release(); c->d_counters.release(); c->d_row_info.release(); c->d_row_aux.release(); c->d_em_info.release();
-    c->d_scatter_scratch.release(); c->d_ypos.release(); c->d_col_gene.release(); c->d_desc.release();
+    c->d_scatter_scratch.release(); c->d_ypos.release(); c->d_col_gene.release(); c->d_gene_stops.release(); c->d_desc.release();
     for (auto &b : c->fb) {
         if (b.h_cols) { cudaFreeHost(b.h_cols); cudaFreeHost(b.h_vals); cudaFreeHost(b.h_start); cudaFreeHost(b.h_nnz); }
         if (b.done) cudaEventDestroy(b.done);
@@ -880,17 +882,20 @@ int scasa_set_gene_map(scasa_ctx *c, const int32_t *gene_of_col, int32_t n_genes
         c->d_gene_cols.upload(cols, c->stream);
         c->d_gene_of_col.upload(goc, c->stream);
         {
-            std::vector<int2> cg((size_t)c->n_cols, make_int2(-1, 0));
-            int mx = 1, n_multi = 0;
+            // member table of gene_rows_kernel: the members of every multi-isoform gene side by side, a stop mark
+            // in front of the first gene and behind every gene
+            std::vector<int2> cg((size_t)c->n_cols, make_int2(-1, -1));
+            std::vector<int32_t> stops{0};
+            int mx = 1, n_multi = 0, slot = 1;
             for (int g = 0; g < n_genes; g++) {
                 const int nm = ptr[(size_t)g + 1] - ptr[(size_t)g];
-                if (nm > 255) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a gene may have at most 255 isoform columns"};
-                const int slot = nm > 1 ? ++n_multi : 0;             // 1 + index among the multi-isoform genes
                 for (int m = ptr[(size_t)g]; m < ptr[(size_t)g + 1]; m++)
-                    cg[(size_t)cols[(size_t)m]] = make_int2(g, (m - ptr[(size_t)g]) | (slot << 8));
+                    cg[(size_t)cols[(size_t)m]] = make_int2(g, nm > 1 ? slot++ : -1);
+                if (nm > 1) { stops.push_back(slot++); n_multi++; }
                 mx = std::max(mx, nm);
             }
-            c->gene_max_members = mx; c->gene_n_multi = n_multi;
+            c->gene_max_members = mx; c->gene_n_multi = n_multi; c->gene_slots = slot;
+            c->d_gene_stops.upload(stops, c->stream);
             c->d_col_gene.upload(cg, c->stream);
         }
         CK(cudaStreamSynchronize(c->stream));
@@ -1124,18 +1129,19 @@ static void run_all(scasa_ctx *c, RangeStats &rs)
     }
     CK(cudaEventRecord(w->ev[4], s));
     if (c->n_genes > 0) {
-        const bool small = c->n_cols < 65535;                        // 16-bit entry indices when no row can hold 65535 entries
+        const bool small = c->n_cols < 65534;                        // 16-bit entry indices when no row can hold 65534 entries
         const int wpt = ((c->n_genes + 31) / 32 + kGeneRowThreads - 1) / kGeneRowThreads;
-        const size_t smem = (size_t)c->gene_n_multi * (8 + (small ? 2 : 4)) + (size_t)wpt * kGeneRowThreads * 8 + 16;
-        if (smem > 200 * 1024) throw ArgErr{SCASA_ERR_UNSUPPORTED, "gene map: too many multi-isoform genes for the gene kernel's shared memory"};
+        const size_t smem = (size_t)kGeneCap * 8 + (size_t)wpt * kGeneRowThreads * 8 + (size_t)c->gene_slots * (small ? 2 : 4) + 16;
+        if (smem > 200 * 1024) throw ArgErr{SCASA_ERR_UNSUPPORTED, "gene map: too many isoforms in multi-isoform genes for the gene kernel's shared memory"};
         const int cps = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->gene_ctas_per_sm, (size_t)(220 * 1024) / (smem + 1024)));
         const int grid = (int)std::min<int64_t>(n_cells, (int64_t)w->n_sm * cps);
+        const int n_stops = c->gene_n_multi + 1;
         if (small) {
             CK(cudaFuncSetAttribute(gene_rows_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            gene_rows_kernel<uint16_t><<<grid, kGeneRowThreads, smem, s>>>(R, n_cells, c->d_col_gene.p, c->n_genes, c->gene_n_multi, wpt, c->gene_max_members);
+            gene_rows_kernel<uint16_t><<<grid, kGeneRowThreads, smem, s>>>(R, n_cells, c->d_col_gene.p, c->n_genes, c->gene_slots, c->d_gene_stops.p, n_stops, wpt);
         } else {
-            CK(cudaFuncSetAttribute(gene_rows_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            gene_rows_kernel<int32_t><<<grid, kGeneRowThreads, smem, s>>>(R, n_cells, c->d_col_gene.p, c->n_genes, c->gene_n_multi, wpt, c->gene_max_members);
+            CK(cudaFuncSetAttribute(gene_rows_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gene_rows_kernel<uint32_t><<<grid, kGeneRowThreads, smem, s>>>(R, n_cells, c->d_col_gene.p, c->n_genes, c->gene_slots, c->d_gene_stops.p, n_stops, wpt);
         }
         CK(cudaGetLastError());
         launches++;

@@ -913,68 +913,75 @@ __global__ void colsum_em_reduce(const double *__restrict__ colpart, int n_chunk
 // scasa_genemat on the sparse rows (scasa_quant_step3_v1.0.0.R:32-46): gene row = column sum over the
 // gene's isoform rows, members added in row order (parasum's colSums, step3:27); single-member genes are
 // copies (step3:38-40).  One CTA per cell (two per SM, 512 threads).
-//   col_gene[j] = {gene of column j or -1, position of j among the gene's members | (1 + slot of the gene among the
-//                  multi-member genes) << 8; slot part 0 for single-member genes}
-//   A  every entry sets its gene's bit in a bitmap over the genes
+//   col_gene[j] = {gene of column j or -1, slot of j in the member table or -1 for single-member genes}
+//   member table (shared memory): the members of every multi-member gene side by side in column order, a fixed
+//   stop mark before the first gene and behind every gene; a slot holds the row entry that carries the member, or empty
+//   A  every entry sets its gene's bit in a bitmap over the genes; entries of multi-member genes enter the table
+//      and leave their value in shared memory
 //   B  a block scan of the bitmap's word counts: an entry's output position is the number of present genes before
 //      its own = word prefix + popcount below its bit; no sort
-//   C  multi-member genes are summed in ROUNDS by member position: in round r the entries that are the r-th member
-//      of their gene either open the gene's accumulator or add to it.  A gene has at most one entry per round, so
-//      there is no race and every sum is taken in member = column order, whatever the thread count.
-//   D  single-member entries write (gene, value) to their position; the entry that opened a multi-member gene
-//      writes the gene's sum.  Output rows are ascending in gene id by construction.
+//   C  an entry of a multi-member gene looks back in the table: another present member before it => done.
+//      Otherwise it is the gene's first present member and adds the later ones walking forward to the stop mark:
+//      every sum is taken by one thread in member = column order, whatever the thread count; no rounds, no barriers.
+//   D  (gene, value or sum) goes to the entry's position.  Output rows are ascending in gene id by construction.
 constexpr int kGeneRowThreads = 512;
 constexpr int kGeneKeep = 7;                 // entries a thread keeps in registers (rows up to 3,584 entries; the rest is re-read)
-template <typename T>                        // T = uint16_t when a row cannot have 65535 entries (smaller shared-memory footprint)
+constexpr int kGeneCap = kGeneKeep * kGeneRowThreads;
+template <typename T>                        // T = uint16_t when a row cannot have 65534 entries (smaller shared-memory footprint)
 __global__ void __launch_bounds__(kGeneRowThreads, 2) gene_rows_kernel(Result R, int64_t n_cells, const int2 *__restrict__ col_gene,
-                                                                       int n_genes, int n_multi, int words_per_thread, int max_members)
+                                                                       int n_genes, int n_slots, const int32_t *__restrict__ stops,
+                                                                       int n_stops, int words_per_thread)
 {
     extern __shared__ __align__(16) unsigned char gene_sm_raw[];
-    constexpr T kEmpty = (T)~(T)0;
+    constexpr T kEmpty = (T)~(T)0, kStop = (T)(kEmpty - 1);
     const int n_words = words_per_thread * kGeneRowThreads;                         // >= ceil(n_genes / 32)
-    double *macc = (double *)gene_sm_raw;                                           // [n_multi] sums of the multi-member genes
-    unsigned *bits = (unsigned *)(macc + n_multi);                                  // [n_words] genes present
+    double *vsm = (double *)gene_sm_raw;                                            // [kGeneCap] values of the multi-member entries
+    unsigned *bits = (unsigned *)(vsm + kGeneCap);                                  // [n_words] genes present
     int *wpre = (int *)(bits + n_words);                                            // [n_words] present genes before the word
-    T *mhead = (T *)(wpre + n_words);                                               // [n_multi] entry that opened the gene's accumulator
+    T *mtab = (T *)(wpre + n_words);                                                // [n_slots] member table
     __shared__ int wsum[kGeneRowThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     for (int i = tid; i < n_words; i += kGeneRowThreads) bits[i] = 0u;
-    for (int i = tid; i < n_multi; i += kGeneRowThreads) mhead[i] = kEmpty;
+    for (int i = tid; i < n_slots; i += kGeneRowThreads) mtab[i] = kEmpty;
     __syncthreads();
+    for (int i = tid; i < n_stops; i += kGeneRowThreads) mtab[stops[i]] = kStop;
+    int64_t nx_base = 0, nx_end = 0;                                  // extent of the row this CTA takes next
+    if (blockIdx.x < n_cells) { nx_base = R.rs_ptr[blockIdx.x]; nx_end = R.rs_ptr[blockIdx.x + 1]; }
     for (int64_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
-        const int64_t base = R.rs_ptr[cell];
-        const int n = (int)(R.rs_ptr[cell + 1] - base);
+        const int64_t base = nx_base;
+        const int n = (int)(nx_end - base);
         const int32_t *col = R.rs_col + base;
         const double *val = R.rs_val + base;
+        const int64_t nx = cell + gridDim.x;
+        if (nx < n_cells) { nx_base = R.rs_ptr[nx]; nx_end = R.rs_ptr[nx + 1]; }
         int2 cg[kGeneKeep];
         double v[kGeneKeep];
 #pragma unroll
         for (int k = 0; k < kGeneKeep; k++) {
             const int i = tid + k * kGeneRowThreads;
-            cg[k] = make_int2(-1, 0); v[k] = 0.0;
+            cg[k] = make_int2(-1, -1); v[k] = 0.0;
             if (i < n) { cg[k] = col_gene[col[i]]; v[k] = val[i]; }
         }
-        // f(entry index, {gene, pos | slot << 8}, value) for every entry of the row this thread owns
-        auto for_entries = [&](auto &&f) {
-#pragma unroll
-            for (int k = 0; k < kGeneKeep; k++) f(tid + k * kGeneRowThreads, cg[k], v[k]);
-            for (int i = tid + kGeneKeep * kGeneRowThreads; i < n; i += kGeneRowThreads) f(i, col_gene[col[i]], val[i]);
-        };
+        const bool long_row = n > kGeneCap;
+        __syncthreads();                                              // the previous cell's reset (and the stop marks) are in place
         // ---- A
-        unsigned pend = 0;                                            // register entries that belong to multi-member genes
 #pragma unroll
         for (int k = 0; k < kGeneKeep; k++)
             if (cg[k].x >= 0) {
                 atomicOr(&bits[cg[k].x >> 5], 1u << (cg[k].x & 31));
-                if ((cg[k].y >> 8) > 0) pend |= 1u << k;
+                if (cg[k].y >= 0) { const int i = tid + k * kGeneRowThreads; mtab[cg[k].y] = (T)i; vsm[i] = v[k]; }
             }
-        const bool long_row = n > kGeneKeep * kGeneRowThreads;
         if (long_row)
-            for (int i = tid + kGeneKeep * kGeneRowThreads; i < n; i += kGeneRowThreads) {
-                const int g = col_gene[col[i]].x;
-                if (g >= 0) atomicOr(&bits[g >> 5], 1u << (g & 31));
+            for (int i = tid + kGeneCap; i < n; i += kGeneRowThreads) {
+                const int2 c = col_gene[col[i]];
+                if (c.x >= 0) { atomicOr(&bits[c.x >> 5], 1u << (c.x & 31)); if (c.y >= 0) mtab[c.y] = (T)i; }
             }
         __syncthreads();
+        if (nx < n_cells) {                                           // the next row on its way into L2 while this one is placed
+            const int nn = (int)min(nx_end - nx_base, (int64_t)kGeneCap);
+            if (tid * 32 < nn) asm volatile("prefetch.global.L2 [%0];" ::"l"(R.rs_col + nx_base + tid * 32));
+            if (tid * 16 < nn) asm volatile("prefetch.global.L2 [%0];" ::"l"(R.rs_val + nx_base + tid * 16));
+        }
         // ---- B: thread owns words [tid*wpt, (tid+1)*wpt)
         const int w0 = tid * words_per_thread;
         int cnt = 0;
@@ -989,50 +996,38 @@ __global__ void __launch_bounds__(kGeneRowThreads, 2) gene_rows_kernel(Result R,
             int run = before + inc - cnt;
             for (int k = 0; k < words_per_thread; k++) { wpre[w0 + k] = run; run += __popc(bits[w0 + k]); }
         }
-        // ---- C (its first barrier also publishes wpre): only the entries still pending are looked at in a round
-        for (int r = 0; r < max_members; r++) {
-            auto visit = [&](int i, int2 c, double x) -> bool {     // true: this entry is done
-                const int ms = (c.y >> 8) - 1, pos = c.y & 0xff;
-                if (pos != r) return false;
-                const T h = mhead[ms];
-                if (h == kEmpty) { mhead[ms] = (T)i; macc[ms] = x; }
-                else macc[ms] += x;
-                return true;
-            };
-            if (pend) {
-#pragma unroll
-                for (int k = 0; k < kGeneKeep; k++)
-                    if ((pend >> k) & 1u)
-                        if (visit(tid + k * kGeneRowThreads, cg[k], v[k])) pend &= ~(1u << k);
-            }
-            bool more = pend != 0;
-            if (long_row)
-                for (int i = tid + kGeneKeep * kGeneRowThreads; i < n; i += kGeneRowThreads) {
-                    const int2 c = col_gene[col[i]];
-                    if (c.x < 0 || (c.y >> 8) == 0) continue;
-                    if ((c.y & 0xff) > r) more = true;
-                    else if ((c.y & 0xff) == r) visit(i, c, val[i]);
-                }
-            if (!__syncthreads_or(more)) break;
-        }
-        // ---- D
-        for_entries([&](int i, int2 c, double x) {
+        __syncthreads();
+        // ---- C + D
+        auto emit = [&](int2 c, double x) {
             if (c.x < 0) return;
-            const int ms = (c.y >> 8) - 1;
-            if (ms >= 0) {
-                if (mhead[ms] != (T)i) return;                        // a later member: already in the opener's sum
-                x = macc[ms];
+            if (c.y >= 0) {
+                for (int t = c.y - 1;; t--) {                         // an earlier member is present: it owns the sum
+                    const T h = mtab[t];
+                    if (h == kStop) break;
+                    if (h != kEmpty) return;
+                }
+                for (int t = c.y + 1;; t++) {
+                    const T h = mtab[t];
+                    if (h == kStop) break;
+                    if (h != kEmpty) x += (int64_t)h < kGeneCap ? vsm[h] : val[h];
+                }
             }
             const int g = c.x;
             const int64_t o = base + wpre[g >> 5] + __popc(bits[g >> 5] & ((1u << (g & 31)) - 1u));
             R.g_col[o] = g; R.g_val[o] = x;
-        });
+        };
+#pragma unroll
+        for (int k = 0; k < kGeneKeep; k++) emit(cg[k], v[k]);
+        if (long_row)
+            for (int i = tid + kGeneCap; i < n; i += kGeneRowThreads) emit(col_gene[col[i]], val[i]);
         if (tid == 0) R.g_len[cell] = total;
         __syncthreads();
-        // ---- reset for the next cell
+        // ---- reset for the next cell (its first barrier publishes this)
         for (int k = 0; k < words_per_thread; k++) bits[w0 + k] = 0u;
-        for_entries([&](int, int2 c, double) { if (c.x >= 0 && (c.y >> 8) > 0) mhead[(c.y >> 8) - 1] = kEmpty; });
-        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kGeneKeep; k++) if (cg[k].y >= 0) mtab[cg[k].y] = kEmpty;
+        if (long_row)
+            for (int i = tid + kGeneCap; i < n; i += kGeneRowThreads) { const int2 c = col_gene[col[i]]; if (c.y >= 0) mtab[c.y] = kEmpty; }
     }
 }
 
