@@ -217,6 +217,7 @@ struct scasa_ctx {
     int host_threads = 0;        // 0 = hardware concurrency
     int fetch_dense_copy = 0;    // 1 = plain dense D2H (SCASA_FETCH_DENSE)
     int n_genes = 0;
+    int pack_threads = 512;                    // threads per CTA of pack_cells_dense_kernel (SCASA_PACK_THREADS=512|1024)
     int gene_ctas_per_sm = 2;                  // gene_rows_kernel: resident CTAs per SM (SCASA_GENE_CTAS)
     int gene_max_members = 1, gene_n_multi = 0;   // most isoforms of a gene; genes with more than one
     DBuf<int2> d_col_gene;                     // per column: {gene or -1, slot in the gene kernel's member table or -1}
@@ -615,6 +616,7 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
         if (getenv("SCASA_FETCH_DENSE")) c->fetch_dense_copy = 1;
         if (getenv("SCASA_POISON")) c->poison = 1;
         if (const char *env = getenv("SCASA_GENE_CTAS")) c->gene_ctas_per_sm = std::max(1, atoi(env));
+        if (const char *env = getenv("SCASA_PACK_THREADS")) c->pack_threads = atoi(env) == 1024 ? 1024 : 512;
         // EM work classes; SCASA_EM_CFG="warps:pairs:bytes:cta_threads:ctas_per_sm,..." overrides (tuning)
         if (const char *env = getenv("SCASA_EM_CFG")) {
             int k = 0;
@@ -941,17 +943,23 @@ static void run_all(scasa_ctx *c, RangeStats &rs)
 
     // ---- pack: eqclass counts -> Y
     if (c->have_eq) {
-        int wpt = (int)((c->n_rows + 32 * 512 - 1) / (32 * 512));           // bitmap words per thread
-        wpt = std::min(wpt, 3);                                              // 3 * 512 * 32 = 49,152 rows per tile (198 KB); more rows: several tiles
-        if (const char *env = getenv("SCASA_PACK_WPT")) wpt = std::max(1, std::min(3, atoi(env)));   // smaller tiles: more CTAs per SM, more passes
-        const size_t dense_smem = (size_t)wpt * 512 * 33 * sizeof(int);       // int32 histogram + touched-row bitmap
+        int n_words = (int)std::min<int64_t>((c->n_rows + 31) / 32, 3 * 512);   // 49,152 rows per tile (198 KB); more rows: several tiles
+        if (const char *env = getenv("SCASA_PACK_WPT")) n_words = std::min(n_words, 512 * std::max(1, std::min(3, atoi(env))));   // smaller tiles: more CTAs per SM, more passes
+        const size_t dense_smem = (size_t)n_words * 33 * sizeof(int);         // int32 histogram + touched-row bitmap
         if (!getenv("SCASA_PACK_SORT")) {
-            CK(cudaFuncSetAttribute(pack_cells_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_smem));
             const int pack_ctas = (int)std::max<size_t>(1, (size_t)(220 * 1024) / (dense_smem + 1024));
             int grid = (int)std::min<int64_t>(n_cells, (int64_t)w->n_sm * pack_ctas);
-            pack_cells_dense_kernel<<<grid, 512, dense_smem, s>>>(n_cells, c->d_cell_ptr.p, c->d_eq_id.p, c->d_eq_count.p,
-                                                                  c->d_eq_row.p, c->n_eq, (int)c->n_rows, wpt, c->d_y_row.p,
-                                                                  c->d_y_val.p, c->d_y_len.p);
+            if (c->pack_threads == 1024) {
+                CK(cudaFuncSetAttribute(pack_cells_dense_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_smem));
+                pack_cells_dense_kernel<1024><<<grid, 1024, dense_smem, s>>>(n_cells, c->d_cell_ptr.p, c->d_eq_id.p, c->d_eq_count.p,
+                                                                           c->d_eq_row.p, c->n_eq, (int)c->n_rows, n_words, c->d_y_row.p,
+                                                                           c->d_y_val.p, c->d_y_len.p);
+            } else {
+                CK(cudaFuncSetAttribute(pack_cells_dense_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_smem));
+                pack_cells_dense_kernel<512><<<grid, 512, dense_smem, s>>>(n_cells, c->d_cell_ptr.p, c->d_eq_id.p, c->d_eq_count.p,
+                                                                         c->d_eq_row.p, c->n_eq, (int)c->n_rows, n_words, c->d_y_row.p,
+                                                                         c->d_y_val.p, c->d_y_len.p);
+            }
         } else {
             int cap = 32;
             while (cap < c->max_cell_entries) cap <<= 1;
@@ -1180,7 +1188,7 @@ static int sync_twin(scasa_ctx *c)
         t->cls_warps[k] = c->cls_warps[k]; t->cls_pairs[k] = c->cls_pairs[k]; t->cls_bytes[k] = c->cls_bytes[k];
         t->cls_cta_threads[k] = c->cls_cta_threads[k]; t->cls_ctas_per_sm[k] = c->cls_ctas_per_sm[k];
     }
-    t->pair_max = c->pair_max; t->pair_ctas_per_sm = c->pair_ctas_per_sm; t->poison = c->poison;
+    t->pair_max = c->pair_max; t->pair_ctas_per_sm = c->pair_ctas_per_sm; t->poison = c->poison; t->pack_threads = c->pack_threads;
     if (c->n_genes > 0 && (t->n_genes != c->n_genes || t->gene_of_col_host != c->gene_of_col_host)) {
         int rc = scasa_set_gene_map(t, c->gene_of_col_host.data(), c->n_genes);
         if (rc) return fail(c, rc, std::string("twin context: ") + scasa_last_error(t));

@@ -186,19 +186,21 @@ struct Tasks {                // task t = chunk * n_em + em index
 // non-zero rows in ascending order.  Integer adds: the result is independent of their order.
 // Thread i owns the contiguous rows [i*seg, (i+1)*seg), seg odd (no bank conflicts); the histogram
 // is left all-zero for the next cell.
-constexpr int kPackBatch = 8;
-__global__ void __launch_bounds__(512) pack_cells_dense_kernel(int64_t n_cells, const int64_t *__restrict__ cell_ptr,
-                                                               const int32_t *__restrict__ eq_id,
-                                                               const int32_t *__restrict__ eq_count,
-                                                               const int32_t *__restrict__ eq_row, int64_t n_eq, int n_rows,
-                                                               int words_per_thread, int32_t *__restrict__ y_row,
-                                                               double *__restrict__ y_val, int32_t *__restrict__ y_len)
+constexpr int kPackEntries = 4096;                                // entries of a cell in registers per pass, over the whole CTA
+template <int TN>                                                 // threads per CTA
+__global__ void __launch_bounds__(TN) pack_cells_dense_kernel(int64_t n_cells, const int64_t *__restrict__ cell_ptr,
+                                                              const int32_t *__restrict__ eq_id,
+                                                              const int32_t *__restrict__ eq_count,
+                                                              const int32_t *__restrict__ eq_row, int64_t n_eq, int n_rows,
+                                                              int n_words, int32_t *__restrict__ y_row,
+                                                              double *__restrict__ y_val, int32_t *__restrict__ y_len)
 {
+    constexpr int kPackBatch = kPackEntries / TN;
     extern __shared__ int pack_sm[];
-    const int n_words = words_per_thread * (int)blockDim.x;       // rows of one tile / 32
     int *hist = pack_sm;                                          // [n_words * 32] counts by row of the tile
     unsigned *bits = (unsigned *)(pack_sm + (size_t)n_words * 32);   // [n_words] rows touched by this cell
-    __shared__ int wsum[16];
+    __shared__ int wsum[TN / 32];
+    const int words_per_thread = (n_words + TN - 1) / TN;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int tile_rows = n_words * 32;
     // X-matrices with more rows than the histogram holds are taken in tiles of tile_rows rows: the cell's entries
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(512) pack_cells_dense_kernel(int64_t n_cells, 
     // gather through eq_row, all gathers before the first atomic, so a batch costs one memory round
     // trip per level instead of one per entry.  The next cell's first batch is loaded while this
     // cell's rows are emitted.
-    const int T = (int)blockDim.x;
+    constexpr int T = TN;
     int e[kPackBatch], c[kPackBatch], r[kPackBatch];
     auto load_entries = [&](int64_t s, int n, int base) {
 #pragma unroll
@@ -250,18 +252,19 @@ __global__ void __launch_bounds__(512) pack_cells_dense_kernel(int64_t n_cells, 
             __syncthreads();
             if (tile == n_tiles - 1) load_entries(s2, n2, 0);                     // in flight during the emission
             // thread owns words [tid*wpt, (tid+1)*wpt): rows in ascending order across threads
-            const int w0 = tid * words_per_thread;
+            const int w0 = tid * words_per_thread, w1 = min(n_words, w0 + words_per_thread);
             int cnt = 0;
-            for (int k = 0; k < words_per_thread; k++) cnt += __popc(bits[w0 + k]);
+            for (int k = w0; k < w1; k++) cnt += __popc(bits[k]);
             int inc = cnt;
             for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += v; }
             if (lane == 31) wsum[w] = inc;
             __syncthreads();
             int base = 0, total = 0;
-            for (int k = 0; k < (int)(blockDim.x >> 5); k++) { int v = wsum[k]; if (k < w) base += v; total += v; }
+#pragma unroll
+            for (int k = 0; k < TN / 32; k++) { int v = wsum[k]; if (k < w) base += v; total += v; }
             int o = emitted + base + inc - cnt;
             if (cnt)
-                for (int k = 0; k < words_per_thread; k++) {
+                for (int k = 0; k < w1 - w0; k++) {
                     unsigned m = bits[w0 + k];
                     bits[w0 + k] = 0;
                     while (m) {
