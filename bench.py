@@ -279,7 +279,7 @@ def main():
     iso_nnz, gene_nnz = g.result_nnz()
 
     # ------------------------------------------------------------------ e2e: host buffers every step
-    e2e = None
+    e2e = e2e_csr = None
     if not args.no_e2e:
         import psutil
         ne = args.e2e_cells or n
@@ -340,9 +340,38 @@ def main():
                            "(sparse rows on the wire, expanded into the caller's dense pageable matrices by host threads)",
                "api": "scasa_b200.api.Scasa.quant -> scasa_quant (chunks in slices, two contexts: transfer of one slice "
                       "overlaps the computation of the next)", "host_threads": nthreads}
+        del h_iso, h_gene
+        # the same call with sparse results (scasa_quant_csr: the dgCMatrix slots of the reference's matrices)
+        from scasa_b200.api import quant_csr
+
+        def csr_step():
+            iso_s, gene_s, cs_, _ = quant_csr([g], h_ptr, h_id, h_cnt, ed.eq_off, ed.eq_tx, core=4, drop_zeros=True, n_threads=nthreads)
+            out = (iso_s.nnz, gene_s.nnz, float(iso_s.val[:1].sum() + gene_s.val[-1:].sum() + cs_[0]))
+            iso_s.close(); gene_s.close()
+            return out
+
+        csr_step()
+        barrier()
+        g.transfer_bytes(reset=True)
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            nz_i, nz_g, _ = csr_step()
+        barrier()
+        tc = time.perf_counter() - t0
+        wire_h2d, wire_d2h = g.transfer_bytes(reset=True)
+        tt = torch.tensor([tc], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tc = float(tt[0]) / args.e2e_steps
+        e2e_csr = {"value": ne * world / tc, "unit": "cells/s", "cells_per_gpu": ne, "s_per_step": tc,
+                   "h2d_bytes_per_step": int(wire_h2d // args.e2e_steps), "d2h_bytes_per_step": int(wire_d2h // args.e2e_steps),
+                   "host_result_bytes": int((nz_i + nz_g) * 12 + 2 * (ne + 1) * 8),
+                   "result_entries": {"isoform": int(nz_i), "gene": int(nz_g)},
+                   "includes": "as e2e, but the results stay sparse on the host (stored zeros dropped): "
+                               "CSR by cell = the p/i/x slots of the dgCMatrix of the reference's tx x cells matrices",
+                   "api": "scasa_b200.api.quant_csr -> scasa_quant_csr", "host_threads": nthreads}
         for a in (h_ptr, h_id, h_cnt):
             _l.pinned_free(a)
-        del h_iso, h_gene
 
     # ------------------------------------------------------------------ e2e_files: bfh.txt in, the two text files out
     e2e_files = None
@@ -455,6 +484,7 @@ def main():
             "clocks": clocks, "roofline": roofline}
     if e2e:
         line["e2e"] = e2e
+        line["e2e_csr"] = e2e_csr
     if e2e_files:
         line["e2e_files"] = e2e_files
     if not args.no_cpu:

@@ -157,6 +157,26 @@ int scasa_quant_files(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, in
                       const char *gene_names, const int32_t *gene_rank, const char *cell_names, int32_t n_threads,
                       double *colsum_out, scasa_files_timing_t *timing);
 
+/* ---- eqclass counts in, sparse matrices out ------------------------------------------------------------------
+ * The results as they are on the device: CSR by cell, columns ascending inside a row.  Read column-wise this IS
+ * the compressed-column form of the reference's tx x cells matrix (step2:166): ptr/col/val are the p/i/x slots
+ * of a Matrix::dgCMatrix with Dim = c(n_cols, n_cells), so an R caller gets `isoform_count` without a dense
+ * 8 * n_cols * n_cells byte matrix ever existing (100k cells: 3.2 GB instead of 26.7 GB).  drop_zeros != 0
+ * removes the stored zeros (columns of EM blocks whose estimate is exactly 0) on the way.  The arrays are
+ * allocated by the library; release them with scasa_csr_free.  gene (needs scasa_set_gene_map), colsum_out and
+ * iters_out may be NULL.  Values, column sums and iteration counts are those of scasa_quant_multi, bit for bit. */
+typedef struct {
+    int64_t n_rows, nnz;     /* cells, stored entries */
+    int64_t *ptr;            /* [n_rows + 1] */
+    int32_t *col;            /* [nnz] */
+    double *val;             /* [nnz] */
+} scasa_csr_t;
+int scasa_quant_csr(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off,
+                    const int64_t *cell_ptr, const int32_t *eq_id, const int32_t *eq_count, int64_t n_eq,
+                    const int32_t *eq_row, int32_t drop_zeros, scasa_csr_t *iso, scasa_csr_t *gene,
+                    double *colsum_out, int32_t *iters_out);
+void scasa_csr_free(scasa_csr_t *m);
+
 /* ---- the same in resident stages (what scasa_estimate is made of) ----------------------- */
 int scasa_stage_counts(scasa_ctx *ctx, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off,
                        const int64_t *y_rowptr, const int32_t *y_rowidx, const double *y_val);

@@ -1,10 +1,12 @@
 ## scasa_quant_step2_patch.R — what replaces lines 88-167 of scasa_quant_step2_v1.0.0.R (the two %dopar% loops over
 ## crpcount_td and estim_chunk, the serial ccrpfun recompute, the stacking and the row filter) when libscasa_cuda is used.
 ## Everything before (loading Sample_eqClass.RData and the X-matrix, step2:35-59) stays as it is; step2:169-170
-## (saveRDS / write.table) stay too in matrix mode and are replaced by the library's writer in file mode.  See INTEGRATION.md.
+## (saveRDS / write.table) stay too in matrix mode and are replaced by the library's writer in file mode; in sparse mode
+## saveRDS stays and write.table needs as.matrix(isoform_count) (or SCASA_FILES=1 for the text file).  See INTEGRATION.md.
 dyn.load("scasa_r.so")
 n_gpus    <- as.integer(Sys.getenv("SCASA_GPUS", "1"))          # GPUs of this box to shard the chunks over
 file_mode <- Sys.getenv("SCASA_FILES", "0") == "1"              # 1: write the two text files directly, no dense matrix in R
+sparse    <- Sys.getenv("SCASA_SPARSE", "0") == "1"             # 1: isoform_count / gene matrix as Matrix::dgCMatrix
 
 flat <- function(L) list(q_off = c(0L, cumsum(sapply(L, nrow))), p_off = c(0L, cumsum(sapply(L, ncol))),
                          x_off = as.numeric(c(0, cumsum(sapply(L, length)))), x = unlist(L, use.names = FALSE))
@@ -61,6 +63,16 @@ if (file_mode) {                                                  # step2:165-17
                   iso_txt, if (have_g) paste0(workdir, "/scasa_gene_expression.txt") else NULL,
                   nl(tx), if (have_g) nl(gene_names) else NULL, gene_rank, nl(allCells))
   file.copy(iso_txt, paste0(workdir, "/scasa_isoform_expression.txt"), overwrite = TRUE)   # the name README.md:80 uses
+} else if (sparse) {                                              # the same matrices, sparse: the form Seurat & co. read anyway
+  library(Matrix)
+  res <- .Call("scasa_r_quant_sparse", ctx, cell_ptr, eq_id, ce$Count, eq_off, eq_tx, core, gene_of, length(gene_names))
+  dgc <- function(m, rn) new("dgCMatrix", p = m[[1]], i = m[[2]], x = m[[3]], Dim = c(length(rn), length(allCells)),
+                             Dimnames = list(rn, allCells))
+  isoform_count <- dgc(res[[1]], tx)[which(res[[3]] > 0), ]       # step2:167
+  if (have_g) {
+    kept <- tapply(res[[3]] > 0, factor(genes, gene_names), sum)
+    saveRDS(list(gene = dgc(res[[2]], gene_names), kept = kept), paste0(workdir, "/scasa_gene_sums_all.RDS"))
+  }
 } else {
   res <- .Call("scasa_r_quant", ctx, cell_ptr, eq_id, ce$Count, eq_off, eq_tx, core, gene_of, length(gene_names))
   iso <- res[[1]]

@@ -10,6 +10,7 @@
 #include <Rinternals.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 #include "scasa_cuda.h"
 
 #define SCASA_R_MAX_GPUS 16
@@ -145,6 +146,54 @@ SEXP scasa_r_quant(SEXP p, SEXP cell_ptr, SEXP eq_id, SEXP eq_count, SEXP eq_off
     SET_VECTOR_ELT(out, 1, gene);
     SET_VECTOR_ELT(out, 2, colsum);
     UNPROTECT(4);
+    return out;
+}
+
+/* The same with sparse results: list(iso = list(p, i, x), gene = list(p, i, x) or NULL, colsum).  p / i / x are the slots of
+ * a Matrix::dgCMatrix with Dim = c(columns, cells) — `new("dgCMatrix", p = , i = , x = , Dim = , Dimnames = )` — i.e. the
+ * reference's tx x cells `isoform_count` (step2:166) and the gene matrix of step 3 without their zeros: no dense matrix on
+ * either side of the call.  Stored zeros are dropped.  R's integer slots limit a matrix to 2^31 - 1 entries. */
+static SEXP csr_to_list(const scasa_csr_t *m)
+{
+    SEXP l = PROTECT(allocVector(VECSXP, 3));
+    SEXP p = PROTECT(allocVector(INTSXP, (R_xlen_t)m->n_rows + 1));
+    SEXP i = PROTECT(allocVector(INTSXP, (R_xlen_t)m->nnz));
+    SEXP x = PROTECT(allocVector(REALSXP, (R_xlen_t)m->nnz));
+    for (int64_t c = 0; c <= m->n_rows; c++) INTEGER(p)[c] = (int)m->ptr[c];
+    if (m->nnz) {
+        memcpy(INTEGER(i), m->col, (size_t)m->nnz * sizeof(int));
+        memcpy(REAL(x), m->val, (size_t)m->nnz * sizeof(double));
+    }
+    SET_VECTOR_ELT(l, 0, p);
+    SET_VECTOR_ELT(l, 1, i);
+    SET_VECTOR_ELT(l, 2, x);
+    UNPROTECT(4);
+    return l;
+}
+SEXP scasa_r_quant_sparse(SEXP p, SEXP cell_ptr, SEXP eq_id, SEXP eq_count, SEXP eq_off, SEXP eq_tx, SEXP core, SEXP gene_of_col,
+                          SEXP n_genes)
+{
+    scasa_r_handle *h = handle_of(p);
+    quant_in q;
+    quant_prepare(h, cell_ptr, eq_off, eq_tx, core, &q);
+    const int want_gene = gene_of_col != R_NilValue, ng = want_gene ? asInteger(n_genes) : 0;
+    if (scasa_set_gene_map(h->ctx[0], want_gene ? INTEGER(gene_of_col) : NULL, ng)) error("%s", scasa_last_error(h->ctx[0]));
+    scasa_csr_t iso, gene;
+    SEXP colsum = PROTECT(allocVector(REALSXP, (R_xlen_t)scasa_n_cols(h->ctx[0])));
+    if (scasa_quant_csr(h->ctx, h->n, q.n, q.nch, q.ch, q.cp, INTEGER(eq_id), INTEGER(eq_count), q.E, q.row, 1 /* drop zeros */,
+                        &iso, want_gene ? &gene : NULL, REAL(colsum), NULL /* iters */))
+        error("%s", scasa_last_error(h->ctx[0]));
+    if (iso.nnz > 2147483647LL || (want_gene && gene.nnz > 2147483647LL)) {
+        scasa_csr_free(&iso);
+        if (want_gene) scasa_csr_free(&gene);
+        error("more than 2^31 - 1 entries: a dgCMatrix cannot hold them; use scasa_r_quant_files or fewer cells per call");
+    }
+    SEXP out = PROTECT(allocVector(VECSXP, 3));
+    SET_VECTOR_ELT(out, 0, csr_to_list(&iso));
+    scasa_csr_free(&iso);
+    if (want_gene) { SET_VECTOR_ELT(out, 1, csr_to_list(&gene)); scasa_csr_free(&gene); }
+    SET_VECTOR_ELT(out, 2, colsum);
+    UNPROTECT(2);
     return out;
 }
 

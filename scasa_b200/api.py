@@ -367,6 +367,56 @@ def quant_files(contexts, cell_ptr, eq_id, eq_count, eq_off, eq_tx, iso_path: st
     return colsum, {k: getattr(tm, k) for k, _ in tm._fields_}
 
 
+class SparseRows:
+    """A scasa_csr_t: CSR by cell over the output columns == the p / i / x slots of the dgCMatrix of the reference's
+    (columns x cells) matrix.  `ptr`, `col`, `val` are views of library memory that live as long as this object."""
+
+    def __init__(self, lib, c: "_l.Csr"):
+        self._L, self._c = lib, c
+        self.n_rows, self.nnz = int(c.n_rows), int(c.nnz)
+        self.ptr = np.ctypeslib.as_array(c.ptr, (self.n_rows + 1,))
+        self.col = np.ctypeslib.as_array(c.col, (max(self.nnz, 1),))[: self.nnz]
+        self.val = np.ctypeslib.as_array(c.val, (max(self.nnz, 1),))[: self.nnz]
+
+    def to_dense(self, n_cols: int) -> np.ndarray:
+        out = np.zeros((self.n_rows, n_cols))
+        out[np.repeat(np.arange(self.n_rows), np.diff(self.ptr)), self.col] = self.val
+        return out
+
+    def close(self):
+        if self._c is not None:
+            self.ptr = self.col = self.val = None
+            self._L.scasa_csr_free(C.byref(self._c))
+            self._c = None
+
+    __del__ = close
+
+
+def quant_csr(contexts, cell_ptr, eq_id, eq_count, eq_off, eq_tx, core: int = 4, drop_zeros: bool = True, want_gene: bool = True,
+              want_iters: bool = False, n_threads: int = 0):
+    """scasa_quant_csr: eqclass counts in (host), sparse isoform and gene matrices out (host), over the given contexts
+    (one per GPU).  Returns (iso: SparseRows, gene: SparseRows | None, colsum, iters | None)."""
+    g0 = contexts[0]
+    L = g0._L
+    cell_ptr = np.ascontiguousarray(cell_ptr, np.int64)
+    eq_id = np.ascontiguousarray(eq_id, np.int32)
+    eq_count = np.ascontiguousarray(eq_count, np.int32)
+    n_cells = len(cell_ptr) - 1
+    chunks = chunk_split(n_cells, core)
+    eq_row = g0.eqclass_map(eq_off, eq_tx, n_threads or 8)
+    colsum = np.empty(g0.n_cols, np.float64)
+    iters = np.zeros((len(chunks) - 1, g0.n_em, 2), np.int32) if want_iters else None
+    iso, gene = _l.Csr(), _l.Csr()
+    arr = (C.c_void_p * len(contexts))(*[c._ctx for c in contexts])
+    rc = L.scasa_quant_csr(arr, len(contexts), n_cells, len(chunks) - 1, _l.ptr(chunks, C.c_int64), _l.ptr(cell_ptr, C.c_int64),
+                           _l.ptr(eq_id, C.c_int32), _l.ptr(eq_count, C.c_int32), len(eq_row), _l.ptr(eq_row, C.c_int32),
+                           1 if drop_zeros else 0, C.byref(iso), C.byref(gene) if want_gene else None, _l.ptr(colsum, C.c_double),
+                           _l.ptr(iters, C.c_int32) if iters is not None else None)
+    if rc:
+        raise _l.ScasaError(rc, L.scasa_last_error(g0._ctx).decode())
+    return SparseRows(L, iso), (SparseRows(L, gene) if want_gene else None), colsum, iters
+
+
 def dense_to_csr(y_dense: np.ndarray):
     """(n_cells, Σq) dense counts -> CSR by cell (rows ascending)."""
     y_dense = np.asarray(y_dense)

@@ -9,6 +9,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <cmath>
@@ -19,6 +20,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <sys/mman.h>
 
 using namespace scasa;
 
@@ -67,6 +69,7 @@ class ExpandPool {
 public:
     struct Job {
         double *dst; int64_t n_cols, n_rows; const int64_t *start; const int32_t *nnz; const int32_t *cols; const double *vals;
+        std::function<void(int64_t, int64_t)> fn;      // set: fn(first row, end row) instead of the expansion
         std::atomic<int64_t> next{0};
         int64_t finished = 0;
         bool done = false;
@@ -87,6 +90,19 @@ public:
     {
         auto j = std::make_shared<Job>();
         j->dst = dst; j->n_cols = n_cols; j->n_rows = n_rows; j->start = start; j->nnz = nnz; j->cols = cols; j->vals = vals;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            queue_.push_back(j);
+        }
+        cv_work_.notify_all();
+        return j;
+    }
+    std::shared_ptr<Job> post_fn(int64_t n_rows, std::function<void(int64_t, int64_t)> fn)
+    {
+        auto j = std::make_shared<Job>();
+        j->dst = nullptr; j->n_cols = 0; j->n_rows = n_rows; j->start = nullptr; j->nnz = nullptr; j->cols = nullptr; j->vals = nullptr;
+        j->fn = std::move(fn);
+        if (n_rows <= 0) { j->done = true; return j; }
         {
             std::lock_guard<std::mutex> lk(m_);
             queue_.push_back(j);
@@ -123,7 +139,8 @@ private:
                 const int64_t r = j->next.fetch_add(8);
                 if (r >= j->n_rows) break;
                 const int64_t e = std::min(r + 8, j->n_rows);
-                scasa::expand_rows(j->dst, j->n_cols, r, e, j->start, j->nnz, j->cols, j->vals);
+                if (j->fn) j->fn(r, e);
+                else scasa::expand_rows(j->dst, j->n_cols, r, e, j->start, j->nnz, j->cols, j->vals);
                 mine += e - r;
             }
             std::lock_guard<std::mutex> lk(m_);
@@ -198,6 +215,11 @@ struct scasa_ctx {
     DBuf<uint32_t> d_ypos;
     int64_t rs_nnz = 0;                  // entries of the result structure of the last run
     std::vector<int64_t> rs_ptr_host;    // fetched on demand after a run
+    std::vector<int64_t> cmp_ptr_host;   // row starts of the result packed without its stored zeros (row_source)
+    DBuf<int32_t> d_cmp_len, d_cmp_col;
+    DBuf<int64_t> d_cmp_ptr;
+    DBuf<double> d_cmp_val;
+    int d2h_compact = 1;                 // drop the stored zeros on the device before a result crosses PCIe (SCASA_D2H_COMPACT=0: off)
     std::vector<int32_t> g_len_host;
     bool have_rs_host = false, have_glen_host = false, ran_genes = false;
     // the trip to the host: two batches in flight (device CSR slice -> pinned staging -> threaded expansion)
@@ -423,6 +445,37 @@ void need_rs_host(scasa_ctx *c, bool genes)
     }
 }
 
+// Where the rows of a result are read from: as the kernels left them (row r = [ptr[r], ptr[r] + len[r]), len == nullptr:
+// full rows), or — compact — packed on the device without their stored zeros.
+struct RowSrc { const int64_t *ptr; const int32_t *len; const int32_t *d_col; const double *d_val; };
+RowSrc row_source(scasa_ctx *c, bool genes, bool compact)
+{
+    need_rs_host(c, genes);
+    RowSrc src{c->rs_ptr_host.data(), genes ? c->g_len_host.data() : nullptr, genes ? c->d_g_col.p : c->d_rs_col.p,
+               genes ? c->d_g_val.p : c->d_rs_val.p};
+    if (!compact || c->n_cells == 0) return src;
+    cudaStream_t s = c->stream;
+    const int64_t n = c->n_cells;
+    const unsigned grid = (unsigned)((n + 7) / 8);
+    int launches = 0;
+    c->d_cmp_len.ensure((size_t)n + 1);
+    c->d_cmp_ptr.ensure((size_t)n + 2);
+    row_nonzeros_kernel<<<grid, 256, 0, s>>>(c->d_rs_ptr.p, genes ? c->d_g_len.p : nullptr, src.d_val, n, c->d_cmp_len.p);
+    CK(cudaGetLastError());
+    exclusive_scan(c, c->d_cmp_len.p, n, c->d_cmp_ptr.p, c->d_totals.p + 2, launches);
+    c->cmp_ptr_host.resize((size_t)n + 1);
+    CK(cudaMemcpyAsync(c->cmp_ptr_host.data(), c->d_cmp_ptr.p, ((size_t)n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    c->wire_d2h += (long long)(n + 1) * 8;
+    const int64_t total = c->cmp_ptr_host[(size_t)n];
+    c->d_cmp_col.ensure((size_t)total + 1);
+    c->d_cmp_val.ensure((size_t)total + 1);
+    row_compact_kernel<<<grid, 256, 0, s>>>(c->d_rs_ptr.p, genes ? c->d_g_len.p : nullptr, src.d_col, src.d_val, n, c->d_cmp_ptr.p,
+                                            c->d_cmp_col.p, c->d_cmp_val.p);
+    CK(cudaGetLastError());
+    return RowSrc{c->cmp_ptr_host.data(), nullptr, c->d_cmp_col.p, c->d_cmp_val.p};
+}
+
 // A CSR result (rows of the isoform matrix, or of the gene matrix when `genes`) -> the caller's dense
 // host matrix.  The sparse rows cross PCIe as they are, in batches of whole rows; while the host threads
 // expand batch k into the caller's matrix (every element written exactly once, streaming stores), batch
@@ -430,12 +483,13 @@ void need_rs_host(scasa_ctx *c, bool genes)
 void fetch_dense(scasa_ctx *c, bool genes, double *out)
 {
     cudaStream_t s = c->stream;
-    need_rs_host(c, genes);
     const int64_t n_rows = c->n_cells, n_cols = genes ? c->n_genes : c->n_cols;
-    const int64_t *ptr = c->rs_ptr_host.data();
-    const int32_t *d_col = genes ? c->d_g_col.p : c->d_rs_col.p;
-    const double *d_val = genes ? c->d_g_val.p : c->d_rs_val.p;
-    if (c->fetch_dense_copy || c->host_threads < 0) {           // expansion on the device, plain dense copy (testing aid)
+    const bool device_expand = c->fetch_dense_copy || c->host_threads < 0;
+    const RowSrc src = row_source(c, genes, c->d2h_compact && !device_expand);   // zeros need not cross PCIe: the expansion writes them
+    const int64_t *ptr = src.ptr;
+    const int32_t *d_col = src.d_col;
+    const double *d_val = src.d_val;
+    if (device_expand) {           // expansion on the device, plain dense copy (testing aid)
         const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(n_rows, ((int64_t)32 << 20) / n_cols));
         c->d_dense_tmp.ensure((size_t)(batch * n_cols));
         for (int64_t r0 = 0; r0 < n_rows; r0 += batch) {
@@ -476,7 +530,7 @@ void fetch_dense(scasa_ctx *c, bool genes, double *out)
         }
         for (int64_t r = r0; r < r1; r++) {
             b.h_start[r - r0] = ptr[r] - e0;
-            b.h_nnz[r - r0] = genes ? c->g_len_host[(size_t)r] : (int32_t)(ptr[r + 1] - ptr[r]);
+            b.h_nnz[r - r0] = src.len ? src.len[r] : (int32_t)(ptr[r + 1] - ptr[r]);
         }
         c->wire_d2h += (long long)ne * 12;
         CK(cudaEventRecord(b.done, s));
@@ -508,6 +562,87 @@ void fetch_dense(scasa_ctx *c, bool genes, double *out)
         fprintf(stderr, "[scasa fetch] %lld x %lld, %lld batches, %lld entries (%.1f per row): wait copy %.3f s, wait expansion %.3f s, %d threads\n",
                 (long long)n_rows, (long long)n_cols, (long long)n_batches, (long long)ptr[n_rows], (double)ptr[n_rows] / (double)n_rows,
                 t_wait_gpu, t_join, nthr);
+}
+
+// A CSR result -> sparse rows on the host, through the same pipeline (pinned staging, batches of whole rows, host
+// threads): row r's entries go to cols/vals (either may be null) at dst_off[r]; with drop0 the stored zeros of a row
+// are left out (its entries move up inside the row's span); count[r] (nullable) = entries written for row r.
+// dst_off == nullptr: rows side by side without gaps (isoform rows: the device layout; gene rows: closed up).
+void fetch_sparse(scasa_ctx *c, bool genes, int32_t *cols, double *vals, const int64_t *dst_off, int64_t *count, bool drop0)
+{
+    cudaStream_t s = c->stream;
+    const int64_t n_rows = c->n_cells;
+    const bool packed = drop0 && c->d2h_compact;                  // zeros already left behind on the device
+    const RowSrc src = row_source(c, genes, packed);
+    if (packed) drop0 = false;
+    const int64_t *ptr = src.ptr;
+    const int32_t *d_col = src.d_col;
+    const double *d_val = src.d_val;
+    const int32_t *glen = src.len;
+    std::vector<int64_t> own_off;
+    if (!dst_off) {
+        own_off.resize((size_t)n_rows + 1);
+        own_off[0] = 0;
+        for (int64_t r = 0; r < n_rows; r++) own_off[(size_t)r + 1] = own_off[(size_t)r] + (glen ? glen[r] : ptr[r + 1] - ptr[r]);
+        dst_off = own_off.data();
+    }
+    int nthr = c->host_threads > 0 ? c->host_threads : (int)std::thread::hardware_concurrency();
+    nthr = std::max(1, std::min(nthr, 256));
+    int64_t max_row = 1;
+    for (int64_t r = 0; r < n_rows; r++) max_row = std::max(max_row, ptr[r + 1] - ptr[r]);
+    const size_t cap = (size_t)std::max<int64_t>(max_row, (int64_t)6 << 20);
+    std::vector<int64_t> cut{0};
+    for (int64_t r = 0; r < n_rows;) {
+        int64_t e = r + 1;
+        while (e < n_rows && ptr[e + 1] - ptr[r] <= (int64_t)cap && e - r < 65536) e++;
+        cut.push_back(e);
+        r = e;
+    }
+    const int64_t n_batches = (int64_t)cut.size() - 1;
+    size_t max_rows = 1;
+    for (int64_t k = 0; k < n_batches; k++) max_rows = std::max(max_rows, (size_t)(cut[(size_t)k + 1] - cut[(size_t)k]));
+    for (auto &b : c->fb) fetch_buf_ensure(c, b, max_rows, cap);
+    auto launch = [&](int64_t k) {
+        scasa_ctx::FetchBuf &b = c->fb[k & 1];
+        const int64_t r0 = cut[(size_t)k], r1 = cut[(size_t)k + 1];
+        const int64_t e0 = ptr[r0], ne = ptr[r1] - e0;
+        if (ne) {
+            if (cols) CK(cudaMemcpyAsync(b.h_cols, d_col + e0, (size_t)ne * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+            if (vals || drop0) CK(cudaMemcpyAsync(b.h_vals, d_val + e0, (size_t)ne * sizeof(double), cudaMemcpyDeviceToHost, s));
+        }
+        c->wire_d2h += (long long)ne * ((cols ? 4 : 0) + (vals || drop0 ? 8 : 0));
+        CK(cudaEventRecord(b.done, s));
+    };
+    ExpandPool &pool = expand_pool(c, nthr);
+    std::shared_ptr<ExpandPool::Job> pending;
+    auto join_all = [&]() { pool.wait(pending); pending.reset(); };
+    struct Joiner { decltype(join_all) &j; ~Joiner() { j(); } } joiner{join_all};
+    if (n_batches > 0) launch(0);
+    for (int64_t k = 0; k < n_batches; k++) {
+        scasa_ctx::FetchBuf &b = c->fb[k & 1];
+        CK(cudaEventSynchronize(b.done));
+        join_all();                                   // batch k-1 reads the buffer that launch(k+1) reuses
+        const int64_t r0 = cut[(size_t)k], nr = cut[(size_t)k + 1] - r0, e0 = ptr[r0];
+        const int32_t *hc = b.h_cols;
+        const double *hv = b.h_vals;
+        pending = pool.post_fn(nr, [=](int64_t a, int64_t e) {
+            for (int64_t i = a; i < e; i++) {
+                const int64_t r = r0 + i, src = ptr[r] - e0, m = glen ? glen[r] : ptr[r + 1] - ptr[r], d = dst_off[r];
+                if (!drop0) {
+                    if (cols) memcpy(cols + d, hc + src, (size_t)m * sizeof(int32_t));
+                    if (vals) memcpy(vals + d, hv + src, (size_t)m * sizeof(double));
+                    if (count) count[r] = m;
+                } else {
+                    int64_t o = d;
+                    for (int64_t t = src; t < src + m; t++)
+                        if (hv[t] != 0.0) { if (cols) cols[o] = hc[t]; if (vals) vals[o] = hv[t]; o++; }
+                    if (count) count[r] = o - d;
+                }
+            }
+        });
+        if (k + 1 < n_batches) launch(k + 1);
+    }
+    join_all();
 }
 
 }  // namespace
@@ -614,6 +749,7 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
                              [&](int32_t x, int32_t y) { return cost[(size_t)x] > cost[(size_t)y]; });
         }
         if (getenv("SCASA_FETCH_DENSE")) c->fetch_dense_copy = 1;
+        if (const char *env = getenv("SCASA_D2H_COMPACT")) c->d2h_compact = atoi(env) != 0;
         if (getenv("SCASA_POISON")) c->poison = 1;
         if (const char *env = getenv("SCASA_GENE_CTAS")) c->gene_ctas_per_sm = std::max(1, atoi(env));
         if (const char *env = getenv("SCASA_PACK_THREADS")) c->pack_threads = atoi(env) == 1024 ? 1024 : 512;
@@ -737,6 +873,7 @@ void scasa_ctx_destroy(scasa_ctx *c)
     c->d_poor.release(); c->d_next.release(); c->d_stats.release(); c->d_flag.release();
     c->d_tdata.release(); c->d_counters.release(); c->d_row_info.release(); c->d_row_aux.release(); c->d_em_info.release();
     c->d_scatter_scratch.release(); c->d_ypos.release(); c->d_col_gene.release(); c->d_gene_stops.release(); c->d_desc.release();
+    c->d_cmp_len.release(); c->d_cmp_col.release(); c->d_cmp_ptr.release(); c->d_cmp_val.release();
     for (auto &b : c->fb) {
         if (b.h_cols) { cudaFreeHost(b.h_cols); cudaFreeHost(b.h_vals); cudaFreeHost(b.h_start); cudaFreeHost(b.h_nnz); }
         if (b.done) cudaEventDestroy(b.done);
@@ -1183,7 +1320,7 @@ static int sync_twin(scasa_ctx *c)
     }
     scasa_ctx *t = c->twin;
     t->pool_owner = c;
-    t->opts = c->opts; t->host_threads = c->host_threads; t->fetch_dense_copy = c->fetch_dense_copy;
+    t->opts = c->opts; t->host_threads = c->host_threads; t->fetch_dense_copy = c->fetch_dense_copy; t->d2h_compact = c->d2h_compact;
     for (int k = 0; k < kClasses; k++) {
         t->cls_warps[k] = c->cls_warps[k]; t->cls_pairs[k] = c->cls_pairs[k]; t->cls_bytes[k] = c->cls_bytes[k];
         t->cls_cta_threads[k] = c->cls_cta_threads[k]; t->cls_ctas_per_sm[k] = c->cls_ctas_per_sm[k];
@@ -1309,10 +1446,7 @@ int scasa_fetch_iso_csr(scasa_ctx *c, int64_t *rowptr, int32_t *cols, double *va
     return guarded(c, [&] {
         need_rs_host(c, false);
         std::copy(c->rs_ptr_host.begin(), c->rs_ptr_host.end(), rowptr);
-        if (cols && c->rs_nnz) CK(cudaMemcpyAsync(cols, c->d_rs_col.p, (size_t)c->rs_nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-        if (vals && c->rs_nnz) CK(cudaMemcpyAsync(vals, c->d_rs_val.p, (size_t)c->rs_nnz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        c->wire_d2h += (long long)c->rs_nnz * ((cols ? 4 : 0) + (vals ? 8 : 0));
+        if ((cols || vals) && c->rs_nnz) fetch_sparse(c, false, cols, vals, rowptr, nullptr, false);
     });
 }
 
@@ -1326,29 +1460,7 @@ int scasa_fetch_gene_csr(scasa_ctx *c, int64_t *rowptr, int32_t *genes, double *
         rowptr[0] = 0;
         for (int64_t r = 0; r < c->n_cells; r++) rowptr[r + 1] = rowptr[r] + c->g_len_host[(size_t)r];
         if (!genes && !vals) return;
-        // the device rows have the capacity of the isoform rows: copy in slabs and close the gaps on the way
-        const int64_t slab = (int64_t)4 << 20;
-        std::vector<int32_t> hc((size_t)slab + 1);
-        std::vector<double> hv((size_t)slab + 1);
-        const int64_t *ptr = c->rs_ptr_host.data();
-        for (int64_t r0 = 0; r0 < c->n_cells;) {
-            int64_t r1 = r0 + 1;
-            while (r1 < c->n_cells && ptr[r1 + 1] - ptr[r0] <= slab) r1++;
-            const int64_t e0 = ptr[r0], ne = ptr[r1] - e0;
-            if (ne > slab) { hc.resize((size_t)ne + 1); hv.resize((size_t)ne + 1); }
-            if (ne) {
-                CK(cudaMemcpyAsync(hc.data(), c->d_g_col.p + e0, (size_t)ne * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-                CK(cudaMemcpyAsync(hv.data(), c->d_g_val.p + e0, (size_t)ne * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-            }
-            CK(cudaStreamSynchronize(c->stream));
-            c->wire_d2h += (long long)ne * 12;
-            for (int64_t r = r0; r < r1; r++) {
-                const int64_t src = ptr[r] - e0, dst = rowptr[r], m = c->g_len_host[(size_t)r];
-                if (genes) std::copy(hc.begin() + src, hc.begin() + src + m, genes + dst);
-                if (vals) std::copy(hv.begin() + src, hv.begin() + src + m, vals + dst);
-            }
-            r0 = r1;
-        }
+        fetch_sparse(c, true, genes, vals, rowptr, nullptr, false);      // the device rows have the capacity of the isoform rows: closed up on the way
     });
 }
 
@@ -1446,11 +1558,39 @@ int scasa_estimate(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const int64_
 // What a quant call can deliver per slice of chunks.  Dense matrices are expanded into the caller's buffers;
 // the sparse sinks receive the slice's CSR rows as they are on the device (for callers that never want the
 // dense form: the text writers).
+// big host arrays without the zero fill of std::vector (the first touch happens in the threads that write them);
+// large ones are aligned to 2 MB and advised for transparent huge pages: 512 times fewer first-touch faults
+inline void *big_alloc(size_t bytes)
+{
+    bytes = std::max<size_t>(bytes, 1);
+    if (bytes < ((size_t)8 << 20)) return malloc(bytes);
+    void *p = nullptr;
+    if (posix_memalign(&p, (size_t)2 << 20, bytes)) return nullptr;
+#ifdef MADV_HUGEPAGE
+    madvise(p, bytes, MADV_HUGEPAGE);
+#endif
+    return p;
+}
+extern "C++" {
+template <class T> struct RawBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    RawBuf() = default;
+    RawBuf(const RawBuf &) = delete;
+    RawBuf &operator=(const RawBuf &) = delete;
+    RawBuf(RawBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    void alloc(size_t m) { release(); n = m; p = (T *)big_alloc(m * sizeof(T)); if (!p) throw std::bad_alloc(); }
+    void release() { free(p); p = nullptr; n = 0; }
+    ~RawBuf() { free(p); }
+};
+}
 struct SparseSink {                       // CSR by cell of the whole sample, assembled from the slices
-    std::vector<int64_t> rowptr;          // [n_cells+1], filled per slice with slice-local offsets; finish() makes them global
-    std::vector<std::vector<int32_t>> cols;   // per slice
-    std::vector<std::vector<double>> vals;
+    std::vector<int64_t> rowptr;          // [n_cells+1]: entries kept per row at [i+1] while the slices arrive, offsets afterwards
+    std::vector<int64_t> src;             // [n_cells]: where the row starts inside its slice's buffers
+    std::vector<RawBuf<int32_t>> cols;    // per slice
+    std::vector<RawBuf<double>> vals;
     std::vector<int64_t> slice_c0, slice_c1;
+    bool drop0 = false;                   // leave the stored zeros behind on the way from the device
 };
 struct QuantOut {
     double *iso = nullptr, *gene = nullptr, *colsum = nullptr;
@@ -1493,33 +1633,27 @@ static int quant_range(scasa_ctx *c, int H0, int H1, const int64_t *chunk_off, c
             if (!rc && out.iso) rc = scasa_fetch_iso(x, out.iso + c0 * c->n_cols);
             if (!rc && out.gene) rc = scasa_fetch_gene(x, out.gene + c0 * (int64_t)c->n_genes);
             if (!rc && out.iters) rc = scasa_fetch_iters(x, out.iters + (int64_t)h0 * c->n_em * 2);
-            if (!rc && out.iso_csr) {
-                SparseSink &k = *out.iso_csr;
+            for (int which_sink = 0; which_sink < 2 && !rc; which_sink++) {
+                SparseSink *kp = which_sink ? out.gene_csr : out.iso_csr;
+                if (!kp) continue;
+                SparseSink &k = *kp;
+                const bool genes = which_sink == 1;
                 const int si = sink_slice0 + sl;
                 k.slice_c0[(size_t)si] = c0; k.slice_c1[(size_t)si] = c1;
                 int64_t nz = 0;
-                rc = scasa_result_nnz(x, &nz, nullptr);
-                if (!rc) {
-                    k.cols[(size_t)si].resize((size_t)nz + 1); k.vals[(size_t)si].resize((size_t)nz + 1);
-                    std::vector<int64_t> rp((size_t)(c1 - c0) + 1);
-                    rc = scasa_fetch_iso_csr(x, rp.data(), k.cols[(size_t)si].data(), k.vals[(size_t)si].data());
-                    for (int64_t i = c0; i < c1; i++) k.rowptr[(size_t)i + 1] = rp[(size_t)(i - c0) + 1] - rp[(size_t)(i - c0)];
-                    k.cols[(size_t)si].resize((size_t)nz); k.vals[(size_t)si].resize((size_t)nz);
-                }
-            }
-            if (!rc && out.gene_csr) {
-                SparseSink &k = *out.gene_csr;
-                const int si = sink_slice0 + sl;
-                k.slice_c0[(size_t)si] = c0; k.slice_c1[(size_t)si] = c1;
-                int64_t nz = 0;
-                rc = scasa_result_nnz(x, nullptr, &nz);
-                if (!rc) {
-                    k.cols[(size_t)si].resize((size_t)nz + 1); k.vals[(size_t)si].resize((size_t)nz + 1);
-                    std::vector<int64_t> rp((size_t)(c1 - c0) + 1);
-                    rc = scasa_fetch_gene_csr(x, rp.data(), k.cols[(size_t)si].data(), k.vals[(size_t)si].data());
-                    for (int64_t i = c0; i < c1; i++) k.rowptr[(size_t)i + 1] = rp[(size_t)(i - c0) + 1] - rp[(size_t)(i - c0)];
-                    k.cols[(size_t)si].resize((size_t)nz); k.vals[(size_t)si].resize((size_t)nz);
-                }
+                rc = genes ? scasa_result_nnz(x, nullptr, &nz) : scasa_result_nnz(x, &nz, nullptr);
+                if (rc) break;
+                k.cols[(size_t)si].alloc((size_t)nz); k.vals[(size_t)si].alloc((size_t)nz);
+                rc = guarded(x, [&] {
+                    need_rs_host(x, genes);
+                    int64_t *off = k.src.data() + c0;                         // rows side by side in the slice's buffers
+                    int64_t run = 0;
+                    for (int64_t i = 0; i < c1 - c0; i++) {
+                        off[i] = run;
+                        run += genes ? x->g_len_host[(size_t)i] : x->rs_ptr_host[(size_t)i + 1] - x->rs_ptr_host[(size_t)i];
+                    }
+                    fetch_sparse(x, genes, k.cols[(size_t)si].p, k.vals[(size_t)si].p, off, k.rowptr.data() + c0 + 1, k.drop0);
+                });
             }
             if (!rc && colparts && c->n_emcols > 0)
                 rc = fetch(x, colparts + (size_t)h0 * c->n_emcols, x->d_colpart.p, (size_t)(h1 - h0) * c->n_emcols * sizeof(double));
@@ -1616,7 +1750,8 @@ static int quant_multi_impl(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cel
     for (SparseSink *k : {out.iso_csr, out.gene_csr})
         if (k) {
             k->rowptr.assign((size_t)n_cells + 1, 0);
-            k->cols.assign((size_t)sl0[(size_t)n_ctx], {}); k->vals.assign((size_t)sl0[(size_t)n_ctx], {});
+            k->src.assign((size_t)n_cells, 0);
+            k->cols = std::vector<RawBuf<int32_t>>((size_t)sl0[(size_t)n_ctx]); k->vals = std::vector<RawBuf<double>>((size_t)sl0[(size_t)n_ctx]);
             k->slice_c0.assign((size_t)sl0[(size_t)n_ctx], 0); k->slice_c1.assign((size_t)sl0[(size_t)n_ctx], 0);
         }
     std::vector<int> rcs((size_t)n_ctx, SCASA_OK);
@@ -1674,40 +1809,103 @@ int scasa_quant_multi(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, in
 // step2:88-170 + step3:21-52 without the dense matrices: the sparse rows of every slice are collected on the
 // host, transposed to transcript-major (step2:166) and streamed through the sparse writer.
 namespace {
-// big host arrays without the zero fill of std::vector (the first touch happens in the threads that write them)
-extern "C++" {
-template <class T> struct RawBuf {
-    T *p = nullptr;
-    size_t n = 0;
-    void alloc(size_t m) { release(); n = m; p = (T *)malloc(std::max<size_t>(m, 1) * sizeof(T)); if (!p) throw std::bad_alloc(); }
-    void release() { free(p); p = nullptr; n = 0; }
-    ~RawBuf() { free(p); }
-};
-}
 struct Flat { std::vector<int64_t> rowptr; RawBuf<int32_t> cols; RawBuf<double> vals; };
-void flatten(SparseSink &k, Flat &f)
+// The slices of a sink -> contiguous arrays (k.rowptr holds the global offsets by now): host threads take blocks of
+// rows; a slice's buffers are released when the last of its rows has been copied.
+void assemble(SparseSink &k, int32_t *cols, double *vals, int n_threads)
 {
-    f.rowptr.swap(k.rowptr);
-    const int64_t nnz = f.rowptr.empty() ? 0 : f.rowptr.back();
-    f.cols.alloc((size_t)nnz); f.vals.alloc((size_t)nnz);
-    std::vector<std::thread> th;                      // a thread per slice: the copies are memory-bound and independent
-    auto copy_slice = [&](size_t si) {
-        if (k.cols[si].empty()) return;
-        const int64_t e0 = f.rowptr[(size_t)k.slice_c0[si]];
-        std::copy(k.cols[si].begin(), k.cols[si].end(), f.cols.p + e0);
-        std::copy(k.vals[si].begin(), k.vals[si].end(), f.vals.p + e0);
-        std::vector<int32_t>().swap(k.cols[si]);
-        std::vector<double>().swap(k.vals[si]);
+    struct Item { size_t si; int64_t r0, r1; };
+    std::vector<Item> items;
+    for (size_t si = 0; si < k.cols.size(); si++)
+        for (int64_t r = k.slice_c0[si]; r < k.slice_c1[si]; r += 256) items.push_back({si, r, std::min(r + 256, k.slice_c1[si])});
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= items.size()) return;
+            const Item &it = items[i];
+            const int32_t *sc = k.cols[it.si].p;
+            const double *sv = k.vals[it.si].p;
+            for (int64_t r = it.r0; r < it.r1; r++) {
+                const int64_t d = k.rowptr[(size_t)r], m = k.rowptr[(size_t)r + 1] - d, o = k.src[(size_t)r];
+                memcpy(cols + d, sc + o, (size_t)m * sizeof(int32_t));
+                memcpy(vals + d, sv + o, (size_t)m * sizeof(double));
+            }
+        }
     };
-    for (size_t si = 0; si < k.cols.size(); si++) {
+    int nthr = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nthr = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::min(nthr, 64), items.size()));
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthr; t++) {
         bool started = false;
-        try { th.emplace_back(copy_slice, si); started = true; } catch (const std::exception &) {}
-        if (!started) copy_slice(si);
+        try { th.emplace_back(work); started = true; } catch (const std::exception &) {}
+        if (!started) break;
     }
+    work();
     for (auto &t : th) t.join();
+    for (auto &b : k.cols) b.release();
+    for (auto &b : k.vals) b.release();
+}
+void flatten(SparseSink &k, Flat &f, int n_threads)
+{
+    const int64_t nnz = k.rowptr.empty() ? 0 : k.rowptr.back();
+    f.cols.alloc((size_t)nnz); f.vals.alloc((size_t)nnz);
+    assemble(k, f.cols.p, f.vals.p, n_threads);
+    f.rowptr.swap(k.rowptr);
+}
+void sink_to_csr(SparseSink &k, int64_t n_cells, scasa_csr_t *out)
+{
+    out->n_rows = n_cells; out->nnz = k.rowptr.empty() ? 0 : k.rowptr.back();
+    out->ptr = (int64_t *)malloc(((size_t)n_cells + 1) * sizeof(int64_t));
+    out->col = (int32_t *)big_alloc((size_t)out->nnz * sizeof(int32_t));
+    out->val = (double *)big_alloc((size_t)out->nnz * sizeof(double));
+    if (!out->ptr || !out->col || !out->val) throw std::bad_alloc();
+    std::copy(k.rowptr.begin(), k.rowptr.end(), out->ptr);
+    assemble(k, out->col, out->val, 0);
 }
 double wall_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 }  // namespace
+
+void scasa_csr_free(scasa_csr_t *m)
+{
+    if (!m) return;
+    free(m->ptr); free(m->col); free(m->val);
+    m->ptr = nullptr; m->col = nullptr; m->val = nullptr; m->nnz = 0; m->n_rows = 0;
+}
+
+int scasa_quant_csr(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off,
+                    const int64_t *cell_ptr, const int32_t *eq_id, const int32_t *eq_count, int64_t n_eq, const int32_t *eq_row,
+                    int32_t drop_zeros, scasa_csr_t *iso, scasa_csr_t *gene, double *colsum_out, int32_t *iters_out)
+{
+    if (!ctxs || n_ctx < 1 || !ctxs[0]) return fail(nullptr, SCASA_ERR_ARG, "null context list");
+    scasa_ctx *c = ctxs[0];
+    if (!iso) return fail(c, SCASA_ERR_ARG, "bad argument");
+    if (gene && c->n_genes <= 0) return fail(c, SCASA_ERR_STATE, "gene matrix asked for, but no gene map");
+    memset(iso, 0, sizeof *iso);
+    if (gene) memset(gene, 0, sizeof *gene);
+    try {
+        SparseSink iso_sink, gene_sink;
+        QuantOut out;
+        iso_sink.drop0 = gene_sink.drop0 = drop_zeros != 0;
+        out.iso_csr = &iso_sink; out.gene_csr = gene ? &gene_sink : nullptr; out.colsum = colsum_out; out.iters = iters_out;
+        const double t0 = wall_now();
+        int rc = quant_multi_impl(ctxs, n_ctx, n_cells, n_chunks, chunk_off, cell_ptr, eq_id, eq_count, n_eq, eq_row, out, 0);
+        if (rc) return rc;
+        const double t1 = wall_now();
+        sink_to_csr(iso_sink, n_cells, iso);
+        if (gene) sink_to_csr(gene_sink, n_cells, gene);
+        if (getenv("SCASA_FETCH_TRACE"))
+            fprintf(stderr, "[scasa quant_csr] %lld cells: slices %.3f s, assembly %.3f s, %lld + %lld entries\n", (long long)n_cells, t1 - t0,
+                    wall_now() - t1, (long long)iso->nnz, (long long)(gene ? gene->nnz : 0));
+        return SCASA_OK;
+    } catch (const std::bad_alloc &) {
+        scasa_csr_free(iso); scasa_csr_free(gene);
+        return fail(c, SCASA_ERR_NOMEM, "host allocation failed");
+    } catch (const std::exception &e) {
+        scasa_csr_free(iso); scasa_csr_free(gene);
+        return fail(c, SCASA_ERR_ARG, e.what());
+    }
+}
 
 int scasa_quant_files(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, int32_t n_chunks, const int64_t *chunk_off,
                       const int64_t *cell_ptr, const int32_t *eq_id, const int32_t *eq_count, int64_t n_eq, const int32_t *eq_row,
@@ -1725,6 +1923,7 @@ int scasa_quant_files(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, in
         SparseSink iso_sink, gene_sink;
         QuantOut out;
         std::vector<double> colsum((size_t)c->n_cols);
+        iso_sink.drop0 = gene_sink.drop0 = true;                 // the writer prints 0 for an absent entry as for a stored zero
         out.iso_csr = &iso_sink; out.gene_csr = gene_path ? &gene_sink : nullptr; out.colsum = colsum.data();
         double t0 = wall_now();
         int rc = quant_multi_impl(ctxs, n_ctx, n_cells, n_chunks, chunk_off, cell_ptr, eq_id, eq_count, n_eq, eq_row, out, 0);
@@ -1735,7 +1934,7 @@ int scasa_quant_files(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, in
         // ---- isoforms: transpose, keep rows with rowSums > 0 (step2:167), write
         t0 = wall_now();
         Flat f;
-        flatten(iso_sink, f);
+        flatten(iso_sink, f, n_threads);
         std::vector<int64_t> colptr((size_t)c->n_cols + 1);
         RawBuf<int32_t> cell_idx;
         RawBuf<double> tvals;
@@ -1767,7 +1966,7 @@ int scasa_quant_files(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, in
         if (gene_path) {
             t0 = wall_now();
             Flat g;
-            flatten(gene_sink, g);
+            flatten(gene_sink, g, n_threads);
             const int64_t ng = c->n_genes;
             std::vector<int64_t> gptr((size_t)ng + 1);
             RawBuf<int32_t> gcell;

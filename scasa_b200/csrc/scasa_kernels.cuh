@@ -1034,6 +1034,48 @@ __global__ void __launch_bounds__(kGeneRowThreads, 2) gene_rows_kernel(Result R,
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Stored zeros out of a CSR result before it crosses PCIe (EM columns whose estimate is exactly 0: a fifth of the
+// entries; the expansion on the host writes zeros anyway and the sparse interfaces drop them).  One warp per row:
+// row_nonzeros_kernel counts, an exclusive scan gives the packed row starts, row_compact_kernel moves the entries
+// (ballot + popcount keep their order).  len == nullptr: full rows.
+__global__ void row_nonzeros_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ len, const double *__restrict__ val,
+                                    int64_t n_rows, int32_t *__restrict__ out)
+{
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t s = ptr[r];
+    const int n = len ? len[r] : (int)(ptr[r + 1] - s);
+    int cnt = 0;
+    for (int i = lane; i < n; i += kWarp) cnt += val[s + i] != 0.0;
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(kFull, cnt, o);
+    if (lane == 0) out[r] = cnt;
+}
+__global__ void row_compact_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ len, const int32_t *__restrict__ col,
+                                   const double *__restrict__ val, int64_t n_rows, const int64_t *__restrict__ out_ptr,
+                                   int32_t *__restrict__ out_col, double *__restrict__ out_val)
+{
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t s = ptr[r];
+    const int n = len ? len[r] : (int)(ptr[r + 1] - s);
+    int64_t o = out_ptr[r];
+    for (int i0 = 0; i0 < n; i0 += kWarp) {
+        const int i = i0 + lane;
+        double v = 0.0;
+        int c = 0;
+        if (i < n) { v = val[s + i]; c = col[s + i]; }
+        const unsigned keep = __ballot_sync(kFull, v != 0.0);
+        if (v != 0.0) {
+            const int64_t d = o + __popc(keep & ((1u << lane) - 1u));
+            out_col[d] = c; out_val[d] = v;
+        }
+        o += __popc(keep);
+    }
+}
+
 // rows [r0, r0 + n) of a CSR result -> dense rows (testing aid: SCASA_FETCH_DENSE); len == nullptr: full rows
 __global__ void expand_rows_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ len, const int32_t *__restrict__ col,
                                    const double *__restrict__ val, int64_t r0, int64_t n, int64_t n_cols, double *__restrict__ out)

@@ -44,6 +44,12 @@ class FilesTiming(C.Structure):
                 ("iso_bytes", C.c_int64), ("gene_bytes", C.c_int64), ("iso_rows", C.c_int64), ("gene_rows", C.c_int64)]
 
 
+class Csr(C.Structure):
+    """scasa_csr_t: library-allocated sparse rows (scasa_quant_csr); release with scasa_csr_free."""
+    _fields_ = [("n_rows", C.c_int64), ("nnz", C.c_int64), ("ptr", C.POINTER(C.c_int64)), ("col", C.POINTER(C.c_int32)),
+                ("val", C.POINTER(C.c_double))]
+
+
 class Timing(C.Structure):
     _fields_ = [("total_ms", C.c_float), ("pack_ms", C.c_float), ("tasks_ms", C.c_float), ("em_ms", C.c_float),
                 ("finish_ms", C.c_float), ("gene_ms", C.c_float), ("em_class_ms", C.c_float * 4),
@@ -70,6 +76,7 @@ SYMBOLS = (
     "scasa_fetch_gene", "scasa_gene_sum", "scasa_eqclass_map", "scasa_last_timing", "scasa_host_alloc",
     "scasa_host_free", "scasa_device_count", "scasa_version", "scasa_set_host_threads", "scasa_expand_pairs", "scasa_quant", "scasa_transfer_bytes", "scasa_bfh_open", "scasa_bfh_close", "scasa_bfh_sizes", "scasa_bfh_read", "scasa_bus_open", "scasa_write_table", "scasa_format_real15", "scasa_set_run_parts", "scasa_eqclass_map_host",
     "scasa_result_nnz", "scasa_fetch_iso_csr", "scasa_fetch_gene_csr", "scasa_quant_multi", "scasa_write_table_sparse", "scasa_csr_transpose", "scasa_quant_files", "scasa_dm0_is_fixed_point",
+    "scasa_quant_csr", "scasa_csr_free",
 )
 
 
@@ -129,6 +136,10 @@ def load():
                                     i32p, C.c_int32]
     L.scasa_quant_files.argtypes = [C.POINTER(vp), C.c_int32, C.c_int64, C.c_int32, i64p, i64p, i32p, i32p, C.c_int64, i32p, C.c_char_p,
                                     C.c_char_p, C.c_char_p, C.c_char_p, i32p, C.c_char_p, C.c_int32, f64p, C.POINTER(FilesTiming)]
+    L.scasa_quant_csr.argtypes = [C.POINTER(vp), C.c_int32, C.c_int64, C.c_int32, i64p, i64p, i32p, i32p, C.c_int64, i32p, C.c_int32,
+                                  C.POINTER(Csr), C.POINTER(Csr), f64p, i32p]
+    L.scasa_csr_free.argtypes = [C.POINTER(Csr)]
+    L.scasa_csr_free.restype = None
     L.scasa_fetch_iso.argtypes = [vp, f64p]
     L.scasa_result_nnz.argtypes = [vp, i64p, i64p]
     L.scasa_fetch_iso_csr.argtypes = [vp, i64p, i32p, f64p]

@@ -8,6 +8,7 @@ typedef unsigned char Rbyte;
 typedef void (*R_CFinalizer_t)(SEXP);
 typedef enum { FALSE = 0, TRUE } Rboolean;
 #define REALSXP 14
+#define INTSXP 13
 extern SEXP R_NilValue;
 int *INTEGER(SEXP);
 double *REAL(SEXP);

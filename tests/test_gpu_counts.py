@@ -360,6 +360,45 @@ def test_quant_files_writes_what_the_dense_path_writes(xm, tmp_path, n):
     assert got == [gnames[k] for k in order] and tm["gene_rows"] == len(order)
 
 
+@pytest.mark.parametrize("drop", [False, True])
+def test_quant_csr_is_the_dense_result_in_sparse_form(xm, drop):
+    """scasa_quant_csr (host eqclass counts in, sparse isoform and gene matrices out: the dgCMatrix slots of the
+    reference's tx x cells matrices) on config C2 over two contexts: expanded, bit for bit the dense matrices of
+    Scasa.quant; column sums and iteration counts equal; columns strictly ascending inside a row; with
+    drop_zeros no stored zero is left and nothing else is lost."""
+    from scasa_b200 import synth
+    from scasa_b200.api import Scasa, quant_csr
+    n = 3955
+    rowptr, rows, vals = synth.CellGenerator(xm, seed=2).counts_csr(0, n)
+    ed = synth.eqclass_dictionary(xm, 2)
+    cell_ptr, eq_id, eq_cnt = synth.counts_to_eqcounts(rowptr, rows, vals, 2)
+    goc = np.asarray(xm.gene_of_col, np.int32)
+    g, g2 = Scasa(xm, device=0), Scasa(xm, device=0)
+    try:
+        g.set_gene_map(goc, len(xm.gene_names))
+        r = g.quant(cell_ptr, eq_id, eq_cnt, ed.eq_off, ed.eq_tx)
+        iso, gene, colsum, iters = quant_csr([g, g2], cell_ptr, eq_id, eq_cnt, ed.eq_off, ed.eq_tx, drop_zeros=drop, want_iters=True)
+        assert iso.n_rows == n and gene.n_rows == n and iso.ptr[0] == 0 and iso.ptr[-1] == iso.nnz == len(iso.col)
+        for m, dense, width in ((iso, r.iso, xm.n_cols), (gene, r.gene, len(xm.gene_names))):
+            assert np.array_equal(m.to_dense(width).view(np.int64), np.asarray(dense).view(np.int64))
+            inner = np.ones(m.nnz, bool)
+            inner[m.ptr[:-1][np.diff(m.ptr) > 0]] = False                      # first entry of every non-empty row
+            assert np.all(np.diff(m.col.astype(np.int64))[inner[1:]] > 0)        # ascending inside a row
+            if drop:
+                assert np.all(m.val != 0) and m.nnz == int(np.count_nonzero(dense))
+            else:
+                assert m.nnz >= int(np.count_nonzero(dense))
+        assert np.array_equal(colsum.view(np.int64), r.colsum.view(np.int64))
+        assert np.array_equal(iters, r.iters)
+        nnz_iso = iso.nnz
+        iso.close(); gene.close()
+        iso2, none, _, _ = quant_csr([g], cell_ptr, eq_id, eq_cnt, ed.eq_off, ed.eq_tx, drop_zeros=drop, want_gene=False)
+        assert none is None and iso2.nnz == nnz_iso
+    finally:
+        g.close()
+        g2.close()
+
+
 def test_error_behaviour_through_the_abi(xm):
     """Malformed input and wrong call order come back as error codes with a message (the R shim turns
     them into stop()); nothing crashes, and the context stays usable afterwards."""

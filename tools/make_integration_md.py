@@ -28,6 +28,7 @@ deliberately thin — every decision lives behind the C ABI (`include/scasa_cuda
 | `scasa_eqclass_map(ctx, E, eq_off, eq_tx, eq_row, threads)`, `scasa_eqclass_map_host(crp, …)` | the block/row decision inside `crpcount_td` + `hamming_correction` (`Rsource:453-546`, `:562-648`) | once per distinct eqclass instead of once per cell and block; the `_host` form needs no GPU |
 | `scasa_quant` / `scasa_quant_multi(ctxs, n_ctx, …)` | the two `foreach` bodies `step2:88-115`, `:128-136`, the stacking `step2:139-165` and (with a gene map) `step3:48` | one call for a whole sample over 1..N GPUs; rows in barcode order (= `order(rownames)`), columns in block order like `cbind(final, BT)`; dense host matrices out; results bitwise independent of the GPU count |
 | `scasa_quant_files(ctxs, n_ctx, …, iso_path, gene_path, …)` | the same plus `step2:165-170` and `step3:51-52` | eqclass counts in, `scasa_isoform_counts.txt` and `scasa_gene_expression.txt` out: no dense matrix in R or anywhere else |
+| `scasa_quant_csr(ctxs, n_ctx, …, drop_zeros, &iso, &gene, …)` + `scasa_csr_free` | the same as `scasa_quant_multi`, results sparse | host eqclass counts in, `scasa_csr_t` out: CSR by cell = the `p`/`i`/`x` slots of the `Matrix::dgCMatrix` of the reference's tx × cells matrices (`step2:166`), so R gets `isoform_count` and the gene matrix without a dense matrix on either side (100k cells: ≈ 3 GB instead of 26.7 + 19.9 GB); bit for bit the values of the dense call (`SCASA_SPARSE=1` in the step-2 patch) |
 | `scasa_stage_eqcounts` + `scasa_run` + `scasa_fetch_iso` / `scasa_fetch_iso_csr` / `scasa_fetch_gene(_csr)` | the stages of the above | the device keeps both results sparse (CSR by cell); the `_csr` forms hand that over as it is |
 | `scasa_bfh_open` / `_sizes` / `_read` / `_close` | `scasa_quant_step1_1_v1.0.0.R:16-68` (bfh.txt → exploded data.table → `Sample_eqClass.RData`) and `step2:59-60` | optional: feeds `scasa_quant` directly, no `.RData` round trip |
 | `scasa_bus_open` (+ the `scasa_bfh_*` accessors) | `scasa_quant_step1_2_v1.0.0.R:28-119` (kallisto/bustools text → `Sample_eqClass.RData`) | optional: library-size filter, duplicated (barcode, UMI) rules and per-cell eqclass counts as in the script |
@@ -52,7 +53,8 @@ with stand-in declarations (`tests/mock_r/`), so a change of the ABI that the sh
 
 ## 3. The patched call site in `scasa_quant_step2_v1.0.0.R` (`integration/scasa_quant_step2_patch.R`)
 
-Set `SCASA_GPUS=<n>` to shard over n GPUs and `SCASA_FILES=1` to let the library write the two text files itself
+Set `SCASA_GPUS=<n>` to shard over n GPUs, `SCASA_SPARSE=1` to get `isoform_count` and the gene matrix as `dgCMatrix`
+(the form Seurat-style downstream code reads; no dense matrix is built) and `SCASA_FILES=1` to let the library write the two text files itself
 (R's `write.table` of a 33k x 100k matrix takes far longer than the quantification). To fuse step 3, `load(txgroup)`
 (`step3:22`) before the patch runs.
 
