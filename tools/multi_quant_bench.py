@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 from scasa_b200 import lib as _l, synth
-from scasa_b200.api import Scasa, quant_files
+from scasa_b200.api import Scasa, quant_csr, quant_files
 from scasa_b200.xmatrix import XMatrix
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 nf = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
@@ -24,7 +24,7 @@ ctx[0].set_gene_map(goc, ng)
 h_iso = np.empty((n, xm.n_cols)); h_gene = np.empty((n, ng))
 threads = os.cpu_count() or 16
 ctx[0].set_host_threads(threads)
-out = {"cells": n, "files_cells": nf, "host_threads": threads, "gpus_present": n_dev, "dense": {}, "files": {}}
+out = {"cells": n, "files_cells": nf, "host_threads": threads, "gpus_present": n_dev, "dense": {}, "csr": {}, "files": {}}
 ref = None
 for k in [g for g in (1, 2, 4, 8) if g <= n_dev]:
     ts = []
@@ -38,6 +38,24 @@ for k in [g for g in (1, 2, 4, 8) if g <= n_dev]:
         ref = chk
     out["dense"][k] = {"s": min(ts[1:]), "cells_per_s": n / min(ts[1:]), "same_sums_as_1_gpu": chk == ref}
     print(k, "GPUs dense:", out["dense"][k], flush=True)
+ref = None
+for k in [g for g in (1, 2, 4, 8) if g <= n_dev]:                  # the same call with sparse host results (scasa_quant_csr)
+    ts = []
+    for rep in range(3):
+        t0 = time.perf_counter()
+        iso, gene, colsum, _ = quant_csr(ctx[:k], cell_ptr, eq_id, eq_cnt, ed.eq_off, ed.eq_tx, drop_zeros=True, n_threads=threads)
+        ts.append(time.perf_counter() - t0)
+        chk = (iso.nnz, gene.nnz, float(iso.val.sum()), float(gene.val.sum()), float(colsum.sum()))
+        iso.close(); gene.close()
+    if ref is None:
+        ref = chk
+    out["csr"][k] = {"s": min(ts[1:]), "cells_per_s": n / min(ts[1:]), "entries": [chk[0], chk[1]], "same_as_1_gpu": chk == ref}
+    print(k, "GPUs sparse:", out["csr"][k], flush=True)
+if nf <= 0:
+    for c in ctx:
+        c.close()
+    print(json.dumps(out))
+    sys.exit(0)
 tmp = tempfile.mkdtemp(prefix="scasa_multi_")
 try:
     bc = synth.barcodes(nf, 4)
