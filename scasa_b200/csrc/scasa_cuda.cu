@@ -170,7 +170,7 @@ struct scasa_ctx {
     std::vector<uint8_t> poor;
     int64_t poor_rows = 0;           // sum of q over poor blocks
     DBuf<int32_t> d_q_off, d_p_off, d_em_blocks, d_em_order, d_em_col0, d_poor_rank, d_poor_col0, d_emcol_col, d_col_emcol;
-    DBuf<int2> d_row_info, d_em_info;
+    DBuf<int2> d_row_info;
     DBuf<int4> d_row_aux;
     DBuf<uint32_t> d_scatter_scratch;
     DBuf<int64_t> d_x_off;
@@ -241,7 +241,7 @@ struct scasa_ctx {
     int n_genes = 0;
     int pack_threads = 512;                    // threads per CTA of pack_cells_dense_kernel (SCASA_PACK_THREADS=512|1024)
     int gene_ctas_per_sm = 2;                  // gene_rows_kernel: resident CTAs per SM (SCASA_GENE_CTAS)
-    int gene_max_members = 1, gene_n_multi = 0;   // most isoforms of a gene; genes with more than one
+    int gene_n_multi = 0;                      // genes with more than one isoform column
     DBuf<int2> d_col_gene;                     // per column: {gene or -1, slot in the gene kernel's member table or -1}
     DBuf<int32_t> d_gene_stops;                // the member table's stop marks
     int gene_slots = 1;
@@ -303,7 +303,7 @@ XDev xdev(scasa_ctx *c)
     X.em_blocks = c->d_em_blocks.p;
     X.poor = c->d_poor.p;
     X.em_order = c->d_em_order.p; X.row_info = c->d_row_info.p; X.row_aux = c->d_row_aux.p;
-    X.em_info = c->d_em_info.p; X.em_col0 = c->d_em_col0.p; X.poor_rank = c->d_poor_rank.p; X.poor_col0 = c->d_poor_col0.p;
+    X.em_col0 = c->d_em_col0.p; X.poor_rank = c->d_poor_rank.p; X.poor_col0 = c->d_poor_col0.p;
     X.n_poor = c->n_poor; X.n_emcols = c->n_emcols;
     return X;
 }
@@ -800,7 +800,7 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
         c->d_em_order.ensure(c->em_order.size() + 1);
         c->d_em_order.upload(c->em_order, c->stream);
         {
-            std::vector<int2> info((size_t)c->n_rows), em_info((size_t)c->n_em);
+            std::vector<int2> info((size_t)c->n_rows);
             std::vector<int4> aux((size_t)c->n_rows);
             std::vector<int32_t> poor_rank((size_t)B), poor_col0, em_col0((size_t)c->n_em + 1, 0), emcol_col;
             int np = 0;
@@ -817,14 +817,12 @@ int scasa_ctx_create(const scasa_xmat_t *dm0, const scasa_crp_t *crp, const scas
             for (int e = 0; e < c->n_em; e++) {
                 const int k = c->em_blocks[(size_t)e], p = c->p_off[k + 1] - c->p_off[k];
                 if (p > 0xffff) throw ArgErr{SCASA_ERR_UNSUPPORTED, "a block may have at most 65535 columns"};
-                em_info[(size_t)e] = make_int2(p | (c->poor[k] ? 1 << 16 : 0), c->p_off[k]);
                 em_col0[(size_t)e + 1] = em_col0[(size_t)e] + p;
                 for (int j = 0; j < p; j++) emcol_col.push_back(c->p_off[k] + j);
             }
             c->n_emcols = em_col0[(size_t)c->n_em];
             c->d_row_info.upload(info, c->stream);
             c->d_row_aux.upload(aux, c->stream);
-            c->d_em_info.ensure(em_info.size() + 1); c->d_em_info.upload(em_info, c->stream);
             c->d_em_col0.upload(em_col0, c->stream);
             c->d_poor_rank.upload(poor_rank, c->stream);
             c->d_poor_col0.ensure(poor_col0.size() + 1); c->d_poor_col0.upload(poor_col0, c->stream);
@@ -871,7 +869,7 @@ void scasa_ctx_destroy(scasa_ctx *c)
                            &c->d_dense_tmp, &c->d_iso_in, &c->d_gene_out};
     for (auto b : f64) b->release();
     c->d_poor.release(); c->d_next.release(); c->d_stats.release(); c->d_flag.release();
-    c->d_tdata.release(); c->d_counters.release(); c->d_row_info.release(); c->d_row_aux.release(); c->d_em_info.release();
+    c->d_tdata.release(); c->d_counters.release(); c->d_row_info.release(); c->d_row_aux.release();
     c->d_scatter_scratch.release(); c->d_ypos.release(); c->d_col_gene.release(); c->d_gene_stops.release(); c->d_desc.release();
     c->d_cmp_len.release(); c->d_cmp_col.release(); c->d_cmp_ptr.release(); c->d_cmp_val.release();
     for (auto &b : c->fb) {
@@ -1025,15 +1023,14 @@ int scasa_set_gene_map(scasa_ctx *c, const int32_t *gene_of_col, int32_t n_genes
             // in front of the first gene and behind every gene
             std::vector<int2> cg((size_t)c->n_cols, make_int2(-1, -1));
             std::vector<int32_t> stops{0};
-            int mx = 1, n_multi = 0, slot = 1;
+            int n_multi = 0, slot = 1;
             for (int g = 0; g < n_genes; g++) {
                 const int nm = ptr[(size_t)g + 1] - ptr[(size_t)g];
                 for (int m = ptr[(size_t)g]; m < ptr[(size_t)g + 1]; m++)
                     cg[(size_t)cols[(size_t)m]] = make_int2(g, nm > 1 ? slot++ : -1);
                 if (nm > 1) { stops.push_back(slot++); n_multi++; }
-                mx = std::max(mx, nm);
             }
-            c->gene_max_members = mx; c->gene_n_multi = n_multi; c->gene_slots = slot;
+            c->gene_n_multi = n_multi; c->gene_slots = slot;
             c->d_gene_stops.upload(stops, c->stream);
             c->d_col_gene.upload(cg, c->stream);
         }

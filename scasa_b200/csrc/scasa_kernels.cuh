@@ -87,7 +87,6 @@ struct XDev {                 // resident X-matrix (DM0) and its derived index m
     const int2 *row_info;     // [n_rows]  {EM index of the row's block or -1, row index inside the block}
     const int4 *row_aux;      // [n_rows]  {first DM0 column of the row's block, poor blocks before it, p | poor << 16 of an EM block
                               //            (0: pass-through), EM index or -1}: all that the per-entry passes need in one load
-    const int2 *em_info;      // [n_em]    {columns p | poor << 16, first DM0 column}
     const int32_t *em_col0;   // [n_em+1]  columns of the EM blocks before this one (index into the per-chunk column sums)
     const int32_t *poor_rank; // [n_blocks] poor blocks with a smaller block id
     const int32_t *poor_col0; // [n_poor]  first DM0 column of the k-th poor block
