@@ -448,7 +448,7 @@ void need_rs_host(scasa_ctx *c, bool genes)
 // Where the rows of a result are read from: as the kernels left them (row r = [ptr[r], ptr[r] + len[r]), len == nullptr:
 // full rows), or — compact — packed on the device without their stored zeros.
 struct RowSrc { const int64_t *ptr; const int32_t *len; const int32_t *d_col; const double *d_val; };
-RowSrc row_source(scasa_ctx *c, bool genes, bool compact)
+RowSrc row_source(scasa_ctx *c, bool genes, bool compact, bool keep_all = false)
 {
     need_rs_host(c, genes);
     RowSrc src{c->rs_ptr_host.data(), genes ? c->g_len_host.data() : nullptr, genes ? c->d_g_col.p : c->d_rs_col.p,
@@ -460,7 +460,7 @@ RowSrc row_source(scasa_ctx *c, bool genes, bool compact)
     int launches = 0;
     c->d_cmp_len.ensure((size_t)n + 1);
     c->d_cmp_ptr.ensure((size_t)n + 2);
-    row_nonzeros_kernel<<<grid, 256, 0, s>>>(c->d_rs_ptr.p, genes ? c->d_g_len.p : nullptr, src.d_val, n, c->d_cmp_len.p);
+    row_nonzeros_kernel<<<grid, 256, 0, s>>>(c->d_rs_ptr.p, genes ? c->d_g_len.p : nullptr, src.d_val, n, c->d_cmp_len.p, keep_all);
     CK(cudaGetLastError());
     exclusive_scan(c, c->d_cmp_len.p, n, c->d_cmp_ptr.p, c->d_totals.p + 2, launches);
     c->cmp_ptr_host.resize((size_t)n + 1);
@@ -471,7 +471,7 @@ RowSrc row_source(scasa_ctx *c, bool genes, bool compact)
     c->d_cmp_col.ensure((size_t)total + 1);
     c->d_cmp_val.ensure((size_t)total + 1);
     row_compact_kernel<<<grid, 256, 0, s>>>(c->d_rs_ptr.p, genes ? c->d_g_len.p : nullptr, src.d_col, src.d_val, n, c->d_cmp_ptr.p,
-                                            c->d_cmp_col.p, c->d_cmp_val.p);
+                                            c->d_cmp_col.p, c->d_cmp_val.p, keep_all);
     CK(cudaGetLastError());
     return RowSrc{c->cmp_ptr_host.data(), nullptr, c->d_cmp_col.p, c->d_cmp_val.p};
 }
@@ -568,13 +568,19 @@ void fetch_dense(scasa_ctx *c, bool genes, double *out)
 // threads): row r's entries go to cols/vals (either may be null) at dst_off[r]; with drop0 the stored zeros of a row
 // are left out (its entries move up inside the row's span); count[r] (nullable) = entries written for row r.
 // dst_off == nullptr: rows side by side without gaps (isoform rows: the device layout; gene rows: closed up).
+void fetch_rows(scasa_ctx *c, const RowSrc &src, int64_t n_rows, int32_t *cols, double *vals, const int64_t *dst_off, int64_t *count,
+                bool drop0);
 void fetch_sparse(scasa_ctx *c, bool genes, int32_t *cols, double *vals, const int64_t *dst_off, int64_t *count, bool drop0)
 {
-    cudaStream_t s = c->stream;
-    const int64_t n_rows = c->n_cells;
     const bool packed = drop0 && c->d2h_compact;                  // zeros already left behind on the device
     const RowSrc src = row_source(c, genes, packed);
-    if (packed) drop0 = false;
+    fetch_rows(c, src, c->n_cells, cols, vals, dst_off, count, drop0 && !packed);
+}
+// the transfer itself; src may also be rows parked on the device by an earlier slice (HeldRows)
+void fetch_rows(scasa_ctx *c, const RowSrc &src, int64_t n_rows, int32_t *cols, double *vals, const int64_t *dst_off, int64_t *count,
+                bool drop0)
+{
+    cudaStream_t s = c->stream;
     const int64_t *ptr = src.ptr;
     const int32_t *d_col = src.d_col;
     const double *d_val = src.d_val;
@@ -1581,13 +1587,18 @@ template <class T> struct RawBuf {
     ~RawBuf() { free(p); }
 };
 }
+struct HeldRows {                         // a slice's result rows, packed, parked on the device until the host arrays can be sized
+    scasa_ctx *ctx = nullptr;             // the context (device, stream, staging buffers) that owns and later drains them
+    DBuf<int32_t> col;
+    DBuf<double> val;
+    std::vector<int64_t> ptr;             // [rows + 1] row starts inside col / val
+    int64_t c0 = 0, c1 = 0;               // cells of the sample
+};
 struct SparseSink {                       // CSR by cell of the whole sample, assembled from the slices
-    std::vector<int64_t> rowptr;          // [n_cells+1]: entries kept per row at [i+1] while the slices arrive, offsets afterwards
-    std::vector<int64_t> src;             // [n_cells]: where the row starts inside its slice's buffers
-    std::vector<RawBuf<int32_t>> cols;    // per slice
-    std::vector<RawBuf<double>> vals;
-    std::vector<int64_t> slice_c0, slice_c1;
-    bool drop0 = false;                   // leave the stored zeros behind on the way from the device
+    std::vector<int64_t> rowptr;          // [n_cells+1]: entries per row at [i+1] while the slices run, offsets afterwards
+    std::vector<HeldRows> held;           // per slice
+    bool drop0 = false;                   // leave the stored zeros behind
+    ~SparseSink() { for (auto &h : held) { if (h.ctx && (h.col.p || h.val.p)) cudaSetDevice(h.ctx->device); h.col.release(); h.val.release(); } }
 };
 struct QuantOut {
     double *iso = nullptr, *gene = nullptr, *colsum = nullptr;
@@ -1635,21 +1646,17 @@ static int quant_range(scasa_ctx *c, int H0, int H1, const int64_t *chunk_off, c
                 if (!kp) continue;
                 SparseSink &k = *kp;
                 const bool genes = which_sink == 1;
-                const int si = sink_slice0 + sl;
-                k.slice_c0[(size_t)si] = c0; k.slice_c1[(size_t)si] = c1;
-                int64_t nz = 0;
-                rc = genes ? scasa_result_nnz(x, nullptr, &nz) : scasa_result_nnz(x, &nz, nullptr);
-                if (rc) break;
-                k.cols[(size_t)si].alloc((size_t)nz); k.vals[(size_t)si].alloc((size_t)nz);
+                HeldRows &h = k.held[(size_t)(sink_slice0 + sl)];
                 rc = guarded(x, [&] {
-                    need_rs_host(x, genes);
-                    int64_t *off = k.src.data() + c0;                         // rows side by side in the slice's buffers
-                    int64_t run = 0;
-                    for (int64_t i = 0; i < c1 - c0; i++) {
-                        off[i] = run;
-                        run += genes ? x->g_len_host[(size_t)i] : x->rs_ptr_host[(size_t)i + 1] - x->rs_ptr_host[(size_t)i];
-                    }
-                    fetch_sparse(x, genes, k.cols[(size_t)si].p, k.vals[(size_t)si].p, off, k.rowptr.data() + c0 + 1, k.drop0);
+                    // pack the rows on the device (without their zeros, or just closed up) and keep them there: the
+                    // host arrays are sized when every slice of every GPU has run (drain_sink)
+                    row_source(x, genes, true, !k.drop0);
+                    CK(cudaStreamSynchronize(x->stream));
+                    h.ctx = x; h.c0 = c0; h.c1 = c1;
+                    std::swap(h.col, x->d_cmp_col);
+                    std::swap(h.val, x->d_cmp_val);
+                    h.ptr.swap(x->cmp_ptr_host);
+                    for (int64_t i = 0; i < c1 - c0; i++) k.rowptr[(size_t)(c0 + i) + 1] = h.ptr[(size_t)i + 1] - h.ptr[(size_t)i];
                 });
             }
             if (!rc && colparts && c->n_emcols > 0)
@@ -1747,9 +1754,7 @@ static int quant_multi_impl(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cel
     for (SparseSink *k : {out.iso_csr, out.gene_csr})
         if (k) {
             k->rowptr.assign((size_t)n_cells + 1, 0);
-            k->src.assign((size_t)n_cells, 0);
-            k->cols = std::vector<RawBuf<int32_t>>((size_t)sl0[(size_t)n_ctx]); k->vals = std::vector<RawBuf<double>>((size_t)sl0[(size_t)n_ctx]);
-            k->slice_c0.assign((size_t)sl0[(size_t)n_ctx], 0); k->slice_c1.assign((size_t)sl0[(size_t)n_ctx], 0);
+            k->held = std::vector<HeldRows>((size_t)sl0[(size_t)n_ctx]);
         }
     std::vector<int> rcs((size_t)n_ctx, SCASA_OK);
     auto rank = [&](int r) {
@@ -1807,50 +1812,54 @@ int scasa_quant_multi(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, in
 // host, transposed to transcript-major (step2:166) and streamed through the sparse writer.
 namespace {
 struct Flat { std::vector<int64_t> rowptr; RawBuf<int32_t> cols; RawBuf<double> vals; };
-// The slices of a sink -> contiguous arrays (k.rowptr holds the global offsets by now): host threads take blocks of
-// rows; a slice's buffers are released when the last of its rows has been copied.
-void assemble(SparseSink &k, int32_t *cols, double *vals, int n_threads)
+// The parked slices of a sink -> the caller's contiguous arrays (k.rowptr holds the global offsets by now).  Every
+// context drains its own slices on its own thread (a GPU's two contexts, and the GPUs, side by side), each through
+// its pinned staging buffers and the host thread pool, straight to the rows' final place; the device memory of a
+// sample's parked rows is released when all of them are on the host.
+int drain_sink(SparseSink &k, int32_t *cols, double *vals)
 {
-    struct Item { size_t si; int64_t r0, r1; };
-    std::vector<Item> items;
-    for (size_t si = 0; si < k.cols.size(); si++)
-        for (int64_t r = k.slice_c0[si]; r < k.slice_c1[si]; r += 256) items.push_back({si, r, std::min(r + 256, k.slice_c1[si])});
-    std::atomic<size_t> next{0};
-    auto work = [&]() {
-        for (;;) {
-            const size_t i = next.fetch_add(1);
-            if (i >= items.size()) return;
-            const Item &it = items[i];
-            const int32_t *sc = k.cols[it.si].p;
-            const double *sv = k.vals[it.si].p;
-            for (int64_t r = it.r0; r < it.r1; r++) {
-                const int64_t d = k.rowptr[(size_t)r], m = k.rowptr[(size_t)r + 1] - d, o = k.src[(size_t)r];
-                memcpy(cols + d, sc + o, (size_t)m * sizeof(int32_t));
-                memcpy(vals + d, sv + o, (size_t)m * sizeof(double));
-            }
+    std::vector<scasa_ctx *> owners;
+    for (auto &h : k.held)
+        if (h.ctx && std::find(owners.begin(), owners.end(), h.ctx) == owners.end()) owners.push_back(h.ctx);
+    std::vector<int> rcs(owners.size(), SCASA_OK);
+    auto drain = [&](size_t oi) {
+        scasa_ctx *x = owners[oi];
+        for (auto &h : k.held) {
+            if (h.ctx != x || rcs[oi]) continue;
+            rcs[oi] = guarded(x, [&] {
+                const int64_t base = k.rowptr[(size_t)h.c0];
+                const RowSrc src{h.ptr.data(), nullptr, h.col.p, h.val.p};
+                if (h.c1 > h.c0 && h.ptr.back() > 0) fetch_rows(x, src, h.c1 - h.c0, cols + base, vals + base, h.ptr.data(), nullptr, false);
+            });
         }
     };
-    int nthr = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
-    nthr = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::min(nthr, 64), items.size()));
     std::vector<std::thread> th;
-    for (int t = 1; t < nthr; t++) {
+    for (size_t oi = 1; oi < owners.size(); oi++) {
         bool started = false;
-        try { th.emplace_back(work); started = true; } catch (const std::exception &) {}
-        if (!started) break;
+        try { th.emplace_back(drain, oi); started = true; } catch (const std::exception &) {}
+        if (!started) drain(oi);
     }
-    work();
+    if (!owners.empty()) drain(0);
     for (auto &t : th) t.join();
-    for (auto &b : k.cols) b.release();
-    for (auto &b : k.vals) b.release();
+    // cudaFree waits for the whole device: the parked rows go when nobody is copying any more
+    for (auto &h : k.held) {
+        if (h.ctx && (h.col.p || h.val.p)) cudaSetDevice(h.ctx->device);
+        h.col.release(); h.val.release();
+        std::vector<int64_t>().swap(h.ptr);
+    }
+    for (size_t oi = 0; oi < owners.size(); oi++)
+        if (rcs[oi]) return oi == 0 ? rcs[oi] : fail(owners[0], rcs[oi], std::string("GPU ") + std::to_string(owners[oi]->device) + ": " + scasa_last_error(owners[oi]));
+    return SCASA_OK;
 }
-void flatten(SparseSink &k, Flat &f, int n_threads)
+int flatten(SparseSink &k, Flat &f)
 {
     const int64_t nnz = k.rowptr.empty() ? 0 : k.rowptr.back();
     f.cols.alloc((size_t)nnz); f.vals.alloc((size_t)nnz);
-    assemble(k, f.cols.p, f.vals.p, n_threads);
+    const int rc = drain_sink(k, f.cols.p, f.vals.p);
     f.rowptr.swap(k.rowptr);
+    return rc;
 }
-void sink_to_csr(SparseSink &k, int64_t n_cells, scasa_csr_t *out)
+int sink_to_csr(SparseSink &k, int64_t n_cells, scasa_csr_t *out)
 {
     out->n_rows = n_cells; out->nnz = k.rowptr.empty() ? 0 : k.rowptr.back();
     out->ptr = (int64_t *)malloc(((size_t)n_cells + 1) * sizeof(int64_t));
@@ -1858,7 +1867,7 @@ void sink_to_csr(SparseSink &k, int64_t n_cells, scasa_csr_t *out)
     out->val = (double *)big_alloc((size_t)out->nnz * sizeof(double));
     if (!out->ptr || !out->col || !out->val) throw std::bad_alloc();
     std::copy(k.rowptr.begin(), k.rowptr.end(), out->ptr);
-    assemble(k, out->col, out->val, 0);
+    return drain_sink(k, out->col, out->val);
 }
 double wall_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 }  // namespace
@@ -1889,10 +1898,11 @@ int scasa_quant_csr(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, int3
         int rc = quant_multi_impl(ctxs, n_ctx, n_cells, n_chunks, chunk_off, cell_ptr, eq_id, eq_count, n_eq, eq_row, out, 0);
         if (rc) return rc;
         const double t1 = wall_now();
-        sink_to_csr(iso_sink, n_cells, iso);
-        if (gene) sink_to_csr(gene_sink, n_cells, gene);
+        rc = sink_to_csr(iso_sink, n_cells, iso);
+        if (!rc && gene) rc = sink_to_csr(gene_sink, n_cells, gene);
+        if (rc) { scasa_csr_free(iso); scasa_csr_free(gene); return rc; }
         if (getenv("SCASA_FETCH_TRACE"))
-            fprintf(stderr, "[scasa quant_csr] %lld cells: slices %.3f s, assembly %.3f s, %lld + %lld entries\n", (long long)n_cells, t1 - t0,
+            fprintf(stderr, "[scasa quant_csr] %lld cells: slices %.3f s, transfer %.3f s, %lld + %lld entries\n", (long long)n_cells, t1 - t0,
                     wall_now() - t1, (long long)iso->nnz, (long long)(gene ? gene->nnz : 0));
         return SCASA_OK;
     } catch (const std::bad_alloc &) {
@@ -1931,7 +1941,8 @@ int scasa_quant_files(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, in
         // ---- isoforms: transpose, keep rows with rowSums > 0 (step2:167), write
         t0 = wall_now();
         Flat f;
-        flatten(iso_sink, f, n_threads);
+        rc = flatten(iso_sink, f);
+        if (rc) return rc;
         std::vector<int64_t> colptr((size_t)c->n_cols + 1);
         RawBuf<int32_t> cell_idx;
         RawBuf<double> tvals;
@@ -1963,7 +1974,8 @@ int scasa_quant_files(scasa_ctx *const *ctxs, int32_t n_ctx, int64_t n_cells, in
         if (gene_path) {
             t0 = wall_now();
             Flat g;
-            flatten(gene_sink, g, n_threads);
+            rc = flatten(gene_sink, g);
+            if (rc) return rc;
             const int64_t ng = c->n_genes;
             std::vector<int64_t> gptr((size_t)ng + 1);
             RawBuf<int32_t> gcell;

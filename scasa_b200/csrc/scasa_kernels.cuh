@@ -1039,7 +1039,7 @@ __global__ void __launch_bounds__(kGeneRowThreads, 2) gene_rows_kernel(Result R,
 // row_nonzeros_kernel counts, an exclusive scan gives the packed row starts, row_compact_kernel moves the entries
 // (ballot + popcount keep their order).  len == nullptr: full rows.
 __global__ void row_nonzeros_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ len, const double *__restrict__ val,
-                                    int64_t n_rows, int32_t *__restrict__ out)
+                                    int64_t n_rows, int32_t *__restrict__ out, bool keep_all)
 {
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= n_rows) return;
@@ -1047,13 +1047,14 @@ __global__ void row_nonzeros_kernel(const int64_t *__restrict__ ptr, const int32
     const int64_t s = ptr[r];
     const int n = len ? len[r] : (int)(ptr[r + 1] - s);
     int cnt = 0;
-    for (int i = lane; i < n; i += kWarp) cnt += val[s + i] != 0.0;
+    if (keep_all) cnt = lane == 0 ? n : 0;                      // rows only closed up (gene rows have the capacity of the isoform rows)
+    else for (int i = lane; i < n; i += kWarp) cnt += val[s + i] != 0.0;
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(kFull, cnt, o);
     if (lane == 0) out[r] = cnt;
 }
 __global__ void row_compact_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ len, const int32_t *__restrict__ col,
                                    const double *__restrict__ val, int64_t n_rows, const int64_t *__restrict__ out_ptr,
-                                   int32_t *__restrict__ out_col, double *__restrict__ out_val)
+                                   int32_t *__restrict__ out_col, double *__restrict__ out_val, bool keep_all)
 {
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= n_rows) return;
@@ -1066,8 +1067,9 @@ __global__ void row_compact_kernel(const int64_t *__restrict__ ptr, const int32_
         double v = 0.0;
         int c = 0;
         if (i < n) { v = val[s + i]; c = col[s + i]; }
-        const unsigned keep = __ballot_sync(kFull, v != 0.0);
-        if (v != 0.0) {
+        const bool mine = i < n && (keep_all || v != 0.0);
+        const unsigned keep = __ballot_sync(kFull, mine);
+        if (mine) {
             const int64_t d = o + __popc(keep & ((1u << lane) - 1u));
             out_col[d] = c; out_val[d] = v;
         }
