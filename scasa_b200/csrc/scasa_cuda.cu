@@ -1561,12 +1561,16 @@ int scasa_estimate(scasa_ctx *c, int64_t n_cells, int32_t n_chunks, const int64_
 // What a quant call can deliver per slice of chunks.  Dense matrices are expanded into the caller's buffers;
 // the sparse sinks receive the slice's CSR rows as they are on the device (for callers that never want the
 // dense form: the text writers).
-// big host arrays without the zero fill of std::vector (the first touch happens in the threads that write them);
-// large ones are aligned to 2 MB and advised for transparent huge pages: 512 times fewer first-touch faults
+// big host arrays without the zero fill of std::vector (the first touch happens in the threads that write them).
+// Arrays of 256 MB and more are aligned to 2 MB and advised for transparent huge pages: a fresh 4.8 GB result is
+// 1.2 M first-touch faults in 4 KB pages (1.1 s per 100k cells measured, the threads queue on the address-space lock)
+// and 2,400 in 2 MB pages (0.36 s).  Smaller arrays stay with malloc: on a host with fragmented memory a huge-page fault
+// can stall in compaction (measured once: 0.07 -> 0.5 s for the 100 MB arrays of a 5,000-cell sample).  SCASA_THP=0: never.
 inline void *big_alloc(size_t bytes)
 {
     bytes = std::max<size_t>(bytes, 1);
-    if (bytes < ((size_t)8 << 20)) return malloc(bytes);
+    static const bool thp = [] { const char *e = getenv("SCASA_THP"); return !e || atoi(e) != 0; }();
+    if (!thp || bytes < ((size_t)256 << 20)) return malloc(bytes);
     void *p = nullptr;
     if (posix_memalign(&p, (size_t)2 << 20, bytes)) return nullptr;
 #ifdef MADV_HUGEPAGE
