@@ -29,6 +29,9 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 namespace {
 
@@ -160,17 +163,41 @@ int scasa_bfh_open(const char *path, int32_t n_threads, scasa_bfh **out)
     *out = nullptr;
     try {
         std::unique_ptr<scasa_bfh> f(new scasa_bfh());
-        FILE *fp = fopen(path, "rb");
-        if (!fp) return bfh_fail(SCASA_ERR_ARG, std::string("cannot open ") + path);
-        fseek(fp, 0, SEEK_END);
-        const long long size = ftell(fp);
-        fseek(fp, 0, SEEK_SET);
-        f->text.resize((size_t)size + 1);
-        const size_t got = size ? fread(f->text.data(), 1, (size_t)size, fp) : 0;
-        fclose(fp);
-        if ((long long)got != size) return bfh_fail(SCASA_ERR_ARG, std::string("short read of ") + path);
-        f->text[(size_t)size] = '\n';
-        const char *b = f->text.data(), *end = b + size;
+        // the file into one malloc'd buffer, read in slices by the threads (a copy out of the page cache each)
+        int fd = open(path, O_RDONLY);
+        if (fd < 0) return bfh_fail(SCASA_ERR_ARG, std::string("cannot open ") + path);
+        struct stat st;
+        if (fstat(fd, &st) != 0) { close(fd); return bfh_fail(SCASA_ERR_ARG, std::string("cannot stat ") + path); }
+        const int64_t size = (int64_t)st.st_size;
+        f->raw = (char *)malloc((size_t)size + 1);
+        if (!f->raw) { close(fd); return bfh_fail(SCASA_ERR_NOMEM, "host allocation failed"); }
+        f->raw_size = size;
+        int nthr = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+        nthr = std::max(1, std::min(nthr, 256));
+        {
+            const int nr = (int)std::max<int64_t>(1, std::min<int64_t>(nthr, size / ((int64_t)8 << 20) + 1));
+            std::vector<char> ok((size_t)nr, 1);
+            auto read_slice = [&](int t) {
+                int64_t at = size * t / nr;
+                const int64_t stop = size * (t + 1) / nr;
+                while (at < stop) {
+                    const ssize_t got = pread(fd, f->raw + at, (size_t)std::min<int64_t>(stop - at, (int64_t)64 << 20), (off_t)at);
+                    if (got <= 0) { ok[(size_t)t] = 0; return; }
+                    at += got;
+                }
+            };
+            std::vector<std::thread> th;
+            int started = 0;
+            try {
+                for (; started < nr - 1; started++) th.emplace_back(read_slice, started);
+            } catch (const std::exception &) {}
+            for (int t = started; t < nr; t++) read_slice(t);
+            for (auto &x : th) x.join();
+            close(fd);
+            for (char k : ok) if (!k) return bfh_fail(SCASA_ERR_ARG, std::string("short read of ") + path);
+        }
+        f->raw[(size_t)size] = '\n';
+        const char *b = f->raw, *end = b + size;
         for (const char *p = b; p < end;) {
             f->line.push_back(p);
             const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
@@ -188,19 +215,27 @@ int scasa_bfh_open(const char *path, int32_t n_threads, scasa_bfh **out)
         if (f->n_tx >= INT32_MAX || f->n_cb >= INT32_MAX || f->n_eq >= INT32_MAX)
             return bfh_fail(SCASA_ERR_UNSUPPORTED, "bfh: more than 2^31 transcripts, barcodes or eqclasses");
 
-        int nthr = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
-        nthr = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(nthr, 256), f->n_eq / 64 + 1));
+        nthr = (int)std::max<int64_t>(1, std::min<int64_t>(nthr, f->n_eq / 64 + 1));
+        // eqclass ranges of equal size in BYTES (a line holds every cell of its class: lengths differ by orders of magnitude)
+        std::vector<int64_t> cut((size_t)nthr + 1, f->n_eq);
+        cut[0] = 0;
+        {
+            const char *b0 = f->line[(size_t)first_eq], *b1 = f->line[(size_t)(first_eq + f->n_eq)];
+            for (int t = 1; t < nthr; t++) {
+                const char *want = b0 + (b1 - b0) * t / nthr;
+                cut[(size_t)t] = std::lower_bound(f->line.begin() + first_eq, f->line.begin() + first_eq + f->n_eq, want) - (f->line.begin() + first_eq);
+            }
+        }
         std::vector<Part> parts((size_t)nthr);
         {
             std::vector<std::thread> th;
             int started = 0;
             try {
                 for (; started < nthr - 1; started++)
-                    th.emplace_back(parse_range, std::cref(*f), first_eq, f->n_eq * started / nthr, f->n_eq * (started + 1) / nthr,
-                                    std::ref(parts[(size_t)started]));
+                    th.emplace_back(parse_range, std::cref(*f), first_eq, cut[(size_t)started], cut[(size_t)started + 1], std::ref(parts[(size_t)started]));
             } catch (const std::exception &) {}      // fewer threads than asked for: this one parses the rest
             for (int t = started; t < nthr; t++)
-                parse_range(*f, first_eq, f->n_eq * t / nthr, f->n_eq * (t + 1) / nthr, parts[(size_t)t]);
+                parse_range(*f, first_eq, cut[(size_t)t], cut[(size_t)t + 1], parts[(size_t)t]);
             for (auto &x : th) x.join();
         }
         for (auto &p : parts) if (!p.err.empty()) return bfh_fail(SCASA_ERR_ARG, p.err);
@@ -247,18 +282,45 @@ int scasa_bfh_open(const char *path, int32_t n_threads, scasa_bfh **out)
         for (int64_t c = 0; c < n_cells; c++) f->cell_ptr[(size_t)c + 1] += f->cell_ptr[(size_t)c];
         f->eq_id.resize((size_t)n_pairs);
         f->eq_count.resize((size_t)n_pairs);
-        std::vector<int64_t> cur(f->cell_ptr.begin(), f->cell_ptr.end() - 1);
-        int64_t e = 0;
-        for (auto &p : parts) {
-            size_t at = 0;
-            for (int64_t np : p.n_pairs) {
-                for (int64_t k = 0; k < np; k++, at++) {
-                    const int64_t pos = cur[(size_t)f->cell_of_cb[(size_t)p.cb[at]]]++;
-                    f->eq_id[(size_t)pos] = (int32_t)e;
-                    f->eq_count[(size_t)pos] = p.cnt[at];
+        // every part scatters its own pairs: its first slot in a cell = the cell's start + what the earlier parts
+        // (earlier in the file) hold for that cell, so the order inside a cell stays the file order
+        {
+            const size_t np_ = parts.size();
+            std::vector<std::vector<int64_t>> cur(np_);
+            std::vector<int64_t> e_first(np_ + 1, 0);
+            for (size_t t = 0; t < np_; t++) e_first[t + 1] = e_first[t] + (int64_t)parts[t].n_pairs.size();
+            auto count_part = [&](size_t t) {
+                cur[t].assign((size_t)n_cells, 0);
+                for (int32_t cb : parts[t].cb) cur[t][(size_t)f->cell_of_cb[(size_t)cb]]++;
+            };
+            auto scatter_part = [&](size_t t) {
+                const Part &p = parts[t];
+                int64_t e = e_first[t];
+                size_t at = 0;
+                for (int64_t np : p.n_pairs) {
+                    for (int64_t k = 0; k < np; k++, at++) {
+                        const int64_t pos = cur[t][(size_t)f->cell_of_cb[(size_t)p.cb[at]]]++;
+                        f->eq_id[(size_t)pos] = (int32_t)e;
+                        f->eq_count[(size_t)pos] = p.cnt[at];
+                    }
+                    e++;
                 }
-                e++;
+            };
+            auto run_all = [&](auto &&fn) {
+                std::vector<std::thread> th;
+                size_t started = 0;
+                try {
+                    for (; started + 1 < np_; started++) th.emplace_back(fn, started);
+                } catch (const std::exception &) {}
+                for (size_t t = started; t < np_; t++) fn(t);
+                for (auto &x : th) x.join();
+            };
+            run_all(count_part);
+            for (int64_t c = 0; c < n_cells; c++) {              // counts -> first slots
+                int64_t at = f->cell_ptr[(size_t)c];
+                for (size_t t = 0; t < np_; t++) { const int64_t m = cur[t][(size_t)c]; cur[t][(size_t)c] = at; at += m; }
             }
+            run_all(scatter_part);
         }
         *out = f.release();
         return SCASA_OK;

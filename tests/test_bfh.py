@@ -57,6 +57,42 @@ def test_bfh_reader_equals_literal_restatement(tmp_path, crlf, trailing):
             assert got == txs
 
 
+def test_bfh_reader_does_not_depend_on_the_thread_count(tmp_path):
+    """More eqclasses, lines of very different lengths (the ranges are cut by bytes), a file read in slices: the
+    arrays are the same for 1, 2, 5 and 16 threads, and eqclass ids ascend inside every cell (the rbind order)."""
+    from scasa_b200.bfh import read_bfh
+    rng = np.random.default_rng(5)
+    path = str(tmp_path / "bfh.txt")
+    n_tx, n_cb, n_eq = 300, 400, 3000
+    tx = [f"NM_{i}" for i in range(n_tx)]
+    cb = ["".join(rng.choice(list("ACGT"), 16)) for _ in range(n_cb)]
+    lines = [str(n_tx), str(n_cb), str(n_eq)] + tx + cb
+    for e in range(n_eq):
+        k = int(rng.integers(1, 8))
+        tids = sorted(rng.choice(n_tx, k, replace=False).tolist())
+        nb = int(rng.integers(200, 390)) if e % 97 == 0 else int(rng.integers(1, 6))      # a few classes hold most cells
+        body, total = [], 0
+        for b in rng.choice(n_cb, nb, replace=False).tolist():
+            numi = int(rng.integers(1, 4))
+            body += [str(b), str(numi)]
+            for _u in range(numi):
+                c = int(rng.integers(1, 9))
+                total += c
+                body += ["".join(rng.choice(list("ACGT"), 10)), str(c)]
+        lines.append("\t".join([str(k)] + [str(t) for t in tids] + [str(total), str(nb)] + body))
+    with open(path, "w", newline="") as fh:
+        fh.write("\n".join(lines) + "\n")
+    a = read_bfh(path, 1)
+    assert len(a.eq_off) == n_eq + 1 and a.cell_ptr[-1] == len(a.eq_id) > 15000
+    for c in range(len(a.barcodes)):
+        assert np.all(np.diff(a.eq_id[a.cell_ptr[c]:a.cell_ptr[c + 1]]) > 0)
+    for threads in (2, 5, 16):
+        b = read_bfh(path, threads)
+        assert a.barcodes == b.barcodes and a.tx_names == b.tx_names
+        for k in ("eq_off", "eq_tx", "cell_ptr", "eq_id", "eq_count"):
+            assert np.array_equal(getattr(a, k), getattr(b, k)), (threads, k)
+
+
 def test_bfh_errors(tmp_path):
     from scasa_b200 import lib
     from scasa_b200.bfh import read_bfh

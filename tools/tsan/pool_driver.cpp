@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <random>
@@ -46,6 +47,12 @@ int main() {
                     }
                 }
                 free(raw);
+                // a row-range job (the sparse fetch): every row visited exactly once, also when it overlaps the other producer's jobs
+                std::vector<int> seen((size_t)n_rows, 0);
+                auto j2 = pool.post_fn(n_rows, [&seen](int64_t a, int64_t e) { for (int64_t i = a; i < e; i++) seen[(size_t)i]++; });
+                pool.wait(j2);
+                for (int v : seen) if (v != 1) { printf("MISMATCH (row job)\n"); exit(1); }
+                pool.wait(pool.post_fn(0, [](int64_t, int64_t) {}));          // an empty job is done at once
             }
         };
         std::thread t1(producer, it * 2 + 1), t2(producer, it * 2 + 2);

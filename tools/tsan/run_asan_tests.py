@@ -6,9 +6,10 @@ L = C.CDLL('/tmp/scasa_tsan/libhost_asan.so')
 L.scasa_last_error.restype = C.c_char_p
 import re
 src = open('/root/repo/scasa_b200/lib.py').read()
+src = re.sub(r",\n\s+", ", ", src)                      # argtypes lists that continue on the next line
 # reuse the argtypes lib.py declares for the host-only entry points
 vp, i32p, i64p, f64p, u8p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_uint8)
-for m in re.finditer(r"^    L\.(scasa_(?:bfh|bus|write|format)[a-z0-9_]*)\.(argtypes|restype) = (.*)$", src, re.M):
+for m in re.finditer(r"^    L\.(scasa_(?:bfh|bus|write|format|csr_transpose)[a-z0-9_]*)\.(argtypes|restype) = (.*)$", src, re.M):
     setattr(getattr(L, m.group(1)), m.group(2), eval(m.group(3)))
 _l.load = lambda: L
 _l._lib = L
