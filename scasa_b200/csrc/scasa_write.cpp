@@ -36,6 +36,19 @@ constexpr int kDigits = 15;        // R_print.digits inside writetable
 constexpr int kKpMax = 22;         // KP_MAX of format.c
 constexpr int kDecMinExp = -308;   // R_dec_min_exponent on IEEE doubles
 
+// powl(10.0L, k) for the exponents a double can have: the values of the very call format.c makes, computed once
+// (powl itself costs ~300 ns, more than the rest of a number's formatting together)
+inline long double pow10l_cached(int k)
+{
+    constexpr int kLo = -700, kHi = 700;
+    static const std::vector<long double> tbl = [] {
+        std::vector<long double> t((size_t)(kHi - kLo + 1));
+        for (int e = kLo; e <= kHi; e++) t[(size_t)(e - kLo)] = powl(10.0L, e);
+        return t;
+    }();
+    return (k >= kLo && k <= kHi) ? tbl[(size_t)(k - kLo)] : powl(10.0L, k);
+}
+
 // format.c scientific() for one finite non-zero |x|, digits = 15 (the long double branch)
 void r_scientific(double x, int &neg, int &kpower, int &nsig, bool &widens)
 {
@@ -46,10 +59,11 @@ void r_scientific(double x, int &neg, int &kpower, int &nsig, bool &widens)
     long double r_prec = r;
     if (std::abs(kp) < 10) {
         if (kp > 0) r_prec /= kTbl[kp]; else if (kp < 0) r_prec *= kTbl[-kp];
-    } else if (kp <= kDecMinExp) r_prec = (r * 1e+303L) / powl(10.0L, kp + 303);
-    else r_prec /= powl(10.0L, kp);
+    } else if (kp <= kDecMinExp) r_prec = (r * 1e+303L) / pow10l_cached(kp + 303);
+    else r_prec /= pow10l_cached(kp);
     if (r_prec < kTbl[R - 1]) { r_prec *= 10.0L; kp--; }
-    double alpha = (double)nearbyintl(r_prec);
+    // nearbyintl (x87 frndint) is slow; below 2^63 llrintl rounds the same way (current mode: to nearest even)
+    double alpha = r_prec < 9.0e18L ? (double)llrintl(r_prec) : (double)nearbyintl(r_prec);
     nsig = R;
     for (int j = 1; j <= R; j++) {
         alpha /= 10.0;
