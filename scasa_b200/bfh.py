@@ -26,7 +26,15 @@ class Bfh:
     def tx_ids(self, xm) -> np.ndarray:
         """eq_tx in the X-matrix's transcript dictionary (what ``scasa_eqclass_map`` wants);
         transcripts the X-matrix does not know get ids past its dictionary."""
-        lut = {name: i for i, name in enumerate(xm.tx_names)}
+        lut = getattr(xm, "_tx_lut", None)                 # the X-matrix's dictionary, built once per X-matrix
+        if lut is None:
+            lut = {}
+            for i, name in enumerate(xm.tx_names):
+                lut[name] = i                               # a repeated name keeps its last index, as the dict comprehension did
+            try:
+                xm._tx_lut = lut
+            except AttributeError:
+                pass
         n = len(xm.tx_names)
         table = np.array([lut.get(name, n + k) for k, name in enumerate(self.tx_names)], np.int32)
         return table[self.eq_tx]
