@@ -41,6 +41,10 @@ deliberately thin — every decision lives behind the C ABI (`include/scasa_cuda
 
 Limits (checked, reported as `SCASA_ERR_UNSUPPORTED`): ≤ 65,535 rows and ≤ 1,024 columns per block, ≤ 65,535 cells per
 chunk, ≤ 16,384 eqclasses per cell, a poor-condition block ≤ 64 rows, a (chunk, block) task ≤ 200 KB of shared memory.
+Gene sums on the device keep a member table in shared memory: (isoform columns of multi-isoform genes + number of such
+genes) × 2 bytes (4 when the X-matrix has ≥ 65,534 columns) + n_genes / 4 + 29 KB must stay ≤ 200 KB — about 85 k such
+columns (42 k for the wide X-matrices); the shipped hg38 annotation needs 65 KB, the 106 k-column synthetic C3 case 174 KB.
+Beyond that `scasa_run` reports it and `scasa_gene_sum` (any size, from a dense isoform matrix) remains.
 
 ## 2. The R shim (`integration/scasa_r.c`: `.Call`, built on the user's machine with `R CMD SHLIB`)
 
